@@ -1,0 +1,72 @@
+"""Builds csrc/*.cu into lib/libparsenet_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+
+One object per .cu (compiled in parallel), linked into a single C-ABI shared library.  The .so stays
+in-tree (git-ignored, NOT gpurun-ignored) so it travels to the GPU box with the snapshot.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libparsenet_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", CSRC,
+         "-I", os.path.join(os.path.dirname(HERE), "include")]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _headers_mtime():
+    m = 0.0
+    for d in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        if os.path.isdir(d):
+            for f in os.listdir(d):
+                if f.endswith((".cuh", ".h")):
+                    m = max(m, os.path.getmtime(os.path.join(d, f)))
+    return m
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    hm = _headers_mtime()
+    jobs = []
+    objs = []
+    for s in _sources():
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(OBJ, s[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hm):
+            jobs.append((src, obj))
+
+    def run(job):
+        src, obj = job
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        return src, p.returncode, p.stdout + p.stderr
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for src, rc, out in ex.map(run, jobs):
+                if verbose or rc != 0:
+                    sys.stderr.write(out)
+                if rc != 0:
+                    raise RuntimeError(f"nvcc failed on {src}")
+    if jobs or not os.path.exists(LIB):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout + p.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,343 @@
+// kNN graph build: tiled fp32 distance + streaming top-k; the N x N matrix never exists in HBM.
+//
+// Replaces (reference, relative to /root/reference):
+//   knn                 src/PointNet.py:9-26  and  src/model.py:9-22
+//   knn_points_normals  src/PointNet.py:29-69
+// which materialise a (B,N,N) fp32 matrix (6.4 GB at B=16,N=10^4) and run a full-row torch.topk.
+//
+// Arithmetic contract (bit-exact with oracle/c/knn_oracle.c): the ranked value is
+//   metric 0:  D = (-xx_j - (-2*dot(x_i,x_j))) - xx_i
+//   metric 1:  D = -(((xx_j - 2*dot(p_i,p_j)) + xx_i) * (1 + (2 - 2*dot(n_i,n_j))))
+// dot / xx are fmaf chains over channels in increasing order starting from +0; ranking is D descending,
+// ties to the lower candidate index.  This stays on the FP32 FMA pipe on purpose: TF32/BF16 tensor-core
+// products would change near-tie ordering (north_star: indices bit-exact).
+//
+// Kernel shape: one CTA = 64 query rows x all candidates, streamed in 128-wide tiles.
+//   * 256 threads, each owns a 4(query) x 8(candidate) register tile; K is streamed in 32-channel chunks
+//     through shared memory stored channel-major so the inner loop is 3 LDS.128 + 32 FFMA.
+//   * the finished 64x128 tile of D goes through shared memory to 8 selection warps (8 rows each):
+//     candidates that beat the row's current k-th best are appended to a per-row buffer (CAP entries);
+//     when it would overflow the owning warp bitonic-sorts it in registers and keeps the best k.
+//   * smem ~105 KB -> 2 CTAs/SM; grid = ceil(N/64) x B  (2512 CTAs at B=16,N=10^4 = 8.5 waves of 296).
+#include "common.cuh"
+
+namespace pn {
+namespace knn {
+
+constexpr int TQ = 64;    // query rows per CTA
+constexpr int TC = 128;   // candidates per tile
+constexpr int KC = 32;    // channels per shared-memory chunk
+constexpr int NT = 256;
+
+__global__ void norms_kernel(const float* __restrict__ x, long long rows, int ld, int c0, int c1,
+                             float* __restrict__ xx) {
+    long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* p = x + r * ld;
+    float acc = 0.f;
+    for (int c = c0; c < c1; ++c) acc = fmaf(p[c], p[c], acc);
+    xx[r] = acc;
+}
+
+// ---- warp bitonic sort of CAP (key desc-distance / asc-index) entries, R = CAP/32 per lane ----
+template <int R>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long (&key)[R], int lane) {
+    constexpr int CAP = R * 32;
+#pragma unroll
+    for (int k = 2; k <= CAP; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int rj = j >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & rj) == 0) {
+                        const int p = r * 32;  // lane bits do not matter for k>=64 & j>=32 direction test below
+                        // direction depends on bit k of the element index p = r*32+lane (k >= 64 here, or k==CAP)
+                        bool up = ((p & k) == 0);
+                        unsigned long long a = key[r], b = key[r ^ rj];
+                        bool sw = up ? (a > b) : (a < b);
+                        key[r] = sw ? b : a;
+                        key[r ^ rj] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int p = r * 32 + lane;
+                    unsigned long long a = key[r];
+                    unsigned long long b = __shfl_xor_sync(FULL, a, j);
+                    bool up = ((p & k) == 0);
+                    bool lower = ((lane & j) == 0);
+                    bool keep_min = (up == lower);
+                    key[r] = keep_min ? (a < b ? a : b) : (a < b ? b : a);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long make_key(float d, int j) {
+    return ((unsigned long long)(~f2ord(d)) << 32) | (unsigned)j;
+}
+
+// sort the row buffer, keep the best k, return new count; *tau_out = k-th best value (or -inf)
+template <int CAP>
+__device__ __forceinline__ int compact_row(float* bv, int* bi, int n, int k, int lane, float* tau_out) {
+    constexpr int R = CAP / 32;
+    unsigned long long key[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int p = r * 32 + lane;
+        key[r] = (p < n) ? make_key(bv[p], bi[p]) : ~0ull;
+    }
+    __syncwarp();
+    warp_bitonic_sort<R>(key, lane);
+    int nn = n < k ? n : k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int p = r * 32 + lane;
+        if (p < nn) {
+            bv[p] = ord2f(~(uint32_t)(key[r] >> 32));
+            bi[p] = (int)(uint32_t)(key[r] & 0xffffffffu);
+        }
+    }
+    __syncwarp();
+    *tau_out = (nn == k) ? bv[k - 1] : -INFINITY;
+    return nn;
+}
+
+template <int METRIC, int CAP, typename IdxT>
+__global__ void __launch_bounds__(NT, 2)
+knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int C, int ld, int k,
+           IdxT* __restrict__ idx_out, float* __restrict__ dist_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout
+    float* xs = reinterpret_cast<float*>(smem_raw);           // [KC][TC]   (aliased by Dt [TQ][TC])
+    float* Dt = xs;
+    float* qs = xs + TQ * TC;                                  // [KC][TQ]
+    float* xxq = qs + KC * TQ;                                 // [TQ]
+    float* xxc = xxq + TQ;                                     // [TC]
+    float* tau = xxc + TC;                                     // [TQ]
+    int* cnt = reinterpret_cast<int*>(tau + TQ);               // [TQ]
+    float* bufv = reinterpret_cast<float*>(cnt + TQ);          // [TQ][CAP]
+    int* bufi = reinterpret_cast<int*>(bufv + TQ * CAP);       // [TQ][CAP]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int q0 = blockIdx.x * TQ;
+    const float* xb = x + (size_t)b * N * ld;
+    const float* xxb = xx + (size_t)b * N;
+    const int tq = tid >> 4;   // 0..15 -> queries 4*tq..4*tq+3
+    const int tc = tid & 15;   // 0..15 -> candidates 4*tc..+3 and 64+4*tc..+3
+
+    if (tid < TQ) {
+        int q = q0 + tid;
+        xxq[tid] = (q < N) ? xxb[q] : 0.f;
+        tau[tid] = -INFINITY;
+        cnt[tid] = 0;
+    }
+    const bool q_resident = (C <= KC);
+    if (q_resident) {
+        for (int e = tid; e < TQ * C; e += NT) {
+            int p = e % TQ, c = e / TQ;
+            int q = q0 + p;
+            qs[c * TQ + p] = (q < N) ? xb[(size_t)q * ld + c] : 0.f;
+        }
+    }
+
+    for (int j0 = 0; j0 < N; j0 += TC) {
+        float acc[4][8];
+        float accn[METRIC == 1 ? 4 : 1][METRIC == 1 ? 8 : 1];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[a][c] = 0.f;
+        if (METRIC == 1) {
+#pragma unroll
+            for (int a = 0; a < (METRIC == 1 ? 4 : 1); ++a)
+#pragma unroll
+                for (int c = 0; c < (METRIC == 1 ? 8 : 1); ++c) accn[a][c] = 0.f;
+        }
+
+        for (int c0 = 0; c0 < C; c0 += KC) {
+            const int kc = min(KC, C - c0);
+            __syncthreads();   // previous readers of xs / Dt / qs are done
+            for (int e = tid; e < TC * kc; e += NT) {
+                int p = e % TC, c = e / TC;
+                int j = j0 + p;
+                xs[c * TC + p] = (j < N) ? xb[(size_t)j * ld + c0 + c] : 0.f;
+            }
+            if (!q_resident) {
+                for (int e = tid; e < TQ * kc; e += NT) {
+                    int p = e % TQ, c = e / TQ;
+                    int q = q0 + p;
+                    qs[c * TQ + p] = (q < N) ? xb[(size_t)q * ld + c0 + c] : 0.f;
+                }
+            }
+            if (c0 == 0 && tid < TC) {
+                int j = j0 + tid;
+                xxc[tid] = (j < N) ? xxb[j] : 0.f;
+            }
+            __syncthreads();
+            if constexpr (METRIC == 0) {
+#pragma unroll 8
+                for (int c = 0; c < kc; ++c) {
+                    float4 qv = *reinterpret_cast<const float4*>(qs + c * TQ + 4 * tq);
+                    float4 xa = *reinterpret_cast<const float4*>(xs + c * TC + 4 * tc);
+                    float4 xc = *reinterpret_cast<const float4*>(xs + c * TC + 64 + 4 * tc);
+                    const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+                    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) acc[a][cc] = fmaf(qa[a], xv[cc], acc[a][cc]);
+                }
+            } else {
+                // C == 6: channels 0..2 positions, 3..5 normals (single chunk)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    float4 qv = *reinterpret_cast<const float4*>(qs + c * TQ + 4 * tq);
+                    float4 xa = *reinterpret_cast<const float4*>(xs + c * TC + 4 * tc);
+                    float4 xc = *reinterpret_cast<const float4*>(xs + c * TC + 64 + 4 * tc);
+                    const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+                    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) {
+                            if (c < 3) acc[a][cc] = fmaf(qa[a], xv[cc], acc[a][cc]);
+                            else accn[a][cc] = fmaf(qa[a], xv[cc], accn[a][cc]);
+                        }
+                }
+            }
+        }
+        __syncthreads();   // all reads of xs done -> reuse as Dt
+        // ---- distances into the shared tile
+        {
+            float xq[4], xc8[8];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) xq[a] = xxq[4 * tq + a];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) xc8[cc] = xxc[(cc < 4 ? 0 : 60) + 4 * tc + cc];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                float dv[8];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    int j = j0 + (cc < 4 ? 0 : 60) + 4 * tc + cc;
+                    float D;
+                    if constexpr (METRIC == 0) {
+                        float inner = __fmul_rn(-2.0f, acc[a][cc]);
+                        D = __fsub_rn(__fsub_rn(-xc8[cc], inner), xq[a]);
+                    } else {
+                        float pd = __fadd_rn(__fsub_rn(xc8[cc], __fmul_rn(2.0f, acc[a][cc])), xq[a]);
+                        float nd = __fsub_rn(2.0f, __fmul_rn(2.0f, accn[a][cc]));
+                        D = -__fmul_rn(pd, __fadd_rn(1.0f, nd));
+                    }
+                    dv[cc] = (j < N) ? D : -INFINITY;
+                }
+                float* row = Dt + (4 * tq + a) * TC;
+                *reinterpret_cast<float4*>(row + 4 * tc) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+                *reinterpret_cast<float4*>(row + 64 + 4 * tc) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+            }
+        }
+        __syncthreads();
+        // ---- selection: warp w owns rows 8w..8w+7
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+            const int row = warp * 8 + r;
+            float t = tau[row];
+            int n = cnt[row];
+            float* bv = bufv + row * CAP;
+            int* bi = bufi + row * CAP;
+#pragma unroll
+            for (int ch = 0; ch < TC / 32; ++ch) {
+                float d = Dt[row * TC + ch * 32 + lane];
+                bool pass = d > t;
+                unsigned m = __ballot_sync(FULL, pass);
+                if (m) {
+                    int c = __popc(m);
+                    if (n + c > CAP) n = compact_row<CAP>(bv, bi, n, k, lane, &t);
+                    if (pass) {
+                        int pos = n + __popc(m & ((1u << lane) - 1u));
+                        bv[pos] = d;
+                        bi[pos] = j0 + ch * 32 + lane;
+                    }
+                    n += c;
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) { tau[row] = t; cnt[row] = n; }
+        }
+        // next iteration starts with __syncthreads()
+    }
+    __syncwarp();
+    // ---- final sort + write-out
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+        const int row = warp * 8 + r;
+        const int q = q0 + row;
+        float t;
+        float* bv = bufv + row * CAP;
+        int* bi = bufi + row * CAP;
+        int n = compact_row<CAP>(bv, bi, cnt[row], k, lane, &t);
+        if (q < N) {
+            size_t o = ((size_t)b * N + q) * k;
+            for (int p = lane; p < k; p += 32) {
+                idx_out[o + p] = (IdxT)((p < n) ? bi[p] : 0);
+                if (dist_out) dist_out[o + p] = (p < n) ? bv[p] : -INFINITY;
+            }
+        }
+    }
+}
+
+static size_t smem_bytes(int cap) {
+    return sizeof(float) * (TQ * TC + KC * TQ + TQ + TC + TQ) + sizeof(int) * TQ +
+           (size_t)TQ * cap * (sizeof(float) + sizeof(int));
+}
+
+template <int METRIC, int CAP, typename IdxT>
+static int launch(const float* x, const float* xx, int B, int N, int C, int ld, int k, void* idx, float* dist,
+                  cudaStream_t st) {
+    auto kern = knn_kernel<METRIC, CAP, IdxT>;
+    size_t sm = smem_bytes(CAP);
+    PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid(cdiv(N, TQ), B);
+    kern<<<grid, NT, sm, st>>>(x, xx, N, C, ld, k, (IdxT*)idx, dist);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("knn_kernel");
+    return PN_OK;
+}
+
+template <int METRIC, typename IdxT>
+static int dispatch_cap(const float* x, const float* xx, int B, int N, int C, int ld, int k, void* idx, float* dist,
+                        cudaStream_t st) {
+    if (k <= 32) return launch<METRIC, 64, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st);
+    if (k <= 96) return launch<METRIC, 128, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st);
+    return launch<METRIC, 256, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st);
+}
+
+}  // namespace knn
+}  // namespace pn
+
+using namespace pn;
+
+extern "C" int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out,
+                      int idx_is_i64, float* dist_out, float* ws_norms, void* stream) {
+    PN_REQUIRE(x && idx_out && ws_norms, "pn_knn: null pointer");
+    PN_REQUIRE(B > 0 && N > 0 && C > 0 && ld >= C, "pn_knn: bad shape B=%d N=%d C=%d ld=%d", B, N, C, ld);
+    PN_REQUIRE(k > 0 && k <= N && k <= 224, "pn_knn: need 0 < k <= min(N,224), got k=%d N=%d", k, N);
+    PN_REQUIRE(metric == 0 || (metric == 1 && C == 6), "pn_knn: metric 1 needs C == 6");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long rows = (long long)B * N;
+    knn::norms_kernel<<<cdiv(rows, 256), 256, 0, st>>>(x, rows, ld, 0, metric == 1 ? 3 : C, ws_norms);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("knn norms_kernel");
+    if (metric == 0) {
+        return idx_is_i64 ? knn::dispatch_cap<0, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st)
+                          : knn::dispatch_cap<0, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st);
+    }
+    return idx_is_i64 ? knn::dispatch_cap<1, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st)
+                      : knn::dispatch_cap<1, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st);
+}

@@ -1,0 +1,62 @@
+"""ctypes binding of lib/libparsenet_b200.so (declared in include/parsenet_b200.h).
+
+Fails loudly when the library is missing — there is deliberately no fallback path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libparsenet_b200.so")
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_f = ctypes.c_float
+c_ll = ctypes.c_longlong
+
+# name -> argtypes (all return int status unless listed in _SPECIAL)
+SIGNATURES = {
+    "pn_knn": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p],
+}
+_SPECIAL = {
+    "pn_last_error": (ctypes.c_char_p, []),
+    "pn_launch_count": (ctypes.c_ulonglong, []),
+    "pn_reset_launch_count": (None, []),
+    "pn_abi_version": (c_i, []),
+}
+
+
+class PnError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python parsenet-codebase_b200/build.py` "
+            "(or __graft_entry__.build()). parsenet_b200 has no CPU/eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.argtypes = argtypes
+        fn.restype = c_i
+    for name, (res, argtypes) in _SPECIAL.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = res
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    if rc != 0:
+        raise PnError(f"{what} failed (rc={rc}): {lib.pn_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib.pn_launch_count())
+
+
+def reset_launch_count():
+    lib.pn_reset_launch_count()

@@ -1,0 +1,68 @@
+"""kNN parity: CUDA path (through the C-ABI) vs the oracle (oracle/c/knn_oracle.c) — bit-exact indices."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _cloud(B, N, C, seed, metric):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, N, C, generator=g) * 0.3
+    if metric == 1:
+        x[..., 3:] = torch.nn.functional.normalize(x[..., 3:], dim=-1)
+    return x
+
+
+@pytest.mark.parametrize("B,N,C,k,metric", [
+    (2, 1000, 3, 10, 0), (2, 777, 6, 80, 1), (1, 2048, 64, 80, 0), (2, 500, 64, 10, 0),
+    (1, 1500, 128, 10, 0), (1, 600, 256, 10, 0), (1, 80, 6, 80, 1), (1, 4000, 64, 80, 0), (1, 300, 64, 200, 0),
+])
+def test_knn_bit_exact_vs_oracle(B, N, C, k, metric):
+    from oracle import knn as oknn
+    from pnb200 import ops
+    x = _cloud(B, N, C, 1234 + N, metric)
+    want, wdist = oknn.knn(x.numpy(), k, metric, return_dist=True)
+    got, gdist = ops.knn_graph(x.cuda(), k, metric, out_dtype=torch.int64, return_dist=True)
+    got = got.cpu().numpy()
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(gdist.cpu().numpy(), wdist)
+
+
+def test_knn_strided_slice_and_int32():
+    from oracle import knn as oknn
+    from pnb200 import ops
+    full = _cloud(2, 900, 256, 7, 0).cuda()
+    sl = full[:, :, 64:128]
+    want = oknn.knn(sl.cpu().contiguous().numpy(), 80, 0)
+    got = ops.knn_graph(sl, 80, 0)
+    assert got.dtype == torch.int32
+    np.testing.assert_array_equal(got.cpu().numpy().astype(np.int64), want)
+
+
+def test_knn_duplicates_tie_break_lower_index():
+    from oracle import knn as oknn
+    from pnb200 import ops
+    x = _cloud(1, 400, 3, 3, 0)
+    x[0, 200:] = x[0, :200]  # exact duplicates -> exact ties
+    want = oknn.knn(x.numpy(), 20, 0)
+    got = ops.knn_graph(x.cuda(), 20, 0, out_dtype=torch.int64).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+def test_knn_full_size_self_first_and_sorted():
+    """BASELINE size (N=10^4,k=80): properties that do not need the O(N^2) CPU oracle on every row."""
+    from oracle import knn as oknn
+    from pnb200 import ops
+    x = _cloud(2, 10000, 64, 11, 0)
+    idx, dist = ops.knn_graph(x.cuda(), 80, 0, out_dtype=torch.int64, return_dist=True)
+    idx = idx.cpu().numpy(); dist = dist.cpu().numpy()
+    assert (np.diff(dist, axis=-1) <= 0).all()
+    assert (idx[:, :, 0] == np.arange(10000)[None]).mean() > 0.999
+    rows = [0, 1, 4999, 9999]
+    for b in range(2):
+        for r in rows:
+            full = oknn.knn_row(x[b].numpy(), r, 0)
+            order = np.lexsort((np.arange(10000), -full))[:80]
+            np.testing.assert_array_equal(idx[b, r], order)
