@@ -14,8 +14,34 @@ c_f = ctypes.c_float
 c_ll = ctypes.c_longlong
 
 # name -> argtypes (all return int status unless listed in _SPECIAL)
+c_d = ctypes.c_double
 SIGNATURES = {
     "pn_knn": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p],
+    # linear.cu
+    "pn_linear_fwd": [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_i, c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "pn_linear_bwd_data": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_p, c_ll, c_p, c_p, c_i, c_p, c_p, c_p,
+                           c_i, c_i, c_i, c_i, c_i, c_i, c_p],
+    "pn_linear_bwd_weight": [c_p, c_ll, c_p, c_ll, c_p, c_p, c_i, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "pn_norm_finalize": [c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_f, c_p, c_p, c_p, c_p],
+    "pn_norm_bwd_apply": [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_p, c_p, c_p],
+    # edgeconv.cu
+    "pn_edge_gather_fwd": [c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p],
+    "pn_edge_apply": [c_p, c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_p],
+    "pn_edge_bwd_prep": [c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "pn_knn_csr_transpose": [c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "pn_edge_bwd": [c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_i,
+                    c_p, c_ll, c_p],
+    # pointwise.cu
+    "pn_colmax_norm": [c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
+    "pn_colmax_bwd_fill": [c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_i, c_p, c_ll, c_p],
+    "pn_logsoftmax_fwd": [c_p, c_ll, c_i, c_i, c_i, c_p, c_p],
+    "pn_logsoftmax_bwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_ll, c_p],
+    "pn_nll_fwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p],
+    "pn_nll_bwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p],
+    "pn_l2norm_fwd": [c_p, c_ll, c_ll, c_i, c_f, c_p, c_ll, c_p, c_p],
+    "pn_l2norm_bwd": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_p, c_ll, c_i, c_p],
+    "pn_triplet_fwd": [c_p, c_ll, c_i, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p],
+    "pn_triplet_bwd": [c_p, c_ll, c_i, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p],
 }
 _SPECIAL = {
     "pn_last_error": (ctypes.c_char_p, []),

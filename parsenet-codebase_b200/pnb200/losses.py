@@ -1,0 +1,117 @@
+"""Segmentation losses on top of the kernels: triplet embedding loss and NLL over primitive types.
+
+Reference: EmbeddingLoss.triplet_loss src/segment_loss.py:31-124, primitive_loss :151.  The random sampling stays on
+the host with numpy so that the draw order (and hence the loss value for a given np.random state) is the
+reference's; only index lists go to the device.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .cabi import lib, check
+from .ops import _ptr, _stream
+
+
+def triplet_sample(labels, N, rng=np.random, max_segments=5):
+    """Consumes host RNG draws exactly like segment_loss.py:60-96.  Returns per-S groups of
+    (anchor rows, negative rows, weight) with rows indexing the flattened (B*N) embedding, and only_one count."""
+    B = labels.shape[0]
+    samples, S_of = [], []
+    for i in range(B):
+        p = labels[i]
+        uniq = np.unique(p)
+        S = min(N // uniq.shape[0] + 1, 30)
+        d = {}
+        for l in uniq:
+            d[l] = rng.choice(list(np.where(np.isin(p, l))[0]), S, replace=True)
+        samples.append(d)
+        S_of.append(S)
+    groups = {}
+    only_one = 0
+    per_shape_norm = []
+    for i in range(B):
+        keys = sorted(samples[i].keys())
+        L = len(keys)
+        if L == 1:
+            only_one += 1
+            per_shape_norm.append(0)
+            continue
+        norm = 0
+        pairs = []
+        for _ in range(min(max_segments * max_segments, L * L)):
+            k1 = rng.choice(L, 1)[0]
+            k2 = rng.choice(L, 1)[0]
+            if k1 == k2:
+                continue
+            norm += 1
+            pairs.append((samples[i][keys[k1]] + i * N, samples[i][keys[k2]] + i * N))
+        per_shape_norm.append(norm)
+        g = groups.setdefault(S_of[i], dict(a=[], n=[], shape=[]))
+        for a, n in pairs:
+            g["a"].append(a); g["n"].append(n); g["shape"].append(i)
+    denom = B - only_one + 1e-8
+    out = []
+    for S, g in groups.items():
+        if not g["a"]:
+            continue
+        w = np.array([1.0 / ((per_shape_norm[i] + 1e-8) * denom) for i in g["shape"]], np.float32)
+        out.append((S, np.stack(g["a"]).astype(np.int32), np.stack(g["n"]).astype(np.int32), w))
+    return out
+
+
+class TripletFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb_bnd, groups, margin):
+        x = emb_bnd.detach()
+        B, N, D = x.shape
+        x2 = x.reshape(B * N, D)
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        E, norms = ops.l2norm_fwd(x2)
+        dev = x.device
+        total = torch.zeros((1,), dtype=torch.float32, device=dev)
+        saved = []
+        for S, a, n, w in groups:
+            T = a.shape[0]
+            a_d = torch.from_numpy(a).to(dev)
+            n_d = torch.from_numpy(n).to(dev)
+            w_d = torch.from_numpy(w).to(dev)
+            pl = torch.empty((T,), dtype=torch.float32, device=dev)
+            ps = torch.empty((T,), dtype=torch.float32, device=dev)
+            check(lib.pn_triplet_fwd(_ptr(E), D, D, _ptr(a_d), _ptr(n_d), T, S, float(margin), _ptr(pl), _ptr(ps),
+                                     _stream()), "pn_triplet_fwd")
+            total = total + (pl * w_d).sum()
+            saved.append((S, a_d, n_d, w_d, ps))
+        ctx.saved = (E, norms, saved, margin, (B, N, D))
+        return total
+
+    @staticmethod
+    def backward(ctx, g):
+        E, norms, saved, margin, (B, N, D) = ctx.saved
+        dE = torch.zeros_like(E)
+        for S, a_d, n_d, w_d, ps in saved:
+            pw = (w_d * g.reshape(())).contiguous()
+            check(lib.pn_triplet_bwd(_ptr(E), D, D, _ptr(a_d), _ptr(n_d), a_d.shape[0], S, float(margin), _ptr(ps),
+                                     _ptr(pw), _ptr(dE), D, _stream()), "pn_triplet_bwd")
+        dx = ops.l2norm_bwd(E, dE, norms)
+        return dx.view(B, N, D), None, None
+
+
+class NllFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logp_bpn, target_bn):
+        lp = logp_bpn.detach().contiguous()
+        tg = target_bn.detach().to(torch.int64).contiguous()
+        B, P, N = lp.shape
+        loss = torch.zeros((1,), dtype=torch.float32, device=lp.device)
+        check(lib.pn_nll_fwd(_ptr(lp), _ptr(tg), B, N, P, _ptr(loss), _stream()), "pn_nll_fwd")
+        ctx.tg, ctx.shape = tg, (B, P, N)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        B, P, N = ctx.shape
+        g = g.reshape(1).contiguous().float()
+        dlp = torch.zeros((B, P, N), dtype=torch.float32, device=g.device)
+        check(lib.pn_nll_bwd(_ptr(ctx.tg), _ptr(g), B, N, P, _ptr(dlp), _stream()), "pn_nll_bwd")
+        return dlp, None

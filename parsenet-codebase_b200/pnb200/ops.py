@@ -36,3 +36,226 @@ def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
         check(lib.pn_knn(_ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), 1 if out_dtype == torch.int64 else 0,
                          _ptr(dist), _ptr(ws), _stream()), "pn_knn")
     return (idx, dist) if return_dist else idx
+
+
+# --------------------------------------------------------------------------------------------- low-level wrappers
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+GN_EPS = 1e-5
+
+
+def _pitch(t):
+    """row pitch (floats) of a (B,Np,C) tensor whose rows are contiguous and shapes are back-to-back"""
+    assert t.dim() == 3 and t.stride(2) == 1 and t.stride(0) == t.shape[1] * t.stride(1), (t.shape, t.stride())
+    return t.stride(1)
+
+
+class Norm:
+    """finalised normalisation of one activation tensor: per-(shape,channel) scale/shift + per-group mean/rstd"""
+    __slots__ = ("mean_rstd", "scale", "shift", "act", "G", "count", "per_shape", "gamma", "beta")
+
+    def __init__(self, mean_rstd, scale, shift, act, G, count, per_shape, gamma, beta):
+        self.mean_rstd, self.scale, self.shift, self.act = mean_rstd, scale, shift, act
+        self.G, self.count, self.per_shape, self.gamma, self.beta = G, count, per_shape, gamma, beta
+
+
+def linear_fwd(A, W, bias=None, sbias=None, in_norm=None, stats_groups=0, per_shape=True):
+    """Y[b,n,:] = act(norm(A[b,n,:])) @ W.T + bias + sbias[b]; returns (Y, stats|None)"""
+    _need_cuda(A, W)
+    B, Np, K = A.shape
+    Nout = W.shape[0]
+    assert W.shape[1] == K and W.stride(1) == 1
+    Y = torch.empty((B, Np, Nout), dtype=torch.float32, device=A.device)
+    stats = None
+    if stats_groups:
+        stats = torch.zeros((B if per_shape else 1, stats_groups, 2), dtype=torch.float64, device=A.device)
+    sc = sh = None
+    act = ACT_NONE
+    if in_norm is not None:
+        sc, sh, act = in_norm.scale, in_norm.shift, in_norm.act
+    check(lib.pn_linear_fwd(_ptr(A), _pitch(A), _ptr(W), W.stride(0), _ptr(bias), _ptr(sbias), _ptr(sc), _ptr(sh),
+                            act, _ptr(Y), Nout, _ptr(stats), B, Np, K, Nout, max(stats_groups, 1),
+                            1 if per_shape else 0, _stream()), "pn_linear_fwd")
+    return Y, stats
+
+
+def norm_finalize(stats, gamma, beta, B, C, count, act, per_shape=True, eps=GN_EPS):
+    S, G = stats.shape[0], stats.shape[1]
+    mr = torch.empty((S, G, 2), dtype=torch.float32, device=stats.device)
+    scale = torch.empty((S, C), dtype=torch.float32, device=stats.device)
+    shift = torch.empty((S, C), dtype=torch.float32, device=stats.device)
+    check(lib.pn_norm_finalize(_ptr(stats), _ptr(gamma), _ptr(beta), S, G, C, float(count), float(eps), _ptr(mr),
+                               _ptr(scale), _ptr(shift), _stream()), "pn_norm_finalize")
+    if S != B:   # batch-wide statistics: kernels index scale/shift per shape
+        scale = scale.expand(B, C).contiguous()
+        shift = shift.expand(B, C).contiguous()
+    return Norm(mr, scale, shift, act, G, float(count), per_shape, gamma, beta)
+
+
+def linear_bwd_data(dY, W, dZ=None, accumulate=False, fin_A=None, fin_norm=None, fin_act=None, K=None):
+    """dZ (+)= dY @ W ; with fin_A: multiplies by act'(pre) of the layer input and accumulates the GN-backward
+    sums (returned).  dZ may be a strided (B,Np,K) view (e.g. a channel slice of the concat-gradient buffer)."""
+    B, Np, Nout = dY.shape
+    K = W.shape[1]
+    if dZ is None:
+        dZ = torch.empty((B, Np, K), dtype=torch.float32, device=dY.device)
+    gsum = None
+    finalize = fin_A is not None
+    sc = sh = gamma = mr = None
+    act = ACT_NONE
+    G, per_shape = 1, 1
+    if finalize:
+        if fin_norm is not None:
+            sc, sh, act, gamma, mr = fin_norm.scale, fin_norm.shift, fin_norm.act, fin_norm.gamma, fin_norm.mean_rstd
+            G, per_shape = fin_norm.G, 1 if fin_norm.per_shape else 0
+            gsum = torch.zeros((mr.shape[0], G, 2), dtype=torch.float64, device=dY.device)
+        else:
+            act = fin_act if fin_act is not None else ACT_NONE
+    check(lib.pn_linear_bwd_data(_ptr(dY), _pitch(dY), _ptr(W), W.stride(0), _ptr(dZ), _pitch(dZ),
+                                 1 if accumulate else 0, 1 if finalize else 0, _ptr(fin_A),
+                                 _pitch(fin_A) if finalize else 0, _ptr(sc), _ptr(sh), act, _ptr(gamma), _ptr(mr),
+                                 _ptr(gsum), B, Np, K, Nout, G, per_shape, _stream()), "pn_linear_bwd_data")
+    return dZ, gsum
+
+
+def norm_bwd_apply(dZ, A, norm, gsum, want_affine_grads=True):
+    """in place: dZ (masked grad wrt norm output) -> grad wrt the pre-norm tensor A; returns (dgamma, dbeta)"""
+    B, Np, C = dZ.shape
+    dg = db = None
+    if want_affine_grads:
+        dg = torch.zeros((C,), dtype=torch.float32, device=dZ.device)
+        db = torch.zeros((C,), dtype=torch.float32, device=dZ.device)
+    check(lib.pn_norm_bwd_apply(_ptr(dZ), _pitch(dZ), _ptr(A), _pitch(A), _ptr(norm.gamma), _ptr(norm.mean_rstd),
+                                _ptr(gsum), B, Np, C, norm.G, 1 if norm.per_shape else 0, norm.count, _ptr(dg),
+                                _ptr(db), _stream()), "pn_norm_bwd_apply")
+    return dg, db
+
+
+def linear_bwd_weight(dY, A, in_norm=None, dW=None, want_bias=True, want_sbias=False):
+    """dW += dY^T @ act(norm(A)); returns (dW, db, dsb).  dW may be a strided column view of a larger weight grad."""
+    B, Np, Nout = dY.shape
+    K = A.shape[2]
+    if dW is None:
+        dW = torch.zeros((Nout, K), dtype=torch.float32, device=dY.device)
+    db = torch.zeros((Nout,), dtype=torch.float32, device=dY.device) if want_bias else None
+    dsb = torch.zeros((B, Nout), dtype=torch.float32, device=dY.device) if want_sbias else None
+    sc = sh = None
+    act = ACT_NONE
+    if in_norm is not None:
+        sc, sh, act = in_norm.scale, in_norm.shift, in_norm.act
+    assert dW.stride(1) == 1
+    check(lib.pn_linear_bwd_weight(_ptr(dY), _pitch(dY), _ptr(A), _pitch(A), _ptr(sc), _ptr(sh), act, _ptr(dW),
+                                   dW.stride(0), _ptr(db), _ptr(dsb), B, Np, K, Nout, _stream()),
+          "pn_linear_bwd_weight")
+    return dW, db, dsb
+
+
+def edge_gather_fwd(PQ, idx, gamma, G, per_shape=True, want_stats=True):
+    B, N, C2 = PQ.shape
+    Cout = C2 // 2
+    k = idx.shape[2]
+    dev = PQ.device
+    esel = torch.empty((B, N, Cout), dtype=torch.float32, device=dev)
+    jsel = torch.empty((B, N, Cout), dtype=torch.int32, device=dev)
+    esum = torch.empty((B, N, Cout), dtype=torch.float32, device=dev)
+    stats = torch.zeros((B if per_shape else 1, G, 2), dtype=torch.float64, device=dev) if want_stats else None
+    assert idx.dtype == torch.int32 and idx.is_contiguous()
+    check(lib.pn_edge_gather_fwd(_ptr(PQ), _pitch(PQ), _ptr(idx), B, N, k, Cout, _ptr(gamma), _ptr(esel),
+                                 _ptr(jsel), _ptr(esum), _ptr(stats), G, 1 if per_shape else 0, _stream()),
+          "pn_edge_gather_fwd")
+    return esel, jsel, esum, stats
+
+
+def edge_apply(esel, norm, out):
+    B, N, Cout = esel.shape
+    check(lib.pn_edge_apply(_ptr(esel), _ptr(norm.scale), _ptr(norm.shift), _ptr(out), _pitch(out), B, N, Cout,
+                            _stream()), "pn_edge_apply")
+    return out
+
+
+def knn_csr_transpose(idx):
+    B, N, k = idx.shape
+    dev = idx.device
+    cnt = torch.zeros((B, N), dtype=torch.int32, device=dev)
+    off = torch.empty((B, N + 1), dtype=torch.int32, device=dev)
+    cursor = torch.empty((B, N), dtype=torch.int32, device=dev)
+    rev = torch.empty((B, N * k), dtype=torch.int32, device=dev)
+    check(lib.pn_knn_csr_transpose(_ptr(idx), B, N, k, _ptr(cnt), _ptr(off), _ptr(cursor), _ptr(rev), _stream()),
+          "pn_knn_csr_transpose")
+    return off, rev
+
+
+def edge_bwd(g, PQ, idx, esel, jsel, esum, norm, dense=True, want_affine_grads=True):
+    """g: grad wrt the activated edge-conv output (B,N,Cout) (may be a strided slice). Returns (dPQ, dgamma, dbeta)."""
+    B, N, C2 = PQ.shape
+    Cout = C2 // 2
+    k = idx.shape[2]
+    dev = PQ.device
+    dy = torch.empty((B, N, Cout), dtype=torch.float32, device=dev)
+    S = norm.mean_rstd.shape[0]
+    gsum = torch.zeros((S, norm.G, 2), dtype=torch.float64, device=dev) if dense else None
+    dg = torch.zeros((Cout,), dtype=torch.float32, device=dev) if want_affine_grads else None
+    db = torch.zeros((Cout,), dtype=torch.float32, device=dev) if want_affine_grads else None
+    check(lib.pn_edge_bwd_prep(_ptr(g), _pitch(g), _ptr(esel), _ptr(norm.scale), _ptr(norm.shift),
+                               _ptr(norm.mean_rstd), _ptr(norm.gamma), B, N, Cout, norm.G,
+                               1 if norm.per_shape else 0, _ptr(dy), _ptr(gsum), _ptr(dg), _ptr(db), _stream()),
+          "pn_edge_bwd_prep")
+    off = rev = None
+    if dense:
+        off, rev = knn_csr_transpose(idx)
+    dPQ = torch.empty((B, N, C2), dtype=torch.float32, device=dev)
+    check(lib.pn_edge_bwd(_ptr(PQ), _pitch(PQ), _ptr(dy), _ptr(esum), _ptr(jsel), _ptr(off), _ptr(rev),
+                          _ptr(norm.mean_rstd), _ptr(gsum), _ptr(norm.scale), B, N, k, Cout, norm.G,
+                          1 if norm.per_shape else 0, norm.count, 1 if dense else 0, _ptr(dPQ), C2, _stream()),
+          "pn_edge_bwd")
+    return dPQ, dg, db
+
+
+def colmax_norm(Y, norm):
+    B, N, C = Y.shape
+    out = torch.empty((B, C), dtype=torch.float32, device=Y.device)
+    arg = torch.empty((B, C), dtype=torch.int32, device=Y.device)
+    ext = torch.empty((B, C), dtype=torch.float32, device=Y.device)
+    check(lib.pn_colmax_norm(_ptr(Y), _pitch(Y), B, N, C, _ptr(norm.scale), _ptr(norm.shift), norm.act, _ptr(out),
+                             _ptr(arg), _ptr(ext), _stream()), "pn_colmax_norm")
+    return out, arg, ext
+
+
+def colmax_bwd_fill(Y, gt, arg, norm, gsum, dense=True):
+    B, N, C = Y.shape
+    dY = torch.empty((B, N, C), dtype=torch.float32, device=Y.device)
+    check(lib.pn_colmax_bwd_fill(_ptr(Y), _pitch(Y), _ptr(gt), _ptr(arg), _ptr(norm.gamma), _ptr(norm.mean_rstd),
+                                 _ptr(gsum), B, N, C, norm.G, 1 if norm.per_shape else 0, norm.count,
+                                 1 if dense else 0, _ptr(dY), C, _stream()), "pn_colmax_bwd_fill")
+    return dY
+
+
+def logsoftmax_fwd(logits):
+    B, N, P = logits.shape
+    logp = torch.empty((B, P, N), dtype=torch.float32, device=logits.device)
+    check(lib.pn_logsoftmax_fwd(_ptr(logits), _pitch(logits), B, N, P, _ptr(logp), _stream()), "pn_logsoftmax_fwd")
+    return logp
+
+
+def logsoftmax_bwd(logp, dlp):
+    B, P, N = logp.shape
+    dl = torch.empty((B, N, P), dtype=torch.float32, device=logp.device)
+    check(lib.pn_logsoftmax_bwd(_ptr(logp), _ptr(dlp), B, N, P, _ptr(dl), P, _stream()), "pn_logsoftmax_bwd")
+    return dl
+
+
+def l2norm_fwd(x2d, eps=1e-12):
+    rows, D = x2d.shape
+    assert x2d.stride(1) == 1
+    y = torch.empty((rows, D), dtype=torch.float32, device=x2d.device)
+    norms = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
+    check(lib.pn_l2norm_fwd(_ptr(x2d), x2d.stride(0), rows, D, float(eps), _ptr(y), D, _ptr(norms), _stream()),
+          "pn_l2norm_fwd")
+    return y, norms
+
+
+def l2norm_bwd(y, dy, norms):
+    rows, D = y.shape
+    dx = torch.empty((rows, D), dtype=torch.float32, device=y.device)
+    check(lib.pn_l2norm_bwd(_ptr(y), y.stride(0), _ptr(dy), dy.stride(0), _ptr(norms), rows, D, _ptr(dx), D, 0,
+                            _stream()), "pn_l2norm_bwd")
+    return dx
