@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — ParSeNet hot path on B200:  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the hot path (BASELINE.json metric) over one batch of synthetic shapes per GPU:
+segmentation network forward (3 kNN graphs + edge-convs + head), triplet + NLL losses, [cluster + fit + residual
+once those stages are enabled in STAGES], backward, gradient all-reduce (N>1) and Adam step.
+Prints ONE JSON line (rank 0).  `value` = shapes/s with inputs resident in HBM; `e2e` = same through the public
+module API with pinned-host inputs copied H2D and the loss read back D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "parsenet-codebase_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+N_POINTS = 10000
+BATCH_PER_GPU = 16
+KNN_K = 80
+EMB = 128
+N_PRIM = 10
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def make_host_batch(B, N, seed):
+    from oracle.port import common  # synthetic generator only (no oracle math on the product path)
+    pts, nrm, lab, prim = common.synth_cloud(B, N, seed=seed, n_patches=8)
+    x = np.concatenate([pts, nrm], 2).transpose(0, 2, 1).copy()       # (B,6,N) as the reference feeds it
+    return (torch.from_numpy(x).pin_memory(), torch.from_numpy(lab).pin_memory(),
+            torch.from_numpy(prim).pin_memory())
+
+
+class HotPath:
+    """the user-facing call sequence of train_parsenet.py:170-198 on our drop-in modules"""
+
+    def __init__(self, device, world):
+        from src.PointNet import PrimitivesEmbeddingDGCNGn
+        from src.segment_loss import EmbeddingLoss, primitive_loss
+        torch.manual_seed(0)
+        self.loss = EmbeddingLoss(margin=1.0)
+        self.model = PrimitivesEmbeddingDGCNGn(embedding=True, emb_size=EMB, primitives=True, num_primitives=N_PRIM,
+                                               loss_function=self.loss.triplet_loss, mode=5, num_channels=6,
+                                               nn_nb=KNN_K).to(device)
+        self.primitive_loss = primitive_loss
+        self.params = [p for p in self.model.parameters() if p.requires_grad]
+        self.opt = torch.optim.Adam(self.params, lr=1e-4)
+        self.world = world
+        self.device = device
+
+    def step(self, x, lab_host, lab, prim):
+        """x (B,6,N) cuda, lab_host numpy (B,N) for the host-side sampler, lab/prim cuda -> loss tensor"""
+        self.opt.zero_grad(set_to_none=True)
+        emb, lp, el = self.model(x, lab, True)
+        loss = el.sum() + self.primitive_loss(lp, prim)
+        loss.backward()
+        if self.world > 1:
+            import torch.distributed as dist
+            grads = [p.grad for p in self.params if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            flat /= self.world
+            o = 0
+            for g in grads:
+                g.copy_(flat[o:o + g.numel()].view_as(g)); o += g.numel()
+        self.opt.step()
+        return loss
+
+
+def run_ours(args):
+    from pnb200 import cabi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    hp = HotPath(dev, world)
+    B = BATCH_PER_GPU
+    host = [make_host_batch(B, N_POINTS, seed=100 * rank + i) for i in range(2)]
+    dev_batches = [tuple(t.to(dev) for t in hb) for hb in host]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step(i):
+        x, lab, prim = dev_batches[i % 2]
+        np.random.seed(i)
+        return hp.step(x, None, lab, prim)
+
+    def e2e_step(i):
+        hx, hl, hpm = host[i % 2]
+        x = hx.to(dev, non_blocking=True); lab = hl.to(dev, non_blocking=True); prim = hpm.to(dev, non_blocking=True)
+        np.random.seed(i)
+        loss = hp.step(x, None, lab, prim)
+        return loss.item()                     # D2H read of the step's result
+
+    for i in range(args.warmup):
+        resident_step(i)
+        e2e_step(i)
+    # ---- timed: resident inputs
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start(); time.sleep(0.3)
+    dominant = "pn_knn"
+    cabi.TIMED[dominant] = []
+    barrier()
+    cabi.reset_launch_count()
+    t_wall0 = time.time()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        flush.zero_()                           # L2 flush between timed iterations (256 MB > 126 MB L2)
+        resident_step(i)
+    ev1.record()
+    barrier()
+    ms_res = ev0.elapsed_time(ev1)
+    launches = cabi.launch_count()
+    kern_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop(dominant)]
+    # ---- timed: end to end (H2D of inputs + D2H of the loss inside the region)
+    barrier()
+    ev2 = torch.cuda.Event(enable_timing=True); ev3 = torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for i in range(args.steps):
+        flush.zero_()
+        e2e_step(i)
+    ev3.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_e2e = ev2.elapsed_time(ev3)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_res, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_res, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    pk = peaks()
+    shapes_total = B * world * args.steps
+    value = shapes_total / (ms_res / 1e3)
+    e2e_v = shapes_total / (ms_e2e / 1e3)
+    # roofline of the dominant kernel: kNN in 64-d feature space (FP32 FMA pipe; algorithmic flop = 2*N^2*C/shape)
+    # reported against the measured dense tensor peak is meaningless for an FP32-exact kernel, so we report the
+    # HBM-side view (algorithmic bytes = N*C*4 + N*k*4 per shape) AND keep flop/s in `note`.
+    c64 = [m for m in kern_ms]
+    per_launch_ms = float(np.mean(c64)) if c64 else None
+    alg_bytes = B * (N_POINTS * 64 * 4 + N_POINTS * KNN_K * 4)
+    achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else None
+    h2d = int(sum(t.numel() * t.element_size() for t in host[0]))
+    out = {
+        "metric": "shapes/sec (10k pts, B=16) seg+spline-fit fwd/bwd at 1/2/4/8 B200; Chamfer err",
+        "value": value, "unit": "shapes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "train_parsenet.py step (config 4 shape: 16 x 10k pts + normals, k=80, mode 5): "
+                               "seg-net fwd + triplet/NLL + bwd + Adam; cluster+fit stages: " + STAGES,
+                   "per_gpu_batch": B, "global_batch": B * world, "n_points": N_POINTS, "knn_k": KNN_K,
+                   "parallelism": f"dp{world}", "l2": "256 MB flush write between timed steps; per-step working set "
+                                                      ">> 126 MB L2"},
+        "e2e": {"value": e2e_v, "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": "knn_kernel (pn_knn: norms + tiled distance/top-k)", "bound": "hbm",
+                     "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": None,
+                     "peak_source": pk["source"],
+                     "note": "kNN is FP32-FMA bound by design (bit-exact indices); HBM fraction is low because the "
+                             "kernel reads each point block from L2, not because of wasted traffic",
+                     "launch_ms": per_launch_ms, "launches_timed": len(c64)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(out))
+
+
+STAGES = "not yet enabled"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_baseline(max_seconds=None):
+    """oracle port (torch CPU restatement of the reference path) timed on this host: one shape of the same
+    workload (N=10^4, k=80), forward + losses + backward."""
+    import torch.nn.functional as F
+    from oracle.port import common, segnet as port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pts, nrm, lab, prim = common.synth_cloud(1, N_POINTS, seed=0, n_patches=8)
+    x = torch.from_numpy(np.concatenate([pts, nrm], 2)).permute(0, 2, 1).contiguous()
+    from src.PointNet import PrimitivesEmbeddingDGCNGn
+    m = PrimitivesEmbeddingDGCNGn(embedding=True, emb_size=EMB, primitives=True, num_primitives=N_PRIM,
+                                  loss_function=None, mode=5, num_channels=6, nn_nb=KNN_K)
+    sd = {n: v.detach().clone().requires_grad_(v.is_floating_point()) for n, v in m.state_dict().items()}
+    t0 = time.time()
+    emb, lp, _, _, _ = port.segnet_fwd(sd, x, KNN_K, 5)
+    np.random.seed(0)
+    el = port.triplet_loss(emb, lab, 1.0)
+    nll = F.nll_loss(lp, torch.from_numpy(prim))
+    (el.sum() + nll).backward()
+    dt = time.time() - t0
+    return {"value": 1.0 / dt, "unit": "shapes/s", "cores": cores, "kind": "port",
+            "sample": f"1 shape x {N_POINTS} pts, k={KNN_K}, seg-net fwd+losses+bwd, {dt:.1f} s wall"}
+
+
+def run_reference(args):
+    """reference arm: the reference's CPU implementation of the path = oracle port on the host cores
+    (the reference itself is Python under /root/reference and cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 2))):
+        base = cpu_baseline()
+        vals.append(base["value"])
+    v = float(np.mean(vals))
+    base["value"] = v
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    print(json.dumps({
+        "impl": "reference",
+        "metric": "shapes/sec (10k pts, B=16) seg+spline-fit fwd/bwd at 1/2/4/8 B200; Chamfer err",
+        "value": v, "unit": "shapes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 / v * BATCH_PER_GPU, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "same as the ours arm; each step is a bounded sample (1 shape) of the batch",
+                   "per_gpu_batch": BATCH_PER_GPU, "n_points": N_POINTS, "knn_k": KNN_K},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -65,14 +65,14 @@ int pn_oracle_knn(const float *x, int B, int N, int C, int ld, int k, int metric
     if (k > N || k <= 0) return 1;
     if (metric == 1 && C != 6) return 2;
     int cx = (metric == 1) ? 3 : C;
-#pragma omp parallel
-    {
-        cand_t *heap = (cand_t *)malloc(sizeof(cand_t) * (size_t)k);
+    for (int b = 0; b < B; ++b) {
+        const float *xb = x + (size_t)b * N * ld;
         float *xx = (float *)malloc(sizeof(float) * (size_t)N);
-#pragma omp for schedule(dynamic, 1) collapse(1)
-        for (int b = 0; b < B; ++b) {
-            const float *xb = x + (size_t)b * N * ld;
-            for (int j = 0; j < N; ++j) xx[j] = dotf(xb + (size_t)j * ld, xb + (size_t)j * ld, 0, cx);
+        for (int j = 0; j < N; ++j) xx[j] = dotf(xb + (size_t)j * ld, xb + (size_t)j * ld, 0, cx);
+#pragma omp parallel
+        {
+            cand_t *heap = (cand_t *)malloc(sizeof(cand_t) * (size_t)k);
+#pragma omp for schedule(dynamic, 16)
             for (int i = 0; i < N; ++i) {
                 const float *xi = xb + (size_t)i * ld;
                 int n = 0;
@@ -101,8 +101,9 @@ int pn_oracle_knn(const float *x, int B, int N, int C, int ld, int k, int metric
                     if (dist_out) dist_out[o + t] = heap[t].d;
                 }
             }
+            free(heap);
         }
-        free(heap); free(xx);
+        free(xx);
     }
     return 0;
 }

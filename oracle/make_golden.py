@@ -81,7 +81,30 @@ def gen_segnet():
     np.savez_compressed(os.path.join(OUT, "segnet.npz"), **out)
 
 
-GENS = {"knn": gen_knn, "segnet": gen_segnet}
+from oracle.make_golden_helpers import clustered_embedding  # noqa: E402
+
+
+def gen_meanshift():
+    MS = rl.ref("src.mean_shift")
+    ms = MS.MeanShift()
+    out = {}
+    for name, (N, ncl, seed, q, it) in {"a": (700, 6, 3, 0.05, 10), "b": (520, 3, 4, 0.1, 5)}.items():
+        X, _ = clustered_embedding(N, 128, ncl, seed)
+        Xr = X.clone().requires_grad_()
+        np.random.seed(seed)
+        newX, center, bw, labels = ms.mean_shift(Xr, N, q, it)
+        g = torch.Generator().manual_seed(seed + 100)
+        w = torch.randn(center.shape, generator=g)
+        w2 = torch.randn(newX.shape, generator=g) * 0.01
+        ((center * w).sum() + (newX * w2).sum()).backward()
+        out[name + "_X"] = X.numpy(); out[name + "_newX"] = newX.detach().numpy()
+        out[name + "_center"] = center.detach().numpy(); out[name + "_bw"] = bw.numpy()
+        out[name + "_labels"] = labels.numpy(); out[name + "_gradX"] = Xr.grad.numpy()
+        out[name + "_meta"] = np.array([N, ncl, seed, it], dtype=np.int64); out[name + "_q"] = np.array(q)
+    np.savez_compressed(os.path.join(OUT, "meanshift.npz"), **out)
+
+
+GENS = {"knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift}
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)

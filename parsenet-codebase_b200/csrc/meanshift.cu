@@ -1,0 +1,605 @@
+// Differentiable mean-shift on the unit hypersphere: fused ("flash"-style) kernels, the N x N kernel matrix never
+// exists in HBM.
+//
+// Replaces (reference, relative to /root/reference):
+//   MeanShift.mean_shift_     src/mean_shift.py:45-79   (per iteration: 2 N x N x d GEMMs + N x N exp, all N x N kept for
+//                                                        autograd: 10 x 400 MB per shape)
+//   MeanShift.compute_bandwidth  src/mean_shift.py:115-137  (N x N GEMM + topk(K))
+// Iteration (gaussian kernel):  S = Y X^T ; K = exp(clamp((S - 1) / b^2, +-75)) ; num = K X ; den = rowsum K
+//                               u = Y + (num/den - Y) ; Y' = u / |u|
+// Forward  : one kernel, row-block owner, streams X tiles:  S-tile GEMM -> exp -> P.X GEMM, den in registers.
+// Backward : recompute S/K per tile (nothing N x N was saved):
+//   rows kernel (owner = 64 rows i): gS = (Gn_i.x_j + gd_i) K c ;  gY_i = sum_j gS x_j
+//   cols kernel (owner = 64 rows j): gX_j += sum_i gS y_i + K Gn_i          (atomics-free, deterministic)
+//   with Gn = g_u / den, gd = -(g_u . t) / den, g_u = (g - Y'(Y'.g)) / |u|   (prep kernel).
+// v1 math: FP32 FMA pipe (fp32-exact products: the exponent is (S-1)/b^2 with b down to 0.003, so single-pass TF32
+// is not usable; the split-TF32 tensor-core main loop is the planned replacement of tile_gemm_*).
+#include "common.cuh"
+
+namespace pn {
+namespace ms {
+
+constexpr int D = 128;        // embedding width (the reference's emb_size; checked by the launchers)
+constexpr int T = 64;         // tile edge (rows of Y / rows of X per tile)
+constexpr int NT = 256;
+constexpr int PK = T + 4;     // pitch of k-major [D][T] tiles
+constexpr int PR = D + 4;     // pitch of row-major [T][D] tiles
+constexpr float CLAMP = 75.f;
+
+// load a [T rows][D] tile of a row-major matrix (row pitch ld) into row-major smem R[T][PR] and/or k-major Kt[D][PK].
+// rows >= nrows are zero filled.  thread t: row = t % 64, float4 column group = t / 64 + 4*i
+__device__ __forceinline__ void load_tile(const float* __restrict__ g, long long ld, int r0, int nrows,
+                                          float* __restrict__ R, float* __restrict__ Kt) {
+    const int t = threadIdx.x;
+    const int r = t & 63;
+    const bool ok = (r0 + r) < nrows;
+    const float* src = g + (long long)(r0 + r) * ld;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int c4 = (t >> 6) + 4 * i;            // 0..31 -> columns 4*c4..4*c4+3
+        float4 v = ok ? *reinterpret_cast<const float4*>(src + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (R) *reinterpret_cast<float4*>(R + r * PR + 4 * c4) = v;
+        if (Kt) {
+            Kt[(4 * c4 + 0) * PK + r] = v.x; Kt[(4 * c4 + 1) * PK + r] = v.y;
+            Kt[(4 * c4 + 2) * PK + r] = v.z; Kt[(4 * c4 + 3) * PK + r] = v.w;
+        }
+    }
+}
+
+// S[4][4] += A^T B over the D channels: A, B k-major [D][PK]; thread (ty,tx): rows 4ty.., cols 4tx..
+__device__ __forceinline__ void gemm_dd(const float* __restrict__ A, const float* __restrict__ B, int ty, int tx,
+                                        float (&acc)[4][4]) {
+#pragma unroll 8
+    for (int kk = 0; kk < D; ++kk) {
+        float4 a = *reinterpret_cast<const float4*>(A + kk * PK + 4 * ty);
+        float4 b = *reinterpret_cast<const float4*>(B + kk * PK + 4 * tx);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+// two products sharing B:  S += A1^T B, G += A2^T B
+__device__ __forceinline__ void gemm_dd2(const float* __restrict__ A1, const float* __restrict__ A2,
+                                         const float* __restrict__ B, int ty, int tx, float (&s)[4][4],
+                                         float (&g)[4][4]) {
+#pragma unroll 8
+    for (int kk = 0; kk < D; ++kk) {
+        float4 a = *reinterpret_cast<const float4*>(A1 + kk * PK + 4 * ty);
+        float4 e = *reinterpret_cast<const float4*>(A2 + kk * PK + 4 * ty);
+        float4 b = *reinterpret_cast<const float4*>(B + kk * PK + 4 * tx);
+        const float av[4] = {a.x, a.y, a.z, a.w}, ev[4] = {e.x, e.y, e.z, e.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                s[i][j] = fmaf(av[i], bv[j], s[i][j]);
+                g[i][j] = fmaf(ev[i], bv[j], g[i][j]);
+            }
+    }
+}
+// O[4][8] += P^T-major [T k][PK m] times R row-major [T k][PR]: rows m = 4ty.., cols 4tx.. and 64+4tx..
+__device__ __forceinline__ void gemm_pr(const float* __restrict__ P, const float* __restrict__ R, int ty, int tx,
+                                        float (&acc)[4][8]) {
+#pragma unroll 8
+    for (int kk = 0; kk < T; ++kk) {
+        float4 a = *reinterpret_cast<const float4*>(P + kk * PK + 4 * ty);
+        float4 b0 = *reinterpret_cast<const float4*>(R + kk * PR + 4 * tx);
+        float4 b1 = *reinterpret_cast<const float4*>(R + kk * PR + 64 + 4 * tx);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+}
+
+__device__ __forceinline__ float kernel_val(float s, float c, bool* clamped) {
+    float e = (s - 1.0f) * c;
+    *clamped = (e > CLAMP) || (e < -CLAMP);
+    e = fminf(fmaxf(e, -CLAMP), CLAMP);
+    return expf(e);
+}
+
+// sum over the 16 threads (tx = lane & 15) that share a row
+__device__ __forceinline__ float row_sum16(float v) {
+    v += __shfl_xor_sync(FULL, v, 8);
+    v += __shfl_xor_sync(FULL, v, 4);
+    v += __shfl_xor_sync(FULL, v, 2);
+    v += __shfl_xor_sync(FULL, v, 1);
+    return v;
+}
+
+// ================================================================================================ forward iteration
+// grid (ceil(N/T), B).  Y, X, Ynew: [B][N][D]; cinv[b] = 1/b^2; den, unorm: [B][N]
+__global__ void __launch_bounds__(NT) ms_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ X, int N,
+                                                    const float* __restrict__ cinv, float* __restrict__ Ynew,
+                                                    float* __restrict__ den_out, float* __restrict__ unorm_out) {
+    extern __shared__ __align__(16) float sm[];
+    float* Yt = sm;                   // [D][PK]   own rows, k-major
+    float* Xt = Yt + D * PK;          // [D][PK]
+    float* Xr = Xt + D * PK;          // [T][PR]
+    float* Ps = Xr + T * PR;          // [T j][PK i]
+    const int b = blockIdx.y, i0 = blockIdx.x * T;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const float* Yb = Y + (long long)b * N * D;
+    const float* Xb = X + (long long)b * N * D;
+    const float c = cinv[b];
+    load_tile(Yb, D, i0, N, nullptr, Yt);
+    float o[4][8];
+    float den[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
+    for (int j0 = 0; j0 < N; j0 += T) {
+        __syncthreads();
+        load_tile(Xb, D, j0, N, Xr, Xt);
+        __syncthreads();
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+        gemm_dd(Yt, Xt, ty, tx, s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool jv = (j0 + 4 * tx + j) < N;
+            float p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bool cl;
+                p[i] = jv ? kernel_val(s[i][j], c, &cl) : 0.f;
+                den[i] += p[i];
+            }
+            *reinterpret_cast<float4*>(Ps + (4 * tx + j) * PK + 4 * ty) = make_float4(p[0], p[1], p[2], p[3]);
+        }
+        __syncthreads();
+        gemm_pr(Ps, Xr, ty, tx, o);
+    }
+    // ---- epilogue: u = y + (num/den - y); Y' = u/|u|
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i0 + 4 * ty + i;
+        float dn = row_sum16(den[i]);
+        float dinv = 1.0f / dn;
+        float u[8];
+        float n2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int col = (j < 4 ? 0 : 60) + 4 * tx + j;
+            float y = Yt[col * PK + 4 * ty + i];
+            float m = o[i][j] * dinv - y;
+            u[j] = y + m;
+            n2 = fmaf(u[j], u[j], n2);
+        }
+        n2 = row_sum16(n2);
+        float nr = sqrtf(n2);
+        if (r < N) {
+            float* dst = Ynew + ((long long)b * N + r) * D;
+            *reinterpret_cast<float4*>(dst + 4 * tx) = make_float4(u[0] / nr, u[1] / nr, u[2] / nr, u[3] / nr);
+            *reinterpret_cast<float4*>(dst + 64 + 4 * tx) = make_float4(u[4] / nr, u[5] / nr, u[6] / nr, u[7] / nr);
+            if (tx == 0) {
+                den_out[(long long)b * N + r] = dn;
+                unorm_out[(long long)b * N + r] = nr;
+            }
+        }
+    }
+}
+
+// ================================================================================================ backward
+// prep (one warp per row): g_u = (g - Y'(Y'.g))/|u| ; t = Y'|u| ; Gn = g_u/den ; gd = -(g_u.t)/den
+__global__ void ms_bwd_prep_kernel(const float* __restrict__ gout, const float* __restrict__ Ynew,
+                                   const float* __restrict__ den, const float* __restrict__ unorm, long long rows,
+                                   float* __restrict__ Gn, float* __restrict__ gd) {
+    long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float4 g = *reinterpret_cast<const float4*>(gout + r * D + 4 * lane);
+    float4 y = *reinterpret_cast<const float4*>(Ynew + r * D + 4 * lane);
+    float dot = g.x * y.x + g.y * y.y + g.z * y.z + g.w * y.w;
+    dot = warp_sum(dot);
+    float nr = unorm[r], dn = den[r];
+    float4 gu = make_float4((g.x - y.x * dot) / nr, (g.y - y.y * dot) / nr, (g.z - y.z * dot) / nr,
+                            (g.w - y.w * dot) / nr);
+    float gt = (gu.x * y.x + gu.y * y.y + gu.z * y.z + gu.w * y.w) * nr;
+    gt = warp_sum(gt);
+    *reinterpret_cast<float4*>(Gn + r * D + 4 * lane) = make_float4(gu.x / dn, gu.y / dn, gu.z / dn, gu.w / dn);
+    if (lane == 0) gd[r] = -gt / dn;
+}
+
+// rows kernel: owner rows i of Yprev; gY[i] = sum_j gS_ij x_j,  gS = (Gn_i.x_j + gd_i) K c (0 where clamped)
+__global__ void __launch_bounds__(NT) ms_bwd_rows_kernel(const float* __restrict__ Yp, const float* __restrict__ X,
+                                                         const float* __restrict__ Gn, const float* __restrict__ gd,
+                                                         int N, const float* __restrict__ cinv,
+                                                         float* __restrict__ gY) {
+    extern __shared__ __align__(16) float sm[];
+    float* Yt = sm;                   // [D][PK]
+    float* Gt = Yt + D * PK;          // [D][PK]
+    float* Xt = Gt + D * PK;          // [D][PK]
+    float* Xr = Xt + D * PK;          // [T][PR]
+    float* Ps = Xr + T * PR;          // [T j][PK i]
+    __shared__ float gds[T];
+    const int b = blockIdx.y, i0 = blockIdx.x * T;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const long long off = (long long)b * N * D;
+    const float c = cinv[b];
+    load_tile(Yp + off, D, i0, N, nullptr, Yt);
+    load_tile(Gn + off, D, i0, N, nullptr, Gt);
+    if (tid < T) gds[tid] = (i0 + tid < N) ? gd[(long long)b * N + i0 + tid] : 0.f;
+    float o[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
+    for (int j0 = 0; j0 < N; j0 += T) {
+        __syncthreads();
+        load_tile(X + off, D, j0, N, Xr, Xt);
+        __syncthreads();
+        float s[4][4], g[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; g[i][j] = 0.f; }
+        gemm_dd2(Yt, Gt, Xt, ty, tx, s, g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool jv = (j0 + 4 * tx + j) < N;
+            float p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bool cl;
+                float k = kernel_val(s[i][j], c, &cl);
+                p[i] = (jv && !cl) ? (g[i][j] + gds[4 * ty + i]) * k * c : 0.f;
+            }
+            *reinterpret_cast<float4*>(Ps + (4 * tx + j) * PK + 4 * ty) = make_float4(p[0], p[1], p[2], p[3]);
+        }
+        __syncthreads();
+        gemm_pr(Ps, Xr, ty, tx, o);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = i0 + 4 * ty + i;
+        if (r < N) {
+            float* dst = gY + off + (long long)r * D;
+            *reinterpret_cast<float4*>(dst + 4 * tx) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+            *reinterpret_cast<float4*>(dst + 64 + 4 * tx) = make_float4(o[i][4], o[i][5], o[i][6], o[i][7]);
+        }
+    }
+}
+
+// cols kernel: owner rows j of X; gX[j] (+)= sum_i gS_ij y_i + K_ij Gn_i
+__global__ void __launch_bounds__(NT) ms_bwd_cols_kernel(const float* __restrict__ Yp, const float* __restrict__ X,
+                                                         const float* __restrict__ Gn, const float* __restrict__ gd,
+                                                         int N, const float* __restrict__ cinv,
+                                                         float* __restrict__ gX, int accumulate) {
+    extern __shared__ __align__(16) float sm[];
+    float* Xt = sm;                   // [D][PK] own rows j
+    float* Yt = Xt + D * PK;          // [D][PK]
+    float* Gt = Yt + D * PK;          // [D][PK]
+    float* Yr = Gt + D * PK;          // [T][PR]
+    float* Gr = Yr + T * PR;          // [T][PR]
+    float* P1 = Gr + T * PR;          // gS  [T i][PK j]
+    float* P2 = P1 + T * PK;          // K   [T i][PK j]
+    __shared__ float gds[T];
+    const int b = blockIdx.y, j0 = blockIdx.x * T;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const long long off = (long long)b * N * D;
+    const float c = cinv[b];
+    load_tile(X + off, D, j0, N, nullptr, Xt);
+    float o[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[i][j] = 0.f;
+    for (int i0 = 0; i0 < N; i0 += T) {
+        __syncthreads();
+        load_tile(Yp + off, D, i0, N, Yr, Yt);
+        load_tile(Gn + off, D, i0, N, Gr, Gt);
+        if (tid < T) gds[tid] = (i0 + tid < N) ? gd[(long long)b * N + i0 + tid] : 0.f;
+        __syncthreads();
+        // here the thread's "rows" are the owned j (4ty..) and "cols" are tile rows i (4tx..):  s[jj][ii]
+        float s[4][4], g[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; g[i][j] = 0.f; }
+        // s = X_j . Y_i ; g = X_j . Gn_i : A = Xt (own), B = Yt / Gt  -> reuse gemm_dd twice (A shared)
+#pragma unroll 8
+        for (int kk = 0; kk < D; ++kk) {
+            float4 a = *reinterpret_cast<const float4*>(Xt + kk * PK + 4 * ty);
+            float4 y4 = *reinterpret_cast<const float4*>(Yt + kk * PK + 4 * tx);
+            float4 g4 = *reinterpret_cast<const float4*>(Gt + kk * PK + 4 * tx);
+            const float av[4] = {a.x, a.y, a.z, a.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w},
+                        gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    s[jj][ii] = fmaf(av[jj], yv[ii], s[jj][ii]);
+                    g[jj][ii] = fmaf(av[jj], gv[ii], g[jj][ii]);
+                }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const bool iv = (i0 + 4 * tx + ii) < N;
+            float p1[4], p2[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                bool cl;
+                float k = iv ? kernel_val(s[jj][ii], c, &cl) : 0.f;
+                p2[jj] = k;
+                p1[jj] = (iv && !cl) ? (g[jj][ii] + gds[4 * tx + ii]) * k * c : 0.f;
+            }
+            *reinterpret_cast<float4*>(P1 + (4 * tx + ii) * PK + 4 * ty) = make_float4(p1[0], p1[1], p1[2], p1[3]);
+            *reinterpret_cast<float4*>(P2 + (4 * tx + ii) * PK + 4 * ty) = make_float4(p2[0], p2[1], p2[2], p2[3]);
+        }
+        __syncthreads();
+        gemm_pr(P1, Yr, ty, tx, o);
+        gemm_pr(P2, Gr, ty, tx, o);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = j0 + 4 * ty + i;
+        if (r < N) {
+            float* dst = gX + off + (long long)r * D;
+            float4 v0 = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+            float4 v1 = make_float4(o[i][4], o[i][5], o[i][6], o[i][7]);
+            if (accumulate) {
+                float4 a0 = *reinterpret_cast<float4*>(dst + 4 * tx), a1 = *reinterpret_cast<float4*>(dst + 64 + 4 * tx);
+                v0.x += a0.x; v0.y += a0.y; v0.z += a0.z; v0.w += a0.w;
+                v1.x += a1.x; v1.y += a1.y; v1.z += a1.z; v1.w += a1.w;
+            }
+            *reinterpret_cast<float4*>(dst + 4 * tx) = v0;
+            *reinterpret_cast<float4*>(dst + 64 + 4 * tx) = v1;
+        }
+    }
+}
+
+// ================================================================================================ K-th smallest distance
+// compute_bandwidth (src/mean_shift.py:130-137): per row i of dist = 2 - 2 X X^T the K-th smallest value.
+// Exact 4-pass radix select on the order-preserving uint key of the fp32 distance; the distances are recomputed in
+// every pass (nothing N x N is stored).  grid (ceil(S/T), B); X rows may be addressed through `rows` (sampled subset).
+__global__ void __launch_bounds__(NT) ms_kth_kernel(const float* __restrict__ X, const int* __restrict__ rows, int S,
+                                                    long long shape_stride, int K, float* __restrict__ kth) {
+    extern __shared__ __align__(16) float sm[];
+    float* Qt = sm;                   // [D][PK]
+    float* Xt = Qt + D * PK;          // [D][PK]
+    unsigned* hist = reinterpret_cast<unsigned*>(Xt + D * PK);   // [T][256]
+    __shared__ unsigned prefix[T];
+    __shared__ int krem[T];
+    const int b = blockIdx.y, i0 = blockIdx.x * T;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const float* Xb = X + (long long)b * shape_stride;
+    const int* rb = rows ? rows + (long long)b * S : nullptr;
+    auto load_rows = [&](int r0, float* Kt) {
+        const int r = tid & 63;
+        const bool ok = (r0 + r) < S;
+        const long long gr = ok ? (rb ? rb[r0 + r] : (r0 + r)) : 0;
+        const float* src = Xb + gr * D;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int c4 = (tid >> 6) + 4 * i;
+            float4 v = ok ? *reinterpret_cast<const float4*>(src + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            Kt[(4 * c4 + 0) * PK + r] = v.x; Kt[(4 * c4 + 1) * PK + r] = v.y;
+            Kt[(4 * c4 + 2) * PK + r] = v.z; Kt[(4 * c4 + 3) * PK + r] = v.w;
+        }
+    };
+    load_rows(i0, Qt);
+    if (tid < T) { prefix[tid] = 0u; krem[tid] = K; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int e = tid; e < T * 256; e += NT) hist[e] = 0u;
+        __syncthreads();
+        for (int j0 = 0; j0 < S; j0 += T) {
+            __syncthreads();
+            load_rows(j0, Xt);
+            __syncthreads();
+            float s[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+            gemm_dd(Qt, Xt, ty, tx, s);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int row = 4 * ty + i;
+                const unsigned pf = prefix[row];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j0 + 4 * tx + j >= S) continue;
+                    float dist = 2.0f - 2.0f * s[i][j];
+                    unsigned key = f2ord(dist);
+                    bool match = (pass == 0) || ((key >> (shift + 8)) == (pf >> (shift + 8)));
+                    if (match) atomicAdd(&hist[row * 256 + ((key >> shift) & 255u)], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        // one warp per 8 rows: find the bin holding the krem-th smallest
+        {
+            const int lane = tid & 31, w = tid >> 5;
+            for (int rr = 0; rr < 8; ++rr) {
+                const int row = w * 8 + rr;
+                int kk = krem[row];
+                // each lane owns 8 consecutive bins
+                unsigned loc[8]; unsigned tot = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { loc[q] = hist[row * 256 + lane * 8 + q]; tot += loc[q]; }
+                unsigned incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned y = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                unsigned excl = incl - tot;
+                bool mine = ((int)excl < kk) && (kk <= (int)incl);
+                if (mine) {
+                    unsigned run = excl;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if ((int)run < kk && kk <= (int)(run + loc[q])) {
+                            prefix[row] = prefix[row] | ((unsigned)(lane * 8 + q) << shift);
+                            krem[row] = kk - (int)run;
+                        }
+                        run += loc[q];
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < T && i0 + tid < S) kth[(long long)b * S + i0 + tid] = ord2f(prefix[tid]);
+}
+
+// ================================================================================================ arg-select (nms)
+// For every query row a (rows of A) pick one candidate j (rows of Bm) — used by MeanShift.nms (src/mean_shift.py:139-179):
+//   MODE 0: argmin_j (2 - 2 a.b_j)                      membership of a point to the nearest shifted centre (:146-149)
+//   MODE 1: argmax_j [ (2 - 2 a.b_j) < thr ] * cnt[j]    neighbour centre with most members (:163-171); thr = b (not b^2)
+//   MODE 2: argmax_j  a.b_j                              final label = most similar kept centre (:177-178)
+// Ties go to the lowest j.  grid (ceil(Ma/T), B).
+template <int MODE>
+__global__ void __launch_bounds__(NT) ms_argsel_kernel(const float* __restrict__ A, long long a_stride, int Ma,
+                                                       const float* __restrict__ Bm, long long b_stride, int Nb,
+                                                       const float* __restrict__ cnt, const float* __restrict__ thr,
+                                                       int* __restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    float* At = sm;
+    float* Bt = At + D * PK;
+    const int b = blockIdx.y, i0 = blockIdx.x * T;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const float* Ab = A + (long long)b * a_stride;
+    const float* Bb = Bm + (long long)b * b_stride;
+    const float* cb = (MODE == 1) ? cnt + (long long)b * Nb : nullptr;
+    const float th = (MODE == 1) ? thr[b] : 0.f;
+    load_tile(Ab, D, i0, Ma, nullptr, At);
+    float best[4]; int bj[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best[i] = (MODE == 0) ? INFINITY : -INFINITY; bj[i] = 0x7fffffff; }
+    for (int j0 = 0; j0 < Nb; j0 += T) {
+        __syncthreads();
+        load_tile(Bb, D, j0, Nb, nullptr, Bt);
+        __syncthreads();
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+        gemm_dd(At, Bt, ty, tx, s);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int jj = j0 + 4 * tx + j;
+            if (jj >= Nb) continue;
+            float cj = (MODE == 1) ? cb[jj] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float v;
+                if (MODE == 0) v = 2.0f - 2.0f * s[i][j];
+                else if (MODE == 1) v = ((2.0f - 2.0f * s[i][j]) < th) ? cj : 0.f;
+                else v = s[i][j];
+                bool better = (MODE == 0) ? (v < best[i]) : (v > best[i]);   // jj increases -> first occurrence kept
+                best[i] = better ? v : best[i];
+                bj[i] = better ? jj : bj[i];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(FULL, best[i], o);
+            int oj = __shfl_xor_sync(FULL, bj[i], o);
+            bool better = (MODE == 0) ? (ov < best[i] || (ov == best[i] && oj < bj[i]))
+                                      : (ov > best[i] || (ov == best[i] && oj < bj[i]));
+            best[i] = better ? ov : best[i];
+            bj[i] = better ? oj : bj[i];
+        }
+        const int r = i0 + 4 * ty + i;
+        if (tx == 0 && r < Ma) out[(long long)b * Ma + r] = bj[i];
+    }
+}
+
+static size_t smem_fwd() { return sizeof(float) * (2 * D * PK + T * PR + T * PK); }
+static size_t smem_rows() { return sizeof(float) * (3 * D * PK + T * PR + T * PK); }
+static size_t smem_cols() { return sizeof(float) * (3 * D * PK + 2 * T * PR + 2 * T * PK); }
+static size_t smem_kth() { return sizeof(float) * (2 * D * PK) + sizeof(unsigned) * T * 256; }
+
+}  // namespace ms
+}  // namespace pn
+
+using namespace pn;
+using namespace pn::ms;
+
+extern "C" int pn_ms_iter_fwd(const float* Y, const float* X, int B, int N, int d, const float* cinv, float* Ynew,
+                              float* den, float* unorm, void* stream) {
+    PN_REQUIRE(Y && X && cinv && Ynew && den && unorm, "pn_ms_iter_fwd: null pointer");
+    PN_REQUIRE(d == D, "pn_ms_iter_fwd: embedding width must be %d (got %d)", D, d);
+    PN_CUDA(cudaFuncSetAttribute(ms_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fwd()));
+    dim3 grid(cdiv(N, T), B);
+    ms_fwd_kernel<<<grid, NT, smem_fwd(), (cudaStream_t)stream>>>(Y, X, N, cinv, Ynew, den, unorm);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_fwd_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_ms_iter_bwd(const float* gout, const float* Ynew, const float* Yprev, const float* X,
+                              const float* den, const float* unorm, int B, int N, int d, const float* cinv,
+                              float* ws_Gn, float* ws_gd, float* gYprev, float* gX, int accumulate_gX,
+                              void* stream) {
+    PN_REQUIRE(gout && Ynew && Yprev && X && den && unorm && cinv && ws_Gn && ws_gd && gYprev && gX,
+               "pn_ms_iter_bwd: null pointer");
+    PN_REQUIRE(d == D, "pn_ms_iter_bwd: embedding width must be %d (got %d)", D, d);
+    cudaStream_t st = (cudaStream_t)stream;
+    long long rows = (long long)B * N;
+    ms_bwd_prep_kernel<<<cdiv(rows, 8), 256, 0, st>>>(gout, Ynew, den, unorm, rows, ws_Gn, ws_gd);
+    PN_COUNT_LAUNCH();
+    PN_CUDA(cudaFuncSetAttribute(ms_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows()));
+    PN_CUDA(cudaFuncSetAttribute(ms_bwd_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols()));
+    dim3 grid(cdiv(N, T), B);
+    ms_bwd_rows_kernel<<<grid, NT, smem_rows(), st>>>(Yprev, X, ws_Gn, ws_gd, N, cinv, gYprev);
+    PN_COUNT_LAUNCH();
+    ms_bwd_cols_kernel<<<grid, NT, smem_cols(), st>>>(Yprev, X, ws_Gn, ws_gd, N, cinv, gX, accumulate_gX);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_bwd kernels");
+    return PN_OK;
+}
+
+extern "C" int pn_ms_kth_dist(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K,
+                              float* kth, void* stream) {
+    PN_REQUIRE(X && kth, "pn_ms_kth_dist: null pointer");
+    PN_REQUIRE(d == D, "pn_ms_kth_dist: embedding width must be %d (got %d)", D, d);
+    PN_REQUIRE(K >= 1 && K <= S, "pn_ms_kth_dist: need 1 <= K <= S (K=%d S=%d)", K, S);
+    PN_CUDA(cudaFuncSetAttribute(ms_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kth()));
+    dim3 grid(cdiv(S, T), B);
+    ms_kth_kernel<<<grid, NT, smem_kth(), (cudaStream_t)stream>>>(X, rows, S, shape_stride, K, kth);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_kth_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_ms_argsel(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride,
+                            int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream) {
+    PN_REQUIRE(A && Bm && out, "pn_ms_argsel: null pointer");
+    PN_REQUIRE(d == D, "pn_ms_argsel: embedding width must be %d (got %d)", D, d);
+    PN_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || (cnt && thr)), "pn_ms_argsel: bad mode/args");
+    PN_REQUIRE(Ma > 0 && Nb > 0, "pn_ms_argsel: empty input");
+    size_t smb = sizeof(float) * 2 * D * PK;
+    dim3 grid(cdiv(Ma, T), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) {
+        PN_CUDA(cudaFuncSetAttribute(ms_argsel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+        ms_argsel_kernel<0><<<grid, NT, smb, st>>>(A, a_stride, Ma, Bm, b_stride, Nb, cnt, thr, out);
+    } else if (mode == 1) {
+        PN_CUDA(cudaFuncSetAttribute(ms_argsel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+        ms_argsel_kernel<1><<<grid, NT, smb, st>>>(A, a_stride, Ma, Bm, b_stride, Nb, cnt, thr, out);
+    } else {
+        PN_CUDA(cudaFuncSetAttribute(ms_argsel_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+        ms_argsel_kernel<2><<<grid, NT, smb, st>>>(A, a_stride, Ma, Bm, b_stride, Nb, cnt, thr, out);
+    }
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_argsel_kernel");
+    return PN_OK;
+}

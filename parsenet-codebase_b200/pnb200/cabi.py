@@ -42,6 +42,11 @@ SIGNATURES = {
     "pn_l2norm_bwd": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_p, c_ll, c_i, c_p],
     "pn_triplet_fwd": [c_p, c_ll, c_i, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p],
     "pn_triplet_bwd": [c_p, c_ll, c_i, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p],
+    # meanshift.cu
+    "pn_ms_iter_fwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "pn_ms_iter_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
+    "pn_ms_kth_dist": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
+    "pn_ms_argsel": [c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
 }
 _SPECIAL = {
     "pn_last_error": (ctypes.c_char_p, []),
@@ -86,3 +91,23 @@ def launch_count():
 
 def reset_launch_count():
     lib.pn_reset_launch_count()
+
+
+# ---- optional per-entry-point device timing (bench.py uses it for the roofline of the dominant kernel)
+TIMED = {}          # name -> list of (start_event, end_event); register a name to start collecting
+
+
+def call(name, *args):
+    fn = getattr(lib, name)
+    ev = TIMED.get(name)
+    if ev is not None:
+        import torch
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        ev.append((a, b))
+    else:
+        rc = fn(*args)
+    if rc != 0:
+        raise PnError(f"{name} failed (rc={rc}): {lib.pn_last_error().decode()}")

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .cabi import lib, check
+from .cabi import lib, check, call
 from .ops import _ptr, _stream
 
 
@@ -78,8 +78,8 @@ class TripletFn(torch.autograd.Function):
             w_d = torch.from_numpy(w).to(dev)
             pl = torch.empty((T,), dtype=torch.float32, device=dev)
             ps = torch.empty((T,), dtype=torch.float32, device=dev)
-            check(lib.pn_triplet_fwd(_ptr(E), D, D, _ptr(a_d), _ptr(n_d), T, S, float(margin), _ptr(pl), _ptr(ps),
-                                     _stream()), "pn_triplet_fwd")
+            call("pn_triplet_fwd", _ptr(E), D, D, _ptr(a_d), _ptr(n_d), T, S, float(margin), _ptr(pl), _ptr(ps),
+                                     _stream())
             total = total + (pl * w_d).sum()
             saved.append((S, a_d, n_d, w_d, ps))
         ctx.saved = (E, norms, saved, margin, (B, N, D))
@@ -91,8 +91,8 @@ class TripletFn(torch.autograd.Function):
         dE = torch.zeros_like(E)
         for S, a_d, n_d, w_d, ps in saved:
             pw = (w_d * g.reshape(())).contiguous()
-            check(lib.pn_triplet_bwd(_ptr(E), D, D, _ptr(a_d), _ptr(n_d), a_d.shape[0], S, float(margin), _ptr(ps),
-                                     _ptr(pw), _ptr(dE), D, _stream()), "pn_triplet_bwd")
+            call("pn_triplet_bwd", _ptr(E), D, D, _ptr(a_d), _ptr(n_d), a_d.shape[0], S, float(margin), _ptr(ps),
+                                     _ptr(pw), _ptr(dE), D, _stream())
         dx = ops.l2norm_bwd(E, dE, norms)
         return dx.view(B, N, D), None, None
 
@@ -104,7 +104,7 @@ class NllFn(torch.autograd.Function):
         tg = target_bn.detach().to(torch.int64).contiguous()
         B, P, N = lp.shape
         loss = torch.zeros((1,), dtype=torch.float32, device=lp.device)
-        check(lib.pn_nll_fwd(_ptr(lp), _ptr(tg), B, N, P, _ptr(loss), _stream()), "pn_nll_fwd")
+        call("pn_nll_fwd", _ptr(lp), _ptr(tg), B, N, P, _ptr(loss), _stream())
         ctx.tg, ctx.shape = tg, (B, P, N)
         return loss.reshape(())
 
@@ -113,5 +113,5 @@ class NllFn(torch.autograd.Function):
         B, P, N = ctx.shape
         g = g.reshape(1).contiguous().float()
         dlp = torch.zeros((B, P, N), dtype=torch.float32, device=g.device)
-        check(lib.pn_nll_bwd(_ptr(ctx.tg), _ptr(g), B, N, P, _ptr(dlp), _stream()), "pn_nll_bwd")
+        call("pn_nll_bwd", _ptr(ctx.tg), _ptr(g), B, N, P, _ptr(dlp), _stream())
         return dlp, None

@@ -2,7 +2,7 @@
 import torch
 
 from . import cabi
-from .cabi import lib, check
+from .cabi import lib, check, call
 
 
 def _ptr(t):
@@ -33,8 +33,8 @@ def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
     dist = torch.empty((B, N, k), dtype=torch.float32, device=x_bnc.device) if return_dist else None
     ws = torch.empty((B * N,), dtype=torch.float32, device=x_bnc.device)
     with torch.cuda.device(x_bnc.device):
-        check(lib.pn_knn(_ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), 1 if out_dtype == torch.int64 else 0,
-                         _ptr(dist), _ptr(ws), _stream()), "pn_knn")
+        call("pn_knn", _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), 1 if out_dtype == torch.int64 else 0,
+                         _ptr(dist), _ptr(ws), _stream())
     return (idx, dist) if return_dist else idx
 
 
@@ -72,9 +72,9 @@ def linear_fwd(A, W, bias=None, sbias=None, in_norm=None, stats_groups=0, per_sh
     act = ACT_NONE
     if in_norm is not None:
         sc, sh, act = in_norm.scale, in_norm.shift, in_norm.act
-    check(lib.pn_linear_fwd(_ptr(A), _pitch(A), _ptr(W), W.stride(0), _ptr(bias), _ptr(sbias), _ptr(sc), _ptr(sh),
+    call("pn_linear_fwd", _ptr(A), _pitch(A), _ptr(W), W.stride(0), _ptr(bias), _ptr(sbias), _ptr(sc), _ptr(sh),
                             act, _ptr(Y), Nout, _ptr(stats), B, Np, K, Nout, max(stats_groups, 1),
-                            1 if per_shape else 0, _stream()), "pn_linear_fwd")
+                            1 if per_shape else 0, _stream())
     return Y, stats
 
 
@@ -83,8 +83,8 @@ def norm_finalize(stats, gamma, beta, B, C, count, act, per_shape=True, eps=GN_E
     mr = torch.empty((S, G, 2), dtype=torch.float32, device=stats.device)
     scale = torch.empty((S, C), dtype=torch.float32, device=stats.device)
     shift = torch.empty((S, C), dtype=torch.float32, device=stats.device)
-    check(lib.pn_norm_finalize(_ptr(stats), _ptr(gamma), _ptr(beta), S, G, C, float(count), float(eps), _ptr(mr),
-                               _ptr(scale), _ptr(shift), _stream()), "pn_norm_finalize")
+    call("pn_norm_finalize", _ptr(stats), _ptr(gamma), _ptr(beta), S, G, C, float(count), float(eps), _ptr(mr),
+                               _ptr(scale), _ptr(shift), _stream())
     if S != B:   # batch-wide statistics: kernels index scale/shift per shape
         scale = scale.expand(B, C).contiguous()
         shift = shift.expand(B, C).contiguous()
@@ -110,10 +110,10 @@ def linear_bwd_data(dY, W, dZ=None, accumulate=False, fin_A=None, fin_norm=None,
             gsum = torch.zeros((mr.shape[0], G, 2), dtype=torch.float64, device=dY.device)
         else:
             act = fin_act if fin_act is not None else ACT_NONE
-    check(lib.pn_linear_bwd_data(_ptr(dY), _pitch(dY), _ptr(W), W.stride(0), _ptr(dZ), _pitch(dZ),
+    call("pn_linear_bwd_data", _ptr(dY), _pitch(dY), _ptr(W), W.stride(0), _ptr(dZ), _pitch(dZ),
                                  1 if accumulate else 0, 1 if finalize else 0, _ptr(fin_A),
                                  _pitch(fin_A) if finalize else 0, _ptr(sc), _ptr(sh), act, _ptr(gamma), _ptr(mr),
-                                 _ptr(gsum), B, Np, K, Nout, G, per_shape, _stream()), "pn_linear_bwd_data")
+                                 _ptr(gsum), B, Np, K, Nout, G, per_shape, _stream())
     return dZ, gsum
 
 
@@ -124,9 +124,9 @@ def norm_bwd_apply(dZ, A, norm, gsum, want_affine_grads=True):
     if want_affine_grads:
         dg = torch.zeros((C,), dtype=torch.float32, device=dZ.device)
         db = torch.zeros((C,), dtype=torch.float32, device=dZ.device)
-    check(lib.pn_norm_bwd_apply(_ptr(dZ), _pitch(dZ), _ptr(A), _pitch(A), _ptr(norm.gamma), _ptr(norm.mean_rstd),
+    call("pn_norm_bwd_apply", _ptr(dZ), _pitch(dZ), _ptr(A), _pitch(A), _ptr(norm.gamma), _ptr(norm.mean_rstd),
                                 _ptr(gsum), B, Np, C, norm.G, 1 if norm.per_shape else 0, norm.count, _ptr(dg),
-                                _ptr(db), _stream()), "pn_norm_bwd_apply")
+                                _ptr(db), _stream())
     return dg, db
 
 
@@ -143,9 +143,8 @@ def linear_bwd_weight(dY, A, in_norm=None, dW=None, want_bias=True, want_sbias=F
     if in_norm is not None:
         sc, sh, act = in_norm.scale, in_norm.shift, in_norm.act
     assert dW.stride(1) == 1
-    check(lib.pn_linear_bwd_weight(_ptr(dY), _pitch(dY), _ptr(A), _pitch(A), _ptr(sc), _ptr(sh), act, _ptr(dW),
-                                   dW.stride(0), _ptr(db), _ptr(dsb), B, Np, K, Nout, _stream()),
-          "pn_linear_bwd_weight")
+    call("pn_linear_bwd_weight", _ptr(dY), _pitch(dY), _ptr(A), _pitch(A), _ptr(sc), _ptr(sh), act, _ptr(dW),
+                                   dW.stride(0), _ptr(db), _ptr(dsb), B, Np, K, Nout, _stream())
     return dW, db, dsb
 
 
@@ -159,16 +158,15 @@ def edge_gather_fwd(PQ, idx, gamma, G, per_shape=True, want_stats=True):
     esum = torch.empty((B, N, Cout), dtype=torch.float32, device=dev)
     stats = torch.zeros((B if per_shape else 1, G, 2), dtype=torch.float64, device=dev) if want_stats else None
     assert idx.dtype == torch.int32 and idx.is_contiguous()
-    check(lib.pn_edge_gather_fwd(_ptr(PQ), _pitch(PQ), _ptr(idx), B, N, k, Cout, _ptr(gamma), _ptr(esel),
-                                 _ptr(jsel), _ptr(esum), _ptr(stats), G, 1 if per_shape else 0, _stream()),
-          "pn_edge_gather_fwd")
+    call("pn_edge_gather_fwd", _ptr(PQ), _pitch(PQ), _ptr(idx), B, N, k, Cout, _ptr(gamma), _ptr(esel),
+                                 _ptr(jsel), _ptr(esum), _ptr(stats), G, 1 if per_shape else 0, _stream())
     return esel, jsel, esum, stats
 
 
 def edge_apply(esel, norm, out):
     B, N, Cout = esel.shape
-    check(lib.pn_edge_apply(_ptr(esel), _ptr(norm.scale), _ptr(norm.shift), _ptr(out), _pitch(out), B, N, Cout,
-                            _stream()), "pn_edge_apply")
+    call("pn_edge_apply", _ptr(esel), _ptr(norm.scale), _ptr(norm.shift), _ptr(out), _pitch(out), B, N, Cout,
+                            _stream())
     return out
 
 
@@ -179,8 +177,7 @@ def knn_csr_transpose(idx):
     off = torch.empty((B, N + 1), dtype=torch.int32, device=dev)
     cursor = torch.empty((B, N), dtype=torch.int32, device=dev)
     rev = torch.empty((B, N * k), dtype=torch.int32, device=dev)
-    check(lib.pn_knn_csr_transpose(_ptr(idx), B, N, k, _ptr(cnt), _ptr(off), _ptr(cursor), _ptr(rev), _stream()),
-          "pn_knn_csr_transpose")
+    call("pn_knn_csr_transpose", _ptr(idx), B, N, k, _ptr(cnt), _ptr(off), _ptr(cursor), _ptr(rev), _stream())
     return off, rev
 
 
@@ -195,18 +192,16 @@ def edge_bwd(g, PQ, idx, esel, jsel, esum, norm, dense=True, want_affine_grads=T
     gsum = torch.zeros((S, norm.G, 2), dtype=torch.float64, device=dev) if dense else None
     dg = torch.zeros((Cout,), dtype=torch.float32, device=dev) if want_affine_grads else None
     db = torch.zeros((Cout,), dtype=torch.float32, device=dev) if want_affine_grads else None
-    check(lib.pn_edge_bwd_prep(_ptr(g), _pitch(g), _ptr(esel), _ptr(norm.scale), _ptr(norm.shift),
+    call("pn_edge_bwd_prep", _ptr(g), _pitch(g), _ptr(esel), _ptr(norm.scale), _ptr(norm.shift),
                                _ptr(norm.mean_rstd), _ptr(norm.gamma), B, N, Cout, norm.G,
-                               1 if norm.per_shape else 0, _ptr(dy), _ptr(gsum), _ptr(dg), _ptr(db), _stream()),
-          "pn_edge_bwd_prep")
+                               1 if norm.per_shape else 0, _ptr(dy), _ptr(gsum), _ptr(dg), _ptr(db), _stream())
     off = rev = None
     if dense:
         off, rev = knn_csr_transpose(idx)
     dPQ = torch.empty((B, N, C2), dtype=torch.float32, device=dev)
-    check(lib.pn_edge_bwd(_ptr(PQ), _pitch(PQ), _ptr(dy), _ptr(esum), _ptr(jsel), _ptr(off), _ptr(rev),
+    call("pn_edge_bwd", _ptr(PQ), _pitch(PQ), _ptr(dy), _ptr(esum), _ptr(jsel), _ptr(off), _ptr(rev),
                           _ptr(norm.mean_rstd), _ptr(gsum), _ptr(norm.scale), B, N, k, Cout, norm.G,
-                          1 if norm.per_shape else 0, norm.count, 1 if dense else 0, _ptr(dPQ), C2, _stream()),
-          "pn_edge_bwd")
+                          1 if norm.per_shape else 0, norm.count, 1 if dense else 0, _ptr(dPQ), C2, _stream())
     return dPQ, dg, db
 
 
@@ -215,31 +210,31 @@ def colmax_norm(Y, norm):
     out = torch.empty((B, C), dtype=torch.float32, device=Y.device)
     arg = torch.empty((B, C), dtype=torch.int32, device=Y.device)
     ext = torch.empty((B, C), dtype=torch.float32, device=Y.device)
-    check(lib.pn_colmax_norm(_ptr(Y), _pitch(Y), B, N, C, _ptr(norm.scale), _ptr(norm.shift), norm.act, _ptr(out),
-                             _ptr(arg), _ptr(ext), _stream()), "pn_colmax_norm")
+    call("pn_colmax_norm", _ptr(Y), _pitch(Y), B, N, C, _ptr(norm.scale), _ptr(norm.shift), norm.act, _ptr(out),
+                             _ptr(arg), _ptr(ext), _stream())
     return out, arg, ext
 
 
 def colmax_bwd_fill(Y, gt, arg, norm, gsum, dense=True):
     B, N, C = Y.shape
     dY = torch.empty((B, N, C), dtype=torch.float32, device=Y.device)
-    check(lib.pn_colmax_bwd_fill(_ptr(Y), _pitch(Y), _ptr(gt), _ptr(arg), _ptr(norm.gamma), _ptr(norm.mean_rstd),
+    call("pn_colmax_bwd_fill", _ptr(Y), _pitch(Y), _ptr(gt), _ptr(arg), _ptr(norm.gamma), _ptr(norm.mean_rstd),
                                  _ptr(gsum), B, N, C, norm.G, 1 if norm.per_shape else 0, norm.count,
-                                 1 if dense else 0, _ptr(dY), C, _stream()), "pn_colmax_bwd_fill")
+                                 1 if dense else 0, _ptr(dY), C, _stream())
     return dY
 
 
 def logsoftmax_fwd(logits):
     B, N, P = logits.shape
     logp = torch.empty((B, P, N), dtype=torch.float32, device=logits.device)
-    check(lib.pn_logsoftmax_fwd(_ptr(logits), _pitch(logits), B, N, P, _ptr(logp), _stream()), "pn_logsoftmax_fwd")
+    call("pn_logsoftmax_fwd", _ptr(logits), _pitch(logits), B, N, P, _ptr(logp), _stream())
     return logp
 
 
 def logsoftmax_bwd(logp, dlp):
     B, P, N = logp.shape
     dl = torch.empty((B, N, P), dtype=torch.float32, device=logp.device)
-    check(lib.pn_logsoftmax_bwd(_ptr(logp), _ptr(dlp), B, N, P, _ptr(dl), P, _stream()), "pn_logsoftmax_bwd")
+    call("pn_logsoftmax_bwd", _ptr(logp), _ptr(dlp), B, N, P, _ptr(dl), P, _stream())
     return dl
 
 
@@ -248,14 +243,13 @@ def l2norm_fwd(x2d, eps=1e-12):
     assert x2d.stride(1) == 1
     y = torch.empty((rows, D), dtype=torch.float32, device=x2d.device)
     norms = torch.empty((rows,), dtype=torch.float32, device=x2d.device)
-    check(lib.pn_l2norm_fwd(_ptr(x2d), x2d.stride(0), rows, D, float(eps), _ptr(y), D, _ptr(norms), _stream()),
-          "pn_l2norm_fwd")
+    call("pn_l2norm_fwd", _ptr(x2d), x2d.stride(0), rows, D, float(eps), _ptr(y), D, _ptr(norms), _stream())
     return y, norms
 
 
 def l2norm_bwd(y, dy, norms):
     rows, D = y.shape
     dx = torch.empty((rows, D), dtype=torch.float32, device=y.device)
-    check(lib.pn_l2norm_bwd(_ptr(y), y.stride(0), _ptr(dy), dy.stride(0), _ptr(norms), rows, D, _ptr(dx), D, 0,
-                            _stream()), "pn_l2norm_bwd")
+    call("pn_l2norm_bwd", _ptr(y), y.stride(0), _ptr(dy), dy.stride(0), _ptr(norms), rows, D, _ptr(dx), D, 0,
+                            _stream())
     return dx

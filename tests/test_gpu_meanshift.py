@@ -1,0 +1,75 @@
+"""Mean-shift parity on the GPU: fused kernels vs golden vectors of the reference and vs the oracle port."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(got, want):
+    got = got.detach().cpu().double().numpy(); want = np.asarray(want, np.float64)
+    return np.abs(got - want).max() / (np.abs(want).max() + 1e-30)
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_meanshift_vs_reference_golden(golden_dir, case):
+    from src.mean_shift import MeanShift
+    g = np.load(os.path.join(golden_dir, "meanshift.npz"))
+    N, ncl, seed, it = [int(v) for v in g[case + "_meta"]]
+    X = torch.from_numpy(g[case + "_X"]).cuda().requires_grad_()
+    ms = MeanShift()
+    np.random.seed(seed)
+    newX, center, bw, labels = ms.mean_shift(X, N, float(g[case + "_q"]), it)
+    assert abs(bw.item() - float(g[case + "_bw"])) <= 1e-5 * float(g[case + "_bw"])
+    np.testing.assert_array_equal(labels.cpu().numpy(), g[case + "_labels"])       # segment labels bit-exact
+    assert _rel(newX, g[case + "_newX"]) < 1e-4
+    assert _rel(center, g[case + "_center"]) < 1e-4
+    gen = torch.Generator().manual_seed(seed + 100)
+    w = torch.randn(center.shape, generator=gen).cuda(); w2 = (torch.randn(newX.shape, generator=gen) * 0.01).cuda()
+    ((center * w).sum() + (newX * w2).sum()).backward()
+    assert _rel(X.grad, g[case + "_gradX"]) < 1e-3
+
+
+def test_meanshift_batched_fresh_inputs_vs_port():
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as port
+    from pnb200 import meanshift as pms
+    B, N, d = 3, 900, 128
+    Xs = [clustered_embedding(N, d, 4 + b, 40 + b)[0] for b in range(B)]
+    bws = torch.tensor([0.2, 0.35, 0.6])
+    Xd = torch.stack(Xs).cuda().requires_grad_()
+    Y = pms.mean_shift_iters(Xd, bws.cuda(), 4)
+    gen = torch.Generator().manual_seed(1)
+    w = torch.randn(B, N, d, generator=gen)
+    (Y * w.cuda()).sum().backward()
+    for b in range(B):
+        xr = Xs[b].clone().requires_grad_()
+        yr = port.mean_shift_iters(xr, bws[b], 4)
+        (yr * w[b]).sum().backward()
+        assert _rel(Y[b], yr.detach().numpy()) < 1e-4
+        assert _rel(Xd.grad[b], xr.grad.numpy()) < 1e-3
+
+
+def test_bandwidth_subset_and_large_k():
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as port
+    from pnb200 import meanshift as pms
+    X, _ = clustered_embedding(1500, 128, 5, 9)
+    for num_samples, q in [(1000, 0.05), (10000, 0.1), (1500, 0.5)]:
+        np.random.seed(3); want = port.compute_bandwidth(X, num_samples, q)
+        np.random.seed(3); got = pms.compute_bandwidth(X.cuda(), num_samples, q)
+        assert abs(got.item() - want.item()) <= 2e-6 * want.item(), (num_samples, q, got.item(), want.item())
+
+
+def test_nms_labels_bit_exact_vs_port():
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as port
+    from pnb200 import meanshift as pms
+    X, _ = clustered_embedding(1100, 128, 7, 17)
+    Y = port.mean_shift_iters(X, torch.tensor(0.3), 6)
+    kept_r, ids_r, lab_r = port.nms(Y, X, torch.tensor(0.3))
+    kept, ids, lab = pms.nms(Y.cuda(), X.cuda(), 0.3)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ids_r.numpy())
+    np.testing.assert_array_equal(lab.cpu().numpy(), lab_r.numpy())

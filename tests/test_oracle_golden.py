@@ -88,3 +88,21 @@ def test_segnet_port_free_running_knn_close_to_reference(golden_dir):
         assert (idx.numpy() == g[f"idx{i}"]).mean() > 0.995
     err = np.abs(emb.numpy() - g["embedding"]) / (np.abs(g["embedding"]) + 1e-2)
     assert (err < 1e-3).mean() > 0.98
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_meanshift_port_matches_reference(golden_dir, case):
+    from oracle.port import meanshift as port
+    g = _load(golden_dir, "meanshift.npz")
+    N, ncl, seed, it = [int(v) for v in g[case + "_meta"]]
+    X = torch.from_numpy(g[case + "_X"]).requires_grad_()
+    np.random.seed(seed)
+    newX, center, bw, labels = port.mean_shift(X, N, float(g[case + "_q"]), it)
+    np.testing.assert_allclose(bw.numpy(), g[case + "_bw"], rtol=1e-6)
+    np.testing.assert_array_equal(labels.numpy(), g[case + "_labels"])
+    np.testing.assert_allclose(newX.detach().numpy(), g[case + "_newX"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(center.detach().numpy(), g[case + "_center"], rtol=1e-5, atol=1e-6)
+    gen = torch.Generator().manual_seed(seed + 100)
+    w = torch.randn(center.shape, generator=gen); w2 = torch.randn(newX.shape, generator=gen) * 0.01
+    ((center * w).sum() + (newX * w2).sum()).backward()
+    np.testing.assert_allclose(X.grad.numpy(), g[case + "_gradX"], rtol=1e-4, atol=1e-6)
