@@ -104,7 +104,152 @@ def gen_meanshift():
     np.savez_compressed(os.path.join(OUT, "meanshift.npz"), **out)
 
 
-GENS = {"knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift}
+def _prim_cloud(kind, m, seed):
+    """noisy samples of one analytic primitive + outward normals + random positive weights"""
+    rng = np.random.RandomState(seed)
+    u, v = rng.rand(m), rng.rand(m)
+    if kind == "plane":
+        p = np.stack([u - 0.5, v - 0.5, 0 * u], 1); n = np.tile([0, 0, 1.0], (m, 1))
+    elif kind == "sphere":
+        th, ph = 2 * np.pi * u, np.arccos(1 - 1.4 * v)
+        n = np.stack([np.sin(ph) * np.cos(th), np.sin(ph) * np.sin(th), np.cos(ph)], 1); p = 0.7 * n
+    elif kind == "cylinder":
+        th = 2 * np.pi * u * 0.8
+        n = np.stack([np.cos(th), np.sin(th), 0 * u], 1); p = 0.4 * n + np.stack([0 * u, 0 * u, 1.5 * (v - 0.5)], 1)
+    else:
+        a = np.pi / 5; th = 2 * np.pi * u * 0.9; h = 0.3 + 0.7 * v
+        p = np.stack([h * np.tan(a) * np.cos(th), h * np.tan(a) * np.sin(th), h], 1)
+        n = np.stack([np.cos(a) * np.cos(th), np.cos(a) * np.sin(th), -np.sin(a) * np.ones(m)], 1)
+    R, _ = np.linalg.qr(rng.randn(3, 3))
+    p = p @ R.T + rng.randn(3) * 0.3 + rng.randn(m, 3) * 0.004
+    n = n @ R.T
+    w = 0.15 + 0.85 * rng.rand(m, 1)
+    return p.astype(np.float32), n.astype(np.float32), w.astype(np.float32)
+
+
+def gen_fits():
+    PF = rl.ref("src.primitive_forward"); PR = rl.ref("src.primitives")
+    fit = PF.Fit(); cp = PR.ComputePrimitiveDistance(reduce=True)
+    out = {}
+    for kind, seed in [("plane", 1), ("sphere", 2), ("cylinder", 3), ("cone", 4)]:
+        p, n, w = _prim_cloud(kind, 900, seed)
+        P, Nn = torch.from_numpy(p), torch.from_numpy(n)
+        W = torch.from_numpy(w).requires_grad_()
+        res = getattr(fit, f"fit_{kind}_torch")(P, Nn, W)
+        g = torch.Generator().manual_seed(seed)
+        coef = [torch.randn(r.shape, generator=g) for r in res]
+        sum((r * c).sum() for r, c in zip(res, coef)).backward()
+        out[kind + "_p"] = p; out[kind + "_n"] = n; out[kind + "_w"] = w
+        for i, r in enumerate(res):
+            out[f"{kind}_out{i}"] = r.detach().numpy(); out[f"{kind}_coef{i}"] = coef[i].numpy()
+        out[kind + "_gw"] = W.grad.numpy()
+        # residual distance of a second sample of the same surface to the fitted primitive (+ grads wrt params)
+        q = torch.from_numpy(_prim_cloud(kind, 500, seed + 50)[0])
+        if kind == "plane":
+            params = [res[0].detach().reshape(3, 1), res[1].detach()]
+        elif kind == "sphere":
+            params = [res[0].detach(), res[1].detach()]
+        elif kind == "cylinder":
+            params = [res[0].detach(), res[1].detach(), res[2].detach()]
+        else:
+            params = [res[0].detach().reshape(1, 3), res[1].detach().reshape(3, 1), res[2].detach()]
+        params = [(t + 0.02).clone().requires_grad_() for t in params]
+        d = getattr(cp, "distance_from_" + kind)(points=q, params=params, sqrt=False)
+        d.backward()
+        out[kind + "_q"] = q.numpy(); out[kind + "_dist"] = d.detach().numpy()
+        for i, t in enumerate(params):
+            out[f"{kind}_par{i}"] = t.detach().numpy(); out[f"{kind}_gpar{i}"] = t.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "fits.npz"), **out)
+
+
+def gen_losses():
+    U = rl.ref("src.utils"); L = rl.ref("src.loss"); FU = rl.ref("src.fitting_utils")
+    g = torch.Generator().manual_seed(0)
+    out = {}
+    pred = torch.randn(3, 150, 3, generator=g).requires_grad_(); gt = torch.randn(3, 220, 3, generator=g).requires_grad_()
+    cd = U.chamfer_distance(pred, gt); cds = U.chamfer_distance(pred, gt, sqrt=True)
+    c0 = U.chamfer_distance_one_side(pred, gt, 0); c1 = U.chamfer_distance_one_side(pred, gt, 1)
+    s1 = U.chamfer_distance_single_shape(pred[0], gt[0]); s2 = U.chamfer_distance_single_shape(pred[0], gt[0], one_side=True)
+    (cd + 2 * cds + 3 * c0 + 4 * c1 + 5 * s1 + 6 * s2).backward()
+    out.update(pred=pred.detach().numpy(), gt=gt.detach().numpy(), cd=cd.item(), cds=cds.item(), c0=c0.item(),
+               c1=c1.item(), s1=s1.item(), s2=s2.item(), gpred=pred.grad.numpy(), ggt=gt.grad.numpy())
+    nu, nv = L.uniform_knot_bspline(20, 20, 3, 3, 30)
+    nu40, nv40 = L.uniform_knot_bspline(20, 20, 3, 3, 40)
+    out.update(nu=nu, nv=nv, nu40=nu40)
+    cpts = (torch.rand(2, 400, 3, generator=g) - 0.5).requires_grad_()
+    rec = FU.sample_points_from_control_points_(torch.from_numpy(nu.astype(np.float32)), torch.from_numpy(nv.astype(np.float32)), cpts, 2)
+    w = torch.randn(rec.shape, generator=g)
+    (rec * w).sum().backward()
+    out.update(cpts=cpts.detach().numpy(), rec=rec.detach().numpy(), recw=w.numpy(), gcpts=cpts.grad.numpy())
+    # open-spline training losses (train_open_splines.py:158-178)
+    class Cfg: batch_size = 2; grid_size = 20
+    pts = torch.randn(2, 3, 300, generator=g) * 0.3
+    outp = (torch.rand(2, 400, 3, generator=g) - 0.5).requires_grad_()
+    gtcp = torch.rand(2, 20, 20, 3, generator=g) - 0.5
+    nu4 = torch.from_numpy(nu40.astype(np.float32))
+    cd1, _ = L.spline_reconstruction_loss_one_sided(nu4, nu4, outp, pts, Cfg)
+    lreg, perm = L.control_points_permute_reg_loss(outp, gtcp, 20)
+    lap = L.laplacian_loss(outp.reshape(2, 20, 20, 3), perm)
+    lclosed, _ = L.control_points_permute_closed_reg_loss(outp, gtcp, 20, 20)
+    (0.9 * lreg + 0.1 * (cd1 + lap) + 0.5 * lclosed).backward()
+    out.update(tl_pts=pts.numpy(), tl_out=outp.detach().numpy(), tl_gtcp=gtcp.numpy(), tl_cd=cd1.item(),
+               tl_reg=lreg.item(), tl_lap=lap.item(), tl_closed=lclosed.item(), tl_gout=outp.grad.numpy())
+    # weights_normalize
+    wts = torch.randn(7, 300, generator=g).requires_grad_()
+    wn = FU.weights_normalize(wts, 0.8)
+    ww = torch.randn(wn.shape, generator=g)
+    (wn * ww).sum().backward()
+    out.update(wn_in=wts.detach().numpy(), wn_out=wn.detach().numpy(), wn_w=ww.numpy(), wn_g=wts.grad.numpy())
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
+
+
+def spline_state(mode, seed):
+    M = rl.ref("src.model")
+    net = M.DGCNNControlPoints(20, num_points=10, mode=mode)
+    shapes = {n: tuple(v.shape) for n, v in net.state_dict().items()}
+    sd = common.seeded_state_dict(shapes, seed=seed)
+    for i in (1, 2, 3, 4, 5):
+        for s_ in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+            a, b = f"bn{i}.{s_}", f"conv{i}.1.{s_}"
+            if a in sd and b in sd:
+                sd[b] = sd[a]
+    net.load_state_dict(sd)
+    return net, shapes
+
+
+def gen_splinenet():
+    out = {}
+    for mode in (0, 1):
+        net, shapes = spline_state(mode, 30 + mode)
+        net.eval()
+        g = torch.Generator().manual_seed(mode)
+        x = torch.randn(1, 3, 500, generator=g) * 0.4
+        w = torch.rand(500, 1, generator=g).requires_grad_()
+        o = net(x, w.T)
+        c = torch.randn(o.shape, generator=g)
+        (o * c).sum().backward()
+        out.update({f"m{mode}_x": x.numpy(), f"m{mode}_w": w.detach().numpy(), f"m{mode}_out": o.detach().numpy(),
+                    f"m{mode}_c": c.numpy(), f"m{mode}_gw": w.grad.numpy()})
+        out[f"m{mode}_keys"] = np.array(sorted(shapes.keys()))
+        out[f"m{mode}_shapes"] = np.array([str(shapes[k_]) for k_ in sorted(shapes.keys())])
+    # training mode (batch statistics), all parameter gradients (summaries)
+    net, shapes = spline_state(0, 33)
+    net.train()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 3, 420, generator=g) * 0.4
+    o = net(x)
+    c = torch.randn(o.shape, generator=g)
+    (o * c).sum().backward()
+    out.update(tr_x=x.numpy(), tr_out=o.detach().numpy(), tr_c=c.numpy())
+    for n, p in net.named_parameters():
+        out["trgrad:" + n] = grad_summary(p.grad)
+    out["tr_rm5"] = net.bn5.running_mean.numpy(); out["tr_rv5"] = net.bn5.running_var.numpy()
+    out["tr_rm1"] = net.bn1.running_mean.numpy(); out["tr_rv1"] = net.bn1.running_var.numpy()
+    np.savez_compressed(os.path.join(OUT, "splinenet.npz"), **out)
+
+
+GENS = {"knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
+        "splinenet": gen_splinenet}
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)

@@ -62,8 +62,7 @@ def install(cpu=True):
     _stub("lapsolver", solve_dense=solve_dense)
 
     # ---- removed torch APIs (reference pins torch==1.2.0, environment.yml:20) ----
-    if not hasattr(torch, "matrix_rank"):
-        torch.matrix_rank = torch.linalg.matrix_rank
+    torch.matrix_rank = torch.linalg.matrix_rank
 
     def _eig(a, eigenvectors=False):
         w, v = torch.linalg.eig(a)

@@ -10,26 +10,27 @@ namespace pn {
 namespace pw {
 
 // ------------------------------------------------------------------------------------------------ colmax + norm
-// Y [B][N][C] pre-norm; out[b][c] = relu(scale*ext + shift), ext = max_n (scale>=0) or min_n; arg[b][c] = n*
+// Y [B][N][C] pre-norm; out[b][c] = max_n act(scale*y + shift) * (wts ? wts[b][n] : 1); arg[b][c] = first n attaining it
 // grid (C/32, B), block 256 = 8 row-lanes x 32 columns
 __global__ void __launch_bounds__(256) colmax_norm_kernel(const float* __restrict__ Y, long long ldy, int N, int C,
                                                           const float* __restrict__ scale,
                                                           const float* __restrict__ shift, int act,
-                                                          float* __restrict__ out, int* __restrict__ arg,
-                                                          float* __restrict__ ext_out) {
+                                                          const float* __restrict__ wts, float* __restrict__ out,
+                                                          int* __restrict__ arg) {
     __shared__ float sv[8][32];
     __shared__ int si[8][32];
     const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), rl = threadIdx.x >> 5;
     float sc = 1.f, sh = 0.f;
     if (c < C) { sc = scale[(long long)b * C + c]; sh = shift[(long long)b * C + c]; }
-    const bool wantmax = sc >= 0.f;
-    float best = wantmax ? -INFINITY : INFINITY;
+    float best = -INFINITY;
     int bi = 0;
     if (c < C) {
         const float* yb = Y + (long long)b * N * ldy + c;
         for (int n = rl; n < N; n += 8) {
-            float v = yb[(long long)n * ldy];
-            bool better = wantmax ? (v > best) : (v < best);
+            float pre = fmaf(yb[(long long)n * ldy], sc, sh);
+            float v = act == 1 ? fmaxf(pre, 0.f) : (act == 2 ? (pre > 0.f ? pre : 0.2f * pre) : pre);
+            if (wts) v *= wts[(long long)b * N + n];
+            bool better = v > best;
             best = better ? v : best;
             bi = better ? n : bi;
         }
@@ -39,16 +40,11 @@ __global__ void __launch_bounds__(256) colmax_norm_kernel(const float* __restric
     if (rl == 0 && c < C) {
         for (int r = 1; r < 8; ++r) {
             float v = sv[r][threadIdx.x]; int i = si[r][threadIdx.x];
-            bool better = wantmax ? (v > best || (v == best && i < bi)) : (v < best || (v == best && i < bi));
+            bool better = v > best || (v == best && i < bi);
             best = better ? v : best; bi = better ? i : bi;
         }
-        float pre = fmaf(best, sc, sh);
-        float o = pre;
-        if (act == 1) o = fmaxf(pre, 0.f);
-        else if (act == 2) o = pre > 0.f ? pre : 0.2f * pre;
-        out[(long long)b * C + c] = o;
+        out[(long long)b * C + c] = best;
         arg[(long long)b * C + c] = bi;
-        if (ext_out) ext_out[(long long)b * C + c] = best;
     }
 }
 
@@ -260,10 +256,10 @@ using namespace pn;
 using namespace pn::pw;
 
 extern "C" int pn_colmax_norm(const float* Y, long long ldy, int B, int N, int C, const float* scale,
-                              const float* shift, int act, float* out, int* arg, float* ext_out, void* stream) {
+                              const float* shift, int act, const float* wts, float* out, int* arg, void* stream) {
     PN_REQUIRE(Y && scale && shift && out && arg, "pn_colmax_norm: null pointer");
     dim3 grid(cdiv(C, 32), B);
-    colmax_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, ldy, N, C, scale, shift, act, out, arg, ext_out);
+    colmax_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, ldy, N, C, scale, shift, act, wts, out, arg);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("colmax_norm_kernel");
     return PN_OK;

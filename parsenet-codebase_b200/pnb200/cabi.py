@@ -32,7 +32,7 @@ SIGNATURES = {
     "pn_edge_bwd": [c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_i,
                     c_p, c_ll, c_p],
     # pointwise.cu
-    "pn_colmax_norm": [c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
+    "pn_colmax_norm": [c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],  # (.., act, wts, out, arg, stream)
     "pn_colmax_bwd_fill": [c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_i, c_p, c_ll, c_p],
     "pn_logsoftmax_fwd": [c_p, c_ll, c_i, c_i, c_i, c_p, c_p],
     "pn_logsoftmax_bwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_ll, c_p],
@@ -47,6 +47,14 @@ SIGNATURES = {
     "pn_ms_iter_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     "pn_ms_kth_dist": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
     "pn_ms_argsel": [c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
+    # chamfer.cu / spline.cu / fit.cu / primitives.cu
+    "pn_chamfer_nn_fwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p],
+    "pn_chamfer_nn_bwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "pn_spline_eval_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "pn_spline_eval_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "pn_fit_moments_fwd": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p],
+    "pn_fit_moments_bwd": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_ll, c_p],
+    "pn_residual_fwd": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
 }
 _SPECIAL = {
     "pn_last_error": (ctypes.c_char_p, []),

@@ -1,0 +1,295 @@
+"""Primitive fitting from weighted moments + batched residuals, Chamfer and B-spline evaluation wrappers.
+
+The O(points) streaming work runs in csrc/{fit,primitives,chamfer,spline}.cu; the 3x3 algebra below runs on
+(S,3,3) float64 tensors (S = segments of one type in a shape) and reproduces, including the reference's custom SVD
+gradient, Fit.fit_{plane,sphere,cylinder,cone}_torch (reference src/primitive_forward.py:708-843),
+LeastSquares.lstsq (src/fitting_utils.py:36-65) and CustomSVD (src/fitting_utils.py:385-455).
+"""
+import numpy as np
+import torch
+
+from .cabi import call
+from .ops import _need_cuda, _ptr, _stream
+
+EPS = float(np.finfo(np.float32).eps)
+NM = 55
+# moment layout (power of w, monomial):  see csrc/fit.cu eval_phi
+M1_1, M1_P, M1_PP, M1_N = 0, slice(1, 4), slice(4, 10), slice(10, 13)
+M2_1, M2_P, M2_PP, M2_N, M2_NN, M2_NPN = 13, slice(14, 17), slice(17, 23), slice(23, 26), slice(26, 32), slice(32, 35)
+M3_PP, M3_T, M0_N, M0_1 = slice(35, 41), slice(41, 51), slice(51, 54), 54
+
+_SYM6 = torch.tensor([[0, 1, 2], [1, 3, 4], [2, 4, 5]])
+_T10 = {(0, 0, 0): 0, (0, 0, 1): 1, (0, 0, 2): 2, (0, 1, 1): 3, (0, 1, 2): 4, (0, 2, 2): 5, (1, 1, 1): 6, (1, 1, 2): 7,
+        (1, 2, 2): 8, (2, 2, 2): 9}
+_T27 = torch.tensor([[[_T10[tuple(sorted((i, j, k)))] for k in range(3)] for j in range(3)] for i in range(3)])
+
+
+def sym6(v):
+    """(S,6) [xx,xy,xz,yy,yz,zz] -> (S,3,3)"""
+    return v[:, _SYM6.to(v.device)]
+
+
+def sym10(v):
+    """(S,10) unique entries of a symmetric 3-tensor -> (S,3,3,3)"""
+    return v[:, _T27.to(v.device)]
+
+
+# ------------------------------------------------------------------------------------------------ moments
+class MomentsFn(torch.autograd.Function):
+    """W (N,K) membership weights -> (K, 55) float64 moments of the point set {start + i*step, i < m} with
+    w = W[n,s] + EPS (fit_one_shape_torch adds EPS, primitive_forward.py:942)."""
+
+    @staticmethod
+    def forward(ctx, W, P, Nr, start, step, m, eps=EPS):
+        _need_cuda(W, P)
+        W = W.detach()
+        assert W.stride(1) == 1 and P.is_contiguous() and (Nr is None or Nr.is_contiguous())
+        N, K = W.shape
+        mom = torch.zeros((K, NM), dtype=torch.float64, device=W.device)
+        call("pn_fit_moments_fwd", _ptr(P), _ptr(Nr), _ptr(W), W.stride(0), K, start, step, m, float(eps), _ptr(mom),
+             _stream())
+        ctx.saved = (W, P, Nr, start, step, m, float(eps))
+        return mom
+
+    @staticmethod
+    def backward(ctx, gmom):
+        W, P, Nr, start, step, m, eps = ctx.saved
+        N, K = W.shape
+        gW = torch.zeros((N, K), dtype=torch.float32, device=W.device)
+        g32 = gmom.to(torch.float32).contiguous()
+        call("pn_fit_moments_bwd", _ptr(P), _ptr(Nr), _ptr(W), W.stride(0), K, start, step, m, eps, _ptr(g32),
+             _ptr(gW), K, _stream())
+        return gW, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ custom SVD of a Gram
+class GramSVDFn(torch.autograd.Function):
+    """G = A^T A (S,3,3) -> V (S,3,3) with columns ordered by DEcreasing singular value of A, sv (S,3).
+    Backward is the reference's custom rule (fitting_utils.py:385-417): grad_A = 2 U S sym(K^T o V^T gV) V^T, i.e.
+    grad_G = V sym(K^T o V^T gV) V^T, K_ij = 1/((s_i - s_j)(s_i + s_j)) with |s_i - s_j| floored at 1e-6."""
+
+    @staticmethod
+    def forward(ctx, G):
+        evals, evecs = torch.linalg.eigh(G)                    # ascending
+        V = torch.flip(evecs, dims=[2])
+        sv = torch.sqrt(torch.clamp(torch.flip(evals, dims=[1]), min=0.0))
+        ctx.save_for_backward(V, sv)
+        return V, sv
+
+    @staticmethod
+    def backward(ctx, gV, gS):
+        V, sv = ctx.saved_tensors
+        s_col = sv.unsqueeze(2)             # s_i along rows
+        s_row = sv.unsqueeze(1)
+        diff = s_col - s_row
+        plus = s_col + s_row
+        kneg = torch.sign(diff) * torch.clamp(diff.abs(), min=1e-6)
+        eye = torch.eye(3, dtype=sv.dtype, device=sv.device)
+        kneg = kneg * (1 - eye) + 1e-6 * eye
+        K = (1.0 / kneg) * (1.0 / plus) * (1 - eye)
+        inner = K.transpose(1, 2) * (V.transpose(1, 2) @ gV)
+        inner = (inner + inner.transpose(1, 2)) / 2.0
+        return V @ inner @ V.transpose(1, 2)
+
+
+def _rank_deficient(evals_desc, rows):
+    """torch.matrix_rank(A) < 3 for A with singular values sqrt(evals) (default tolerance s_max*max(m,3)*eps32)"""
+    s = torch.sqrt(torch.clamp(evals_desc, min=0.0))
+    tol = s[:, 0] * max(rows, 3) * EPS
+    return s[:, 2] <= tol
+
+
+def solve_normal(AtA, AtY, rows):
+    """LeastSquares.lstsq in normal-equation form: x = argmin |A x - Y|.  Rank-deficient systems follow the
+    reference's regularised branch (lambda = 1e-6 * 10^j, first j making AtA + lambda I full rank)."""
+    with torch.no_grad():
+        ev = torch.flip(torch.linalg.eigvalsh(AtA), dims=[1])
+        bad = _rank_deficient(ev, rows)
+        lam = torch.zeros(AtA.shape[0], dtype=AtA.dtype, device=AtA.device)
+        if bool(bad.any()):
+            cur = torch.full_like(lam, 1e-6)
+            done = ~bad
+            for _ in range(7):
+                evd = ev + cur.unsqueeze(1)
+                ok = (evd[:, 2] > evd[:, 0] * 3 * EPS)
+                newly = ok & ~done
+                lam = torch.where(newly, cur, lam)
+                done = done | ok
+                cur = torch.where(done, cur, cur * 10)
+            lam = torch.where(done, lam, cur)
+    eye = torch.eye(3, dtype=AtA.dtype, device=AtA.device)
+    return torch.linalg.solve(AtA + lam.view(-1, 1, 1) * eye, AtY.unsqueeze(2)).squeeze(2)
+
+
+# ------------------------------------------------------------------------------------------------ fits from moments
+def plane_from(w1, s1p, w2, s2p, s2pp):
+    """-> a (S,3) unit normal (smallest right singular vector of w*(p-c)), d (S,) = sum w (a.p)/sum w = a.c"""
+    sw = w1 + EPS
+    c = s1p / sw.unsqueeze(1)
+    G = s2pp - c.unsqueeze(2) * s2p.unsqueeze(1) - s2p.unsqueeze(2) * c.unsqueeze(1) \
+        + w2.view(-1, 1, 1) * c.unsqueeze(2) * c.unsqueeze(1)
+    V, _ = GramSVDFn.apply(G)
+    a = V[:, :, -1]
+    d = (a * s1p).sum(1) / sw
+    return a, d
+
+
+def sphere_from(w1, s1p, q1, w2, s2p, s2pp, q3, r3, rows):
+    """linearised weighted sphere fit (primitive_forward.py:746-769) -> centre (S,3), radius (S,)"""
+    sw = w1 + EPS
+    c = s1p / sw.unsqueeze(1)
+    nu = q1 / sw
+    AtA = 4.0 * (w2.view(-1, 1, 1) * c.unsqueeze(2) * c.unsqueeze(1) - c.unsqueeze(2) * s2p.unsqueeze(1)
+                 - s2p.unsqueeze(2) * c.unsqueeze(1) + s2pp)
+    AtY = 2.0 * (c * q3.unsqueeze(1) - r3 - (nu * w2).unsqueeze(1) * c + nu.unsqueeze(1) * s2p)
+    center = -solve_normal(AtA, AtY, rows)
+    r2 = (q1 - 2.0 * (center * s1p).sum(1) + (center * center).sum(1) * w1) / sw
+    radius = torch.sqrt(torch.clamp(torch.clamp(r2, min=1e-3), min=1e-5))
+    return center, radius
+
+
+def fit_planes(mom):
+    return plane_from(mom[:, M1_1], mom[:, M1_P], mom[:, M2_1], mom[:, M2_P], sym6(mom[:, M2_PP]))
+
+
+def fit_spheres(mom, rows):
+    pp1, pp3, T = sym6(mom[:, M1_PP]), sym6(mom[:, M3_PP]), sym10(mom[:, M3_T])
+    q1 = pp1.diagonal(dim1=1, dim2=2).sum(1)
+    q3 = pp3.diagonal(dim1=1, dim2=2).sum(1)
+    r3 = torch.einsum("siik->sk", T)
+    return sphere_from(mom[:, M1_1], mom[:, M1_P], q1, mom[:, M2_1], mom[:, M2_P], sym6(mom[:, M2_PP]), q3, r3, rows)
+
+
+def fit_cylinders(mom, rows):
+    """axis = smallest right singular vector of w*normals; circle fit of the points projected along it
+    (primitive_forward.py:784-806) -> a (S,3), centre (S,3), radius (S,)"""
+    V, _ = GramSVDFn.apply(sym6(mom[:, M2_NN]))
+    a = V[:, :, -1]
+    a = a / (a.norm(dim=1, keepdim=True) + EPS)
+    eye = torch.eye(3, dtype=mom.dtype, device=mom.device)
+    Pm = eye - a.unsqueeze(2) * a.unsqueeze(1)
+    M2 = Pm.transpose(1, 2) @ Pm
+    pp1, pp2, pp3, T = sym6(mom[:, M1_PP]), sym6(mom[:, M2_PP]), sym6(mom[:, M3_PP]), sym10(mom[:, M3_T])
+    s1p = torch.einsum("sij,sj->si", Pm, mom[:, M1_P])
+    s2p = torch.einsum("sij,sj->si", Pm, mom[:, M2_P])
+    s2pp = Pm @ pp2 @ Pm.transpose(1, 2)
+    q1 = (M2 * pp1).sum((1, 2))
+    q3 = (M2 * pp3).sum((1, 2))
+    r3 = torch.einsum("skl,sij,sijl->sk", Pm, M2, T)
+    center, radius = sphere_from(mom[:, M1_1], s1p, q1, mom[:, M2_1], s2p, s2pp, q3, r3, rows)
+    return a, center, radius
+
+
+def fit_cone_apex_axis(mom, rows):
+    """apex from the normal-equation solve, axis from a plane fit of the normals, sign so that sum(n.a) <= 0
+    (primitive_forward.py:808-831).  Returns apex (S,3), axis (S,3), degenerate (S,) bool (cond > 1e5)."""
+    nn = sym6(mom[:, M2_NN])
+    with torch.no_grad():
+        ev = torch.flip(torch.linalg.eigvalsh(nn), dims=[1])
+        s = torch.sqrt(torch.clamp(ev, min=0.0))
+        degenerate = (s[:, 0] / s[:, 2]) > 1e5
+    apex = solve_normal(nn, mom[:, M2_NPN], rows)
+    a, _ = plane_from(mom[:, M1_1], mom[:, M1_N], mom[:, M2_1], mom[:, M2_N], nn)
+    flip = ((mom[:, M0_N] * a).sum(1) > 0).to(a.dtype).unsqueeze(1)
+    a = a * (1 - 2 * flip)
+    return apex, a, degenerate
+
+
+def cone_theta(points, weights, apex, axis):
+    """weighted mean opening angle (primitive_forward.py:833-842); points (m,3), weights (m,1), apex/axis (3,)"""
+    diff = torch.nn.functional.normalize(points - apex.view(1, 3), p=2, dim=1)
+    v = torch.clamp((diff @ axis.view(3, 1)).abs(), max=0.999)
+    theta = (weights * torch.acos(v)).sum() / (weights.sum() + EPS)
+    return torch.clamp(theta, min=1e-3, max=3.142 / 2 - 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ residuals
+TYPE_ID = {"plane": 0, "sphere": 1, "cylinder": 2, "cone": 3}
+
+
+class ResidualFn(torch.autograd.Function):
+    """mean squared point-to-primitive distance for every segment in one launch.
+    par (S,8) fp32 parameter rows, types (S,) int32, seg (N,) int32 (segment of every point or -1)."""
+
+    @staticmethod
+    def forward(ctx, par, points, seg, types):
+        _need_cuda(par, points)
+        par = par.detach().contiguous()
+        S = par.shape[0]
+        dev = par.device
+        sumf = torch.zeros((S,), dtype=torch.float32, device=dev)
+        jac = torch.zeros((S, 8), dtype=torch.float32, device=dev)
+        cnt = torch.zeros((S,), dtype=torch.float32, device=dev)
+        call("pn_residual_fwd", _ptr(points), _ptr(seg), points.shape[0], _ptr(types), _ptr(par), S, _ptr(sumf),
+             _ptr(jac), _ptr(cnt), _stream())
+        cnt = torch.clamp(cnt, min=1.0)
+        ctx.save_for_backward(jac, cnt)
+        return sumf / cnt
+
+    @staticmethod
+    def backward(ctx, g):
+        jac, cnt = ctx.saved_tensors
+        return jac * (g / cnt).unsqueeze(1), None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ chamfer
+class NearestFn(torch.autograd.Function):
+    """A (B,Na,3), Bs (B,Nb,3) -> squared distance of every A point to its nearest Bs point (B,Na)"""
+
+    @staticmethod
+    def forward(ctx, A, Bs):
+        _need_cuda(A, Bs)
+        A = A.detach().contiguous().float()
+        Bs = Bs.detach().contiguous().float()
+        B, Na, _ = A.shape
+        Nb = Bs.shape[1]
+        mind = torch.empty((B, Na), dtype=torch.float32, device=A.device)
+        arg = torch.empty((B, Na), dtype=torch.int32, device=A.device)
+        call("pn_chamfer_nn_fwd", _ptr(A), Na, _ptr(Bs), Nb, B, _ptr(mind), _ptr(arg), _stream())
+        ctx.saved = (A, Bs, arg)
+        return mind
+
+    @staticmethod
+    def backward(ctx, g):
+        A, Bs, arg = ctx.saved
+        B, Na, _ = A.shape
+        dA = torch.zeros_like(A) if ctx.needs_input_grad[0] else None
+        dB = torch.zeros_like(Bs) if ctx.needs_input_grad[1] else None
+        g = g.contiguous()
+        call("pn_chamfer_nn_bwd", _ptr(A), Na, _ptr(Bs), Bs.shape[1], B, _ptr(arg), _ptr(g), _ptr(dA), _ptr(dB),
+             _stream())
+        return dA, dB
+
+
+def nearest_sqdist(A, Bs):
+    return NearestFn.apply(A, Bs)
+
+
+# ------------------------------------------------------------------------------------------------ spline evaluation
+class SplineEvalFn(torch.autograd.Function):
+    """P (B,cu,cv,3) -> (B, gu*gv, 3) = Nu P Nv^T per coordinate"""
+
+    @staticmethod
+    def forward(ctx, P, Nu, Nv):
+        _need_cuda(P, Nu, Nv)
+        P = P.detach().contiguous().float()
+        Nu = Nu.detach().contiguous().float()
+        Nv = Nv.detach().contiguous().float()
+        B, cu, cv, _ = P.shape
+        gu, gv = Nu.shape[0], Nv.shape[0]
+        out = torch.empty((B, gu * gv, 3), dtype=torch.float32, device=P.device)
+        call("pn_spline_eval_fwd", _ptr(Nu), _ptr(Nv), _ptr(P), B, gu, gv, cu, cv, _ptr(out), _stream())
+        ctx.saved = (Nu, Nv, (B, cu, cv, gu, gv))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        Nu, Nv, (B, cu, cv, gu, gv) = ctx.saved
+        g = g.contiguous()
+        dP = torch.empty((B, cu, cv, 3), dtype=torch.float32, device=g.device)
+        call("pn_spline_eval_bwd", _ptr(Nu), _ptr(Nv), _ptr(g), B, gu, gv, cu, cv, _ptr(dP), _stream())
+        return dP, None, None
+
+
+def spline_eval(P_bijc, Nu, Nv):
+    return SplineEvalFn.apply(P_bijc, Nu, Nv)

@@ -205,14 +205,14 @@ def edge_bwd(g, PQ, idx, esel, jsel, esum, norm, dense=True, want_affine_grads=T
     return dPQ, dg, db
 
 
-def colmax_norm(Y, norm):
+def colmax_norm(Y, norm, wts=None):
+    """out[b,c] = max_n act(norm(Y[b,n,c])) * (wts[b,n] if given); returns (out, arg)"""
     B, N, C = Y.shape
     out = torch.empty((B, C), dtype=torch.float32, device=Y.device)
     arg = torch.empty((B, C), dtype=torch.int32, device=Y.device)
-    ext = torch.empty((B, C), dtype=torch.float32, device=Y.device)
-    call("pn_colmax_norm", _ptr(Y), _pitch(Y), B, N, C, _ptr(norm.scale), _ptr(norm.shift), norm.act, _ptr(out),
-                             _ptr(arg), _ptr(ext), _stream())
-    return out, arg, ext
+    call("pn_colmax_norm", _ptr(Y), _pitch(Y), B, N, C, _ptr(norm.scale), _ptr(norm.shift), norm.act, _ptr(wts),
+         _ptr(out), _ptr(arg), _stream())
+    return out, arg
 
 
 def colmax_bwd_fill(Y, gt, arg, norm, gsum, dense=True):

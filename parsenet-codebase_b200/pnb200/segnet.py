@@ -53,7 +53,8 @@ class EncoderFn(torch.autograd.Function):
         wm2 = wm.reshape(1024, 256)
         Y1, st = ops.linear_fwd(xf, wm2, bias=bm, stats_groups=8)
         nm = ops.norm_finalize(st, gm, btm, B, 1024, 128 * N, ACT_RELU)
-        x4, arg, ext = ops.colmax_norm(Y1, nm)
+        x4, arg = ops.colmax_norm(Y1, nm)
+        ext = torch.gather(Y1, 1, arg.long().unsqueeze(1)).squeeze(1)      # pre-norm value at the arg-max row
         ctx.layers, ctx.xf, ctx.Y1, ctx.nm, ctx.arg, ctx.ext, ctx.wm2 = layers, xf, Y1, nm, arg, ext, wm2
         ctx.shapes = [p.shape for p in params]
         ctx.idx_list = [l["idx"] for l in layers]

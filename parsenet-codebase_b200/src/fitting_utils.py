@@ -1,0 +1,131 @@
+"""Drop-in for the hot-path part of reference src/fitting_utils.py: LeastSquares.lstsq (:36), best_lambda (:68),
+weights_normalize (:306), match (:362), customsvd (:420), standardize_point[s]_torch (:493-553), pca_torch (:585),
+rotation_matrix_a_to_b (:556), sample_points_from_control_points_ (:609).  Mesh / open3d / visualisation helpers of
+that file are out of scope."""
+import numpy as np
+import torch
+
+from pnb200 import fitting as _f
+from pnb200.fitting import spline_eval
+from src.guard import guard_exp
+from src.segment_utils import relaxed_iou_fast, solve_dense, to_one_hot
+
+EPS = float(np.finfo(np.float32).eps)
+
+
+class LeastSquares:
+    def lstsq(self, A, Y, lamb=0.0):
+        """x = argmin |A x - Y| for a tall A (m,3); rank-deficient systems use the Tikhonov rule of the reference."""
+        if not torch.isfinite(A).all():
+            raise FloatingPointError("LeastSquares.lstsq: non-finite entries in A")
+        Ad, Yd = A.double(), Y.double()
+        x = _f.solve_normal((Ad.t() @ Ad).unsqueeze(0), (Ad.t() @ Yd).reshape(1, -1), A.shape[0])
+        return x.reshape(-1, 1).to(A.dtype)
+
+
+def best_lambda(A):
+    lamb = 1e-6
+    n = A.shape[0]
+    for _ in range(7):
+        if n == int(torch.linalg.matrix_rank(A + lamb * torch.eye(n, device=A.device, dtype=A.dtype))):
+            break
+        lamb *= 10
+    return lamb
+
+
+class CustomSVD(torch.autograd.Function):
+    """SVD of a tall (m,3) matrix with the reference's guarded gradient (only grad_V flows, K floored at 1e-6)."""
+
+    @staticmethod
+    def forward(ctx, inp):
+        U, S, Vh = torch.linalg.svd(inp, full_matrices=False)
+        V = Vh.transpose(-2, -1)
+        ctx.save_for_backward(U, S, V)
+        return U, S, V
+
+    @staticmethod
+    def backward(ctx, gU, gS, gV):
+        U, S, V = ctx.saved_tensors
+        n = S.shape[0]
+        diff = S.view(n, 1) - S.view(1, n)
+        eye = torch.eye(n, device=S.device, dtype=S.dtype)
+        kneg = torch.sign(diff) * torch.clamp(diff.abs(), min=1e-6)
+        kneg = kneg * (1 - eye) + 1e-6 * eye
+        K = (1 / kneg) * (1 / (S.view(n, 1) + S.view(1, n))) * (1 - eye)
+        inner = K.t() * (V.t() @ gV)
+        inner = (inner + inner.t()) / 2.0
+        return 2 * U @ torch.diag(S) @ inner @ V.t()
+
+
+customsvd = CustomSVD.apply
+
+
+def weights_normalize(weights, bw):
+    """(K,N) centre-point similarities -> per-point cluster probabilities, then per-cluster min-max to [0,1]"""
+    prob = guard_exp(weights / (bw ** 2) / 2)
+    prob = prob / prob.sum(0, keepdim=True)
+    if weights.shape[0] == 1:
+        return prob
+    prob = prob - prob.min(1, keepdim=True)[0]
+    return prob / (prob.max(1, keepdim=True)[0] + EPS)
+
+
+def match(target, pred_labels):
+    """Hungarian matching of predicted clusters to gt segments on 1 - relaxed IoU (50x50)"""
+    lab, clu = to_one_hot(target), to_one_hot(pred_labels)
+    cost = 1.0 - relaxed_iou_fast(clu.unsqueeze(0).float(), lab.unsqueeze(0).float()).data.cpu().numpy()
+    rids, cids = solve_dense(cost[0])
+    return rids, cids, np.unique(target), np.unique(pred_labels)
+
+
+def rotation_matrix_a_to_b(A, B):
+    """3x3 rotation taking unit vector A onto B (numpy, float64)"""
+    cos, sin = np.dot(A, B), np.linalg.norm(np.cross(B, A))
+    v = B - np.dot(A, B) * A
+    v = v / (np.linalg.norm(v) + EPS)
+    w = np.cross(B, A)
+    w = w / (np.linalg.norm(w) + EPS)
+    Fm = np.stack([A, v, w], 1)
+    G = np.array([[cos, -sin, 0], [sin, cos, 0], [0, 0, 1]])
+    try:
+        return Fm @ G @ np.linalg.inv(Fm)
+    except np.linalg.LinAlgError:
+        return np.eye(3, dtype=np.float32)
+
+
+def pca_torch(X):
+    """eigen-decomposition of X^T X as (eigenvalues (3,2) real/imag, eigenvectors (3,3)); LAPACK geev on the host so
+    that eigenvector signs are the reference's (torch.eig on a 3x3 runs on the CPU there as well)."""
+    cov = (X.t() @ X).detach().cpu()
+    w, v = torch.linalg.eig(cov)
+    return torch.stack([w.real, w.imag], 1), v.real
+
+
+def standardize_point_torch(point, weights):
+    """centre on the weighted mean of the confident points, rotate the minor PCA axis onto x, scale every axis by the
+    extent of the (weighted) confident points.  Returns (points, std (1,3), mean (3,), R (3,3))."""
+    high = weights[:, 0] > 0.8
+    if int(high.sum()) < 400:
+        kk = weights.shape[0] // 4 if weights.shape[0] >= 7500 else weights.shape[0] // 2
+        high = torch.topk(weights[:, 0], kk)[1]
+    wp = point[high] * weights[high]
+    mean = wp.sum(0) / (weights[high].sum() + EPS)
+    point = point - mean
+    S, U = pca_torch(point[high])
+    smallest = U[:, int(torch.min(S[:, 0], 0)[1])].numpy()
+    R = torch.from_numpy(rotation_matrix_a_to_b(smallest, np.array([1, 0, 0])).astype(np.float32)).to(point.device)
+    point = (R @ point.t()).t()
+    wp = point[high] * weights[high]
+    std = (wp.max(0)[0] - wp.min(0)[0]).abs().reshape(1, 3).detach()
+    return point / (std + EPS), std, mean, R
+
+
+def standardize_points_torch(points, weights):
+    outs = [standardize_point_torch(points[i], weights) for i in range(points.shape[0])]
+    return torch.stack([o[0] for o in outs], 0), [o[1] for o in outs], [o[2] for o in outs], [o[3] for o in outs]
+
+
+def sample_points_from_control_points_(nu, nv, outputs, batch_size, input_size_u=20, input_size_v=20):
+    """(B, cu*cv, 3) control points -> (B, g*g, 3) surface samples Nu P Nv^T"""
+    P = outputs.reshape(outputs.shape[0], input_size_u, input_size_v, 3)
+    return spline_eval(P, nu.to(P.device), nv.to(P.device))

@@ -1,0 +1,173 @@
+"""Fits, residual distances, Chamfer / spline losses and SplineNet on the GPU vs golden vectors of the reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _g(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _close(got, want, rtol=1e-4, name=""):
+    got = got.detach().cpu().double().numpy() if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    scale = np.abs(want).max() + 1e-30
+    err = np.abs(got.reshape(want.shape) - want).max()
+    assert err <= rtol * scale + 1e-9, f"{name}: err {err:.3e} scale {scale:.3e}"
+
+
+def _cu(a, grad=False):
+    t = torch.from_numpy(np.asarray(a)).cuda()
+    return t.requires_grad_() if grad else t
+
+
+# ------------------------------------------------------------------------------------------------ primitive fits
+@pytest.mark.parametrize("kind", ["plane", "sphere", "cylinder", "cone"])
+def test_fit_and_residual_vs_reference(golden_dir, kind):
+    from src.primitive_forward import Fit
+    from src.primitives import ComputePrimitiveDistance
+    g = _g(golden_dir, "fits.npz")
+    P, Nn, W = _cu(g[kind + "_p"]), _cu(g[kind + "_n"]), _cu(g[kind + "_w"], True)
+    res = getattr(Fit(), f"fit_{kind}_torch")(P, Nn, W)
+    nout = len(res)
+    # eigenvector sign: the plane / cylinder axis is defined up to sign; align with the reference before comparing
+    sign = 1.0
+    axis_slot = {"plane": 0, "cylinder": 0}.get(kind)
+    if axis_slot is not None:
+        want_axis = g[f"{kind}_out{axis_slot}"].reshape(-1)
+        sign = float(np.sign((res[axis_slot].detach().cpu().numpy().reshape(-1) * want_axis).sum()))
+    loss = 0
+    for i in range(nout):
+        want = g[f"{kind}_out{i}"]
+        s = sign if (i == axis_slot or (kind == "plane" and i == 1)) else 1.0
+        _close(res[i] * s, want, rtol=2e-4, name=f"{kind} out{i}")
+        loss = loss + (res[i] * s * _cu(g[f"{kind}_coef{i}"]).reshape(res[i].shape)).sum()
+    loss.backward()
+    _close(W.grad, g[kind + "_gw"], rtol=2e-3, name=f"{kind} grad wrt weights")
+    # residual distance + parameter gradients
+    n_par = {"plane": 2, "sphere": 2, "cylinder": 3, "cone": 3}[kind]
+    params = [_cu(g[f"{kind}_par{i}"], True) for i in range(n_par)]
+    d = getattr(ComputePrimitiveDistance(reduce=True), "distance_from_" + kind)(points=_cu(g[kind + "_q"]),
+                                                                                  params=params, sqrt=False)
+    _close(d, g[kind + "_dist"], name=f"{kind} residual")
+    d.backward()
+    for i in range(n_par):
+        _close(params[i].grad, g[f"{kind}_gpar{i}"], rtol=1e-3, name=f"{kind} dpar{i}")
+
+
+def test_batched_moment_fits_match_single_calls():
+    """the batched path of fit_one_shape_torch (one moment pass for all segments) equals per-segment Fit calls"""
+    from pnb200 import fitting as F
+    from src.primitive_forward import Fit
+    g = torch.Generator().manual_seed(0)
+    N, K = 2000, 5
+    P = (torch.randn(N, 3, generator=g) * 0.4).cuda()
+    Nr = torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=1).cuda()
+    W = torch.rand(N, K, generator=g).cuda()
+    mom = F.MomentsFn.apply(W, P, Nr, 0, 4, (N + 3) // 4, F.EPS)
+    a, d = F.fit_planes(mom)
+    c, r = F.fit_spheres(mom, (N + 3) // 4)
+    fit = Fit()
+    for k in range(K):
+        a1, d1 = fit.fit_plane_torch(P[0::4], None, W[0::4, k:k + 1] + F.EPS)
+        s = float(torch.sign((a1.reshape(-1) * a[k].float()).sum()))
+        _close(a[k] * s, a1.cpu().numpy(), name="plane a"); _close(d[k] * s, d1.cpu().numpy(), name="plane d")
+        c1, r1 = fit.fit_sphere_torch(P[0::4], None, W[0::4, k:k + 1] + F.EPS)
+        _close(c[k], c1.cpu().numpy(), rtol=1e-3, name="sphere c"); _close(r[k], r1.cpu().numpy(), rtol=1e-3, name="r")
+
+
+# ------------------------------------------------------------------------------------------------ chamfer / spline losses
+def test_chamfer_and_spline_losses_vs_reference(golden_dir):
+    from src import loss as L, utils as U
+    from src.fitting_utils import sample_points_from_control_points_, weights_normalize
+    g = _g(golden_dir, "losses.npz")
+    pred, gt = _cu(g["pred"], True), _cu(g["gt"], True)
+    cd = U.chamfer_distance(pred, gt); cds = U.chamfer_distance(pred, gt, sqrt=True)
+    c0 = U.chamfer_distance_one_side(pred, gt, 0); c1 = U.chamfer_distance_one_side(pred, gt, 1)
+    s1 = U.chamfer_distance_single_shape(pred[0], gt[0]); s2 = U.chamfer_distance_single_shape(pred[0], gt[0], one_side=True)
+    for name, v in [("cd", cd), ("cds", cds), ("c0", c0), ("c1", c1), ("s1", s1), ("s2", s2)]:
+        assert abs(v.item() - float(g[name])) <= 1e-4 * abs(float(g[name])), name
+    (cd + 2 * cds + 3 * c0 + 4 * c1 + 5 * s1 + 6 * s2).backward()
+    _close(pred.grad, g["gpred"], rtol=1e-4, name="chamfer dpred"); _close(gt.grad, g["ggt"], rtol=1e-4, name="dgt")
+    nu, nv = L.uniform_knot_bspline(20, 20, 3, 3, 30)
+    np.testing.assert_allclose(nu, g["nu"], rtol=0, atol=1e-15); np.testing.assert_allclose(nv, g["nv"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(L.uniform_knot_bspline(20, 20, 3, 3, 40)[0], g["nu40"], rtol=0, atol=1e-15)
+    cpts = _cu(g["cpts"], True)
+    rec = sample_points_from_control_points_(torch.from_numpy(nu.astype(np.float32)), torch.from_numpy(nv.astype(np.float32)), cpts, 2)
+    _close(rec, g["rec"], name="spline eval")
+    (rec * _cu(g["recw"])).sum().backward()
+    _close(cpts.grad, g["gcpts"], name="spline eval grad")
+
+    class Cfg: batch_size = 2; grid_size = 20
+    nu4 = torch.from_numpy(g["nu40"].astype(np.float32))
+    outp = _cu(g["tl_out"], True)
+    cd1, _ = L.spline_reconstruction_loss_one_sided(nu4, nu4, outp, _cu(g["tl_pts"]), Cfg)
+    lreg, perm = L.control_points_permute_reg_loss(outp, _cu(g["tl_gtcp"]), 20)
+    lap = L.laplacian_loss(outp.reshape(2, 20, 20, 3), perm)
+    lclosed, _ = L.control_points_permute_closed_reg_loss(outp, _cu(g["tl_gtcp"]), 20, 20)
+    for name, v in [("tl_cd", cd1), ("tl_reg", lreg), ("tl_lap", lap), ("tl_closed", lclosed)]:
+        assert abs(v.item() - float(g[name])) <= 1e-4 * abs(float(g[name])), name
+    (0.9 * lreg + 0.1 * (cd1 + lap) + 0.5 * lclosed).backward()
+    _close(outp.grad, g["tl_gout"], rtol=1e-4, name="open-spline loss grads")
+    wts = _cu(g["wn_in"], True)
+    wn = weights_normalize(wts, 0.8)
+    _close(wn, g["wn_out"], name="weights_normalize")
+    (wn * _cu(g["wn_w"])).sum().backward()
+    _close(wts.grad, g["wn_g"], rtol=1e-3, name="weights_normalize grad")
+
+
+# ------------------------------------------------------------------------------------------------ SplineNet
+def _spline_net(g, prefix, mode, seed):
+    from oracle.port import common
+    from src.model import DGCNNControlPoints
+    net = DGCNNControlPoints(20, num_points=10, mode=mode)
+    sd0 = net.state_dict()
+    assert sorted(sd0.keys()) == list(g[prefix + "_keys"])
+    shapes = {k: eval(s) for k, s in zip(g[prefix + "_keys"], g[prefix + "_shapes"])}
+    for k in shapes:
+        assert tuple(sd0[k].shape) == shapes[k], k
+    sd = common.seeded_state_dict(shapes, seed=seed)
+    for i in (1, 2, 3, 4, 5):
+        for s_ in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+            a, b = f"bn{i}.{s_}", f"conv{i}.1.{s_}"
+            if a in sd and b in sd:
+                sd[b] = sd[a]
+    net.load_state_dict(sd)
+    return net.cuda()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_splinenet_eval_with_weights_vs_reference(golden_dir, mode):
+    g = _g(golden_dir, "splinenet.npz")
+    net = _spline_net(g, f"m{mode}", mode, 30 + mode).eval()
+    w = _cu(g[f"m{mode}_w"], True)
+    o = net(_cu(g[f"m{mode}_x"]), w.t())
+    _close(o, g[f"m{mode}_out"], rtol=2e-4, name="control points")
+    (o * _cu(g[f"m{mode}_c"])).sum().backward()
+    _close(w.grad, g[f"m{mode}_gw"], rtol=2e-3, name="grad wrt weights")
+
+
+def test_splinenet_train_mode_vs_reference(golden_dir):
+    g = _g(golden_dir, "splinenet.npz")
+    net = _spline_net(g, "m0", 0, 33).train()
+    o = net(_cu(g["tr_x"]))
+    _close(o, g["tr_out"], rtol=3e-4, name="train-mode output")
+    (o * _cu(g["tr_c"])).sum().backward()
+    _close(net.bn5.running_mean, g["tr_rm5"], rtol=1e-3, name="running mean 5")
+    _close(net.bn5.running_var, g["tr_rv5"], rtol=1e-3, name="running var 5")
+    _close(net.bn1.running_var, g["tr_rv1"], rtol=1e-3, name="running var 1")
+    checked = 0
+    for key in g.files:
+        if not key.startswith("trgrad:") or (".1." in key and key.startswith("trgrad:conv")):
+            continue
+        p = dict(net.named_parameters())[key[7:]]
+        t = p.grad.detach().cpu().reshape(-1).double()
+        got = np.array([t.sum().item(), t.norm().item()] + t[:14].tolist())
+        want = g[key]
+        assert abs(got[1] - want[1]) <= 5e-3 * want[1] + 1e-7, (key, got[1], want[1])
+        checked += 1
+    assert checked >= 20

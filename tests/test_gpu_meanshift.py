@@ -8,6 +8,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _canon(labels):
+    """relabel by order of first appearance: equal arrays <=> identical partitions of the points"""
+    labels = np.asarray(labels)
+    _, first = np.unique(labels, return_index=True)
+    order = labels[np.sort(first)]
+    remap = {int(l): i for i, l in enumerate(order)}
+    return np.array([remap[int(l)] for l in labels]), order
+
+
 def _rel(got, want):
     got = got.detach().cpu().double().numpy(); want = np.asarray(want, np.float64)
     return np.abs(got - want).max() / (np.abs(want).max() + 1e-30)
@@ -23,12 +32,18 @@ def test_meanshift_vs_reference_golden(golden_dir, case):
     np.random.seed(seed)
     newX, center, bw, labels = ms.mean_shift(X, N, float(g[case + "_q"]), it)
     assert abs(bw.item() - float(g[case + "_bw"])) <= 1e-5 * float(g[case + "_bw"])
-    np.testing.assert_array_equal(labels.cpu().numpy(), g[case + "_labels"])       # segment labels bit-exact
+    # Segment assignment is bit-exact as a PARTITION.  The cluster numbering is the sorted index of a representative
+    # shifted point picked by argmin among numerically coincident points (mean_shift.py:149,171): it depends on the
+    # GEMM summation order even between the reference's own CPU and GPU runs, so it is compared up to renumbering.
+    got_c, got_order = _canon(labels.cpu().numpy())
+    want_c, want_order = _canon(g[case + "_labels"])
+    np.testing.assert_array_equal(got_c, want_c)
     assert _rel(newX, g[case + "_newX"]) < 1e-4
-    assert _rel(center, g[case + "_center"]) < 1e-4
+    assert _rel(center[torch.as_tensor(got_order).cuda()], g[case + "_center"][want_order]) < 1e-4
     gen = torch.Generator().manual_seed(seed + 100)
-    w = torch.randn(center.shape, generator=gen).cuda(); w2 = (torch.randn(newX.shape, generator=gen) * 0.01).cuda()
-    ((center * w).sum() + (newX * w2).sum()).backward()
+    w = torch.randn(center.shape, generator=gen); w2 = (torch.randn(newX.shape, generator=gen) * 0.01).cuda()
+    wp = torch.empty_like(w); wp[torch.as_tensor(got_order)] = w[torch.as_tensor(want_order)]   # same weight per cluster
+    ((center * wp.cuda()).sum() + (newX * w2).sum()).backward()
     assert _rel(X.grad, g[case + "_gradX"]) < 1e-3
 
 
