@@ -248,8 +248,47 @@ def gen_splinenet():
     np.savez_compressed(os.path.join(OUT, "splinenet.npz"), **out)
 
 
+from oracle.make_golden_helpers import e2e_inputs  # noqa: E402
+
+
+def gen_e2e():
+    RU = rl.ref("src.residual_utils"); FO = rl.ref("src.fitting_optimization"); PF = rl.ref("src.primitive_forward")
+    PR = rl.ref("src.primitives"); MS = rl.ref("src.mean_shift"); L = rl.ref("src.loss")
+    N = 1400
+    pts, nrm, lab, prim, emb, logp = e2e_inputs(N, 77)
+    ev = RU.Evaluation.__new__(RU.Evaluation)
+    ev.res_loss = PR.ResidualLoss()
+    fm = FO.FittingModule.__new__(FO.FittingModule)
+    fm.fitting = PF.Fit()
+    nu, nv = L.uniform_knot_bspline(20, 20, 3, 3, 30)
+    fm.nu = torch.from_numpy(nu.astype(np.float32)); fm.nv = torch.from_numpy(nv.astype(np.float32))
+    fm.open_control_decoder, _ = spline_state(0, 41); fm.closed_control_decoder, _ = spline_state(1, 42)
+    fm.open_control_decoder.eval(); fm.closed_control_decoder.eval()
+    ev.fitter = fm
+    ev.ms = MS.MeanShift()
+    E = emb.clone().requires_grad_()
+    np.random.seed(5)
+    res, extra = ev.fitting_loss(E, torch.from_numpy(pts), torch.from_numpy(nrm), lab, prim.copy(), logp,
+                                 quantile=0.015, iterations=10, lamb=0.1)
+    res[0].backward()
+    params, cluster_ids, weights = extra
+    out = dict(N=np.array(N), loss=res[0].detach().numpy(), geo=np.array(res[1] if res[1] is not None else np.nan),
+               spl=np.array(res[2] if res[2] is not None else np.nan), s_iou=np.array(res[3]), p_iou=np.array(res[4]),
+               cluster_ids=cluster_ids, gradE=E.grad.numpy(), weights=weights.detach().numpy())
+    kinds = []
+    for k, v in sorted(params.items()):
+        if v is None:
+            kinds.append(f"{k}:none"); continue
+        kinds.append(f"{k}:{v[0]}")
+        for i, t in enumerate(v[1:]):
+            out[f"par_{k}_{i}"] = t.detach().numpy()
+    out["kinds"] = np.array(kinds)
+    np.savez_compressed(os.path.join(OUT, "e2e.npz"), **out)
+    print("e2e loss", res[0].item(), "geo", res[1], "spline", res[2], "siou", res[3], "kinds", kinds)
+
+
 GENS = {"knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
-        "splinenet": gen_splinenet}
+        "splinenet": gen_splinenet, "e2e": gen_e2e}
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
