@@ -2,8 +2,8 @@
 """bench.py — ParSeNet hot path on B200:  python bench.py --gpus N --steps K --warmup W [--impl reference]
 
 One "step" = one pass of the hot path (BASELINE.json metric) over one batch of synthetic shapes per GPU:
-segmentation network forward (3 kNN graphs + edge-convs + head), triplet + NLL losses, [cluster + fit + residual
-once those stages are enabled in STAGES], backward, gradient all-reduce (N>1) and Adam step.
+segmentation network forward (3 kNN graphs + edge-convs + head), triplet + NLL losses, Evaluation.fitting_loss
+(mean-shift clustering, Hungarian match, primitive / spline fit, residual), backward, gradient all-reduce (N>1), Adam.
 Prints ONE JSON line (rank 0).  `value` = shapes/s with inputs resident in HBM; `e2e` = same through the public
 module API with pinned-host inputs copied H2D and the loss read back D2H inside the timed region.
 """
@@ -95,28 +95,47 @@ def make_host_batch(B, N, seed):
             torch.from_numpy(prim).pin_memory())
 
 
+def seeded_splinenet(mode, seed, device):
+    """SplineNet with seeded random weights (the pretrained open/closed_spline.pth files are not available)"""
+    from src.model import DGCNNControlPoints
+    torch.manual_seed(seed)
+    return DGCNNControlPoints(20, num_points=10, mode=mode).to(device).eval()
+
+
 class HotPath:
-    """the user-facing call sequence of train_parsenet.py:170-198 on our drop-in modules"""
+    """the user-facing call sequence of train_parsenet_e2e.py:218-277 on our drop-in modules:
+    seg-net forward (+ triplet loss) -> NLL -> Evaluation.fitting_loss (mean-shift, match, fit, residual) -> backward"""
 
     def __init__(self, device, world):
         from src.PointNet import PrimitivesEmbeddingDGCNGn
+        from src.residual_utils import Evaluation
         from src.segment_loss import EmbeddingLoss, primitive_loss
         torch.manual_seed(0)
         self.loss = EmbeddingLoss(margin=1.0)
         self.model = PrimitivesEmbeddingDGCNGn(embedding=True, emb_size=EMB, primitives=True, num_primitives=N_PRIM,
                                                loss_function=self.loss.triplet_loss, mode=5, num_channels=6,
                                                nn_nb=KNN_K).to(device)
+        self.evaluation = Evaluation(open_decoder=seeded_splinenet(0, 1, device),
+                                     closed_decoder=seeded_splinenet(1, 2, device))
         self.primitive_loss = primitive_loss
         self.params = [p for p in self.model.parameters() if p.requires_grad]
         self.opt = torch.optim.Adam(self.params, lr=1e-4)
         self.world = world
         self.device = device
+        self.clusters = []
 
-    def step(self, x, lab_host, lab, prim):
-        """x (B,6,N) cuda, lab_host numpy (B,N) for the host-side sampler, lab/prim cuda -> loss tensor"""
+    def step(self, x, lab_np, prim_np, lab, prim):
+        """x (B,6,N) cuda; lab_np/prim_np numpy (B,N) for the host-side matching; lab/prim cuda -> loss tensor"""
         self.opt.zero_grad(set_to_none=True)
         emb, lp, el = self.model(x, lab, True)
-        loss = el.sum() + self.primitive_loss(lp, prim)
+        loss = el.mean() + self.primitive_loss(lp, prim)
+        if FIT_STAGE:
+            pts = x[:, 0:3].permute(0, 2, 1).contiguous()
+            nrm = x[:, 3:6].permute(0, 2, 1).contiguous()
+            res, extra = self.evaluation.fitting_loss(emb.permute(0, 2, 1), pts, nrm, lab_np, prim_np.copy(), lp,
+                                                      quantile=0.025, iterations=MS_ITERS, lamb=0.1)
+            loss = loss + torch.stack([r.reshape(()) for r in res[0::5]]).mean()
+            self.clusters.append(len(np.unique(extra[1])))
         loss.backward()
         if self.world > 1:
             import torch.distributed as dist
@@ -156,16 +175,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_np = [(hb[1].numpy(), hb[2].numpy()) for hb in host]
+
     def resident_step(i):
         x, lab, prim = dev_batches[i % 2]
         np.random.seed(i)
-        return hp.step(x, None, lab, prim)
+        return hp.step(x, host_np[i % 2][0], host_np[i % 2][1], lab, prim)
 
     def e2e_step(i):
         hx, hl, hpm = host[i % 2]
         x = hx.to(dev, non_blocking=True); lab = hl.to(dev, non_blocking=True); prim = hpm.to(dev, non_blocking=True)
         np.random.seed(i)
-        loss = hp.step(x, None, lab, prim)
+        loss = hp.step(x, host_np[i % 2][0], host_np[i % 2][1], lab, prim)
         return loss.item()                     # D2H read of the step's result
 
     for i in range(args.warmup):
@@ -175,7 +196,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start(); time.sleep(0.3)
-    dominant = "pn_knn"
+    dominant = "pn_ms_iter_fwd" if FIT_STAGE else "pn_knn"
     cabi.TIMED[dominant] = []
     barrier()
     cabi.reset_launch_count()
@@ -213,13 +234,24 @@ def run_ours(args):
     shapes_total = B * world * args.steps
     value = shapes_total / (ms_res / 1e3)
     e2e_v = shapes_total / (ms_e2e / 1e3)
-    # roofline of the dominant kernel: kNN in 64-d feature space (FP32 FMA pipe; algorithmic flop = 2*N^2*C/shape)
-    # reported against the measured dense tensor peak is meaningless for an FP32-exact kernel, so we report the
-    # HBM-side view (algorithmic bytes = N*C*4 + N*k*4 per shape) AND keep flop/s in `note`.
-    c64 = [m for m in kern_ms]
-    per_launch_ms = float(np.mean(c64)) if c64 else None
-    alg_bytes = B * (N_POINTS * 64 * 4 + N_POINTS * KNN_K * 4)
-    achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else None
+    per_launch_ms = float(np.mean(kern_ms)) if kern_ms else None
+    if FIT_STAGE:
+        # dominant kernel: ms_fwd_kernel (one mean-shift iteration over the whole batch, 2 fused N x N x d products)
+        alg_flop = B * 4.0 * N_POINTS * N_POINTS * EMB          # 4 N^2 d flop / shape / iteration
+        achieved = alg_flop / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms else None
+        roof = {"kernel": "ms_fwd_kernel (pn_ms_iter_fwd: one fused mean-shift iteration, batch of %d shapes)" % B,
+                "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": (achieved / pk["tf_sustained"]) if achieved else None, "traffic": None,
+                "peak_source": pk["source"] + " (cuBLAS bf16, sustained)",
+                "note": "v1 runs fp32-exact on the FP32 FMA pipe (nominal ~72 TFLOP/s), not yet on tcgen05; "
+                        "algorithmic flop = 4*N^2*d per shape per iteration",
+                "launch_ms": per_launch_ms, "launches_timed": len(kern_ms)}
+    else:
+        alg_bytes = B * (N_POINTS * 64 * 4 + N_POINTS * KNN_K * 4)
+        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else None
+        roof = {"kernel": "knn_kernel (pn_knn)", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"],
+                "unit": "GB/s", "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": None,
+                "peak_source": pk["source"], "launch_ms": per_launch_ms, "launches_timed": len(kern_ms)}
     h2d = int(sum(t.numel() * t.element_size() for t in host[0]))
     out = {
         "metric": "shapes/sec (10k pts, B=16) seg+spline-fit fwd/bwd at 1/2/4/8 B200; Chamfer err",
@@ -227,7 +259,9 @@ def run_ours(args):
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "train_parsenet.py step (config 4 shape: 16 x 10k pts + normals, k=80, mode 5): "
-                               "seg-net fwd + triplet/NLL + bwd + Adam; cluster+fit stages: " + STAGES,
+                               "seg-net fwd + triplet/NLL" + (" + Evaluation.fitting_loss (mean-shift %d it, match, primitive/"
+                               "spline fit, residual)" % MS_ITERS if FIT_STAGE else "") + " + bwd + Adam; random-init "
+                               "weights (seg net and SplineNets)",
                    "per_gpu_batch": B, "global_batch": B * world, "n_points": N_POINTS, "knn_k": KNN_K,
                    "parallelism": f"dp{world}", "l2": "256 MB flush write between timed steps; per-step working set "
                                                       ">> 126 MB L2"},
@@ -235,20 +269,16 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "knn_kernel (pn_knn: norms + tiled distance/top-k)", "bound": "hbm",
-                     "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": None,
-                     "peak_source": pk["source"],
-                     "note": "kNN is FP32-FMA bound by design (bit-exact indices); HBM fraction is low because the "
-                             "kernel reads each point block from L2, not because of wasted traffic",
-                     "launch_ms": per_launch_ms, "launches_timed": len(c64)},
+        "roofline": roof,
     }
+    out["config"]["mean_clusters_per_shape_last"] = (float(np.mean(hp.clusters[-4:])) if hp.clusters else None)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
 
 
-STAGES = "not yet enabled"
+FIT_STAGE = True
+MS_ITERS = 10
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm

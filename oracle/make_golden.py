@@ -268,6 +268,14 @@ def gen_e2e():
     ev.ms = MS.MeanShift()
     E = emb.clone().requires_grad_()
     np.random.seed(5)
+    captured = {}
+    orig_sep = ev.separate_losses
+
+    def sep(distance, gt_points, lamb=1.0):
+        captured.update({k: (v[0], float(v[1])) for k, v in distance.items()})
+        return orig_sep(distance, gt_points, lamb=lamb)
+
+    ev.separate_losses = sep
     res, extra = ev.fitting_loss(E, torch.from_numpy(pts), torch.from_numpy(nrm), lab, prim.copy(), logp,
                                  quantile=0.015, iterations=10, lamb=0.1)
     res[0].backward()
@@ -283,6 +291,8 @@ def gen_e2e():
         for i, t in enumerate(v[1:]):
             out[f"par_{k}_{i}"] = t.detach().numpy()
     out["kinds"] = np.array(kinds)
+    out["seg_kind"] = np.array([captured[k][0] for k in sorted(captured)])
+    out["seg_dist"] = np.array([captured[k][1] for k in sorted(captured)])
     np.savez_compressed(os.path.join(OUT, "e2e.npz"), **out)
     print("e2e loss", res[0].item(), "geo", res[1], "spline", res[2], "siou", res[3], "kinds", kinds)
 

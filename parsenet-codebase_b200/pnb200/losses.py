@@ -59,6 +59,32 @@ def triplet_sample(labels, N, rng=np.random, max_segments=5):
     return out
 
 
+class L2NormFn(torch.autograd.Function):
+    """F.normalize(x, p=2, dim=-1) for (..., D) tensors (rows contiguous) on the pn_l2norm_* kernels"""
+
+    @staticmethod
+    def forward(ctx, x):
+        shp = x.shape
+        x2 = x.detach().reshape(-1, shp[-1])
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        y, norms = ops.l2norm_fwd(x2)
+        ctx.saved = (y, norms, shp)
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, g):
+        y, norms, shp = ctx.saved
+        g2 = g.reshape(-1, shp[-1])
+        if g2.stride(1) != 1:
+            g2 = g2.contiguous()
+        return ops.l2norm_bwd(y, g2, norms).view(shp)
+
+
+def l2_normalize(x):
+    return L2NormFn.apply(x)
+
+
 class TripletFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, emb_bnd, groups, margin):

@@ -44,17 +44,27 @@ class Evaluation:
     def fitting_loss(self, embedding, points, normals, labels, primitives, primitives_log_prob, quantile=0.125,
                      iterations=5, lamb=1.0, debug=False, eval=False):
         """embedding (B,N,d), points/normals (B,N,3), labels/primitives numpy (B,N), log-probs (B,P,N).
-        Returns ([loss, geometric mean, spline mean, seg IoU, type IoU], [parameters, cluster ids, weights]) of the
-        LAST shape, like the reference (which is only ever called with B = 1); the loss entries of several shapes are
-        concatenated in order."""
+        Returns ([loss, geometric mean, spline mean, seg IoU, type IoU] per shape, concatenated in order,
+        [parameters, cluster ids, weights] of the LAST shape) — the reference is only ever called with B = 1.
+        The mean-shift iterations of all shapes run as ONE batched launch sequence (per-shape bandwidths)."""
         if eval:
             raise NotImplementedError("Evaluation.fitting_loss(eval=True) is outside the hot path")
+        from pnb200 import meanshift as _ms
+        from pnb200.losses import l2_normalize
         B = embedding.shape[0]
-        embedding = torch.nn.functional.normalize(embedding, p=2, dim=2)
+        embedding = l2_normalize(embedding)
         prim_pred = torch.max(primitives_log_prob, 1)[1].data.cpu().numpy()
+        with torch.no_grad():
+            bws = torch.stack([torch.clamp(self.ms.compute_bandwidth(embedding[b], 10000, quantile), min=_ms.BW_FLOOR)
+                               for b in range(B)])
+        shifted = _ms.mean_shift_iters(embedding, bws, iterations)
         out, parameters, cluster_ids, weights = [], None, None, None
         for b in range(B):
-            center, bandwidth, cluster_ids = self.guard_mean_shift(embedding[b], quantile, iterations)
+            with torch.no_grad():
+                _, ids, cluster_ids = self.ms.nms(shifted[b], embedding[b], bws[b])
+            center, bandwidth = shifted[b][ids], bws[b]
+            if torch.unique(cluster_ids).shape[0] > 49:      # rare: grow the quantile for this shape only (ref :76-83)
+                center, bandwidth, cluster_ids = self.guard_mean_shift(embedding[b], quantile * 1.2, iterations)
             weights = center @ embedding[b].t()
             loss, parameters, _, rows, cols, distance = self.residual_train_mode(
                 points[b], normals[b], labels[b], cluster_ids, primitives[b], weights, bandwidth, lamb=lamb)
