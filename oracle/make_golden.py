@@ -251,11 +251,11 @@ def gen_splinenet():
 from oracle.make_golden_helpers import e2e_inputs  # noqa: E402
 
 
-def gen_e2e():
+def gen_e2e(no_cylinder=False, fname="e2e.npz"):
     RU = rl.ref("src.residual_utils"); FO = rl.ref("src.fitting_optimization"); PF = rl.ref("src.primitive_forward")
     PR = rl.ref("src.primitives"); MS = rl.ref("src.mean_shift"); L = rl.ref("src.loss")
     N = 1400
-    pts, nrm, lab, prim, emb, logp = e2e_inputs(N, 77)
+    pts, nrm, lab, prim, emb, logp = e2e_inputs(N, 77, no_cylinder)
     ev = RU.Evaluation.__new__(RU.Evaluation)
     ev.res_loss = PR.ResidualLoss()
     fm = FO.FittingModule.__new__(FO.FittingModule)
@@ -293,12 +293,12 @@ def gen_e2e():
     out["kinds"] = np.array(kinds)
     out["seg_kind"] = np.array([captured[k][0] for k in sorted(captured)])
     out["seg_dist"] = np.array([captured[k][1] for k in sorted(captured)])
-    np.savez_compressed(os.path.join(OUT, "e2e.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, fname), **out)
     print("e2e loss", res[0].item(), "geo", res[1], "spline", res[2], "siou", res[3], "kinds", kinds)
 
 
 GENS = {"knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
-        "splinenet": gen_splinenet, "e2e": gen_e2e}
+        "splinenet": gen_splinenet, "e2e": gen_e2e, "e2e_nocyl": lambda: gen_e2e(True, "e2e_nocyl.npz")}
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)

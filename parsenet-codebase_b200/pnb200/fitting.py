@@ -43,7 +43,7 @@ class MomentsFn(torch.autograd.Function):
     def forward(ctx, W, P, Nr, start, step, m, eps=EPS):
         _need_cuda(W, P)
         W = W.detach()
-        assert W.stride(1) == 1 and P.is_contiguous() and (Nr is None or Nr.is_contiguous())
+        assert (W.shape[1] == 1 or W.stride(1) == 1) and P.is_contiguous() and (Nr is None or Nr.is_contiguous())
         N, K = W.shape
         mom = torch.zeros((K, NM), dtype=torch.float64, device=W.device)
         call("pn_fit_moments_fwd", _ptr(P), _ptr(Nr), _ptr(W), W.stride(0), K, start, step, m, float(eps), _ptr(mom),

@@ -129,7 +129,7 @@ def fit_one_shape_torch(data, fitter, weights, bw, eval=False, sample_points=Fal
     N = points.shape[0]
     n_half = (N + 1) // 2            # points[0::2]
     n_quarter = (n_half + 1) // 2    # ...[0::2] again for analytic primitives
-    W = weights if weights.stride(1) == 1 else weights.contiguous()
+    W = weights if (weights.shape[1] == 1 or weights.stride(1) == 1) else weights.contiguous()
     mom = None
     spline_count = 0
     plan = []
