@@ -1,0 +1,116 @@
+/* parsenet_b200.h — C ABI of libparsenet_b200.so (hand-written sm_100a kernels for the ParSeNet hot path).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Conventions for every entry point
+ *   - all pointers are DEVICE pointers (fp32 / int32 / fp64 as typed); the caller owns every buffer, the library
+ *     allocates nothing and keeps no state besides an error string and a launch counter;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and never synchronise;
+ *   - return value 0 = ok, non-zero = error (pn_last_error() gives the message) — callers raise, nothing falls back;
+ *   - activations are point-major: (shape b, point n, channel c) at base[(b*Np + n)*pitch + c]; `ld*` arguments are
+ *     row pitches in elements, so channel slices of a wider buffer can be passed without copies;
+ *   - buffers documented "zeroed" must be zero-filled by the caller (they are accumulated with atomics).
+ * Each declaration cites the reference code (relative to Hippogriff/parsenet-codebase) that it replaces.
+ * The reference has no native layer: its FFI for this path is "call a torch op"; INTEGRATION.md shows the
+ * ctypes binding (parsenet-codebase_b200/pnb200/cabi.py) a maintainer would add to call these from src/*.py.
+ */
+#ifndef PARSENET_B200_H
+#define PARSENET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+
+/* ---- cabi.cu ---- */
+/* replaces: (error string of the last failing call on this thread; the reference drops into ipdb instead) */
+const char* pn_last_error();
+/* replaces: (number of kernel launches issued through this library; bench.py gpu_launches) */
+unsigned long long pn_launch_count();
+void pn_reset_launch_count();
+int pn_abi_version();
+
+/* ---- chamfer.cu ---- */
+/* replaces: chamfer_distance / _one_side / _single_shape: src/utils.py:273-358 */
+int pn_chamfer_nn_fwd(const float* A, int Na, const float* Bs, int Nb, int B, float* mind, int* arg, void* stream);
+/* replaces: autograd of the min over the broadcast difference tensor */
+int pn_chamfer_nn_bwd(const float* A, int Na, const float* Bs, int Nb, int B, const int* arg, const float* g, float* dA_accum, float* dB_accum, void* stream);
+
+/* ---- edgeconv.cu ---- */
+/* replaces: get_graph_feature[_with_normals] + conv + norm + LeakyReLU + max over k: src/PointNet.py:72-140,176-192; src/model.py:25-53,140-154 */
+int pn_edge_gather_fwd(const float* PQ, long long ldpq, const int* idx, int B, int N, int k, int Cout, const float* gamma, float* esel, int* jsel, float* esum, double* stats, int G, int stats_per_shape, void* stream);
+/* replaces: same (activation of the selected extreme) */
+int pn_edge_apply(const float* esel, const float* scale, const float* shift, float* out, long long ldo, int B, int N, int Cout, void* stream);
+/* replaces: autograd of the edge-conv block */
+int pn_edge_bwd_prep(const float* g, long long ldg, const float* esel, const float* scale, const float* shift, const float* mean_rstd, const float* gamma, int B, int N, int Cout, int G, int stats_per_shape, float* dy, double* gsum, float* dgamma, float* dbeta, void* stream);
+/* replaces: autograd of feature[idx] gather (index_put in the reference): src/PointNet.py:93 */
+int pn_knn_csr_transpose(const int* idx, int B, int N, int k, int* cnt, int* off, int* cursor, int* rev, void* stream);
+/* replaces: autograd of the edge-conv block */
+int pn_edge_bwd(const float* PQ, long long ldpq, const float* dy, const float* esum, const int* jsel, const int* off, const int* rev, const float* mean_rstd, const double* gsum, const float* scale, int B, int N, int k, int Cout, int G, int stats_per_shape, double count, int dense, float* dPQ, long long lddpq, void* stream);
+
+/* ---- fit.cu ---- */
+/* replaces: Fit.fit_{plane,sphere,cylinder,cone}_torch reductions: src/primitive_forward.py:708-843; LeastSquares.lstsq src/fitting_utils.py:36-65; CustomSVD :420-455 */
+int pn_fit_moments_fwd(const float* P, const float* Nr, const float* W, long long ldw, int S, int start, int step, int m, float eps, double* mom_zeroed, void* stream);
+/* replaces: autograd of the weighted reductions w.r.t. the membership weights */
+int pn_fit_moments_bwd(const float* P, const float* Nr, const float* W, long long ldw, int S, int start, int step, int m, float eps, const float* gmom, float* gW, long long ldg, void* stream);
+
+/* ---- knn.cu ---- */
+/* replaces: src/PointNet.py:9-26 (knn), :29-69 (knn_points_normals); src/model.py:9-22 */
+int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, float* ws_norms, void* stream);
+
+/* ---- linear.cu ---- */
+/* replaces: Conv1d/Conv2d(k=1) + GroupNorm/BatchNorm + ReLU chains: src/PointNet.py:157-165,194-196,274-284; src/model.py:74-99,155-176 */
+int pn_linear_fwd(const float* A, long long lda, const float* W, long long ldw, const float* bias, const float* sbias, const float* in_scale, const float* in_shift, int in_act, float* Y, long long ldy, double* stats, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream);
+/* replaces: autograd of the same chains (torch built-in in the reference) */
+int pn_linear_bwd_data(const float* dY, long long lddy, const float* W, long long ldw, float* dZ, long long lddz, int accumulate, int finalize, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, const float* gamma, const float* mean_rstd, double* gsum, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream);
+/* replaces: autograd of the same chains (torch built-in in the reference) */
+int pn_linear_bwd_weight(const float* dY, long long lddy, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, float* dW, long long lddw, float* db, float* dsb, int B, int Np, int K, int Nout, void* stream);
+/* replaces: nn.GroupNorm / nn.BatchNorm statistics: src/PointNet.py:151-155,166-169; src/model.py:69-73,98-99 */
+int pn_norm_finalize(const double* stats, const float* gamma, const float* beta, int S, int G, int C, double count, float eps, float* mean_rstd, float* scale, float* shift, void* stream);
+/* replaces: autograd of nn.GroupNorm / nn.BatchNorm */
+int pn_norm_bwd_apply(float* dZ, long long lddz, const float* A, long long lda, const float* gamma, const float* mean_rstd, const double* gsum, int B, int Np, int C, int G, int stats_per_shape, double count, float* dgamma, float* dbeta, void* stream);
+
+/* ---- meanshift.cu ---- */
+/* replaces: MeanShift.mean_shift_ (one iteration): src/mean_shift.py:58-77 */
+int pn_ms_iter_fwd(const float* Y, const float* X, int B, int N, int d, const float* cinv, float* Ynew, float* den, float* unorm, void* stream);
+/* replaces: autograd of one mean-shift iteration */
+int pn_ms_iter_bwd(const float* gout, const float* Ynew, const float* Yprev, const float* X, const float* den, const float* unorm, int B, int N, int d, const float* cinv, float* ws_Gn, float* ws_gd, float* gYprev, float* gX, int accumulate_gX, void* stream);
+/* replaces: MeanShift.compute_bandwidth: src/mean_shift.py:130-135 (2 - 2 X X^T, topk(K, largest=False)[:, -1]) */
+int pn_ms_kth_dist(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K, float* kth, void* stream);
+/* replaces: MeanShift.nms: src/mean_shift.py:146-149 (mode 0), :163-171 (mode 1), :177-178 (mode 2) */
+int pn_ms_argsel(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream);
+
+/* ---- pointwise.cu ---- */
+/* replaces: F.relu(bnmlp1(mlp1(x))).max(dim=2): src/PointNet.py:194-196; x*weights + adaptive_max_pool1d: src/model.py:165-169 */
+int pn_colmax_norm(const float* Y, long long ldy, int B, int N, int C, const float* scale, const float* shift, int act, const float* wts, float* out, int* arg, void* stream);
+/* replaces: autograd of the above */
+int pn_colmax_bwd_fill(const float* Y, long long ldy, const float* gt, const int* arg, const float* gamma, const float* mean_rstd, const double* gsum, int B, int N, int C, int G, int stats_per_shape, double count, int dense, float* dY, long long lddy, void* stream);
+/* replaces: LogSoftmax(dim=1): src/PointNet.py:284 */
+int pn_logsoftmax_fwd(const float* logits, long long ldl, int B, int N, int P, float* logp, void* stream);
+/* replaces: autograd of LogSoftmax */
+int pn_logsoftmax_bwd(const float* logp, const float* dlp, int B, int N, int P, float* dlogits, long long ldd, void* stream);
+/* replaces: primitive_loss = NLLLoss: src/segment_loss.py:151 */
+int pn_nll_fwd(const float* logp, const long long* target, int B, int N, int P, float* loss_zeroed, void* stream);
+/* replaces: autograd of NLLLoss */
+int pn_nll_bwd(const long long* target, const float* gout, int B, int N, int P, float* dlp_zeroed, void* stream);
+/* replaces: torch.nn.functional.normalize: src/segment_loss.py:45, src/residual_utils.py:108 */
+int pn_l2norm_fwd(const float* x, long long ldx, long long rows, int D, float eps, float* y, long long ldy, float* norms, void* stream);
+/* replaces: autograd of normalize */
+int pn_l2norm_bwd(const float* y, long long ldy, const float* dy, long long lddy, const float* norms, long long rows, int D, float* dx, long long lddx, int accumulate, void* stream);
+/* replaces: EmbeddingLoss.triplet_loss inner loop: src/segment_loss.py:98-119 */
+int pn_triplet_fwd(const float* E, long long lde, int D, const int* a_idx, const int* n_idx, int T, int S, float margin, float* pair_loss, float* pair_sat, void* stream);
+/* replaces: autograd of the triplet loss */
+int pn_triplet_bwd(const float* E, long long lde, int D, const int* a_idx, const int* n_idx, int T, int S, float margin, const float* pair_sat, const float* pair_w, float* dE, long long ldde, void* stream);
+
+/* ---- primitives.cu ---- */
+/* replaces: ComputePrimitiveDistance.distance_from_{plane,sphere,cylinder,cone}: src/primitives.py:100-195 */
+int pn_residual_fwd(const float* P, const int* seg, int N, const int* type, const float* par, int S, float* sumf_zeroed, float* jac_zeroed, float* cnt_zeroed, void* stream);
+
+/* ---- spline.cu ---- */
+/* replaces: sample_points_from_control_points_: src/fitting_utils.py:609-622; src/loss.py:161-165,179-183 */
+int pn_spline_eval_fwd(const float* Nu, const float* Nv, const float* P, int B, int gu, int gv, int cu, int cv, float* out, void* stream);
+/* replaces: autograd of Nu P Nv^T */
+int pn_spline_eval_bwd(const float* Nu, const float* Nv, const float* g, int B, int gu, int gv, int cu, int cv, float* dP, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PARSENET_B200_H */
