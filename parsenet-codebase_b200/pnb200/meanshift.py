@@ -76,6 +76,31 @@ def compute_bandwidth(X_nd, num_samples, quantile, rng=np.random):
     return torch.sqrt(torch.clamp(kth, min=SQRT_FLOOR)).mean()
 
 
+def compute_bandwidth_batched(X_bnd, num_samples, quantile, rng=np.random):
+    """compute_bandwidth for a batch of shapes in ONE launch (N <= num_samples, i.e. every row is used; the host RNG
+    is still consumed once per shape like the reference would).  Returns (B,) bandwidths (before the 0.003 floor)."""
+    _need_cuda(X_bnd)
+    B, N, d = X_bnd.shape
+    if N > int(num_samples):
+        return torch.stack([compute_bandwidth(X_bnd[b], num_samples, quantile, rng) for b in range(B)])
+    for _ in range(B):
+        rng.shuffle(np.arange(N))
+    K = int(quantile * num_samples)
+    X = X_bnd.detach().contiguous()
+    kth = torch.empty((B, N), dtype=torch.float32, device=X.device)
+    call("pn_ms_kth_dist", _ptr(X), None, B, N, N * d, d, K, _ptr(kth), _stream())
+    return torch.sqrt(torch.clamp(kth, min=SQRT_FLOOR)).mean(1)
+
+
+def nearest_center_batched(X_bnd, Y_bnd):
+    """membership of every point to its nearest shifted point (nms step 1) for a batch of shapes in one launch"""
+    B, N, d = X_bnd.shape
+    X, Y = X_bnd.detach().contiguous(), Y_bnd.detach().contiguous()
+    out = torch.empty((B, N), dtype=torch.int32, device=X.device)
+    call("pn_ms_argsel", 0, _ptr(X), N * d, N, _ptr(Y), N * d, N, B, d, None, None, _ptr(out), _stream())
+    return out
+
+
 def _argsel(mode, A, Bm, cnt=None, thr=None):
     Ma, d = A.shape
     Nb = Bm.shape[0]
@@ -84,12 +109,14 @@ def _argsel(mode, A, Bm, cnt=None, thr=None):
     return out
 
 
-def nms(centers_nd, X_nd, b):
-    """non-max suppression of the shifted points [mean_shift.py:139-179] -> (kept centres, their ids, labels int64)"""
+def nms(centers_nd, X_nd, b, member=None):
+    """non-max suppression of the shifted points [mean_shift.py:139-179] -> (kept centres, their ids, labels int64).
+    `member` (N,) int32: precomputed nearest-centre ids (from nearest_center_batched)."""
     centers = centers_nd.detach().contiguous()
     X = X_nd.detach().contiguous()
     N = X.shape[0]
-    member = _argsel(0, X, centers)                                  # nearest shifted centre per point
+    if member is None:
+        member = _argsel(0, X, centers)                              # nearest shifted centre per point
     counts = torch.bincount(member.long(), minlength=centers.shape[0]).to(torch.float32)
     uniq = torch.nonzero(counts > 0).flatten()                        # sorted, like np.unique
     thr = torch.as_tensor(b, dtype=torch.float32, device=X.device).reshape(1)

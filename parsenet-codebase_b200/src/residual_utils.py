@@ -55,13 +55,14 @@ class Evaluation:
         embedding = l2_normalize(embedding)
         prim_pred = torch.max(primitives_log_prob, 1)[1].data.cpu().numpy()
         with torch.no_grad():
-            bws = torch.stack([torch.clamp(self.ms.compute_bandwidth(embedding[b], 10000, quantile), min=_ms.BW_FLOOR)
-                               for b in range(B)])
+            bws = torch.clamp(_ms.compute_bandwidth_batched(embedding, 10000, quantile), min=_ms.BW_FLOOR)
         shifted = _ms.mean_shift_iters(embedding, bws, iterations)
+        with torch.no_grad():
+            members = _ms.nearest_center_batched(embedding, shifted)
         out, parameters, cluster_ids, weights = [], None, None, None
         for b in range(B):
             with torch.no_grad():
-                _, ids, cluster_ids = self.ms.nms(shifted[b], embedding[b], bws[b])
+                _, ids, cluster_ids = _ms.nms(shifted[b], embedding[b], bws[b], member=members[b])
             center, bandwidth = shifted[b][ids], bws[b]
             if torch.unique(cluster_ids).shape[0] > 49:      # rare: grow the quantile for this shape only (ref :76-83)
                 center, bandwidth, cluster_ids = self.guard_mean_shift(embedding[b], quantile * 1.2, iterations)
