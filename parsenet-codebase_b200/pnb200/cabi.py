@@ -44,6 +44,7 @@ SIGNATURES = {
     "pn_triplet_bwd": [c_p, c_ll, c_i, c_p, c_p, c_i, c_i, c_f, c_p, c_p, c_p, c_ll, c_p],
     # meanshift.cu
     "pn_ms_iter_fwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "pn_ms_iter_fwd_tc": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "pn_ms_iter_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     "pn_ms_kth_dist": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
     "pn_ms_argsel": [c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p],

@@ -9,7 +9,11 @@ import torch
 from .cabi import call
 from .ops import _need_cuda, _ptr, _stream
 
+import os
+
 BW_FLOOR = 0.003      # mean_shift.py:34
+# forward iteration kernel: "tc" = tcgen05 split-TF32 tensor-core kernel (csrc/meanshift_tc.cu), "simt" = fp32 FMA kernel
+FWD_IMPL = os.environ.get("PN_MS_FWD", "tc")
 SQRT_FLOOR = 1e-6     # guard_sqrt(top_k, 1e-6), mean_shift.py:135
 
 
@@ -28,8 +32,8 @@ class MeanShiftItersFn(torch.autograd.Function):
             Yn = torch.empty_like(X)
             den = torch.empty((B, N), dtype=torch.float32, device=X.device)
             un = torch.empty((B, N), dtype=torch.float32, device=X.device)
-            call("pn_ms_iter_fwd", _ptr(Ys[-1]), _ptr(X), B, N, d, _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un),
-                 _stream())
+            call("pn_ms_iter_fwd_tc" if FWD_IMPL == "tc" else "pn_ms_iter_fwd", _ptr(Ys[-1]), _ptr(X), B, N, d,
+                 _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
             Ys.append(Yn); dens.append(den); norms.append(un)
         ctx.saved = (X, cinv, Ys, dens, norms)
         return Ys[-1].clone() if iterations == 0 else Ys[-1]
