@@ -1,14 +1,14 @@
 // Mean-shift iteration on the 5th-gen tensor cores (tcgen05 + TMEM), split-TF32 (3 MMAs per product) for fp32-level
 // accuracy.  Same contract as ms_fwd_kernel in meanshift.cu (reference src/mean_shift.py:58-77).
 //
-// One CTA = 128 query rows of Y, 9 warps, warp-specialised and mbarrier-pipelined:
-//   warps 0-3  epilogue : thread = one row.  S tile TMEM -> regs, P = exp(clamp((S-1)/b^2)), row sum, tf32 split,
+// One CTA = 128 query rows of Y, 13 warps, warp-specialised and mbarrier-pipelined:
+//   warps 0-7  epilogue : thread = (row, half of the columns).  S tile TMEM -> regs, P = exp(clamp((S-1)/b^2)), row sum, tf32 split,
 //                         P -> TMEM; every FLUSH tiles the O accumulator is drained into fp32 registers (the tensor
 //                         core accumulates with truncation; short chains keep the bias at the 1e-6 level)
-//   warps 4-7  loaders  : X tile (32 rows) LDG -> tf32 split -> two K-major no-swizzle core-matrix layouts in smem
+//   warps 8-11 loaders  : X tile (32 rows) LDG -> tf32 split -> two K-major no-swizzle core-matrix layouts in smem
 //                         XA[j][d] (B operand of S = Y.X^T) and the transposed XB[d][j] (B operand of O += P.X),
 //                         2 stages x 64 KB
-//   warp 8     MMA      : one thread issues tcgen05.mma (kind::tf32, M=128): 48 x (N=32,K=8) per tile for S, 12 x
+//   warp 12    MMA      : one thread issues tcgen05.mma (kind::tf32, M=128): 48 x (N=32,K=8) per tile for S, 12 x
 //                         (N=128,K=8) for O; every A operand comes from TENSOR MEMORY (Y split once, P per tile)
 //   TMEM cols: Y_big [0,128) Y_small [128,256) S0 [256,288) S1 [288,320) P_big [320,352) P_small [352,384) O [384,512)
 // Issue order G1(0) G1(1) G2(0) G1(2) G2(1) ... so the exp of tile t overlaps the S-MMA of tile t+1.
@@ -22,8 +22,9 @@ using namespace tc05;
 constexpr int D = 128;
 constexpr int BM = 128;       // query rows per CTA
 constexpr int BN = 32;        // X rows per tile
-constexpr int NT = 288;       // 4 epilogue + 4 loader + 1 MMA warp
-constexpr int NSTAGE = 2;
+constexpr int NT = 416;       // 8 epilogue + 4 loader + 1 MMA warp
+constexpr int EPI_WARPS = 8, LOAD_WARP0 = 8, MMA_WARP = 12, EPI_THREADS = 256;
+constexpr int NSTAGE = 3;
 constexpr int FLUSH = 16;     // tiles per O accumulation chain
 constexpr float CLAMP = 75.f;
 constexpr uint32_t C_YB = 0, C_YS = 128, C_S0 = 256, C_PB = 320, C_PS = 352, C_O = 384, TMEM_COLS = 512;
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ Bars bars;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float part[4][BM];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, i0 = blockIdx.x * BM;
@@ -50,12 +52,12 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
     const float* Xb = X + (long long)b * N * D;
     const int ntiles = (N + BN - 1) / BN;
 
-    if (warp == 8) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.x_full[s], 128); mbar_init(&bars.x_empty[s], 1); }
-        for (int k = 0; k < 2; ++k) { mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], 128); }
-        mbar_init(&bars.p_full, 128); mbar_init(&bars.p_empty, 1);
-        mbar_init(&bars.o_flush, 128); mbar_init(&bars.o_done, 1);
+        for (int k = 0; k < 2; ++k) { mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); }
+        mbar_init(&bars.p_full, EPI_THREADS); mbar_init(&bars.p_empty, 1);
+        mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
         mbar_fence_init();
     }
     tc_fence_before();
@@ -63,16 +65,18 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
     tc_fence_after();
     const uint32_t tb = tmem_base_s;
 
-    if (warp < 4) {
+    if (warp < EPI_WARPS) {
         // =============================================================================== epilogue warps
-        const int row = warp * 32 + lane;
-        const uint32_t la = (uint32_t)(warp * 32) << 16;
+        // thread = (row, column half h): TMEM lane quarter q = warp & 3, h = warp >> 2
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t la = (uint32_t)(q * 32) << 16;
         const bool ok = (i0 + row) < N;
         const float c = cinv[b];
-        const float* yr = Yb + (long long)(i0 + row) * D;
-        // Y row -> TMEM (tf32 big / small)
+        const float* yr = Yb + (long long)(i0 + row) * D + 64 * h;
+        // Y row half -> TMEM (tf32 big / small)
 #pragma unroll 1
-        for (int c0 = 0; c0 < D; c0 += 16) {
+        for (int c0 = 0; c0 < 64; c0 += 16) {
             uint32_t vb[16], vs[16];
 #pragma unroll
             for (int e = 0; e < 16; e += 4) {
@@ -80,55 +84,51 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                 const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    float big = to_tf32(f[u]);
+                    float big = tf32_hi(f[u]);
                     vb[e + u] = __float_as_uint(big);
                     vs[e + u] = __float_as_uint(f[u] - big);
                 }
             }
-            tmem_st16(tb + la + C_YB + c0, vb);
-            tmem_st16(tb + la + C_YS + c0, vs);
+            tmem_st16(tb + la + C_YB + 64 * h + c0, vb);
+            tmem_st16(tb + la + C_YS + 64 * h + c0, vs);
         }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bars.p_full);          // phase 0 of p_full doubles as "Y is in TMEM" (consumed by the MMA warp)
-        float oacc[D];
+        float oacc[64];
 #pragma unroll
-        for (int e = 0; e < D; ++e) oacc[e] = 0.f;
+        for (int e = 0; e < 64; ++e) oacc[e] = 0.f;
         float den = 0.f;
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
             const int k = t & 1;
-            const int j0 = t * BN;
+            const int j0 = t * BN + 16 * h;
             mbar_wait(&bars.s_full[k], (t >> 1) & 1);
             tc_fence_after();
-            uint32_t pb[32], ps[32];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                uint32_t sv[16];
-                tmem_ld16(tb + la + C_S0 + 32 * k + 16 * hh, sv);
-                tmem_ld_wait();
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    float e = (__uint_as_float(sv[u]) - 1.0f) * c;
-                    e = fminf(fmaxf(e, -CLAMP), CLAMP);
-                    float p = (j0 + 16 * hh + u < N) ? expf(e) : 0.f;
-                    den += p;
-                    float big = to_tf32(p);
-                    pb[16 * hh + u] = __float_as_uint(big);
-                    ps[16 * hh + u] = __float_as_uint(p - big);
-                }
-            }
+            uint32_t sv[16], pb[16], ps[16];
+            tmem_ld16(tb + la + C_S0 + 32 * k + 16 * h, sv);
+            tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&bars.s_empty[k]);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                float e = (__uint_as_float(sv[u]) - 1.0f) * c;
+                e = fminf(fmaxf(e, -CLAMP), CLAMP);
+                float p = (j0 + u < N) ? __expf(e) : 0.f;
+                den += p;
+                float big = tf32_hi(p);
+                pb[u] = __float_as_uint(big);
+                ps[u] = __float_as_uint(p - big);
+            }
             // P buffer free?  (G2 of tile t-1 finished)   p_empty completes once per tile; first wait passes (fresh)
             mbar_wait(&bars.p_empty, (t & 1) ^ 1);
             tc_fence_after();
             if (t > 0 && (t % FLUSH) == 0) {
-                // drain the O accumulator (sum over the previous FLUSH tiles) into registers
+                // drain this thread's half of the O accumulator (sum over the previous FLUSH tiles) into registers
 #pragma unroll
-                for (int c0 = 0; c0 < D; c0 += 16) {
+                for (int c0 = 0; c0 < 64; c0 += 16) {
                     uint32_t ov[16];
-                    tmem_ld16(tb + la + C_O + c0, ov);
+                    tmem_ld16(tb + la + C_O + 64 * h + c0, ov);
                     tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 16; ++e) oacc[c0 + e] += __uint_as_float(ov[e]);
@@ -136,30 +136,24 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                 tc_fence_before();
                 mbar_arrive(&bars.o_flush);
             }
-            {
-                uint32_t h0[16], h1[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) { h0[u] = pb[u]; h1[u] = pb[16 + u]; }
-                tmem_st16(tb + la + C_PB, h0);
-                tmem_st16(tb + la + C_PB + 16, h1);
-#pragma unroll
-                for (int u = 0; u < 16; ++u) { h0[u] = ps[u]; h1[u] = ps[16 + u]; }
-                tmem_st16(tb + la + C_PS, h0);
-                tmem_st16(tb + la + C_PS + 16, h1);
-            }
+            tmem_st16(tb + la + C_PB + 16 * h, pb);
+            tmem_st16(tb + la + C_PS + 16 * h, ps);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars.p_full);      // phase t+1
         }
-        // ---- final: last O chain
+        // ---- final: last O chain, then u = y + (O/den - y), Y' = u/|u|
         mbar_wait(&bars.o_done, 0);
         tc_fence_after();
+        part[h][row] = den;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float dn = part[0][row] + part[1][row];
+        const float dinv = 1.0f / dn;
         float n2 = 0.f;
-        const float dinv = 1.0f / den;
 #pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 16) {
+        for (int c0 = 0; c0 < 64; c0 += 16) {
             uint32_t ov[16];
-            tmem_ld16(tb + la + C_O + c0, ov);
+            tmem_ld16(tb + la + C_O + 64 * h + c0, ov);
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
@@ -171,46 +165,61 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                 n2 = fmaf(uu, uu, n2);
             }
         }
-        const float nr = sqrtf(n2);
+        part[2 + h][row] = n2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float nr = sqrtf(part[2][row] + part[3][row]);
         if (ok) {
-            float* dst = Ynew + ((long long)b * N + i0 + row) * D;
+            float* dst = Ynew + ((long long)b * N + i0 + row) * D + 64 * h;
 #pragma unroll
-            for (int e = 0; e < D; e += 4)
+            for (int e = 0; e < 64; e += 4)
                 *reinterpret_cast<float4*>(dst + e) =
                     make_float4(oacc[e] / nr, oacc[e + 1] / nr, oacc[e + 2] / nr, oacc[e + 3] / nr);
-            den_out[(long long)b * N + i0 + row] = den;
-            unorm_out[(long long)b * N + i0 + row] = nr;
+            if (h == 0) {
+                den_out[(long long)b * N + i0 + row] = dn;
+                unorm_out[(long long)b * N + i0 + row] = nr;
+            }
         }
         tc_fence_before();
-    } else if (warp < 8) {
+    } else if (warp < MMA_WARP) {
         // =============================================================================== loader warps
-        const int lw = warp - 4;                 // 0..3
+        const int lw = warp - LOAD_WARP0;        // 0..3
         const int j = lane;                      // row inside the tile
         const int l4 = lane & 3;
         const int jg = lane >> 2;                // 4-row group for the transposed copy
+        // software prefetch: the global loads of tile t+1 are issued before tile t is processed / before the stage
+        // of tile t+1 is known to be free, so only the split + shared-memory stores sit on the stage-release path
+        float4 vin[8], vnx[8];
+        {
+            const bool ok0 = j < N;
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+                vin[it] = ok0 ? *reinterpret_cast<const float4*>(Xb + (long long)j * D + 4 * (lw + 4 * it))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
             const int s = t % NSTAGE;
+            {
+                const int jn = (t + 1) * BN + j;
+                const bool okn = (t + 1 < ntiles) && (jn < N);
+#pragma unroll
+                for (int it = 0; it < 8; ++it)
+                    vnx[it] = okn ? *reinterpret_cast<const float4*>(Xb + (long long)jn * D + 4 * (lw + 4 * it))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             mbar_wait(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
             unsigned char* st = smem + s * STAGE_BYTES;
             unsigned char* xa_b = st;
             unsigned char* xa_s = st + XA_BYTES;
             unsigned char* xb_b = st + 2 * XA_BYTES;
             unsigned char* xb_s = st + 2 * XA_BYTES + XB_BYTES;
-            const int jj = t * BN + j;
-            const bool ok = jj < N;
-            const float* src = Xb + (long long)jj * D;
-            float4 vin[8];
-#pragma unroll
-            for (int it = 0; it < 8; ++it)          // all 8 loads in flight before the first use
-                vin[it] = ok ? *reinterpret_cast<const float4*>(src + 4 * (lw + 4 * it)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int c4 = lw + 4 * it;      // float4 column 0..31
                 float f0 = vin[it].x, f1 = vin[it].y, f2 = vin[it].z, f3 = vin[it].w;
                 // XA: chunk (j, c4) as is
                 {
-                    const float b0 = to_tf32(f0), b1 = to_tf32(f1), b2 = to_tf32(f2), b3 = to_tf32(f3);
+                    const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
                     const uint32_t oa = (uint32_t)(c4 * XA_LBO + (j >> 3) * 128 + (j & 7) * 16);
                     *reinterpret_cast<float4*>(xa_b + oa) = make_float4(b0, b1, b2, b3);
                     *reinterpret_cast<float4*>(xa_s + oa) = make_float4(f0 - b0, f1 - b1, f2 - b2, f3 - b3);
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                     f0 = od ? sc : f0; f1 = od ? f1 : sc; f2 = od ? sd : f2; f3 = od ? f3 : sd;
                 }
                 {
-                    const float b0 = to_tf32(f0), b1 = to_tf32(f1), b2 = to_tf32(f2), b3 = to_tf32(f3);
+                    const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
                     const int d = 4 * c4 + l4;
                     const uint32_t ob = (uint32_t)(jg * XB_LBO + (d >> 3) * 128 + (d & 7) * 16);
                     *reinterpret_cast<float4*>(xb_b + ob) = make_float4(b0, b1, b2, b3);
@@ -239,30 +248,37 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
             }
             fence_async_smem();
             mbar_arrive(&bars.x_full[s]);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) vin[it] = vnx[it];
         }
-    } else if (lane == 0) {
-        // =============================================================================== MMA issuer (one thread)
+    } else {
+        // =============================================================================== MMA warp
+        // The whole warp runs this warp-uniform code (descriptors stay in uniform registers); one elected lane issues.
+        const bool leader = elect_one();
         const uint32_t idesc_s = make_idesc(2, BM, BN, 0, 0);
         const uint32_t idesc_o = make_idesc(2, BM, D, 0, 0);
         const uint32_t sbase = smem_u32(smem);
         auto gemm2 = [&](int u) {
             mbar_wait(&bars.p_full, (u + 1) & 1);              // phase u+1 (phase 0 was the Y-ready arrival)
-            if (u > 0 && (u % FLUSH) == 0) mbar_wait(&bars.o_flush, ((u / FLUSH) - 1) & 1);
+            const bool fresh = (u % FLUSH) == 0;
+            if (u > 0 && fresh) mbar_wait(&bars.o_flush, ((u / FLUSH) - 1) & 1);
             tc_fence_after();
             const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
-            const uint32_t b_b = st + 2 * XA_BYTES, b_s = b_b + XB_BYTES;
-            const bool fresh = (u % FLUSH) == 0;
-            const uint64_t db0 = make_smem_desc(b_b, XB_LBO, SBO, 0), ds0 = make_smem_desc(b_s, XB_LBO, SBO, 0);
+            const uint64_t db0 = make_smem_desc(st + 2 * XA_BYTES, XB_LBO, SBO, 0);
+            const uint64_t ds0 = make_smem_desc(st + 2 * XA_BYTES + XB_BYTES, XB_LBO, SBO, 0);
+            if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < BN / 8; ++ks) {
-                const uint64_t db = db0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
-                const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
-                mma_tf32_ts(tb + C_O, tb + C_PS + ks * 8, db, idesc_o, !(fresh && ks == 0));
-                mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, ds, idesc_o, 1);
-                mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, db, idesc_o, 1);
+                for (int ks = 0; ks < BN / 8; ++ks) {
+                    const uint64_t db = db0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
+                    const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
+                    mma_tf32_ts(tb + C_O, tb + C_PS + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, ds, idesc_o, 1);
+                    mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, db, idesc_o, 1);
+                }
+                mma_commit(&bars.x_empty[u % NSTAGE]);
+                mma_commit(&bars.p_empty);
             }
-            mma_commit(&bars.x_empty[u % NSTAGE]);
-            mma_commit(&bars.p_empty);
+            __syncwarp();
         };
         mbar_wait(&bars.p_full, 0);                             // Y rows are in TMEM
         tc_fence_after();
@@ -273,25 +289,29 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
             mbar_wait(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t st = sbase + s * STAGE_BYTES;
-            const uint32_t a_b = st, a_s = st + XA_BYTES;
+            const uint64_t db0 = make_smem_desc(st, XA_LBO, SBO, 0);
+            const uint64_t ds0 = make_smem_desc(st + XA_BYTES, XA_LBO, SBO, 0);
             const uint32_t d_s = tb + C_S0 + 32 * k;
-            const uint64_t db0 = make_smem_desc(a_b, XA_LBO, SBO, 0), ds0 = make_smem_desc(a_s, XA_LBO, SBO, 0);
+            if (leader) {
 #pragma unroll
-            for (int ks = 0; ks < D / 8; ++ks) {
-                const uint64_t db = db0 + (uint64_t)(ks * ((2 * XA_LBO) >> 4));
-                const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XA_LBO) >> 4));
-                mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0);
-                mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
-                mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
+                for (int ks = 0; ks < D / 8; ++ks) {
+                    const uint64_t db = db0 + (uint64_t)(ks * ((2 * XA_LBO) >> 4));
+                    const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XA_LBO) >> 4));
+                    mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
+                }
+                mma_commit(&bars.s_full[k]);
             }
-            mma_commit(&bars.s_full[k]);
+            __syncwarp();
             if (t > 0) gemm2(t - 1);
         }
         gemm2(ntiles - 1);
-        mma_commit(&bars.o_done);
+        if (leader) mma_commit(&bars.o_done);
+        __syncwarp();
     }
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tb, TMEM_COLS);
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
 }
 
 }  // namespace mstc

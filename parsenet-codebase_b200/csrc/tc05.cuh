@@ -71,6 +71,14 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_
     return d;
 }
 
+// one elected lane of a fully converged warp (the rest of the warp keeps executing the same, warp-uniform code so
+// that descriptors / addresses stay in uniform registers: measured 16.5 cyc per N=32 MMA vs 46.5 with an `if (lane==0)` loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- MMA issue (one thread).  D[tmem] (+)= A * B
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -151,5 +159,8 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// "big" part of a split-TF32 operand by truncation (one LOP3): x = big + small exactly, small has <= 13 significant
+// bits and is itself truncated to tf32 by the tensor core (error <= 2^-21 |x|)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 }  // namespace tc05
