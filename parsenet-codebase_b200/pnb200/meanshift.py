@@ -14,6 +14,7 @@ import os
 BW_FLOOR = 0.003      # mean_shift.py:34
 # forward iteration kernel: "tc" = tcgen05 split-TF32 tensor-core kernel (csrc/meanshift_tc.cu), "simt" = fp32 FMA kernel
 FWD_IMPL = os.environ.get("PN_MS_FWD", "tc")
+BWD_IMPL = os.environ.get("PN_MS_BWD", "tc")
 SQRT_FLOOR = 1e-6     # guard_sqrt(top_k, 1e-6), mean_shift.py:135
 
 
@@ -48,7 +49,7 @@ class MeanShiftItersFn(torch.autograd.Function):
         gd = torch.empty((B, N), dtype=torch.float32, device=X.device)
         for it in range(len(dens) - 1, -1, -1):
             gprev = torch.empty_like(X)
-            call("pn_ms_iter_bwd", _ptr(g), _ptr(Ys[it + 1]), _ptr(Ys[it]), _ptr(X), _ptr(dens[it]),
+            call("pn_ms_iter_bwd_tc" if BWD_IMPL == "tc" else "pn_ms_iter_bwd", _ptr(g), _ptr(Ys[it + 1]), _ptr(Ys[it]), _ptr(X), _ptr(dens[it]),
                  _ptr(norms[it]), B, N, d, _ptr(cinv), _ptr(Gn), _ptr(gd), _ptr(gprev), _ptr(gX), 1, _stream())
             g = gprev
         gX += g            # Y_0 = X.clone()
