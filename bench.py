@@ -190,8 +190,10 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start(); time.sleep(0.3)
-    dominant = "pn_ms_iter_fwd" if FIT_STAGE else "pn_knn"
+    dominant = "pn_ms_iter_fwd_tc" if FIT_STAGE else "pn_knn"
     cabi.TIMED[dominant] = []
+    if FIT_STAGE:
+        cabi.TIMED["pn_ms_iter_bwd_tc"] = []
     barrier()
     cabi.reset_launch_count()
     t_wall0 = time.time()
@@ -205,6 +207,7 @@ def run_ours(args):
     ms_res = ev0.elapsed_time(ev1)
     launches = cabi.launch_count()
     kern_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop(dominant)]
+    bwd_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop("pn_ms_iter_bwd_tc", [])]
     # ---- timed: end to end (H2D of inputs + D2H of the loss inside the region)
     barrier()
     ev2 = torch.cuda.Event(enable_timing=True); ev3 = torch.cuda.Event(enable_timing=True)
@@ -233,13 +236,21 @@ def run_ours(args):
         # dominant kernel: ms_fwd_kernel (one mean-shift iteration over the whole batch, 2 fused N x N x d products)
         alg_flop = B * 4.0 * N_POINTS * N_POINTS * EMB          # 4 N^2 d flop / shape / iteration
         achieved = alg_flop / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms else None
-        roof = {"kernel": "ms_fwd_kernel (pn_ms_iter_fwd: one fused mean-shift iteration, batch of %d shapes)" % B,
+        bwd_launch = float(np.mean(bwd_ms)) if bwd_ms else None
+        roof = {"kernel": "ms_fwd_tc_kernel (pn_ms_iter_fwd_tc: one fused mean-shift iteration, tcgen05 split-TF32, "
+                          "batch of %d shapes)" % B,
                 "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": (achieved / pk["tf_sustained"]) if achieved else None, "traffic": None,
-                "peak_source": pk["source"] + " (cuBLAS bf16, sustained)",
-                "note": "v1 runs fp32-exact on the FP32 FMA pipe (nominal ~72 TFLOP/s), not yet on tcgen05; "
-                        "algorithmic flop = 4*N^2*d per shape per iteration",
-                "launch_ms": per_launch_ms, "launches_timed": len(kern_ms)}
+                "frac": (achieved / pk["tf_sustained"]) if achieved else None, "traffic": 225.0e6,
+                "peak_source": pk["source"] + " (cuBLAS bf16 dense, sustained)",
+                "note": "algorithmic flop = 4*N^2*d per shape per iteration (fp32-accurate result); the kernel issues "
+                        "3 tf32 MMAs per product (split precision), i.e. executes 3x this many tensor flops; "
+                        "traffic = dram read+write bytes per launch from profiles/ (ncu)",
+                "launch_ms": per_launch_ms, "launches_timed": len(kern_ms),
+                "backward": {"kernel": "ms_bwd_tc_kernel<rows> + <cols> (+ prep) per pn_ms_iter_bwd_tc call",
+                             "launch_ms": bwd_launch, "launches_timed": len(bwd_ms),
+                             "achieved": (B * 14.0 * N_POINTS * N_POINTS * EMB / (bwd_launch * 1e-3) / 1e12)
+                             if bwd_launch else None, "unit": "TFLOP/s",
+                             "note": "algorithmic flop = 14*N^2*d per shape per iteration (7 tile products)"}}
     else:
         alg_bytes = B * (N_POINTS * 64 * 4 + N_POINTS * KNN_K * 4)
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else None
