@@ -1,0 +1,71 @@
+"""tcgen05 (split-TF32) mean-shift kernels vs the fp32 FMA-pipe kernels of the same C-ABI contract, and vs the oracle
+port: the tensor-core path must stay fp32-accurate (1e-4 relative on shifted points, 1e-3 on gradients)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B, N, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.nn.functional.normalize(torch.randn(B, N, 128, generator=g), dim=2).cuda()
+    Y = torch.nn.functional.normalize(X + 0.05 * torch.randn(B, N, 128, generator=g).cuda(), dim=2)
+    bw = torch.tensor([0.25, 0.6, 1.2, 0.003][:B] + [0.5] * max(0, B - 4))
+    cinv = (1.0 / (bw * bw)).cuda().contiguous()
+    return X, Y, cinv
+
+
+def _fwd(name, X, Y, cinv):
+    from pnb200.cabi import call
+    B, N, d = X.shape
+    Yn = torch.empty_like(X); den = torch.empty(B, N, device="cuda"); un = torch.empty(B, N, device="cuda")
+    call(name, Y.data_ptr(), X.data_ptr(), B, N, d, cinv.data_ptr(), Yn.data_ptr(), den.data_ptr(), un.data_ptr(),
+         torch.cuda.current_stream().cuda_stream)
+    return Yn, den, un
+
+
+@pytest.mark.parametrize("B,N", [(1, 31), (2, 129), (3, 1000), (4, 2113)])
+def test_tc_forward_matches_fp32_pipe(B, N):
+    X, Y, cinv = _setup(B, N)
+    r = _fwd("pn_ms_iter_fwd", X, Y, cinv)
+    t = _fwd("pn_ms_iter_fwd_tc", X, Y, cinv)
+    for a, b, tol in zip(r, t, (1e-4, 1e-4, 1e-4)):
+        assert torch.isfinite(b).all()
+        assert ((a - b).abs().max() / a.abs().max()).item() < tol
+
+
+@pytest.mark.parametrize("B,N", [(1, 64), (2, 200), (3, 1111)])
+def test_tc_backward_matches_fp32_pipe(B, N):
+    from pnb200.cabi import call
+    X, Y, cinv = _setup(B, N, 1)
+    Yn, den, un = _fwd("pn_ms_iter_fwd", X, Y, cinv)
+    g = torch.randn_like(X)
+    outs = []
+    for name in ("pn_ms_iter_bwd", "pn_ms_iter_bwd_tc"):
+        Gn = torch.empty_like(X); gd = torch.empty(B, N, device="cuda")
+        gY = torch.empty_like(X); gX = torch.randn_like(X) * 0 + 0.5        # accumulate onto a known value
+        call(name, g.data_ptr(), Yn.data_ptr(), Y.data_ptr(), X.data_ptr(), den.data_ptr(), un.data_ptr(), B, N, 128,
+             cinv.data_ptr(), Gn.data_ptr(), gd.data_ptr(), gY.data_ptr(), gX.data_ptr(), 1,
+             torch.cuda.current_stream().cuda_stream)
+        outs.append((gY, gX))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.isfinite(b).all()
+        assert ((a - b).abs().max() / a.abs().max()).item() < 1e-3
+
+
+def test_tc_full_iterations_vs_oracle_port():
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as port
+    from pnb200 import meanshift as pms
+    assert pms.FWD_IMPL == "tc" and pms.BWD_IMPL == "tc"
+    X, _ = clustered_embedding(1500, 128, 6, 5)
+    Xd = X.cuda().unsqueeze(0).requires_grad_()
+    Y = pms.mean_shift_iters(Xd, torch.tensor([0.3]).cuda(), 10)
+    w = torch.randn(1500, 128, generator=torch.Generator().manual_seed(2))
+    (Y[0] * w.cuda()).sum().backward()
+    xr = X.clone().requires_grad_()
+    yr = port.mean_shift_iters(xr, torch.tensor(0.3), 10)
+    (yr * w).sum().backward()
+    assert ((Y[0].cpu() - yr).abs().max() / yr.abs().max()).item() < 1e-4
+    assert ((Xd.grad[0].cpu() - xr.grad).abs().max() / xr.grad.abs().max()).item() < 1e-3
