@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
         const int row = q * 32 + lane;
         const uint32_t la = (uint32_t)(q * 32) << 16;
         const bool ok = (i0 + row) < N;
-        const float c = cinv[b];
+        const float c2 = cinv[b] * 1.4426950408889634f;          // exp(e) = 2^(e * log2 e); clamp moves to the log2 domain
+        const float CL2 = CLAMP * 1.4426950408889634f;
         const float* yr = Yb + (long long)(i0 + row) * D + 64 * h;
         // Y row half -> TMEM (tf32 big / small)
 #pragma unroll 1
@@ -112,9 +113,9 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
             mbar_arrive(&bars.s_empty[k]);
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
-                float e = (__uint_as_float(sv[u]) - 1.0f) * c;
-                e = fminf(fmaxf(e, -CLAMP), CLAMP);
-                float p = (j0 + u < N) ? __expf(e) : 0.f;
+                float e = (__uint_as_float(sv[u]) - 1.0f) * c2;
+                e = fminf(fmaxf(e, -CL2), CL2);
+                float p = (j0 + u < N) ? ex2_approx(e) : 0.f;
                 den += p;
                 float big = tf32_hi(p);
                 pb[u] = __float_as_uint(big);

@@ -73,6 +73,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
         const int vrow = q * 32 + lane;                         // TMEM lane
         const uint32_t la = (uint32_t)(q * 32) << 16;
         const float c = cinv[b];
+        const float c2 = c * 1.4426950408889634f, CL2 = CLAMP * 1.4426950408889634f;
         // ---- A operand rows -> TMEM (split)
         const float* arow;
         bool aok;
@@ -141,10 +142,10 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
                         float g = ex[vrow * 32 + ((16 * h + u + vrow) & 31)];
-                        float e = (__uint_as_float(sv[u]) - 1.0f) * c;
-                        const bool cl = (e > CLAMP) || (e < -CLAMP);
-                        e = fminf(fmaxf(e, -CLAMP), CLAMP);
-                        float kk = __expf(e);
+                        float e = (__uint_as_float(sv[u]) - 1.0f) * c2;
+                        const bool cl = (e > CL2) || (e < -CL2);
+                        e = fminf(fmaxf(e, -CL2), CL2);
+                        float kk = ex2_approx(e);
                         float p = (!cl && (j0 + u < N)) ? (g + gd_row) * kk * c : 0.f;
                         float big = tf32_hi(p);
                         pb[u] = __float_as_uint(big);
@@ -163,10 +164,10 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                 for (int u = 0; u < 8; ++u) {
                     const bool iv = (i0t + u) < N;
                     const float gdi = iv ? gdb[i0t + u] : 0.f;
-                    float e = (__uint_as_float(s8[u]) - 1.0f) * c;
-                    const bool cl = (e > CLAMP) || (e < -CLAMP);
-                    e = fminf(fmaxf(e, -CLAMP), CLAMP);
-                    float kk = iv ? __expf(e) : 0.f;
+                    float e = (__uint_as_float(s8[u]) - 1.0f) * c2;
+                    const bool cl = (e > CL2) || (e < -CL2);
+                    e = fminf(fmaxf(e, -CL2), CL2);
+                    float kk = iv ? ex2_approx(e) : 0.f;
                     float p1 = (!cl && iv) ? (__uint_as_float(g8[u]) + gdi) * kk * c : 0.f;
                     float b1 = tf32_hi(p1), b2 = tf32_hi(kk);
                     pb[u] = __float_as_uint(b1);       ps[u] = __float_as_uint(p1 - b1);       // gS^T -> cols 8h..

@@ -171,6 +171,12 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// 2^x, one MUFU (inputs here are clamped to |x| <= 75*log2(e) < 126, so no denormal handling is needed)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // "big" part of a split-TF32 operand by truncation (one LOP3): x = big + small exactly, small has <= 13 significant
 // bits and is itself truncated to tf32 by the tensor core (error <= 2^-21 |x|)
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }

@@ -15,6 +15,8 @@ BW_FLOOR = 0.003      # mean_shift.py:34
 # forward iteration kernel: "tc" = tcgen05 split-TF32 tensor-core kernel (csrc/meanshift_tc.cu), "simt" = fp32 FMA kernel
 FWD_IMPL = os.environ.get("PN_MS_FWD", "tc")
 BWD_IMPL = os.environ.get("PN_MS_BWD", "tc")
+KTH_IMPL = os.environ.get("PN_MS_KTH", "tc")
+_KTH = {"tc": "pn_ms_kth_dist_tc", "simt": "pn_ms_kth_dist"}
 SQRT_FLOOR = 1e-6     # guard_sqrt(top_k, 1e-6), mean_shift.py:135
 
 
@@ -77,7 +79,7 @@ def compute_bandwidth(X_nd, num_samples, quantile, rng=np.random):
     if S < N:                                   # a strict subset: the choice of rows matters
         rows = torch.from_numpy(L[:S].astype(np.int32)).to(X.device)
     kth = torch.empty((S,), dtype=torch.float32, device=X.device)
-    call("pn_ms_kth_dist", _ptr(X), _ptr(rows), 1, S, N * d, d, K, _ptr(kth), _stream())
+    call(_KTH[KTH_IMPL], _ptr(X), _ptr(rows), 1, S, N * d, d, K, _ptr(kth), _stream())
     return torch.sqrt(torch.clamp(kth, min=SQRT_FLOOR)).mean()
 
 
@@ -93,7 +95,7 @@ def compute_bandwidth_batched(X_bnd, num_samples, quantile, rng=np.random):
     K = int(quantile * num_samples)
     X = X_bnd.detach().contiguous()
     kth = torch.empty((B, N), dtype=torch.float32, device=X.device)
-    call("pn_ms_kth_dist", _ptr(X), None, B, N, N * d, d, K, _ptr(kth), _stream())
+    call(_KTH[KTH_IMPL], _ptr(X), None, B, N, N * d, d, K, _ptr(kth), _stream())
     return torch.sqrt(torch.clamp(kth, min=SQRT_FLOOR)).mean(1)
 
 

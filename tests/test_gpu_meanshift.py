@@ -75,7 +75,7 @@ def test_bandwidth_subset_and_large_k():
     for num_samples, q in [(1000, 0.05), (10000, 0.1), (1500, 0.5)]:
         np.random.seed(3); want = port.compute_bandwidth(X, num_samples, q)
         np.random.seed(3); got = pms.compute_bandwidth(X.cuda(), num_samples, q)
-        assert abs(got.item() - want.item()) <= 2e-6 * want.item(), (num_samples, q, got.item(), want.item())
+        assert abs(got.item() - want.item()) <= 1e-5 * want.item(), (num_samples, q, got.item(), want.item())
 
 
 def test_nms_labels_bit_exact_vs_port():

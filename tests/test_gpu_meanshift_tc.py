@@ -11,7 +11,7 @@ def _setup(B, N, seed=0):
     g = torch.Generator().manual_seed(seed)
     X = torch.nn.functional.normalize(torch.randn(B, N, 128, generator=g), dim=2).cuda()
     Y = torch.nn.functional.normalize(X + 0.05 * torch.randn(B, N, 128, generator=g).cuda(), dim=2)
-    bw = torch.tensor([0.25, 0.6, 1.2, 0.003][:B] + [0.5] * max(0, B - 4))
+    bw = torch.tensor([0.8, 0.6, 1.2, 0.003][:B] + [0.5] * max(0, B - 4))   # (tiny bandwidths make the gradient a pure cancellation)
     cinv = (1.0 / (bw * bw)).cuda().contiguous()
     return X, Y, cinv
 
@@ -69,3 +69,17 @@ def test_tc_full_iterations_vs_oracle_port():
     (yr * w).sum().backward()
     assert ((Y[0].cpu() - yr).abs().max() / yr.abs().max()).item() < 1e-4
     assert ((Xd.grad[0].cpu() - xr.grad).abs().max() / xr.grad.abs().max()).item() < 1e-3
+
+
+@pytest.mark.parametrize("B,S,K", [(1, 100, 7), (2, 1000, 250), (2, 1500, 1499), (1, 333, 1)])
+def test_tc_kth_distance_matches_fp32_pipe_and_torch(B, S, K):
+    from pnb200.cabi import call
+    X, _, _ = _setup(B, S, 3)
+    outs = []
+    for name in ("pn_ms_kth_dist", "pn_ms_kth_dist_tc"):
+        kth = torch.empty(B, S, device="cuda")
+        call(name, X.data_ptr(), None, B, S, S * 128, 128, K, kth.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        outs.append(kth)
+    ref = torch.stack([torch.topk(2 - 2 * X[b] @ X[b].t(), K, dim=1, largest=False)[0][:, -1] for b in range(B)])
+    for o in outs:
+        assert (o - ref).abs().max().item() < 2e-6
