@@ -78,6 +78,16 @@ int pn_ms_kth_dist(const float* X, const int* rows, int B, int S, long long shap
 /* replaces: MeanShift.nms: src/mean_shift.py:146-149 (mode 0), :163-171 (mode 1), :177-178 (mode 2) */
 int pn_ms_argsel(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream);
 
+/* ---- meanshift_tc.cu / meanshift_tc_bwd.cu / meanshift_tc_kth.cu (tcgen05 split-TF32 versions, d must be 128) ---- */
+/* replaces: MeanShift.mean_shift_ (one iteration): src/mean_shift.py:58-77 — same contract as pn_ms_iter_fwd */
+int pn_ms_iter_fwd_tc(const float* Y, const float* X, int B, int N, int d, const float* cinv, float* Ynew, float* den, float* unorm, void* stream);
+/* replaces: autograd of one mean-shift iteration — same contract as pn_ms_iter_bwd */
+int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const float* Yprev, const float* X, const float* den, const float* unorm, int B, int N, int d, const float* cinv, float* ws_Gn, float* ws_gd, float* gYprev, float* gX, int accumulate_gX, void* stream);
+/* replaces: MeanShift.compute_bandwidth: src/mean_shift.py:130-135 — same contract as pn_ms_kth_dist */
+int pn_ms_kth_dist_tc(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K, float* kth, void* stream);
+/* replaces: (debug aid, no reference counterpart: host-mapped progress words written by the tcgen05 pipelines; NULL disables) */
+int pn_debug_set_progress(int* host_mapped_words);
+
 /* ---- pointwise.cu ---- */
 /* replaces: F.relu(bnmlp1(mlp1(x))).max(dim=2): src/PointNet.py:194-196; x*weights + adaptive_max_pool1d: src/model.py:165-169 */
 int pn_colmax_norm(const float* Y, long long ldy, int B, int N, int C, const float* scale, const float* shift, int act, const float* wts, float* out, int* arg, void* stream);
