@@ -16,6 +16,7 @@ constexpr uint32_t C_AB = 0, C_AS = 128, C_D0 = 256, TMEM_COLS = 512;
 constexpr int XA_BYTES = BN * D * 4, STAGE_BYTES = 2 * XA_BYTES;     // big + small, 32 KB
 constexpr uint32_t XA_LBO = BN * 16, SBO = 128;
 constexpr int HP = 257;                                              // histogram row pitch (words)
+constexpr int CAND = 8;                                              // distinct last-pass bins remembered per row
 
 struct Bars { uint64_t x_full[NSTAGE], x_empty[NSTAGE], s_full[2], s_empty[2], a_ready; };
 
@@ -29,6 +30,11 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
     __shared__ uint32_t tmem_base_s;
     __shared__ unsigned prefix[BM];
     __shared__ int krem[BM];
+    // last pass: first column seen in every occupied low-byte bin, packed (bin << 24) | column.  The K-th element's
+    // column lets the epilogue recompute that ONE distance with an fp32 FMA chain: the tensor core accumulates with
+    // truncation, which biases every S by the same ~1e-6 (harmless for the ranking, visible in the bandwidth mean).
+    __shared__ unsigned cand[BM][CAND];
+    __shared__ int ncand[BM];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, i0 = blockIdx.x * BM;
@@ -45,7 +51,7 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
         mbar_fence_init();
     }
     for (int e = tid; e < BM * HP; e += NT) hist[e] = 0u;
-    if (tid < BM) { prefix[tid] = 0u; krem[tid] = K; }
+    if (tid < BM) { prefix[tid] = 0u; krem[tid] = K; ncand[tid] = 0; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -101,7 +107,14 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
                     const float dist = 2.0f - 2.0f * __uint_as_float(sv[u]);
                     const unsigned key = f2ord(dist);
                     const bool match = (pass == 0) || ((key >> (shift + 8)) == (pf >> (shift + 8)));
-                    if (match) atomicAdd(&hrow[(key >> shift) & 255u], 1u);
+                    if (match) {
+                        const unsigned bin = (key >> shift) & 255u;
+                        const unsigned old = atomicAdd(&hrow[bin], 1u);
+                        if (pass == 3 && old == 0u) {
+                            const int slot = atomicAdd(&ncand[row], 1);
+                            if (slot < CAND) cand[row][slot] = (bin << 24) | (unsigned)(j0 + u);
+                        }
+                    }
                 }
             }
             if (t == ntiles - 1) {
@@ -123,7 +136,28 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
-        if (h == 0 && ok) kth[(long long)b * S + i0 + row] = ord2f(prefix[row]);
+        if (h == 0 && ok) {
+            float val = ord2f(prefix[row]);
+            const unsigned digit = prefix[row] & 255u;
+            const int nc = min(ncand[row], CAND);
+            int jsel = -1;
+            for (int c = 0; c < nc; ++c)
+                if ((cand[row][c] >> 24) == digit) jsel = (int)(cand[row][c] & 0xffffffu);
+            if (jsel >= 0) {
+                // exact fp32 value of the selected pair (4 interleaved FMA chains)
+                const float4* xi = reinterpret_cast<const float4*>(row_ptr(i0 + row));
+                const float4* xj = reinterpret_cast<const float4*>(row_ptr(jsel));
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+                for (int c = 0; c < D / 4; ++c) {
+                    const float4 u4 = xi[c], v4 = xj[c];
+                    a0 = fmaf(u4.x, v4.x, a0); a1 = fmaf(u4.y, v4.y, a1);
+                    a2 = fmaf(u4.z, v4.z, a2); a3 = fmaf(u4.w, v4.w, a3);
+                }
+                val = 2.0f - 2.0f * ((a0 + a1) + (a2 + a3));
+            }
+            kth[(long long)b * S + i0 + row] = val;
+        }
     } else if (warp < MMA_WARP) {
         const int lw = warp - LOAD_WARP0;
         const int j = lane;
@@ -204,7 +238,7 @@ extern "C" int pn_ms_kth_dist_tc(const float* X, const int* rows, int B, int S, 
                                  float* kth, void* stream) {
     PN_REQUIRE(X && kth, "pn_ms_kth_dist_tc: null pointer");
     PN_REQUIRE(d == mstck::D, "pn_ms_kth_dist_tc: embedding width must be %d (got %d)", mstck::D, d);
-    PN_REQUIRE(K >= 1 && K <= S, "pn_ms_kth_dist_tc: need 1 <= K <= S (K=%d S=%d)", K, S);
+    PN_REQUIRE(K >= 1 && K <= S && S < (1 << 24), "pn_ms_kth_dist_tc: need 1 <= K <= S < 2^24 (K=%d S=%d)", K, S);
     size_t sm = mstck::NSTAGE * mstck::STAGE_BYTES + (size_t)mstck::BM * mstck::HP * sizeof(unsigned) + 1024;
     PN_CUDA(cudaFuncSetAttribute(mstck::ms_kth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(cdiv(S, mstck::BM), B);
