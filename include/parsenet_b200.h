@@ -114,6 +114,12 @@ int pn_triplet_bwd(const float* E, long long lde, int D, const int* a_idx, const
 /* replaces: ComputePrimitiveDistance.distance_from_{plane,sphere,cylinder,cone}: src/primitives.py:100-195 */
 int pn_residual_fwd(const float* P, const int* seg, int N, const int* type, const float* par, int S, float* sumf_zeroed, float* jac_zeroed, float* cnt_zeroed, void* stream);
 
+/* ---- small3.cu ---- */
+/* replaces: CustomSVD (torch.svd of the weighted (m,3) matrix, via the eigen-decomposition of its 3x3 Gram matrix): src/fitting_utils.py:420-455; torch.eig in pca_torch :585 */
+int pn_sym3_eigh(const double* G, int S, double* w_asc, double* V, void* stream);
+/* replaces: LeastSquares.lstsq + best_lambda (matrix_rank / qr / inverse, Tikhonov retry): src/fitting_utils.py:36-85 */
+int pn_lstsq3(const double* AtA, const double* AtY, int S, int rows, double eps32, double* x, double* Minv, double* lam, void* stream);
+
 /* ---- spline.cu ---- */
 /* replaces: sample_points_from_control_points_: src/fitting_utils.py:609-622; src/loss.py:161-165,179-183 */
 int pn_spline_eval_fwd(const float* Nu, const float* Nv, const float* P, int B, int gu, int gv, int cu, int cv, float* out, void* stream);

@@ -24,14 +24,38 @@ _T10 = {(0, 0, 0): 0, (0, 0, 1): 1, (0, 0, 2): 2, (0, 1, 1): 3, (0, 1, 2): 4, (0
 _T27 = torch.tensor([[[_T10[tuple(sorted((i, j, k)))] for k in range(3)] for j in range(3)] for i in range(3)])
 
 
+_DEV_CONST = {}
+
+
+def _dev_const(name, t, device):
+    """index tables live on the device once (a .to(device) per call is a blocking pageable H2D copy)"""
+    key = (name, str(device))
+    c = _DEV_CONST.get(key)
+    if c is None:
+        c = _DEV_CONST[key] = t.to(device)
+    return c
+
+
 def sym6(v):
     """(S,6) [xx,xy,xz,yy,yz,zz] -> (S,3,3)"""
-    return v[:, _SYM6.to(v.device)]
+    return v[:, _dev_const("sym6", _SYM6, v.device)]
 
 
 def sym10(v):
     """(S,10) unique entries of a symmetric 3-tensor -> (S,3,3,3)"""
-    return v[:, _T27.to(v.device)]
+    return v[:, _dev_const("t27", _T27, v.device)]
+
+
+def eigh3(G):
+    """(S,3,3) float64 symmetric -> eigenvalues ascending (S,3), eigenvectors in columns (S,3,3); never synchronises
+    (csrc/small3.cu; torch.linalg.eigh on CUDA blocks the host on the cusolver info read-back)"""
+    G = G.detach().to(torch.float64).contiguous()
+    S = G.shape[0]
+    w = torch.empty((S, 3), dtype=torch.float64, device=G.device)
+    V = torch.empty((S, 3, 3), dtype=torch.float64, device=G.device)
+    if S:
+        call("pn_sym3_eigh", _ptr(G), S, _ptr(w), _ptr(V), _stream())
+    return w, V
 
 
 # ------------------------------------------------------------------------------------------------ moments
@@ -70,7 +94,7 @@ class GramSVDFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, G):
-        evals, evecs = torch.linalg.eigh(G)                    # ascending
+        evals, evecs = eigh3(G)                                # ascending
         V = torch.flip(evecs, dims=[2])
         sv = torch.sqrt(torch.clamp(torch.flip(evals, dims=[1]), min=0.0))
         ctx.save_for_backward(V, sv)
@@ -92,33 +116,35 @@ class GramSVDFn(torch.autograd.Function):
         return V @ inner @ V.transpose(1, 2)
 
 
-def _rank_deficient(evals_desc, rows):
-    """torch.matrix_rank(A) < 3 for A with singular values sqrt(evals) (default tolerance s_max*max(m,3)*eps32)"""
-    s = torch.sqrt(torch.clamp(evals_desc, min=0.0))
-    tol = s[:, 0] * max(rows, 3) * EPS
-    return s[:, 2] <= tol
+class Lstsq3Fn(torch.autograd.Function):
+    """x = (AtA + lambda I)^-1 AtY with the reference's rank rule for lambda (csrc/small3.cuh lstsq3), (S,3,3),(S,3)
+    float64 -> (S,3).  Backward is the one of a linear solve with lambda held fixed (what autograd does for the
+    reference's torch.inverse path): gAtY = M^-1 g, gAtA = -gAtY x^T."""
+
+    @staticmethod
+    def forward(ctx, AtA, AtY, rows):
+        A = AtA.detach().to(torch.float64).contiguous()
+        Y = AtY.detach().to(torch.float64).contiguous()
+        S = A.shape[0]
+        x = torch.empty((S, 3), dtype=torch.float64, device=A.device)
+        minv = torch.empty((S, 3, 3), dtype=torch.float64, device=A.device)
+        lam = torch.empty((S,), dtype=torch.float64, device=A.device)
+        if S:
+            call("pn_lstsq3", _ptr(A), _ptr(Y), S, int(rows), float(EPS), _ptr(x), _ptr(minv), _ptr(lam), _stream())
+        ctx.save_for_backward(x, minv)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        x, minv = ctx.saved_tensors
+        gy = (minv @ g.unsqueeze(2)).squeeze(2)
+        return -gy.unsqueeze(2) * x.unsqueeze(1), gy, None
 
 
 def solve_normal(AtA, AtY, rows):
     """LeastSquares.lstsq in normal-equation form: x = argmin |A x - Y|.  Rank-deficient systems follow the
     reference's regularised branch (lambda = 1e-6 * 10^j, first j making AtA + lambda I full rank)."""
-    with torch.no_grad():
-        ev = torch.flip(torch.linalg.eigvalsh(AtA), dims=[1])
-        bad = _rank_deficient(ev, rows)
-        lam = torch.zeros(AtA.shape[0], dtype=AtA.dtype, device=AtA.device)
-        if bool(bad.any()):
-            cur = torch.full_like(lam, 1e-6)
-            done = ~bad
-            for _ in range(7):
-                evd = ev + cur.unsqueeze(1)
-                ok = (evd[:, 2] > evd[:, 0] * 3 * EPS)
-                newly = ok & ~done
-                lam = torch.where(newly, cur, lam)
-                done = done | ok
-                cur = torch.where(done, cur, cur * 10)
-            lam = torch.where(done, lam, cur)
-    eye = torch.eye(3, dtype=AtA.dtype, device=AtA.device)
-    return torch.linalg.solve(AtA + lam.view(-1, 1, 1) * eye, AtY.unsqueeze(2)).squeeze(2)
+    return Lstsq3Fn.apply(AtA, AtY, rows)
 
 
 # ------------------------------------------------------------------------------------------------ fits from moments
@@ -185,7 +211,7 @@ def fit_cone_apex_axis(mom, rows):
     (primitive_forward.py:808-831).  Returns apex (S,3), axis (S,3), degenerate (S,) bool (cond > 1e5)."""
     nn = sym6(mom[:, M2_NN])
     with torch.no_grad():
-        ev = torch.flip(torch.linalg.eigvalsh(nn), dims=[1])
+        ev = torch.flip(eigh3(nn)[0], dims=[1])
         s = torch.sqrt(torch.clamp(ev, min=0.0))
         degenerate = (s[:, 0] / s[:, 2]) > 1e5
     apex = solve_normal(nn, mom[:, M2_NPN], rows)

@@ -10,6 +10,7 @@ import torch
 from . import ops
 from .cabi import lib, check, call
 from .ops import _ptr, _stream
+from .staging import arena
 
 
 def triplet_sample(labels, N, rng=np.random, max_segments=5):
@@ -19,11 +20,15 @@ def triplet_sample(labels, N, rng=np.random, max_segments=5):
     samples, S_of = [], []
     for i in range(B):
         p = labels[i]
-        uniq = np.unique(p)
+        # rows of every label, ascending, via one stable sort (== np.where(np.isin(p, l))[0] per label)
+        uniq, counts = np.unique(p, return_counts=True)
+        order = np.argsort(p, kind="stable")
+        starts = np.concatenate([[0], np.cumsum(counts)])
         S = min(N // uniq.shape[0] + 1, 30)
         d = {}
-        for l in uniq:
-            d[l] = rng.choice(list(np.where(np.isin(p, l))[0]), S, replace=True)
+        for li, l in enumerate(uniq):
+            # rng.choice(rows, S, replace=True) == rows[rng.randint(0, len(rows), S)] (same legacy draws)
+            d[l] = order[starts[li]:starts[li + 1]][rng.randint(0, counts[li], size=S)]
         samples.append(d)
         S_of.append(S)
     groups = {}
@@ -39,8 +44,8 @@ def triplet_sample(labels, N, rng=np.random, max_segments=5):
         norm = 0
         pairs = []
         for _ in range(min(max_segments * max_segments, L * L)):
-            k1 = rng.choice(L, 1)[0]
-            k2 = rng.choice(L, 1)[0]
+            k1 = rng.randint(0, L, size=1)[0]          # == rng.choice(L, 1)[0], same draws
+            k2 = rng.randint(0, L, size=1)[0]
             if k1 == k2:
                 continue
             norm += 1
@@ -97,11 +102,11 @@ class TripletFn(torch.autograd.Function):
         dev = x.device
         total = torch.zeros((1,), dtype=torch.float32, device=dev)
         saved = []
+        stage = arena("triplet", dev)
+        stage.reset()
         for S, a, n, w in groups:
             T = a.shape[0]
-            a_d = torch.from_numpy(a).to(dev)
-            n_d = torch.from_numpy(n).to(dev)
-            w_d = torch.from_numpy(w).to(dev)
+            a_d, n_d, w_d = stage.upload(a, dev), stage.upload(n, dev), stage.upload(w, dev)
             pl = torch.empty((T,), dtype=torch.float32, device=dev)
             ps = torch.empty((T,), dtype=torch.float32, device=dev)
             call("pn_triplet_fwd", _ptr(E), D, D, _ptr(a_d), _ptr(n_d), T, S, float(margin), _ptr(pl), _ptr(ps),

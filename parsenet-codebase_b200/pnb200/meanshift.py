@@ -132,3 +132,45 @@ def nms(centers_nd, X_nd, b, member=None):
     kept = centers[ids].contiguous()
     labels = _argsel(2, X, kept).long()
     return kept, ids, labels
+
+
+def nms_batched(Y_bnd, X_bnd, bw_b, member=None):
+    """nms (mean_shift.py:139-179) for a batch of shapes with ONE blocking read-back instead of ~5 per shape.
+    Returns (ids, labels, K): ids = list of (K_b,) int64 device tensors (kept centre rows of Y, ascending),
+    labels (B,N) int64 device tensor (position of the nearest kept centre), K = list of K_b (host ints).
+    Same arithmetic as nms(): the occupied-centre rows of the neighbour arg-select are a subset of the all-rows
+    launch used here, and padding the kept list with a repeat of its first entry cannot win an arg-max tie
+    (first occurrence wins)."""
+    Y = Y_bnd.detach().contiguous()
+    X = X_bnd.detach().contiguous()
+    B, N, d = X.shape
+    dev = X.device
+    if member is None:
+        member = nearest_center_batched(X, Y)
+    counts = torch.zeros((B, N), dtype=torch.float32, device=dev)
+    counts.scatter_add_(1, member.long(), torch.ones((B, N), dtype=torch.float32, device=dev))
+    thr = bw_b.detach().to(torch.float32).reshape(B).contiguous()
+    nbr = torch.empty((B, N), dtype=torch.int32, device=dev)
+    call("pn_ms_argsel", 1, _ptr(Y), N * d, N, _ptr(Y), N * d, N, B, d, _ptr(counts), _ptr(thr), _ptr(nbr), _stream())
+    # neighbours chosen by OCCUPIED centres are kept; unoccupied rows scatter into a dump column
+    tgt = torch.where(counts > 0, nbr.long(), torch.full_like(nbr, N, dtype=torch.int64))
+    mark = torch.zeros((B, N + 1), dtype=torch.bool, device=dev)
+    mark.scatter_(1, tgt, torch.ones((B, N), dtype=torch.bool, device=dev))
+    kept = mark[:, :N].nonzero().cpu().numpy()                       # (T,2) rows sorted by (shape, id): THE sync
+    K = np.bincount(kept[:, 0], minlength=B).astype(np.int64)
+    Kmax = int(K.max())
+    starts = np.concatenate([[0], np.cumsum(K)])
+    pad = np.empty((B, Kmax), dtype=np.int64)
+    for b in range(B):
+        ids_b = kept[starts[b]:starts[b + 1], 1]
+        pad[b, :K[b]] = ids_b
+        pad[b, K[b]:] = ids_b[0]
+    from .staging import arena
+    stage = arena("nms", dev)
+    stage.reset()
+    pad_d = stage.upload(pad, dev)
+    centres = torch.gather(Y, 1, pad_d.unsqueeze(2).expand(B, Kmax, d)).contiguous()
+    lab = torch.empty((B, N), dtype=torch.int32, device=dev)
+    call("pn_ms_argsel", 2, _ptr(X), N * d, N, _ptr(centres), Kmax * d, Kmax, B, d, None, None, _ptr(lab), _stream())
+    ids = [pad_d[b, :int(K[b])] for b in range(B)]
+    return ids, lab.long(), [int(k) for k in K]

@@ -99,11 +99,14 @@ class PrimitivesEmbeddingDGCNGn(nn.Module):
                 self.bn_prim_prob1.bias, self.mlp_prim_prob2.weight, self.mlp_prim_prob2.bias)
 
     def forward(self, points, labels, compute_loss=True, idx_override=None):
+        # the label copy blocks the host; do it BEFORE the network is enqueued so the host-side triplet sampling of
+        # loss_function overlaps the kernels (the reference copies after the forward, src/PointNet.py:286)
+        labels_np = labels.data.cpu().numpy() if compute_loss else None
         x4, first_layer_features = self.encoder(points, idx_override)
         emb_pm, primitives_log_prob = HeadFn.apply(x4, first_layer_features.permute(0, 2, 1), *self._head_params())
         embedding = emb_pm.permute(0, 2, 1)                          # (B, emb, N) view, as the reference returns
         if compute_loss:
-            embed_loss = self.loss_function(embedding, labels.data.cpu().numpy())
+            embed_loss = self.loss_function(embedding, labels_np)
         else:
             embed_loss = torch.zeros(1, device=points.device)
         return embedding, primitives_log_prob, embed_loss

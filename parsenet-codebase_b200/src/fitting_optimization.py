@@ -20,13 +20,20 @@ class FittingModule:
         self.closed_control_decoder = closed_decoder if closed_decoder is not None else \
             initialize_closed_spline_model(closed_splinenet_path, 1)
 
+    def _basis_on(self, device):
+        """the 30x20 basis matrices move to the device once (a per-call .to(device) is a blocking pageable copy)"""
+        if self.nu.device != device:
+            self.nu, self.nv = self.nu.to(device), self.nv.to(device)
+
     def forward_pass_open_spline(self, points, ids, weights, if_optimize=False):
+        self._basis_on(points.device)
         rec = forward_pass_open_spline(points.detach().unsqueeze(0), self.open_control_decoder, self.nu, self.nv,
                                        if_optimize=if_optimize, weights=weights)[1]
         self.fitting.parameters[ids] = ["open-spline", rec]
         return rec
 
     def forward_pass_closed_spline(self, points, ids, weights, if_optimize=False):
+        self._basis_on(points.device)
         rec = forward_closed_splines(points.detach().unsqueeze(0), self.closed_control_decoder, self.nu, self.nv,
                                      if_optimize=if_optimize, weights=weights)[2]
         self.fitting.parameters[ids] = ["closed-spline", rec]

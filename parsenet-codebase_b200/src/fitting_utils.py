@@ -8,7 +8,7 @@ import torch
 from pnb200 import fitting as _f
 from pnb200.fitting import spline_eval
 from src.guard import guard_exp
-from src.segment_utils import relaxed_iou_fast, solve_dense, to_one_hot
+from src.segment_utils import iou_cost_host, relaxed_iou_fast, solve_dense, to_one_hot
 
 EPS = float(np.finfo(np.float32).eps)
 
@@ -72,9 +72,7 @@ def weights_normalize(weights, bw):
 
 def match(target, pred_labels):
     """Hungarian matching of predicted clusters to gt segments on 1 - relaxed IoU (50x50)"""
-    lab, clu = to_one_hot(target), to_one_hot(pred_labels)
-    cost = 1.0 - relaxed_iou_fast(clu.unsqueeze(0).float(), lab.unsqueeze(0).float()).data.cpu().numpy()
-    rids, cids = solve_dense(cost[0])
+    rids, cids = solve_dense(iou_cost_host(pred_labels, target))
     return rids, cids, np.unique(target), np.unique(pred_labels)
 
 
@@ -103,20 +101,33 @@ def pca_torch(X):
 
 def standardize_point_torch(point, weights):
     """centre on the weighted mean of the confident points, rotate the minor PCA axis onto x, scale every axis by the
-    extent of the (weighted) confident points.  Returns (points, std (1,3), mean (3,), R (3,3))."""
-    high = weights[:, 0] > 0.8
-    if int(high.sum()) < 400:
-        kk = weights.shape[0] // 4 if weights.shape[0] >= 7500 else weights.shape[0] // 2
-        high = torch.topk(weights[:, 0], kk)[1]
-    wp = point[high] * weights[high]
-    mean = wp.sum(0) / (weights[high].sum() + EPS)
+    extent of the (weighted) confident points.  Returns (points, std (1,3), mean (3,), R (3,3)).
+    The confident subset (w > 0.8, or the top N/4 | N/2 weights when fewer than 400 pass, reference :516-522) is kept
+    as a device-side MASK instead of an index list: sums / extrema over the subset become masked reductions, so the
+    only host round trip left is the 3x3 covariance needed by LAPACK (eigenvector signs must be the reference's)."""
+    from pnb200.staging import arena
+    N = weights.shape[0]
+    w0 = weights[:, 0].detach()
+    thr = w0 > 0.8
+    kk = N // 4 if N >= 7500 else N // 2
+    top = torch.zeros(N, dtype=torch.bool, device=point.device).scatter_(
+        0, torch.topk(w0, kk)[1], torch.ones(kk, dtype=torch.bool, device=point.device))
+    mask = torch.where(thr.sum() < 400, top, thr).unsqueeze(1)                 # (N,1) bool
+    m = mask.to(point.dtype)
+    wm = weights * m
+    mean = (point * wm).sum(0) / (wm.sum() + EPS)
     point = point - mean
-    S, U = pca_torch(point[high])
+    Xm = (point * m).detach()
+    S, U = pca_torch(Xm)
     smallest = U[:, int(torch.min(S[:, 0], 0)[1])].numpy()
-    R = torch.from_numpy(rotation_matrix_a_to_b(smallest, np.array([1, 0, 0])).astype(np.float32)).to(point.device)
+    R_np = rotation_matrix_a_to_b(smallest, np.array([1, 0, 0])).astype(np.float32)
+    R = arena("fit", point.device).upload(R_np, point.device)
+    # the inverse used when mapping the surface back (torch.inverse on the device would block on its info read-back)
+    R._pn_inv = arena("fit", point.device).upload(np.linalg.inv(R_np).astype(np.float32), point.device)
     point = (R @ point.t()).t()
-    wp = point[high] * weights[high]
-    std = (wp.max(0)[0] - wp.min(0)[0]).abs().reshape(1, 3).detach()
+    wp = point * weights
+    inf = torch.full_like(wp, float("inf"))
+    std = (torch.where(mask, wp, -inf).max(0)[0] - torch.where(mask, wp, inf).min(0)[0]).abs().reshape(1, 3).detach()
     return point / (std + EPS), std, mean, R
 
 

@@ -17,7 +17,10 @@ CLOSED_IDS, OPEN_IDS = (0, 6, 7, 9), (2, 8)
 def _unstandardize(x, scale, R, mean):
     """(n,3) standardised -> original frame: scale per axis, inverse rotation, shift"""
     t = x * scale.reshape(1, 3)
-    return (torch.inverse(R) @ t.t()).t() + mean
+    Rinv = getattr(R, "_pn_inv", None)
+    if Rinv is None:
+        Rinv = torch.inverse(R)
+    return (Rinv @ t.t()).t() + mean
 
 
 def forward_pass_open_spline(input_points_, control_decoder, nu, nv, viz=False, weights=None, if_optimize=True):
@@ -156,7 +159,7 @@ def fit_one_shape_torch(data, fitter, weights, bw, eval=False, sample_points=Fal
             cols = [c for p, c in analytic if p == kind_id]
             if not cols:
                 continue
-            sub = mom[torch.as_tensor(cols, device=mom.device)]
+            sub = torch.stack([mom[c] for c in cols], 0)         # (no index upload: that would block the host)
             if fn == "plane":
                 a, dd = _f.fit_planes(sub)
                 for i, c in enumerate(cols):
@@ -171,17 +174,19 @@ def fit_one_shape_torch(data, fitter, weights, bw, eval=False, sample_points=Fal
                     fits[c] = ["cylinder", a[i].float().reshape(3, 1), ce[i].float().reshape(1, 3), r[i].float()]
             else:
                 apex, axis, deg = _f.fit_cone_apex_axis(sub, n_quarter)
-                deg = deg.cpu().numpy()
-                pq, nq = points[0::4], None
+                pq = points[0::4]
+                dev = points.device
+                x_axis = _f._dev_const("x_axis", torch.tensor([1.0, 0.0, 0.0]), dev)
                 for i, c in enumerate(cols):
-                    if deg[i]:
-                        dev = points.device
-                        fits[c] = ["cone", torch.zeros((1, 3), device=dev),
-                                   torch.tensor([[1.0], [0.0], [0.0]], device=dev), torch.zeros(1, device=dev)]
-                        continue
                     wq = (W[0::4, c:c + 1] + EPS)
                     th = _f.cone_theta(pq, wq, apex[i].float(), axis[i].float())
-                    fits[c] = ["cone", apex[i].float().reshape(1, 3), axis[i].float().reshape(3, 1), th]
+                    # ill-conditioned normals (cond > 1e5): constant zero apex / x axis / zero angle (reference
+                    # :818-823), selected on the device so that no flag has to be read back
+                    bad = deg[i]
+                    ap = torch.where(bad, torch.zeros_like(apex[i]), apex[i]).float()
+                    ax = torch.where(bad, x_axis.to(axis.dtype), axis[i]).float()
+                    th = torch.where(bad, torch.zeros_like(th), th)
+                    fits[c] = ["cone", ap.reshape(1, 3), ax.reshape(3, 1), th]
     for prim, d, col, label_index in plan:
         if prim is None:
             recon.append(None)

@@ -11,6 +11,18 @@ from src.utils import chamfer_distance_single_shape
 EPS = np.finfo(np.float32).eps
 
 
+_TYPE_CONST = {}
+
+
+def _type_const(kind, dev):
+    """0-d int32 device constant holding the kernel's type id (uploading a fresh id list per call would block)"""
+    key = (kind, str(dev))
+    t = _TYPE_CONST.get(key)
+    if t is None:
+        t = _TYPE_CONST[key] = torch.tensor(TYPE_ID[kind], dtype=torch.int32, device=dev)
+    return t
+
+
 def _pack(kind, params):
     """-> (8,) parameter row in the kernel's layout"""
     z = params[0].new_zeros
@@ -86,7 +98,7 @@ class ResidualLoss:
             pts = torch.cat([Points[k] for k in analytic], 0).contiguous().float()
             seg = torch.cat([torch.full((Points[k].shape[0],), i, dtype=torch.int32, device=dev)
                              for i, k in enumerate(analytic)])
-            typ = torch.tensor([TYPE_ID[parameters[k][0]] for k in analytic], dtype=torch.int32, device=dev)
+            typ = torch.stack([_type_const(parameters[k][0], dev) for k in analytic])
             dist = ResidualFn.apply(par, pts, seg, typ)
             for i, k in enumerate(analytic):
                 out[k] = [parameters[k][0], dist[i]]

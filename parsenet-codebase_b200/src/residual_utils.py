@@ -10,7 +10,7 @@ from src.fitting_utils import match, to_one_hot, weights_normalize
 from src.mean_shift import MeanShift
 from src.primitive_forward import fit_one_shape_torch
 from src.primitives import ResidualLoss
-from src.segment_utils import SIOU_matched_segments
+from src.segment_utils import SIOU_matched_segments, segment_types_device
 
 
 def convert_to_one_hot(data):
@@ -46,68 +46,117 @@ class Evaluation:
         """embedding (B,N,d), points/normals (B,N,3), labels/primitives numpy (B,N), log-probs (B,P,N).
         Returns ([loss, geometric mean, spline mean, seg IoU, type IoU] per shape, concatenated in order,
         [parameters, cluster ids, weights] of the LAST shape) — the reference is only ever called with B = 1.
-        The mean-shift iterations of all shapes run as ONE batched launch sequence (per-shape bandwidths)."""
+        Bandwidths, mean-shift iterations and the nms of ALL shapes run as batched launches; the host reads the
+        cluster ids back once, does the matching with numpy, and the per-shape fit/residual launches are enqueued
+        without further synchronisation (loss statistics are read back once at the end)."""
         if eval:
             raise NotImplementedError("Evaluation.fitting_loss(eval=True) is outside the hot path")
         from pnb200 import meanshift as _ms
         from pnb200.losses import l2_normalize
+        from pnb200.staging import arena
         B = embedding.shape[0]
+        dev = embedding.device
         embedding = l2_normalize(embedding)
-        prim_pred = torch.max(primitives_log_prob, 1)[1].data.cpu().numpy()
+        prim_pred_dev = torch.max(primitives_log_prob, 1)[1]                          # (B,N), stays on the device
         with torch.no_grad():
             bws = torch.clamp(_ms.compute_bandwidth_batched(embedding, 10000, quantile), min=_ms.BW_FLOOR)
         shifted = _ms.mean_shift_iters(embedding, bws, iterations)
         with torch.no_grad():
             members = _ms.nearest_center_batched(embedding, shifted)
-        out, parameters, cluster_ids, weights = [], None, None, None
+            ids, labels_dev, _ = _ms.nms_batched(shifted, embedding, bws, members)   # one blocking read-back
+        cluster_np = labels_dev.cpu().numpy()
+        bw_host = bws.detach().cpu().numpy()
+        self._stage = arena("fit", dev)
+        self._stage.reset()
+        out, lazies, metrics = [], [], []
+        parameters, weights = None, None
         for b in range(B):
-            with torch.no_grad():
-                _, ids, cluster_ids = _ms.nms(shifted[b], embedding[b], bws[b], member=members[b])
-            center, bandwidth = shifted[b][ids], bws[b]
-            if torch.unique(cluster_ids).shape[0] > 49:      # rare: grow the quantile for this shape only (ref :76-83)
-                center, bandwidth, cluster_ids = self.guard_mean_shift(embedding[b], quantile * 1.2, iterations)
+            center, bandwidth = shifted[b][ids[b]], float(bw_host[b])
+            if np.unique(cluster_np[b]).shape[0] > 49:       # rare: grow the quantile for this shape only (ref :76-83)
+                center, bw_t, cl = self.guard_mean_shift(embedding[b], quantile * 1.2, iterations)
+                cluster_np[b], bandwidth = cl.data.cpu().numpy(), float(bw_t)
             weights = center @ embedding[b].t()
             loss, parameters, _, rows, cols, distance = self.residual_train_mode(
-                points[b], normals[b], labels[b], cluster_ids, primitives[b], weights, bandwidth, lamb=lamb)
+                points[b], normals[b], labels[b], cluster_np[b], primitives[b], weights, bandwidth, lamb=lamb,
+                lazy=True)
+            lazies.append(loss)
             with torch.no_grad():
-                s_iou, p_iou, _, _ = SIOU_matched_segments(labels[b], cluster_ids.data.cpu().numpy(), prim_pred[b],
-                                                           primitives[b], weights.t())
-            out = out + loss + [s_iou, p_iou]
-        return out, [parameters, cluster_ids.data.cpu().numpy(), weights]
+                metrics.append(segment_types_device(prim_pred_dev[b], weights))
+            out.append(loss[0])
+        # ---- ONE read-back for every deferred statistic of the step
+        flat = [t for l in lazies for t in l[1:] if t is not None] + metrics
+        host = torch.cat([t.reshape(-1).double() for t in flat]).cpu().numpy() if flat else np.zeros(0)
+        pos = 0
+        res = []
+        for b in range(B):
+            vals = []
+            for t in lazies[b][1:]:
+                if t is None:
+                    vals.append(None)
+                else:
+                    vals.append(float(host[pos])); pos += 1
+            lazies[b] = vals
+        for b in range(B):
+            K = metrics[b].shape[0]
+            seg_type = host[pos:pos + K].astype(np.int64); pos += K
+            s_iou, p_iou, _, _ = SIOU_matched_segments(labels[b], cluster_np[b], None, primitives[b], None,
+                                                       prim_pred_seg=seg_type)
+            res = res + [out[b]] + lazies[b] + [s_iou, p_iou]
+        return res, [parameters, cluster_np[B - 1], weights]
 
-    def residual_train_mode(self, points, normals, labels, cluster_ids, primitives, weights, bw, lamb=1.0):
+    def residual_train_mode(self, points, normals, labels, cluster_ids, primitives, weights, bw, lamb=1.0,
+                            lazy=False):
+        """match clusters to gt segments (host), fit every matched segment from the membership weights, residuals.
+        lazy=True keeps the loss statistics as device scalars (no synchronisation inside)."""
         if not isinstance(cluster_ids, np.ndarray):
             cluster_ids = cluster_ids.data.cpu().numpy()
         rows, cols, unique_target, unique_pred = match(labels, cluster_ids)
-        data = []
+        stage = getattr(self, "_stage", None)
+        entries, chunks = [], []
         for index, i in enumerate(unique_pred):
             gt_i = labels == cols[i]
             if gt_i.sum() == 0 or (cluster_ids == i).sum() == 0:
                 continue
             l = stats.mode(primitives[gt_i])[0]
-            gt_idx = torch.from_numpy(np.nonzero(gt_i)[0]).to(points.device)
-            data.append([points, normals, l, points[gt_idx], None, (index, i)])
+            entries.append((l, (index, i)))
+            chunks.append(np.nonzero(gt_i)[0])
+        data = []
+        if entries:
+            allidx = np.concatenate(chunks).astype(np.int64)
+            idx_dev = stage.upload(allidx, points.device) if stage is not None else \
+                torch.from_numpy(allidx).to(points.device)
+            o = 0
+            for (l, key), ch in zip(entries, chunks):
+                data.append([points, normals, l, points[idx_dev[o:o + ch.shape[0]]], None, key])
+                o += ch.shape[0]
         w = weights_normalize(weights, float(bw)).t()
         gt_points, _ = fit_one_shape_torch(data, self.fitter, w, bw, eval=False)
         distance = self.res_loss.residual_loss(gt_points, self.fitter.fitting.parameters)
-        return self.separate_losses(distance, gt_points, lamb=lamb), self.fitter.fitting.parameters, None, rows, \
-            cols, distance
+        return self.separate_losses(distance, gt_points, lamb=lamb, lazy=lazy), self.fitter.fitting.parameters, \
+            None, rows, cols, distance
 
-    def separate_losses(self, distance, gt_points, lamb=1.0):
+    def separate_losses(self, distance, gt_points, lamb=1.0, lazy=False):
         """mean residual over fitted segments (spline terms weighted by lamb); residuals > 1 are treated as degenerate
-        and replaced by the constant 0.1 (reference :333-378)"""
+        and replaced by the constant 0.1 (reference :333-378).  Returns [loss, geometric mean, spline mean]; the two
+        means are python floats (or None), or 0-d device tensors when lazy=True (nothing synchronises then)."""
         terms, geo, spl = [], [], []
         for v in sorted(gt_points.keys()):
             if gt_points[v] is None:
                 continue
-            if distance[v][1] > 1:
-                distance[v][1] = torch.ones(1, device=distance[v][1].device)[0] * 0.1
+            d = distance[v][1]
+            d = torch.where(d > 1, torch.full_like(d, 0.1), d)
+            distance[v][1] = d
             if distance[v][0] in ("closed-spline", "open-spline"):
-                spl.append(distance[v][1].item())
-                terms.append(distance[v][1] * lamb)
+                spl.append(d.detach().reshape(()))
+                terms.append(d * lamb)
             else:
-                geo.append(distance[v][1].item())
-                terms.append(distance[v][1])
+                geo.append(d.detach().reshape(()))
+                terms.append(d)
         dev = next(iter(distance.values()))[1].device if distance else "cuda"
-        loss = torch.mean(torch.stack(terms)) if terms else torch.zeros(1, device=dev)
-        return [loss, float(np.mean(geo)) if geo else None, float(np.mean(spl)) if spl else None]
+        loss = torch.mean(torch.stack([t.reshape(()) for t in terms])) if terms else torch.zeros(1, device=dev)
+        g = torch.stack(geo).double().mean() if geo else None
+        sp = torch.stack(spl).double().mean() if spl else None
+        if not lazy:
+            g = float(g) if g is not None else None
+            sp = float(sp) if sp is not None else None
+        return [loss, g, sp]

@@ -55,18 +55,53 @@ def mean_IOU_primitive_segment(matching, predicted_labels, labels, pred_prim, gt
     return np.mean(ious), np.mean(prim_ious), pairs
 
 
-def SIOU_matched_segments(target, pred_labels, primitives_pred, primitives, weights):
+_MERGE = ((0, 9), (6, 9), (7, 9), (8, 2))          # closed splines -> 9, open splines -> 2 (reference :151-159)
+_MERGE_LUT = {}
+
+
+def iou_cost_host(pred_labels, target, K=50):
+    """1 - relaxed IoU between the one-hot memberships of two label vectors, from their K x K confusion matrix.
+    Bit-identical to `1 - relaxed_iou_fast(to_one_hot(pred), to_one_hot(target))`: every count is an integer
+    < 2^24, so the fp32 matmul of the reference is exact and the remaining arithmetic is the same fp32 expression."""
+    pred_labels = np.asarray(pred_labels).astype(np.int64)
+    target = np.asarray(target).astype(np.int64)
+    if pred_labels.min() < 0 or target.min() < 0 or pred_labels.max() >= K or target.max() >= K:
+        raise ValueError(f"labels must lie in [0, {K})")
+    conf = np.bincount(pred_labels * K + target, minlength=K * K).reshape(K, K).astype(np.float32)
+    n_p, n_g = conf.sum(1, keepdims=True), conf.sum(0, keepdims=True)
+    return np.float32(1.0) - conf / (n_p + n_g - conf + np.float32(1e-7))
+
+
+def segment_types_device(prim_pred_point, weights_kn):
+    """per-point predicted primitive ids (N,) int64 + membership weights (K,N) -> (K,) majority type of every cluster
+    (reference: to_one_hot(primitives_pred, 10) after the type merge, primitive_type_segment_torch).  Device only."""
+    dev = weights_kn.device
+    lut = _MERGE_LUT.get(str(dev))
+    if lut is None:
+        table = np.arange(10)
+        for src, dst in _MERGE:
+            table[src] = dst
+        lut = _MERGE_LUT[str(dev)] = torch.from_numpy(table).to(dev)
+    merged = lut[prim_pred_point]
+    hot = torch.zeros((merged.shape[0], 10), device=dev).scatter_(1, merged.unsqueeze(1), 1.0)
+    return torch.max(hot.t() @ weights_kn.t(), 0)[1]
+
+
+def SIOU_matched_segments(target, pred_labels, primitives_pred, primitives, weights, prim_pred_seg=None):
     """segment IoU + primitive-type IoU over Hungarian-matched (predicted, gt) segments.
-    NOTE: like the reference, the primitive-id arrays are merged in place (0,6,7 -> 9; 8 -> 2)."""
+    NOTE: like the reference, the primitive-id arrays are merged in place (0,6,7 -> 9; 8 -> 2).
+    prim_pred_seg: optional precomputed (K,) majority type per cluster (segment_types_device), in which case
+    primitives_pred / weights are not needed and nothing touches the device."""
     for arr in (primitives, primitives_pred):
-        for src, dst in ((0, 9), (6, 9), (7, 9), (8, 2)):
+        if arr is None:
+            continue
+        for src, dst in _MERGE:
             arr[arr == src] = dst
-    dev = weights.device.index if weights.is_cuda else 0
-    lab_hot, clu_hot = to_one_hot(target, device_id=dev), to_one_hot(pred_labels, device_id=dev)
-    cost = 1.0 - relaxed_iou_fast(clu_hot.unsqueeze(0).float(), lab_hot.unsqueeze(0).float()).data.cpu().numpy()
-    matching = [list(solve_dense(cost[0]))]
-    prim_hot = to_one_hot(primitives_pred, 10, dev).float()
-    prim_pred = primitive_type_segment_torch(prim_hot, weights).data.cpu().numpy()
-    s_iou, p_iou, pairs = mean_IOU_primitive_segment(matching, pred_labels[None], target[None], prim_pred[None],
+    matching = [list(solve_dense(iou_cost_host(pred_labels, target)))]
+    if prim_pred_seg is None:
+        dev = weights.device
+        pp = torch.from_numpy(np.asarray(primitives_pred).astype(np.int64)).to(dev)
+        prim_pred_seg = segment_types_device(pp, weights.t()).data.cpu().numpy()
+    s_iou, p_iou, pairs = mean_IOU_primitive_segment(matching, pred_labels[None], target[None], prim_pred_seg[None],
                                                      primitives[None])
     return s_iou, p_iou, matching, pairs

@@ -224,9 +224,9 @@ def test_evaluation_fitting_loss_vs_reference(golden_dir, variant):
     captured = {}
     orig_sep = ev.separate_losses
 
-    def sep(distance, gt_points, lamb=1.0):
+    def sep(distance, gt_points, lamb=1.0, **kw):
         captured.update({k: (v[0], float(v[1])) for k, v in distance.items()})
-        return orig_sep(distance, gt_points, lamb=lamb)
+        return orig_sep(distance, gt_points, lamb=lamb, **kw)
 
     ev.separate_losses = sep
     res, extra = ev.fitting_loss(E, torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda(), lab, prim.copy(),

@@ -55,16 +55,17 @@ def phased_step(i, rec):
 for i in range(2):
     phased_step(i, [])
 rec = []
-for i in range(3):
+for i in range(int(os.environ.get("PROF_STEPS", "3"))):
     phased_step(10 + i, rec)
 names = ["seg-net fwd + triplet", "nll + input slices", "fitting_loss (bandwidth, mean-shift, nms, match, fit, residual)",
          "backward", "adam"]
 with open(out + "_phases.txt", "w") as f:
     a = np.array(rec) * 1e3
-    f.write("# wall ms per phase (sync after each phase), mean of 3 steps, B=16 x N=10000\n")
+    f.write(f"# wall ms per phase (sync after each phase), mean of {len(rec)} steps, B=16 x N=10000\n")
     for n, m in zip(names, a.mean(0)):
         f.write(f"{m:9.2f} ms  {n}\n")
     f.write(f"{a.sum(1).mean():9.2f} ms  total\n")
+    f.write("# per step: " + " | ".join(" ".join(f"{v:.1f}" for v in row) for row in a) + "\n")
 print(open(out + "_phases.txt").read())
 
 # ---- kernel table
@@ -88,6 +89,8 @@ with open(out + "_kernels.txt", "w") as f:
     for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
         f.write(f"| `{n}` | {c} | {t / 1e3:.3f} | {100 * t / tot:.1f}% |\n")
 print(open(out + "_kernels.txt").read()[:6000])
+with open(out + "_cpu_ops.txt", "w") as f:
+    f.write(p.key_averages().table(sort_by="self_cpu_time_total", row_limit=40, max_name_column_width=70))
 
 # ---- host synchronisation points
 torch.cuda.set_sync_debug_mode("warn")
