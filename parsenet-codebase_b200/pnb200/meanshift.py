@@ -39,7 +39,8 @@ class MeanShiftItersFn(torch.autograd.Function):
                  _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
             Ys.append(Yn); dens.append(den); norms.append(un)
         ctx.saved = (X, cinv, Ys, dens, norms)
-        return Ys[-1].clone() if iterations == 0 else Ys[-1]
+        # (fresh view: an output object kept in ctx would form a reference cycle, see segnet.EncoderFn.forward)
+        return Ys[-1].clone() if iterations == 0 else Ys[-1].view_as(Ys[-1])
 
     @staticmethod
     def backward(ctx, g):

@@ -58,7 +58,9 @@ class EncoderFn(torch.autograd.Function):
         ctx.layers, ctx.xf, ctx.Y1, ctx.nm, ctx.arg, ctx.ext, ctx.wm2 = layers, xf, Y1, nm, arg, ext, wm2
         ctx.shapes = [p.shape for p in params]
         ctx.idx_list = [l["idx"] for l in layers]
-        return x4, xf
+        # outputs are returned as fresh views: an output object stored in ctx would close a reference cycle
+        # (ctx -> tensor -> grad_fn -> ctx) that only the cyclic GC frees, i.e. GBs of activations per step would pile up
+        return x4, xf.view_as(xf)
 
     @staticmethod
     def backward(ctx, g4, gxf):
@@ -138,7 +140,7 @@ class HeadFn(torch.autograd.Function):
         ctx.t = dict(x4=x4, xf=xf, W1=W1, Wg=Wg, Wl=Wl, W2=W2, Ws1=Ws1, Ws2=Ws2, Wp1=Wp1, Wp2=Wp2, Y1=Y1, Y2=Y2,
                      Ye=Ye, Yp=Yp, f1=f1, f2=f2, fe=fe, fp=fp, logp=logp)
         ctx.shapes = [p.shape for p in params]
-        return emb, logp
+        return emb, logp.view_as(logp)      # (fresh view: see EncoderFn.forward)
 
     @staticmethod
     def backward(ctx, gemb, glogp):

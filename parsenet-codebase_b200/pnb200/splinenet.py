@@ -100,7 +100,7 @@ class SplineNetFn(torch.autograd.Function):
         ctx.shapes = [p.shape for p in params]
         ctx.has_w = weights is not None
         ctx.wshape = None if weights is None else weights.shape
-        return out
+        return out.view_as(out)             # (fresh view: see segnet.EncoderFn.forward)
 
     @staticmethod
     def backward(ctx, gout):
