@@ -59,7 +59,8 @@ def build(force=False, verbose=False):
                     sys.stderr.write(out)
                 if rc != 0:
                     raise RuntimeError(f"nvcc failed on {src}")
-    if jobs or not os.path.exists(LIB):
+    stale = not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
+    if jobs or stale:
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
         p = subprocess.run(cmd, capture_output=True, text=True)
         if p.returncode != 0:

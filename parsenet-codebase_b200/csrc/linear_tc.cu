@@ -1,0 +1,269 @@
+// Per-point linear layer forward on the 5th-gen tensor cores (tcgen05 + TMEM), split-TF32 (3 MMAs per product) for
+// fp32-level accuracy.  Same contract as linear_fwd_kernel in linear.cu:
+//   Y = act(norm(A)) . W^T + bias (+ per-shape bias),  epilogue accumulates sum / sum^2 of Y per (shape, group)
+// Replaces Conv1d/Conv2d(k=1) + GroupNorm + ReLU chains, src/PointNet.py:157-165,194-196,274-284; src/model.py:155-176.
+//
+// One CTA = one 128 x 128 output tile, 9 warps, warp-specialised and mbarrier-pipelined:
+//   warps 0-3 epilogue : thread = output row (TMEM lane).  accumulator TMEM -> regs, + bias, group statistics, store
+//   warps 4-7 loaders  : thread = operand row.  A rows: LDG.128 -> producer norm + activation -> tf32 split (big by
+//                        truncation, small = exact remainder) ; W rows: LDG.128 -> split ; both into the K-major
+//                        no-swizzle core-matrix layout [k/4][row/8][8][16 B], 3 stages x 32 KB (16 k per stage)
+//   warp 8     MMA     : one elected lane issues tcgen05.mma kind::tf32 M=128 N=128 K=8, per k-step
+//                        As.Bb, Ab.Bs, Ab.Bb (small terms first) into 128 TMEM columns; tcgen05.commit frees the stage
+// 2 CTAs per SM (96 KB smem, 128 TMEM columns each): one CTA's epilogue overlaps the other's main loop.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace pn {
+namespace lintc {
+using namespace tc05;
+
+constexpr int BM = 128, BN = 128, BK = 16, NSTAGE = 3;
+constexpr int EPI_THREADS = 128, LOAD_WARP0 = 4, LOAD_THREADS = 128, MMA_WARP = 8, NT = 288;
+constexpr int OP_BYTES = BM * BK * 4;                 // one operand part of one stage (8 KB)
+constexpr int STAGE_BYTES = 4 * OP_BYTES;             // A big, A small, W big, W small
+constexpr uint32_t LBO = BM * 16, SBO = 128, TMEM_COLS = 128;
+constexpr int MAXG = 4;                               // statistics groups per 128-column tile (channels/group >= 32)
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+__device__ __forceinline__ float act_fwd(float v, int act) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+    return v;
+}
+
+struct Args {
+    const float* A; long long lda;      // [B*Np][K]
+    const float* W; long long ldw;      // [Nout][K]
+    const float* bias;                  // [Nout] or null
+    const float* sbias;                 // [B][Nout] or null
+    const float* in_scale; const float* in_shift; int in_act;     // [B][K] or null
+    float* Y; long long ldy;            // [B*Np][Nout]
+    double* stats;                      // [S][G][2] or null
+    int B, Np, K, Nout, G, stats_per_shape;
+};
+
+struct Bars { uint64_t full[NSTAGE], empty[NSTAGE], acc_full; };
+
+// grid (tiles_m * B, tiles_n)
+__global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    float* sc_s = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);      // [K] producer scale (or unused)
+    float* sh_s = sc_s + p.K;                                                 // [K] producer shift
+    __shared__ Bars bars;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[BN];
+    __shared__ double gacc[MAXG][2];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_m = (p.Np + BM - 1) / BM;
+    const int b = blockIdx.x / tiles_m;
+    const int m0 = (blockIdx.x % tiles_m) * BM;
+    const int n0 = blockIdx.y * BN;
+    const int nch = (p.K + BK - 1) / BK;
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.full[s], LOAD_THREADS); mbar_init(&bars.empty[s], 1); }
+        mbar_init(&bars.acc_full, 1);
+        mbar_fence_init();
+    }
+    if (p.in_scale)
+        for (int k = tid; k < p.K; k += NT) {
+            sc_s[k] = p.in_scale[(long long)b * p.K + k];
+            sh_s[k] = p.in_shift[(long long)b * p.K + k];
+        }
+    if (tid < BN) {
+        const int n = n0 + tid;
+        float v = 0.f;
+        if (n < p.Nout) {
+            if (p.bias) v += p.bias[n];
+            if (p.sbias) v += p.sbias[(long long)b * p.Nout + n];
+        }
+        bias_s[tid] = v;
+    }
+    if (tid < MAXG * 2) gacc[tid >> 1][tid & 1] = 0.0;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+
+    if (warp < 4) {
+        // =============================================================================== epilogue warps
+        const int row = 32 * warp + lane;
+        const uint32_t la = (uint32_t)(32 * warp) << 16;
+        const int r = m0 + row;
+        const bool ok = r < p.Np;
+        float* yrow = p.Y + ((long long)b * p.Np + (ok ? r : 0)) * p.ldy + n0;
+        const int cpg = p.stats ? p.Nout / p.G : 1;
+        mbar_wait(&bars.acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= p.Nout) break;                       // Nout % 32 == 0 (checked on the host)
+            uint32_t v[32];
+            tmem_ld32(tb + la + c0, v);
+            tmem_ld_wait();
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+                float4 o;
+                o.x = __uint_as_float(v[e]) + bias_s[c0 + e];
+                o.y = __uint_as_float(v[e + 1]) + bias_s[c0 + e + 1];
+                o.z = __uint_as_float(v[e + 2]) + bias_s[c0 + e + 2];
+                o.w = __uint_as_float(v[e + 3]) + bias_s[c0 + e + 3];
+                if (ok) {
+                    *reinterpret_cast<float4*>(yrow + c0 + e) = o;
+                    s += (o.x + o.y) + (o.z + o.w);
+                    q = fmaf(o.x, o.x, q); q = fmaf(o.y, o.y, q); q = fmaf(o.z, o.z, q); q = fmaf(o.w, o.w, q);
+                }
+            }
+            if (p.stats) {
+                double ds = warp_sum((double)s), dq = warp_sum((double)q);
+                if (lane == 0) {
+                    const int gl = (n0 + c0) / cpg - n0 / cpg;       // group of this 32-column chunk, local to the tile
+                    atomicAdd(&gacc[gl][0], ds);
+                    atomicAdd(&gacc[gl][1], dq);
+                }
+            }
+        }
+        tc_fence_before();
+        if (p.stats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tid < MAXG * 2) {
+                const int gl = tid >> 1;
+                const int g = n0 / cpg + gl;
+                if (g < p.G && (long long)g * cpg < (long long)min(p.Nout, n0 + BN) && gacc[gl][tid & 1] != 0.0)
+                    atomicAdd(&p.stats[((long long)(p.stats_per_shape ? b : 0) * p.G + g) * 2 + (tid & 1)],
+                              gacc[gl][tid & 1]);
+            }
+        }
+    } else if (warp < MMA_WARP) {
+        // =============================================================================== loader warps
+        const int lt = tid - LOAD_WARP0 * 32;          // operand row 0..127
+        const int ra = m0 + lt, rw = n0 + lt;
+        const bool oka = ra < p.Np, okw = rw < p.Nout;
+        const float* arow = p.A + ((long long)b * p.Np + (oka ? ra : 0)) * p.lda;
+        const float* wrow = p.W + (long long)(okw ? rw : 0) * p.ldw;
+        const uint32_t roff = (uint32_t)((lt >> 3) * 128 + (lt & 7) * 16);
+        const bool has_norm = p.in_scale != nullptr;
+        const int act = p.in_act;
+        float4 va[4], vw[4], na[4], nw[4];
+        auto fetch = [&](int kc, float4 (&xa)[4], float4 (&xw)[4]) {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int k = kc * BK + 4 * c4;
+                const bool kin = (kc < nch) && (k < p.K);
+                xa[c4] = (kin && oka) ? *reinterpret_cast<const float4*>(arow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xw[c4] = (kin && okw) ? *reinterpret_cast<const float4*>(wrow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        fetch(0, va, vw);
+#pragma unroll 1
+        for (int kc = 0; kc < nch; ++kc) {
+            const int s = kc % NSTAGE;
+            fetch(kc + 1, na, nw);
+            mbar_wait(&bars.empty[s], ((kc / NSTAGE) & 1) ^ 1);
+            unsigned char* st = smem + s * STAGE_BYTES;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                const int k = kc * BK + 4 * c4;
+                float f0 = va[c4].x, f1 = va[c4].y, f2 = va[c4].z, f3 = va[c4].w;
+                if (oka && k < p.K) {
+                    if (has_norm) {
+                        const float4 sc = *reinterpret_cast<const float4*>(sc_s + k);
+                        const float4 sh = *reinterpret_cast<const float4*>(sh_s + k);
+                        f0 = fmaf(f0, sc.x, sh.x); f1 = fmaf(f1, sc.y, sh.y);
+                        f2 = fmaf(f2, sc.z, sh.z); f3 = fmaf(f3, sc.w, sh.w);
+                    }
+                    f0 = act_fwd(f0, act); f1 = act_fwd(f1, act); f2 = act_fwd(f2, act); f3 = act_fwd(f3, act);
+                }
+                const uint32_t o = (uint32_t)(c4 * LBO) + roff;
+                {
+                    const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
+                    *reinterpret_cast<float4*>(st + o) = make_float4(b0, b1, b2, b3);
+                    *reinterpret_cast<float4*>(st + OP_BYTES + o) = make_float4(f0 - b0, f1 - b1, f2 - b2, f3 - b3);
+                }
+                {
+                    const float w0 = vw[c4].x, w1 = vw[c4].y, w2 = vw[c4].z, w3 = vw[c4].w;
+                    const float b0 = tf32_hi(w0), b1 = tf32_hi(w1), b2 = tf32_hi(w2), b3 = tf32_hi(w3);
+                    *reinterpret_cast<float4*>(st + 2 * OP_BYTES + o) = make_float4(b0, b1, b2, b3);
+                    *reinterpret_cast<float4*>(st + 3 * OP_BYTES + o) = make_float4(w0 - b0, w1 - b1, w2 - b2, w3 - b3);
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(&bars.full[s]);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) { va[c4] = na[c4]; vw[c4] = nw[c4]; }
+        }
+    } else {
+        // =============================================================================== MMA warp
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc(2, BM, BN, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+#pragma unroll 1
+        for (int kc = 0; kc < nch; ++kc) {
+            const int s = kc % NSTAGE;
+            mbar_wait(&bars.full[s], (kc / NSTAGE) & 1);
+            tc_fence_after();
+            const uint32_t st = sbase + s * STAGE_BYTES;
+            const uint64_t dab = make_smem_desc(st, LBO, SBO, 0);
+            const uint64_t das = make_smem_desc(st + OP_BYTES, LBO, SBO, 0);
+            const uint64_t dwb = make_smem_desc(st + 2 * OP_BYTES, LBO, SBO, 0);
+            const uint64_t dws = make_smem_desc(st + 3 * OP_BYTES, LBO, SBO, 0);
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * ((2 * LBO) >> 4));
+                    mma_tf32_ss(tb, das + adv, dwb + adv, idesc, (kc | ks) ? 1u : 0u);
+                    mma_tf32_ss(tb, dab + adv, dws + adv, idesc, 1u);
+                    mma_tf32_ss(tb, dab + adv, dwb + adv, idesc, 1u);
+                }
+                mma_commit(&bars.empty[s]);
+            }
+            __syncwarp();
+        }
+        if (leader) mma_commit(&bars.acc_full);
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace lintc
+}  // namespace pn
+
+using namespace pn;
+
+// 1 if pn_linear_fwd_tc accepts this problem (the caller uses pn_linear_fwd otherwise)
+extern "C" int pn_linear_fwd_tc_supported(const float* A, long long lda, const float* W, long long ldw, const float* Y,
+                                          long long ldy, int Np, int K, int Nout, int G, int has_stats) {
+    using namespace lintc;
+    if (!aligned16(A) || !aligned16(W) || !aligned16(Y) || lda % 4 || ldw % 4 || ldy % 4) return 0;
+    if (K % 4 || K < 16 || K > 4096 || Nout % 32 || Nout < 32 || Np < 1) return 0;
+    if (has_stats && (G <= 0 || Nout % G || (Nout / G) % 32)) return 0;
+    return 1;
+}
+
+extern "C" int pn_linear_fwd_tc(const float* A, long long lda, const float* W, long long ldw, const float* bias,
+                                const float* sbias, const float* in_scale, const float* in_shift, int in_act, float* Y,
+                                long long ldy, double* stats, int B, int Np, int K, int Nout, int G,
+                                int stats_per_shape, void* stream) {
+    using namespace lintc;
+    PN_REQUIRE(A && W && Y, "pn_linear_fwd_tc: null pointer");
+    PN_REQUIRE(B > 0 && Np > 0, "pn_linear_fwd_tc: bad shape");
+    PN_REQUIRE(pn_linear_fwd_tc_supported(A, lda, W, ldw, Y, ldy, Np, K, Nout, G, stats != nullptr),
+               "pn_linear_fwd_tc: unsupported problem (K=%d Nout=%d G=%d; need 16-byte aligned rows, K %% 4 == 0, "
+               "Nout %% 32 == 0, channels/group %% 32 == 0)", K, Nout, G);
+    Args p{A, lda, W, ldw, bias, sbias, in_scale, in_shift, in_act, Y, ldy, stats, B, Np, K, Nout, G, stats_per_shape};
+    size_t sm = (size_t)NSTAGE * STAGE_BYTES + 2 * (size_t)K * sizeof(float) + 1024;
+    PN_CUDA(cudaFuncSetAttribute(linear_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid(cdiv(Np, BM) * B, cdiv(Nout, BN));
+    linear_fwd_tc_kernel<<<grid, NT, sm, (cudaStream_t)stream>>>(p);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("linear_fwd_tc_kernel");
+    return PN_OK;
+}
