@@ -59,6 +59,10 @@ int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void*
 /* ---- linear.cu ---- */
 /* replaces: Conv1d/Conv2d(k=1) + GroupNorm/BatchNorm + ReLU chains: src/PointNet.py:157-165,194-196,274-284; src/model.py:74-99,155-176 */
 int pn_linear_fwd(const float* A, long long lda, const float* W, long long ldw, const float* bias, const float* sbias, const float* in_scale, const float* in_shift, int in_act, float* Y, long long ldy, double* stats, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream);
+/* replaces: same as pn_linear_fwd, on the tcgen05 tensor cores (split-TF32, fp32-level accuracy); linear_tc.cu.  Needs 16-byte aligned rows, K % 4 == 0, Nout % 32 == 0 and (with stats) channels-per-group % 32 == 0 */
+int pn_linear_fwd_tc(const float* A, long long lda, const float* W, long long ldw, const float* bias, const float* sbias, const float* in_scale, const float* in_shift, int in_act, float* Y, long long ldy, double* stats, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream);
+/* replaces: (query: 1 if pn_linear_fwd_tc accepts the problem, else the caller uses pn_linear_fwd) */
+int pn_linear_fwd_tc_supported(const float* A, long long lda, const float* W, long long ldw, const float* Y, long long ldy, int Np, int K, int Nout, int G, int has_stats);
 /* replaces: autograd of the same chains (torch built-in in the reference) */
 int pn_linear_bwd_data(const float* dY, long long lddy, const float* W, long long ldw, float* dZ, long long lddz, int accumulate, int finalize, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, const float* gamma, const float* mean_rstd, double* gsum, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream);
 /* replaces: autograd of the same chains (torch built-in in the reference) */

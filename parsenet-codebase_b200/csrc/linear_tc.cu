@@ -4,10 +4,11 @@
 // Replaces Conv1d/Conv2d(k=1) + GroupNorm + ReLU chains, src/PointNet.py:157-165,194-196,274-284; src/model.py:155-176.
 //
 // One CTA = one 128 x 128 output tile, 9 warps, warp-specialised and mbarrier-pipelined:
-//   warps 0-3 epilogue : thread = output row (TMEM lane).  accumulator TMEM -> regs, + bias, group statistics, store
-//   warps 4-7 loaders  : thread = operand row.  A rows: LDG.128 -> producer norm + activation -> tf32 split (big by
-//                        truncation, small = exact remainder) ; W rows: LDG.128 -> split ; both into the K-major
-//                        no-swizzle core-matrix layout [k/4][row/8][8][16 B], 3 stages x 32 KB (16 k per stage)
+//   warps 0-3 epilogue : thread = output row (TMEM lane).  accumulator TMEM -> regs, + bias, group statistics; each warp
+//                        transposes its 32 x 32 chunk through shared memory so that stores are 4 rows x 128 B per STG.128
+//   warps 4-7 loaders  : 4 lanes cover the 64 B a row contributes to a stage (a warp reads 8 rows x 64 B per LDG.128).
+//                        A: producer norm + activation -> tf32 split (big by truncation, small = exact remainder);
+//                        W: split ; both into the K-major no-swizzle core-matrix layout, 3 stages x 32.5 KB (16 k each)
 //   warp 8     MMA     : one elected lane issues tcgen05.mma kind::tf32 M=128 N=128 K=8, per k-step
 //                        As.Bb, Ab.Bs, Ab.Bb (small terms first) into 128 TMEM columns; tcgen05.commit frees the stage
 // 2 CTAs per SM (96 KB smem, 128 TMEM columns each): one CTA's epilogue overlaps the other's main loop.
@@ -20,9 +21,12 @@ using namespace tc05;
 
 constexpr int BM = 128, BN = 128, BK = 16, NSTAGE = 3;
 constexpr int EPI_THREADS = 128, LOAD_WARP0 = 4, LOAD_THREADS = 128, MMA_WARP = 8, NT = 288;
-constexpr int OP_BYTES = BM * BK * 4;                 // one operand part of one stage (8 KB)
+// K-major no-swizzle core-matrix layout [k/4][row/8][8][16 B].  The distance between k-chunks (LBO) is padded by 32 B:
+// a loader quarter-warp stores 2 rows x 4 k-chunks per STS.128, which then lands in 8 distinct 16-byte bank groups.
+constexpr uint32_t LBO = BM * 16 + 32, SBO = 128, TMEM_COLS = 128;
+constexpr int OP_BYTES = (BK / 4) * LBO;              // one operand part of one stage
 constexpr int STAGE_BYTES = 4 * OP_BYTES;             // A big, A small, W big, W small
-constexpr uint32_t LBO = BM * 16, SBO = 128, TMEM_COLS = 128;
+constexpr int EPI_PITCH = 36;                         // floats per row of the per-warp 32 x 32 store-transpose tile
 constexpr int MAXG = 4;                               // statistics groups per 128-column tile (channels/group >= 32)
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
@@ -94,8 +98,10 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
         const uint32_t la = (uint32_t)(32 * warp) << 16;
         const int r = m0 + row;
         const bool ok = r < p.Np;
-        float* yrow = p.Y + ((long long)b * p.Np + (ok ? r : 0)) * p.ldy + n0;
         const int cpg = p.stats ? p.Nout / p.G : 1;
+        // per-warp store-transpose tile in the (by then idle) pipeline stages: [32 rows][EPI_PITCH]
+        float* tr = reinterpret_cast<float*>(smem) + warp * 32 * EPI_PITCH;
+        const int sub_r = lane >> 3, sub_c = 4 * (lane & 7);     // store phase: 4 rows x 8 lanes x 16 B per instruction
         mbar_wait(&bars.acc_full, 0);
         tc_fence_after();
 #pragma unroll 1
@@ -112,12 +118,23 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
                 o.y = __uint_as_float(v[e + 1]) + bias_s[c0 + e + 1];
                 o.z = __uint_as_float(v[e + 2]) + bias_s[c0 + e + 2];
                 o.w = __uint_as_float(v[e + 3]) + bias_s[c0 + e + 3];
+                *reinterpret_cast<float4*>(tr + lane * EPI_PITCH + e) = o;
                 if (ok) {
-                    *reinterpret_cast<float4*>(yrow + c0 + e) = o;
                     s += (o.x + o.y) + (o.z + o.w);
                     q = fmaf(o.x, o.x, q); q = fmaf(o.y, o.y, q); q = fmaf(o.z, o.z, q); q = fmaf(o.w, o.w, q);
                 }
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = sub_r + 4 * i;                    // row inside this warp's 32
+                const int gr = m0 + 32 * warp + rr;
+                if (gr < p.Np) {
+                    const float4 o = *reinterpret_cast<const float4*>(tr + rr * EPI_PITCH + sub_c);
+                    *reinterpret_cast<float4*>(p.Y + ((long long)b * p.Np + gr) * p.ldy + n0 + c0 + sub_c) = o;
+                }
+            }
+            __syncwarp();
             if (p.stats) {
                 double ds = warp_sum((double)s), dq = warp_sum((double)q);
                 if (lane == 0) {
@@ -140,22 +157,23 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
         }
     } else if (warp < MMA_WARP) {
         // =============================================================================== loader warps
-        const int lt = tid - LOAD_WARP0 * 32;          // operand row 0..127
-        const int ra = m0 + lt, rw = n0 + lt;
-        const bool oka = ra < p.Np, okw = rw < p.Nout;
-        const float* arow = p.A + ((long long)b * p.Np + (oka ? ra : 0)) * p.lda;
-        const float* wrow = p.W + (long long)(okw ? rw : 0) * p.ldw;
-        const uint32_t roff = (uint32_t)((lt >> 3) * 128 + (lt & 7) * 16);
+        const int lt = tid - LOAD_WARP0 * 32;          // 0..127
+        const int c4 = lt & 3;                         // 16-byte k-chunk of the stage handled by this thread
+        const int rb = lt >> 2;                        // rows rb, rb+32, rb+64, rb+96 of both operands
+        const float* abase = p.A + (long long)b * p.Np * p.lda;
         const bool has_norm = p.in_scale != nullptr;
         const int act = p.in_act;
         float4 va[4], vw[4], na[4], nw[4];
         auto fetch = [&](int kc, float4 (&xa)[4], float4 (&xw)[4]) {
+            const int k = kc * BK + 4 * c4;
+            const bool kin = (kc < nch) && (k < p.K);
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const int k = kc * BK + 4 * c4;
-                const bool kin = (kc < nch) && (k < p.K);
-                xa[c4] = (kin && oka) ? *reinterpret_cast<const float4*>(arow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                xw[c4] = (kin && okw) ? *reinterpret_cast<const float4*>(wrow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 4; ++i) {
+                const int ra = m0 + rb + 32 * i, rw = n0 + rb + 32 * i;
+                xa[i] = (kin && ra < p.Np) ? *reinterpret_cast<const float4*>(abase + (long long)ra * p.lda + k)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                xw[i] = (kin && rw < p.Nout) ? *reinterpret_cast<const float4*>(p.W + (long long)rw * p.ldw + k)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         fetch(0, va, vw);
@@ -165,27 +183,31 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
             fetch(kc + 1, na, nw);
             mbar_wait(&bars.empty[s], ((kc / NSTAGE) & 1) ^ 1);
             unsigned char* st = smem + s * STAGE_BYTES;
+            const int k = kc * BK + 4 * c4;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_norm && k < p.K) {
+                sc = *reinterpret_cast<const float4*>(sc_s + k);
+                sh = *reinterpret_cast<const float4*>(sh_s + k);
+            }
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const int k = kc * BK + 4 * c4;
-                float f0 = va[c4].x, f1 = va[c4].y, f2 = va[c4].z, f3 = va[c4].w;
-                if (oka && k < p.K) {
+            for (int i = 0; i < 4; ++i) {
+                const int row = rb + 32 * i;
+                float f0 = va[i].x, f1 = va[i].y, f2 = va[i].z, f3 = va[i].w;
+                if ((m0 + row) < p.Np && k < p.K) {      // (padding rows / columns must stay exactly zero)
                     if (has_norm) {
-                        const float4 sc = *reinterpret_cast<const float4*>(sc_s + k);
-                        const float4 sh = *reinterpret_cast<const float4*>(sh_s + k);
                         f0 = fmaf(f0, sc.x, sh.x); f1 = fmaf(f1, sc.y, sh.y);
                         f2 = fmaf(f2, sc.z, sh.z); f3 = fmaf(f3, sc.w, sh.w);
                     }
                     f0 = act_fwd(f0, act); f1 = act_fwd(f1, act); f2 = act_fwd(f2, act); f3 = act_fwd(f3, act);
                 }
-                const uint32_t o = (uint32_t)(c4 * LBO) + roff;
+                const uint32_t o = (uint32_t)(c4 * LBO + (row >> 3) * 128 + (row & 7) * 16);
                 {
                     const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
                     *reinterpret_cast<float4*>(st + o) = make_float4(b0, b1, b2, b3);
                     *reinterpret_cast<float4*>(st + OP_BYTES + o) = make_float4(f0 - b0, f1 - b1, f2 - b2, f3 - b3);
                 }
                 {
-                    const float w0 = vw[c4].x, w1 = vw[c4].y, w2 = vw[c4].z, w3 = vw[c4].w;
+                    const float w0 = vw[i].x, w1 = vw[i].y, w2 = vw[i].z, w3 = vw[i].w;
                     const float b0 = tf32_hi(w0), b1 = tf32_hi(w1), b2 = tf32_hi(w2), b3 = tf32_hi(w3);
                     *reinterpret_cast<float4*>(st + 2 * OP_BYTES + o) = make_float4(b0, b1, b2, b3);
                     *reinterpret_cast<float4*>(st + 3 * OP_BYTES + o) = make_float4(w0 - b0, w1 - b1, w2 - b2, w3 - b3);
@@ -194,7 +216,7 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
             fence_async_smem();
             mbar_arrive(&bars.full[s]);
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) { va[c4] = na[c4]; vw[c4] = nw[c4]; }
+            for (int i = 0; i < 4; ++i) { va[i] = na[i]; vw[i] = nw[i]; }
         }
     } else {
         // =============================================================================== MMA warp

@@ -109,10 +109,14 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
                     const bool match = (pass == 0) || ((key >> (shift + 8)) == (pf >> (shift + 8)));
                     if (match) {
                         const unsigned bin = (key >> shift) & 255u;
-                        const unsigned old = atomicAdd(&hrow[bin], 1u);
-                        if (pass == 3 && old == 0u) {
-                            const int slot = atomicAdd(&ncand[row], 1);
-                            if (slot < CAND) cand[row][slot] = (bin << 24) | (unsigned)(j0 + u);
+                        if (pass < 3) {
+                            atomicAdd(&hrow[bin], 1u);          // result unused: a fire-and-forget shared-memory RED
+                        } else {
+                            const unsigned old = atomicAdd(&hrow[bin], 1u);
+                            if (old == 0u) {
+                                const int slot = atomicAdd(&ncand[row], 1);
+                                if (slot < CAND) cand[row][slot] = (bin << 24) | (unsigned)(j0 + u);
+                            }
                         }
                     }
                 }

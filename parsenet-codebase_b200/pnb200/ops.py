@@ -1,4 +1,6 @@
 """torch-facing ops: thin wrappers + autograd.Functions over the C-ABI kernels (no eager fallback)."""
+import os
+
 import torch
 
 from . import cabi
@@ -41,6 +43,7 @@ def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
 # --------------------------------------------------------------------------------------------- low-level wrappers
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 GN_EPS = 1e-5
+LINEAR_IMPL = os.environ.get("PN_LINEAR", "tc")
 
 
 def _pitch(t):
@@ -72,7 +75,15 @@ def linear_fwd(A, W, bias=None, sbias=None, in_norm=None, stats_groups=0, per_sh
     act = ACT_NONE
     if in_norm is not None:
         sc, sh, act = in_norm.scale, in_norm.shift, in_norm.act
-    call("pn_linear_fwd", _ptr(A), _pitch(A), _ptr(W), W.stride(0), _ptr(bias), _ptr(sbias), _ptr(sc), _ptr(sh),
+    # dense per-point MLP GEMMs run on the tcgen05 tensor cores (split-TF32) whenever the tile constraints hold;
+    # tiny / oddly shaped problems (K = 6 first edge-conv, 10 logits, per-channel BatchNorm statistics, M < 128) stay
+    # on the FP32-pipe kernel.  PN_LINEAR=simt forces the latter (used by the A/B parity test).
+    entry = "pn_linear_fwd"
+    if LINEAR_IMPL == "tc" and Np >= 128 and lib.pn_linear_fwd_tc_supported(
+            _ptr(A), _pitch(A), _ptr(W), W.stride(0), _ptr(Y), Nout, Np, K, Nout, max(stats_groups, 1),
+            1 if stats_groups else 0):
+        entry = "pn_linear_fwd_tc"
+    call(entry, _ptr(A), _pitch(A), _ptr(W), W.stride(0), _ptr(bias), _ptr(sbias), _ptr(sc), _ptr(sh),
                             act, _ptr(Y), Nout, _ptr(stats), B, Np, K, Nout, max(stats_groups, 1),
                             1 if per_shape else 0, _stream())
     return Y, stats

@@ -1,0 +1,72 @@
+"""tcgen05 (split-TF32) per-point linear layer vs the fp32 FMA-pipe kernel of the same C-ABI contract and vs a
+float64 torch reference of Y = act(norm(A)) W^T + bias + sbias with per-(shape, group) sum / sum-of-squares."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(name, A, W, bias, sbias, sc, sh, act, G):
+    from pnb200.cabi import call
+    B, Np, K = A.shape
+    Nout = W.shape[0]
+    Y = torch.full((B, Np, Nout), float("nan"), device="cuda")
+    stats = torch.zeros((B, G, 2), dtype=torch.float64, device="cuda") if G else None
+    p = lambda t: None if t is None else t.data_ptr()
+    call(name, p(A), A.stride(1), p(W), W.stride(0), p(bias), p(sbias), p(sc), p(sh), act, p(Y), Nout, p(stats), B, Np,
+         K, Nout, max(G, 1), 1, torch.cuda.current_stream().cuda_stream)
+    return Y, stats
+
+
+@pytest.mark.parametrize("B,Np,K,Nout,G,act,norm", [
+    (1, 128, 64, 128, 2, 0, False),        # one full tile
+    (2, 300, 256, 1024, 8, 1, True),       # mlp1 shape (ragged rows), ReLU(GroupNorm(.)) on load
+    (3, 1000, 512, 256, 4, 1, True),       # head conv2
+    (2, 777, 256, 128, 0, 2, True),        # embedding layer, LeakyReLU, no statistics
+    (1, 2113, 64, 256, 2, 0, False),       # edge-conv P/Q GEMM (K = 64)
+    (2, 129, 20, 32, 1, 0, False),         # K not a multiple of the 16-wide stage, one column chunk
+])
+def test_linear_fwd_tc_matches_simt_and_fp64(B, Np, K, Nout, G, act, norm):
+    g = torch.Generator().manual_seed(B * 1000 + Np)
+    A = torch.randn(B, Np, K, generator=g).cuda()
+    W = (torch.randn(Nout, K, generator=g) / K ** 0.5).cuda()
+    bias = torch.randn(Nout, generator=g).cuda()
+    sbias = torch.randn(B, Nout, generator=g).cuda()
+    sc = (torch.rand(B, K, generator=g) + 0.5).cuda() if norm else None
+    sh = torch.randn(B, K, generator=g).cuda() if norm else None
+    Ys, Ss = _run("pn_linear_fwd", A, W, bias, sbias, sc, sh, act, G)
+    Yt, St = _run("pn_linear_fwd_tc", A, W, bias, sbias, sc, sh, act, G)
+    X = A.double()
+    if norm:
+        X = X * sc.double().unsqueeze(1) + sh.double().unsqueeze(1)
+    X = torch.relu(X) if act == 1 else (torch.where(X > 0, X, 0.2 * X) if act == 2 else X)
+    Yr = X @ W.double().t() + bias.double() + sbias.double().unsqueeze(1)
+    assert torch.isfinite(Yt).all()
+    scale = Yr.abs().max().item()
+    err_t = (Yt.double() - Yr).abs().max().item() / scale
+    err_s = (Ys.double() - Yr).abs().max().item() / scale
+    print(f"rel err vs fp64: tc {err_t:.2e}, fp32 pipe {err_s:.2e}")
+    # split-TF32 keeps ~21 mantissa bits per product; the tensor core accumulates with truncation, which adds a bias of
+    # ~0.5 ulp per accumulation step (K/8 steps): 3e-6 at K = 512.  Far inside the 1e-4 budget of the north star.
+    assert err_t < 1e-5, err_t
+    if G:
+        cpg = Nout // G
+        ref = torch.stack([Yr.view(B, Np, G, cpg).sum((1, 3)), (Yr ** 2).view(B, Np, G, cpg).sum((1, 3))], 2)
+        # sums are compared against the magnitude they are made of (sum |y|, sum y^2): a group sum can cancel to ~0
+        mag = torch.stack([Yr.abs().view(B, Np, G, cpg).sum((1, 3)), ref[:, :, 1]], 2)
+        assert ((St - ref).abs() / mag).max().item() < 1e-5
+        assert ((Ss - ref).abs() / mag).max().item() < 1e-5
+
+
+def test_linear_dispatch_uses_tensor_cores_for_mlp_shapes():
+    """ops.linear_fwd routes the dense MLP shapes to pn_linear_fwd_tc and the tiny ones to the FP32-pipe kernel"""
+    from pnb200 import cabi, ops
+    A = torch.randn(2, 256, 256, device="cuda")
+    W = torch.randn(512, 256, device="cuda")
+    cabi.TIMED["pn_linear_fwd_tc"] = []
+    cabi.TIMED["pn_linear_fwd"] = []
+    ops.linear_fwd(A, W, stats_groups=8)
+    ops.linear_fwd(torch.randn(2, 256, 6, device="cuda"), torch.randn(128, 6, device="cuda"))
+    torch.cuda.synchronize()
+    n_tc, n_simt = len(cabi.TIMED.pop("pn_linear_fwd_tc")), len(cabi.TIMED.pop("pn_linear_fwd"))
+    assert (n_tc, n_simt) == ((1, 1) if ops.LINEAR_IMPL == "tc" else (0, 2))
