@@ -89,6 +89,8 @@ int pn_ms_iter_fwd_tc(const float* Y, const float* X, int B, int N, int d, const
 int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const float* Yprev, const float* X, const float* den, const float* unorm, int B, int N, int d, const float* cinv, float* ws_Gn, float* ws_gd, float* gYprev, float* gX, int accumulate_gX, void* stream);
 /* replaces: MeanShift.compute_bandwidth: src/mean_shift.py:130-135 — same contract as pn_ms_kth_dist */
 int pn_ms_kth_dist_tc(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K, float* kth, void* stream);
+/* replaces: MeanShift.nms arg-selects: src/mean_shift.py:146-149 (mode 0), :163-171 (mode 1) — same contract as pn_ms_argsel for modes 0 and 1; meanshift_tc_argsel.cu */
+int pn_ms_argsel_tc(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream);
 /* replaces: (debug aid, no reference counterpart: host-mapped progress words written by the tcgen05 pipelines; NULL disables) */
 int pn_debug_set_progress(int* host_mapped_words);
 

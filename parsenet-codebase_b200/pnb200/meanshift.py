@@ -16,7 +16,12 @@ BW_FLOOR = 0.003      # mean_shift.py:34
 FWD_IMPL = os.environ.get("PN_MS_FWD", "tc")
 BWD_IMPL = os.environ.get("PN_MS_BWD", "tc")
 KTH_IMPL = os.environ.get("PN_MS_KTH", "tc")
+ARGSEL_IMPL = os.environ.get("PN_MS_ARGSEL", "tc")      # modes 0 / 1 of the nms arg-selects (mode 2 is always simt)
 _KTH = {"tc": "pn_ms_kth_dist_tc", "simt": "pn_ms_kth_dist"}
+
+
+def _argsel_entry(mode, d):
+    return "pn_ms_argsel_tc" if (ARGSEL_IMPL == "tc" and mode in (0, 1) and d == 128) else "pn_ms_argsel"
 SQRT_FLOOR = 1e-6     # guard_sqrt(top_k, 1e-6), mean_shift.py:135
 
 
@@ -105,7 +110,7 @@ def nearest_center_batched(X_bnd, Y_bnd):
     B, N, d = X_bnd.shape
     X, Y = X_bnd.detach().contiguous(), Y_bnd.detach().contiguous()
     out = torch.empty((B, N), dtype=torch.int32, device=X.device)
-    call("pn_ms_argsel", 0, _ptr(X), N * d, N, _ptr(Y), N * d, N, B, d, None, None, _ptr(out), _stream())
+    call(_argsel_entry(0, d), 0, _ptr(X), N * d, N, _ptr(Y), N * d, N, B, d, None, None, _ptr(out), _stream())
     return out
 
 
@@ -113,7 +118,8 @@ def _argsel(mode, A, Bm, cnt=None, thr=None):
     Ma, d = A.shape
     Nb = Bm.shape[0]
     out = torch.empty((Ma,), dtype=torch.int32, device=A.device)
-    call("pn_ms_argsel", mode, _ptr(A), 0, Ma, _ptr(Bm), 0, Nb, 1, d, _ptr(cnt), _ptr(thr), _ptr(out), _stream())
+    call(_argsel_entry(mode, d), mode, _ptr(A), 0, Ma, _ptr(Bm), 0, Nb, 1, d, _ptr(cnt), _ptr(thr), _ptr(out),
+         _stream())
     return out
 
 
@@ -152,7 +158,8 @@ def nms_batched(Y_bnd, X_bnd, bw_b, member=None):
     counts.scatter_add_(1, member.long(), torch.ones((B, N), dtype=torch.float32, device=dev))
     thr = bw_b.detach().to(torch.float32).reshape(B).contiguous()
     nbr = torch.empty((B, N), dtype=torch.int32, device=dev)
-    call("pn_ms_argsel", 1, _ptr(Y), N * d, N, _ptr(Y), N * d, N, B, d, _ptr(counts), _ptr(thr), _ptr(nbr), _stream())
+    call(_argsel_entry(1, d), 1, _ptr(Y), N * d, N, _ptr(Y), N * d, N, B, d, _ptr(counts), _ptr(thr), _ptr(nbr),
+         _stream())
     # neighbours chosen by OCCUPIED centres are kept; unoccupied rows scatter into a dump column
     tgt = torch.where(counts > 0, nbr.long(), torch.full_like(nbr, N, dtype=torch.int64))
     mark = torch.zeros((B, N + 1), dtype=torch.bool, device=dev)

@@ -78,13 +78,51 @@ def test_bandwidth_subset_and_large_k():
         assert abs(got.item() - want.item()) <= 1e-5 * want.item(), (num_samples, q, got.item(), want.item())
 
 
-def test_nms_labels_bit_exact_vs_port():
+def _canon(l):
+    """relabel by first occurrence: equal outputs <=> identical partitions"""
+    _, first = np.unique(l, return_index=True)
+    order = l[np.sort(first)]
+    m = {int(v): i for i, v in enumerate(order)}
+    return np.array([m[int(v)] for v in l])
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_nms_labels_bit_exact_vs_port(impl, monkeypatch):
+    """FP32-pipe arg-selects: kept centre ids AND labels bit-exact vs the oracle port.  tcgen05 arg-selects: the
+    representative among numerically coincident shifted points depends on the rounding of the dot products (declared
+    deviation 'cluster numbering'), so the pin is the PARTITION: same cluster count, identical
+    segment assignment after relabelling by first occurrence."""
     from oracle.make_golden_helpers import clustered_embedding
     from oracle.port import meanshift as port
     from pnb200 import meanshift as pms
+    monkeypatch.setattr(pms, "ARGSEL_IMPL", impl)
     X, _ = clustered_embedding(1100, 128, 7, 17)
     Y = port.mean_shift_iters(X, torch.tensor(0.3), 6)
     kept_r, ids_r, lab_r = port.nms(Y, X, torch.tensor(0.3))
     kept, ids, lab = pms.nms(Y.cuda(), X.cuda(), 0.3)
-    np.testing.assert_array_equal(ids.cpu().numpy(), ids_r.numpy())
-    np.testing.assert_array_equal(lab.cpu().numpy(), lab_r.numpy())
+    if impl == "simt":
+        np.testing.assert_array_equal(ids.cpu().numpy(), ids_r.numpy())
+        np.testing.assert_array_equal(lab.cpu().numpy(), lab_r.numpy())
+    else:
+        assert ids.shape[0] == ids_r.shape[0]
+        np.testing.assert_array_equal(_canon(lab.cpu().numpy()), _canon(lab_r.numpy()))
+
+
+def test_nms_batched_equals_per_shape_nms():
+    """the batched nms (one read-back for all shapes) reproduces the per-shape nms: same kept ids, same labels"""
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as port
+    from pnb200 import meanshift as pms
+    Xs, Ys = [], []
+    for seed, ncl in ((17, 7), (18, 3), (19, 12)):
+        X, _ = clustered_embedding(1100, 128, ncl, seed)
+        Xs.append(X)
+        Ys.append(port.mean_shift_iters(X, torch.tensor(0.3), 6))
+    X, Y = torch.stack(Xs).cuda(), torch.stack(Ys).cuda()
+    bw = torch.tensor([0.3, 0.25, 0.35]).cuda()
+    ids, lab, K = pms.nms_batched(Y, X, bw)
+    for b in range(3):
+        _, ids_b, lab_b = pms.nms(Y[b], X[b], bw[b])
+        assert K[b] == ids_b.shape[0]
+        np.testing.assert_array_equal(ids[b].cpu().numpy(), ids_b.cpu().numpy())
+        np.testing.assert_array_equal(lab[b].cpu().numpy(), lab_b.cpu().numpy())
