@@ -68,7 +68,7 @@ class Evaluation:
         bw_host = bws.detach().cpu().numpy()
         self._stage = arena("fit", dev)
         self._stage.reset()
-        out, lazies, metrics = [], [], []
+        out, lazies, metrics, matchings = [], [], [], []
         parameters, weights = None, None
         for b in range(B):
             center, bandwidth = shifted[b][ids[b]], float(bw_host[b])
@@ -80,6 +80,7 @@ class Evaluation:
                 points[b], normals[b], labels[b], cluster_np[b], primitives[b], weights, bandwidth, lamb=lamb,
                 lazy=True)
             lazies.append(loss)
+            matchings.append((rows, cols))
             with torch.no_grad():
                 metrics.append(segment_types_device(prim_pred_dev[b], weights))
             out.append(loss[0])
@@ -100,7 +101,7 @@ class Evaluation:
             K = metrics[b].shape[0]
             seg_type = host[pos:pos + K].astype(np.int64); pos += K
             s_iou, p_iou, _, _ = SIOU_matched_segments(labels[b], cluster_np[b], None, primitives[b], None,
-                                                       prim_pred_seg=seg_type)
+                                                       prim_pred_seg=seg_type, matching=matchings[b])
             res = res + [out[b]] + lazies[b] + [s_iou, p_iou]
         return res, [parameters, cluster_np[B - 1], weights]
 
@@ -117,7 +118,7 @@ class Evaluation:
             gt_i = labels == cols[i]
             if gt_i.sum() == 0 or (cluster_ids == i).sum() == 0:
                 continue
-            l = stats.mode(primitives[gt_i])[0]
+            l = np.bincount(primitives[gt_i]).argmax()       # == scipy.stats.mode(...)[0] (smallest of the most frequent)
             entries.append((l, (index, i)))
             chunks.append(np.nonzero(gt_i)[0])
         data = []

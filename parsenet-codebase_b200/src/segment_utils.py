@@ -39,15 +39,24 @@ def _merge_types(p):
 
 
 def mean_IOU_primitive_segment(matching, predicted_labels, labels, pred_prim, gt_prim):
+    """segment IoU and primitive-type agreement over the matched (predicted r, gt c) pairs (reference :66-112).
+    Intersections / unions come from one confusion matrix per shape (exact integer counts) instead of 2 x 50 boolean
+    passes over the points; the gt type of a segment is the type of its first point, as in the reference."""
     ious, prim_ious, pairs = [], [], []
     for b in range(labels.shape[0]):
         iou_b, prim_b, pairs = [], [], []
+        pl, gl = np.asarray(predicted_labels[b]).astype(np.int64), np.asarray(labels[b]).astype(np.int64)
+        K = int(max(pl.max(), gl.max(), max(matching[b][0]), max(matching[b][1]))) + 1
+        conf = np.bincount(pl * K + gl, minlength=K * K).reshape(K, K)
+        n_p, n_g = conf.sum(1), conf.sum(0)
+        first = np.full(K, -1, dtype=np.int64)
+        first[gl[::-1]] = np.arange(gl.shape[0] - 1, -1, -1)      # last write wins -> lowest index of every label
         for r, c in zip(*matching[b]):
-            pi, gi = predicted_labels[b] == r, labels[b] == c
-            if gi.sum() == 0 or pi.sum() == 0 or gi.sum() < 100:
+            if n_g[c] == 0 or n_p[r] == 0 or n_g[c] < 100:
                 continue
-            iou_b.append(np.logical_and(pi, gi).sum() / (np.logical_or(pi, gi).sum() + 1e-8))
-            g_t, p_t = gt_prim[b][gi][0], pred_prim[b][r]
+            inter = conf[r, c]
+            iou_b.append(inter / (n_p[r] + n_g[c] - inter + 1e-8))
+            g_t, p_t = gt_prim[b][first[c]], pred_prim[b][r]
             prim_b.append(g_t == p_t)
             pairs.append([g_t, p_t])
         ious.append(np.mean(iou_b))
@@ -87,17 +96,22 @@ def segment_types_device(prim_pred_point, weights_kn):
     return torch.max(hot.t() @ weights_kn.t(), 0)[1]
 
 
-def SIOU_matched_segments(target, pred_labels, primitives_pred, primitives, weights, prim_pred_seg=None):
+def SIOU_matched_segments(target, pred_labels, primitives_pred, primitives, weights, prim_pred_seg=None,
+                          matching=None):
     """segment IoU + primitive-type IoU over Hungarian-matched (predicted, gt) segments.
     NOTE: like the reference, the primitive-id arrays are merged in place (0,6,7 -> 9; 8 -> 2).
     prim_pred_seg: optional precomputed (K,) majority type per cluster (segment_types_device), in which case
-    primitives_pred / weights are not needed and nothing touches the device."""
+    primitives_pred / weights are not needed and nothing touches the device.
+    matching: optional (rows, cols) of the Hungarian solve on the same (pred_labels, target) pair (fitting_utils.match
+    computes exactly this cost matrix), to avoid solving it twice."""
     for arr in (primitives, primitives_pred):
         if arr is None:
             continue
+        lut = np.arange(max(int(arr.max()) + 1, 10))
         for src, dst in _MERGE:
-            arr[arr == src] = dst
-    matching = [list(solve_dense(iou_cost_host(pred_labels, target)))]
+            lut[src] = dst
+        arr[...] = lut[arr]
+    matching = [list(matching)] if matching is not None else [list(solve_dense(iou_cost_host(pred_labels, target)))]
     if prim_pred_seg is None:
         dev = weights.device
         pp = torch.from_numpy(np.asarray(primitives_pred).astype(np.int64)).to(dev)
