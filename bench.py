@@ -233,24 +233,31 @@ def run_ours(args):
     e2e_v = shapes_total / (ms_e2e / 1e3)
     per_launch_ms = float(np.mean(kern_ms)) if kern_ms else None
     if FIT_STAGE:
-        # dominant kernel: ms_fwd_kernel (one mean-shift iteration over the whole batch, 2 fused N x N x d products)
-        alg_flop = B * 4.0 * N_POINTS * N_POINTS * EMB          # 4 N^2 d flop / shape / iteration
-        achieved = alg_flop / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms else None
+        # dominant kernels: the tcgen05 mean-shift backward (ms_bwd_tc_kernel<rows> + <cols>, one pn_ms_iter_bwd_tc call
+        # per iteration: 55 % of the device time of a step) and forward (ms_fwd_tc_kernel, 13 %).  SURVEY 8(d):
+        # 4 N^2 d flop / shape / iteration forward, 7 tile products = 14 N^2 d backward.
+        fwd_flop = B * 4.0 * N_POINTS * N_POINTS * EMB
+        bwd_flop = B * 14.0 * N_POINTS * N_POINTS * EMB
         bwd_launch = float(np.mean(bwd_ms)) if bwd_ms else None
-        roof = {"kernel": "ms_fwd_tc_kernel (pn_ms_iter_fwd_tc: one fused mean-shift iteration, tcgen05 split-TF32, "
-                          "batch of %d shapes)" % B,
+        achieved = bwd_flop / (bwd_launch * 1e-3) / 1e12 if bwd_launch else None
+        fwd_ach = fwd_flop / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms else None
+        roof = {"kernel": "ms_bwd_tc_kernel<rows> + ms_bwd_tc_kernel<cols> (+ prep) = one pn_ms_iter_bwd_tc call: backward "
+                          "of one mean-shift iteration, tcgen05 split-TF32, batch of %d shapes" % B,
                 "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": (achieved / pk["tf_sustained"]) if achieved else None, "traffic": 225.0e6,
+                "frac": (achieved / pk["tf_sustained"]) if achieved else None,
+                "traffic": (164.6 + 61.3 + 246.7 + 59.9 + 165.1 + 54.5) * 1e6,
                 "peak_source": pk["source"] + " (cuBLAS bf16 dense, sustained)",
-                "note": "algorithmic flop = 4*N^2*d per shape per iteration (fp32-accurate result); the kernel issues "
-                        "3 tf32 MMAs per product (split precision), i.e. executes 3x this many tensor flops; "
-                        "traffic = dram read+write bytes per launch from profiles/ (ncu)",
-                "launch_ms": per_launch_ms, "launches_timed": len(kern_ms),
-                "backward": {"kernel": "ms_bwd_tc_kernel<rows> + <cols> (+ prep) per pn_ms_iter_bwd_tc call",
-                             "launch_ms": bwd_launch, "launches_timed": len(bwd_ms),
-                             "achieved": (B * 14.0 * N_POINTS * N_POINTS * EMB / (bwd_launch * 1e-3) / 1e12)
-                             if bwd_launch else None, "unit": "TFLOP/s",
-                             "note": "algorithmic flop = 14*N^2*d per shape per iteration (7 tile products)"}}
+                "note": "algorithmic flop = 14*N^2*d per shape per iteration (7 tile products, fp32-accurate result); the "
+                        "kernels issue 3 tf32 MMAs per product (split precision) plus one recomputed product, i.e. ~3.4x "
+                        "this many tensor flops at the tf32 rate (half the bf16 rate): the ceiling of this formulation is "
+                        "~1/7 of the bf16 peak.  ncu (profiles/r01_ncu_meanshift_tc.md): tensor pipe active 50 %, l1tex "
+                        "(shared-memory operand traffic) 70-81 %, DRAM 0.4 %.  traffic = dram read+write bytes of "
+                        "rows+cols+prep per call from the same ncu capture",
+                "launch_ms": bwd_launch, "launches_timed": len(bwd_ms),
+                "forward": {"kernel": "ms_fwd_tc_kernel (pn_ms_iter_fwd_tc)", "launch_ms": per_launch_ms,
+                            "launches_timed": len(kern_ms), "achieved": fwd_ach, "unit": "TFLOP/s",
+                            "frac": (fwd_ach / pk["tf_sustained"]) if fwd_ach else None, "traffic": 127.8e6,
+                            "note": "algorithmic flop = 4*N^2*d per shape per iteration; ncu: tensor pipe active 57 %"}}
     else:
         alg_bytes = B * (N_POINTS * 64 * 4 + N_POINTS * KNN_K * 4)
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else None

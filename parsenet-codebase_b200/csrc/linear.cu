@@ -146,7 +146,8 @@ struct NormAct {
 };
 
 // ================================================================================================ forward
-// grid: (tiles_m_per_shape * B, tiles_n).  Rows of one CTA never straddle two shapes.
+// grid: (tiles_n, tiles_m_per_shape * B): column tiles of one row block are adjacent in launch order (A rows re-used out of
+// L2 instead of re-read from DRAM once per column tile).  Rows of one CTA never straddle two shapes.
 struct FwdArgs {
     const float* A; long long lda;     // [B*Np][K]
     const float* W; long long ldw;     // [Nout][K]
@@ -164,9 +165,9 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_kernel(FwdArgs p) {
     Tile& S = *reinterpret_cast<Tile*>(smem_raw);
     __shared__ float csum[BN], csq[BN];
     const int tiles_m = (p.Np + BM - 1) / BM;
-    const int b = blockIdx.x / tiles_m;
-    const int m0 = (blockIdx.x % tiles_m) * BM;            // row inside the shape
-    const int n0 = blockIdx.y * BN;
+    const int b = blockIdx.y / tiles_m;
+    const int m0 = (blockIdx.y % tiles_m) * BM;            // row inside the shape
+    const int n0 = blockIdx.x * BN;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const float* Ab = p.A + (long long)b * p.Np * p.lda;
     NormAct xf{p.in_scale, p.in_shift, p.K, p.in_act, (long long)b * p.K};
@@ -283,9 +284,9 @@ __global__ void __launch_bounds__(NT, 2) linear_bwd_data_kernel(BwdDataArgs p) {
     Tile& S = *reinterpret_cast<Tile*>(smem_raw);
     __shared__ float c1[BN], c2[BN];
     const int tiles_m = (p.Np + BM - 1) / BM;
-    const int b = blockIdx.x / tiles_m;
-    const int m0 = (blockIdx.x % tiles_m) * BM;
-    const int k0 = blockIdx.y * BN;                 // output column block (over K)
+    const int b = blockIdx.y / tiles_m;
+    const int m0 = (blockIdx.y % tiles_m) * BM;
+    const int k0 = blockIdx.x * BN;                 // output column block (over K)
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const float* dYb = p.dY + (long long)b * p.Np * p.lddy;
     Ident id;
@@ -562,7 +563,8 @@ extern "C" int pn_linear_fwd(const float* A, long long lda, const float* W, long
     p.vecW = aligned16(W) && ldw % 4 == 0;
     p.vecY = aligned16(Y) && ldy % 4 == 0;
     PN_REQUIRE(set_smem((const void*)linear_fwd_kernel) == 0, "pn_linear_fwd: smem attribute");
-    dim3 grid(cdiv(Np, BM) * B, cdiv(Nout, BN));
+    PN_REQUIRE((long long)cdiv(Np, BM) * B <= 65535, "pn_linear_fwd: too many row tiles (%d x %d)", cdiv(Np, BM), B);
+    dim3 grid(cdiv(Nout, BN), cdiv(Np, BM) * B);
     linear_fwd_kernel<<<grid, NT, sizeof(Tile), (cudaStream_t)stream>>>(p);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("linear_fwd_kernel");
@@ -583,7 +585,8 @@ extern "C" int pn_linear_bwd_data(const float* dY, long long lddy, const float* 
     p.vecW = aligned16(W) && ldw % 4 == 0;
     p.vecdZ = aligned16(dZ) && lddz % 4 == 0;
     PN_REQUIRE(set_smem((const void*)linear_bwd_data_kernel) == 0, "pn_linear_bwd_data: smem attribute");
-    dim3 grid(cdiv(Np, BM) * B, cdiv(K, BN));
+    PN_REQUIRE((long long)cdiv(Np, BM) * B <= 65535, "pn_linear_bwd_data: too many row tiles (%d x %d)", cdiv(Np, BM), B);
+    dim3 grid(cdiv(K, BN), cdiv(Np, BM) * B);
     linear_bwd_data_kernel<<<grid, NT, sizeof(Tile), (cudaStream_t)stream>>>(p);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("linear_bwd_data_kernel");

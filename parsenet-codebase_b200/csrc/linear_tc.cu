@@ -49,7 +49,8 @@ struct Args {
 
 struct Bars { uint64_t full[NSTAGE], empty[NSTAGE], acc_full; };
 
-// grid (tiles_m * B, tiles_n)
+// grid (tiles_n, tiles_m * B): the column tiles of one row block are adjacent in launch order, so the A rows they share
+// are read from DRAM once and re-used out of L2 (with the row block outermost ncu showed A re-read once per column tile)
 __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sc_s = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);      // [K] producer scale (or unused)
@@ -61,9 +62,9 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_m = (p.Np + BM - 1) / BM;
-    const int b = blockIdx.x / tiles_m;
-    const int m0 = (blockIdx.x % tiles_m) * BM;
-    const int n0 = blockIdx.y * BN;
+    const int b = blockIdx.y / tiles_m;
+    const int m0 = (blockIdx.y % tiles_m) * BM;
+    const int n0 = blockIdx.x * BN;
     const int nch = (p.K + BK - 1) / BK;
 
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -283,7 +284,8 @@ extern "C" int pn_linear_fwd_tc(const float* A, long long lda, const float* W, l
     Args p{A, lda, W, ldw, bias, sbias, in_scale, in_shift, in_act, Y, ldy, stats, B, Np, K, Nout, G, stats_per_shape};
     size_t sm = (size_t)NSTAGE * STAGE_BYTES + 2 * (size_t)K * sizeof(float) + 1024;
     PN_CUDA(cudaFuncSetAttribute(linear_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    dim3 grid(cdiv(Np, BM) * B, cdiv(Nout, BN));
+    PN_REQUIRE((long long)cdiv(Np, BM) * B <= 65535, "pn_linear_fwd_tc: too many row tiles (%d x %d)", cdiv(Np, BM), B);
+    dim3 grid(cdiv(Nout, BN), cdiv(Np, BM) * B);
     linear_fwd_tc_kernel<<<grid, NT, sm, (cudaStream_t)stream>>>(p);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("linear_fwd_tc_kernel");

@@ -78,7 +78,7 @@ def test_bandwidth_subset_and_large_k():
         assert abs(got.item() - want.item()) <= 1e-5 * want.item(), (num_samples, q, got.item(), want.item())
 
 
-def _canon(l):
+def _canon_labels(l):
     """relabel by first occurrence: equal outputs <=> identical partitions"""
     _, first = np.unique(l, return_index=True)
     order = l[np.sort(first)]
@@ -105,7 +105,7 @@ def test_nms_labels_bit_exact_vs_port(impl, monkeypatch):
         np.testing.assert_array_equal(lab.cpu().numpy(), lab_r.numpy())
     else:
         assert ids.shape[0] == ids_r.shape[0]
-        np.testing.assert_array_equal(_canon(lab.cpu().numpy()), _canon(lab_r.numpy()))
+        np.testing.assert_array_equal(_canon_labels(lab.cpu().numpy()), _canon_labels(lab_r.numpy()))
 
 
 def test_nms_batched_equals_per_shape_nms():
