@@ -97,6 +97,11 @@ class GramSVDFn(torch.autograd.Function):
         evals, evecs = eigh3(G)                                # ascending
         V = torch.flip(evecs, dims=[2])
         sv = torch.sqrt(torch.clamp(torch.flip(evals, dims=[1]), min=0.0))
+        # A null direction of the Gram matrix comes out of the eigen-solver as a tiny NEGATIVE eigenvalue about half of
+        # the time -> singular value exactly 0 -> 1/(s_i + s_i) = inf on the diagonal of K -> inf * 0 = NaN in the
+        # backward (seen as NaN gradients after ~10 optimizer steps).  An fp32 SVD of the (m,3) matrix, which is what
+        # the reference differentiates, returns ~eps32 * s_max there; use the same floor.
+        sv = torch.maximum(sv, (EPS * sv[:, :1]).clamp(min=1e-30))
         ctx.save_for_backward(V, sv)
         return V, sv
 
@@ -107,10 +112,12 @@ class GramSVDFn(torch.autograd.Function):
         s_row = sv.unsqueeze(1)
         diff = s_col - s_row
         plus = s_col + s_row
-        kneg = torch.sign(diff) * torch.clamp(diff.abs(), min=1e-6)
+        # (sign(0) := +1: two null directions floored to the same value must not give 1/0)
+        sgn = torch.where(diff >= 0, torch.ones_like(diff), -torch.ones_like(diff))
+        kneg = sgn * torch.clamp(diff.abs(), min=1e-6)
         eye = torch.eye(3, dtype=sv.dtype, device=sv.device)
         kneg = kneg * (1 - eye) + 1e-6 * eye
-        K = (1.0 / kneg) * (1.0 / plus) * (1 - eye)
+        K = (1.0 / kneg) * (1.0 / torch.clamp(plus, min=1e-8)) * (1 - eye)     # (|K| <= 1e14, the reference's fp32 range)
         inner = K.transpose(1, 2) * (V.transpose(1, 2) @ gV)
         inner = (inner + inner.transpose(1, 2)) / 2.0
         return V @ inner @ V.transpose(1, 2)
