@@ -30,7 +30,8 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
     __shared__ uint32_t tmem_base_s;
     __shared__ unsigned prefix[BM];
     __shared__ int krem[BM];
-    // last pass: first column seen in every occupied low-byte bin, packed (bin << 24) | column.  The K-th element's
+    // last pass: the (few) columns whose key shares the top 24 bits with the K-th one, packed (bin << 24) | column
+    // (rows with more than CAND of them, i.e. many identical points, keep the tensor-core value).  The K-th element's
     // column lets the epilogue recompute that ONE distance with an fp32 FMA chain: the tensor core accumulates with
     // truncation, which biases every S by the same ~1e-6 (harmless for the ranking, visible in the bandwidth mean).
     __shared__ unsigned cand[BM][CAND];
@@ -109,14 +110,10 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
                     const bool match = (pass == 0) || ((key >> (shift + 8)) == (pf >> (shift + 8)));
                     if (match) {
                         const unsigned bin = (key >> shift) & 255u;
-                        if (pass < 3) {
-                            atomicAdd(&hrow[bin], 1u);          // result unused: a fire-and-forget shared-memory RED
-                        } else {
-                            const unsigned old = atomicAdd(&hrow[bin], 1u);
-                            if (old == 0u) {
-                                const int slot = atomicAdd(&ncand[row], 1);
-                                if (slot < CAND) cand[row][slot] = (bin << 24) | (unsigned)(j0 + u);
-                            }
+                        atomicAdd(&hrow[bin], 1u);              // result unused: a fire-and-forget shared-memory RED
+                        if (pass == 3) {                        // rare: shares the top 24 key bits with the K-th element
+                            const int slot = atomicAdd(&ncand[row], 1);
+                            if (slot < CAND) cand[row][slot] = (bin << 24) | (unsigned)(j0 + u);
                         }
                     }
                 }

@@ -87,6 +87,15 @@ class MomentsFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------ custom SVD of a Gram
+def floor_singular_values(sv):
+    """(S,3) descending singular values.  A null direction of the Gram matrix comes out of the eigen-solver as a tiny
+    NEGATIVE eigenvalue about half of the time -> singular value exactly 0 -> 1/(s_i + s_i) = inf on the diagonal of K
+    -> inf * 0 = NaN in the backward (seen as NaN gradients after ~10 optimizer steps, spread to every rank by the
+    gradient all-reduce).  An fp32 SVD of the (m,3) matrix, which is what the reference differentiates, returns
+    ~eps32 * s_max there; use the same floor."""
+    return torch.maximum(sv, (EPS * sv[:, :1]).clamp(min=1e-30))
+
+
 class GramSVDFn(torch.autograd.Function):
     """G = A^T A (S,3,3) -> V (S,3,3) with columns ordered by DEcreasing singular value of A, sv (S,3).
     Backward is the reference's custom rule (fitting_utils.py:385-417): grad_A = 2 U S sym(K^T o V^T gV) V^T, i.e.
@@ -96,12 +105,7 @@ class GramSVDFn(torch.autograd.Function):
     def forward(ctx, G):
         evals, evecs = eigh3(G)                                # ascending
         V = torch.flip(evecs, dims=[2])
-        sv = torch.sqrt(torch.clamp(torch.flip(evals, dims=[1]), min=0.0))
-        # A null direction of the Gram matrix comes out of the eigen-solver as a tiny NEGATIVE eigenvalue about half of
-        # the time -> singular value exactly 0 -> 1/(s_i + s_i) = inf on the diagonal of K -> inf * 0 = NaN in the
-        # backward (seen as NaN gradients after ~10 optimizer steps).  An fp32 SVD of the (m,3) matrix, which is what
-        # the reference differentiates, returns ~eps32 * s_max there; use the same floor.
-        sv = torch.maximum(sv, (EPS * sv[:, :1]).clamp(min=1e-30))
+        sv = floor_singular_values(torch.sqrt(torch.clamp(torch.flip(evals, dims=[1]), min=0.0)))
         ctx.save_for_backward(V, sv)
         return V, sv
 
