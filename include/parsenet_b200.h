@@ -131,6 +131,10 @@ int pn_lstsq3(const double* AtA, const double* AtY, int S, int rows, double eps3
 int pn_spline_eval_fwd(const float* Nu, const float* Nv, const float* P, int B, int gu, int gv, int cu, int cv, float* out, void* stream);
 /* replaces: autograd of Nu P Nv^T */
 int pn_spline_eval_bwd(const float* Nu, const float* Nv, const float* g, int B, int gu, int gv, int cu, int cv, float* dP, void* stream);
+/* float64 instances of the same tensor-product kernels.  Run with the pseudo-inverse basis matrices Nu^+ (cu x gu), Nv^+ they
+   replace the gridded control-point solve approximation.fit_bezier_surface: src/approximation.py:308-334 (numpy float64) */
+int pn_spline_eval_fwd_f64(const double* Nu, const double* Nv, const double* P, int B, int gu, int gv, int cu, int cv, double* out, void* stream);
+int pn_spline_eval_bwd_f64(const double* Nu, const double* Nv, const double* g, int B, int gu, int gv, int cu, int cv, double* dP, void* stream);
 
 #ifdef __cplusplus
 }

@@ -297,7 +297,28 @@ def gen_e2e(no_cylinder=False, fname="e2e.npz"):
     print("e2e loss", res[0].item(), "geo", res[1], "spline", res[2], "siou", res[3], "kinds", kinds)
 
 
-GENS = {"knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
+def gen_cfg1():
+    """BASELINE config 1: open-spline fit only.  Random 20x20x3 control grid (seed 0) -> 30x30 surface samples with the
+    reference's sample_points_from_control_points_ -> control points recovered by the reference's own gridded solve
+    approximation.fit_bezier_surface (float64) and by its Kronecker lstsq (fit_bezier_surface_fit_kronecker)."""
+    FU = rl.ref("src.fitting_utils"); L = rl.ref("src.loss"); AP = rl.ref("src.approximation")
+    rs = np.random.RandomState(0)
+    cp = rs.rand(2, 20, 20, 3)
+    nu, nv = L.uniform_knot_bspline(20, 20, 3, 3, 30)
+    S = FU.sample_points_from_control_points_(torch.from_numpy(nu), torch.from_numpy(nv),
+                                              torch.from_numpy(cp.reshape(2, 400, 3)), 2).numpy()      # (2,900,3) f64
+    rec = np.stack([AP.fit_bezier_surface(S[b].reshape(30, 30, 3), nu, nv) for b in range(2)], 0)
+    A_u = np.repeat(nu, 30, axis=0); A_v = np.tile(nv, (30, 1))                                        # per-point basis rows
+    rec_k = AP.fit_bezier_surface_fit_kronecker(S[0], A_u, A_v)
+    # a noisy, non-interpolating case: least-squares control points of perturbed samples
+    Sn = S + 0.01 * rs.randn(*S.shape)
+    rec_n = np.stack([AP.fit_bezier_surface(Sn[b].reshape(30, 30, 3), nu, nv) for b in range(2)], 0)
+    print("cfg1: max |cp - rec| gridded", np.abs(rec - cp).max(), "kronecker", np.abs(rec_k - cp[0]).max(),
+          "cond(nu)", np.linalg.cond(nu))
+    np.savez_compressed(os.path.join(OUT, "cfg1.npz"), cp=cp, S=S, rec=rec, rec_k=rec_k, Sn=Sn, rec_n=rec_n, nu=nu, nv=nv)
+
+
+GENS = {"cfg1": gen_cfg1, "knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
         "splinenet": gen_splinenet, "e2e": gen_e2e, "e2e_nocyl": lambda: gen_e2e(True, "e2e_nocyl.npz")}
 
 if __name__ == "__main__":

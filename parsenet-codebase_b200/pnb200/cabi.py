@@ -58,6 +58,8 @@ SIGNATURES = {
     "pn_chamfer_nn_bwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "pn_spline_eval_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "pn_spline_eval_bwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "pn_spline_eval_fwd_f64": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
+    "pn_spline_eval_bwd_f64": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p, c_p],
     "pn_fit_moments_fwd": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p],
     "pn_fit_moments_bwd": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_ll, c_p],
     "pn_residual_fwd": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],

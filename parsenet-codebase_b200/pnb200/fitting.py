@@ -304,29 +304,64 @@ def nearest_sqdist(A, Bs):
 
 # ------------------------------------------------------------------------------------------------ spline evaluation
 class SplineEvalFn(torch.autograd.Function):
-    """P (B,cu,cv,3) -> (B, gu*gv, 3) = Nu P Nv^T per coordinate"""
+    """P (B,cu,cv,3) -> (B, gu*gv, 3) = Nu P Nv^T per coordinate.  float32, or float64 when P is float64"""
 
     @staticmethod
     def forward(ctx, P, Nu, Nv):
         _need_cuda(P, Nu, Nv)
-        P = P.detach().contiguous().float()
-        Nu = Nu.detach().contiguous().float()
-        Nv = Nv.detach().contiguous().float()
+        f64 = P.dtype == torch.float64
+        dt = torch.float64 if f64 else torch.float32
+        P = P.detach().contiguous().to(dt)
+        Nu = Nu.detach().contiguous().to(dt)
+        Nv = Nv.detach().contiguous().to(dt)
         B, cu, cv, _ = P.shape
         gu, gv = Nu.shape[0], Nv.shape[0]
-        out = torch.empty((B, gu * gv, 3), dtype=torch.float32, device=P.device)
-        call("pn_spline_eval_fwd", _ptr(Nu), _ptr(Nv), _ptr(P), B, gu, gv, cu, cv, _ptr(out), _stream())
-        ctx.saved = (Nu, Nv, (B, cu, cv, gu, gv))
+        out = torch.empty((B, gu * gv, 3), dtype=dt, device=P.device)
+        call("pn_spline_eval_fwd_f64" if f64 else "pn_spline_eval_fwd", _ptr(Nu), _ptr(Nv), _ptr(P), B, gu, gv, cu, cv,
+             _ptr(out), _stream())
+        ctx.saved = (Nu, Nv, (B, cu, cv, gu, gv), f64)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        Nu, Nv, (B, cu, cv, gu, gv) = ctx.saved
-        g = g.contiguous()
-        dP = torch.empty((B, cu, cv, 3), dtype=torch.float32, device=g.device)
-        call("pn_spline_eval_bwd", _ptr(Nu), _ptr(Nv), _ptr(g), B, gu, gv, cu, cv, _ptr(dP), _stream())
+        Nu, Nv, (B, cu, cv, gu, gv), f64 = ctx.saved
+        g = g.contiguous().to(Nu.dtype)
+        dP = torch.empty((B, cu, cv, 3), dtype=Nu.dtype, device=g.device)
+        call("pn_spline_eval_bwd_f64" if f64 else "pn_spline_eval_bwd", _ptr(Nu), _ptr(Nv), _ptr(g), B, gu, gv, cu, cv,
+             _ptr(dP), _stream())
         return dP, None, None
 
 
 def spline_eval(P_bijc, Nu, Nv):
     return SplineEvalFn.apply(P_bijc, Nu, Nv)
+
+
+# ------------------------------------------------------------------------------------------------ control-point solve
+_PINV = {}
+
+
+def pinv_basis(N_gc, device):
+    """(g, c) basis matrix -> its left pseudo-inverse (N^T N)^-1 N^T  (c, g), float64 on the host once, cached as a
+    float64 device constant (the reference forms exactly this product, src/approximation.py:319-323)"""
+    N64 = np.asarray(N_gc.detach().cpu().numpy() if isinstance(N_gc, torch.Tensor) else N_gc, dtype=np.float64)
+    key = (N64.shape, hash(N64.tobytes()), str(device))
+    t = _PINV.get(key)
+    if t is None:
+        pinv = np.linalg.inv(N64.T @ N64) @ N64.T
+        t = _PINV[key] = torch.from_numpy(pinv).to(device)
+    return t
+
+
+def fit_control_points_grid(S_bguv3, nu, nv):
+    """Least-squares control grid of gridded surface samples: P = Nu^+ S (Nv^+)^T per coordinate.
+    S (B, gu, gv, 3) cuda -> (B, cu, cv, 3), same dtype as S.  Replaces approximation.fit_bezier_surface (reference
+    src/approximation.py:308-334, numpy float64, one shape at a time): the solve is the SAME tensor-product kernel as
+    the surface evaluation, run with the pseudo-inverse basis matrices, and is differentiable w.r.t. the samples.
+    The arithmetic is float64 like the reference's: ||Nu^+||_1 ||Nv^+||_1 ~ 8e4 for the 30 -> 20 cubic basis, so an
+    fp32 solve (even fp32 rounding of the samples alone) sits at 3e-4, above the 1e-4 parity bar."""
+    _need_cuda(S_bguv3)
+    B, gu, gv, _ = S_bguv3.shape
+    pu, pv = pinv_basis(nu, S_bguv3.device), pinv_basis(nv, S_bguv3.device)
+    assert pu.shape[1] == gu and pv.shape[1] == gv, "basis matrices do not match the sample grid"
+    out = SplineEvalFn.apply(S_bguv3.double(), pu, pv).view(B, pu.shape[0], pv.shape[0], 3)
+    return out.to(S_bguv3.dtype)

@@ -262,3 +262,45 @@ def test_evaluation_fitting_loss_vs_reference(golden_dir, variant):
         assert rel < 2e-2
     # with a cylinder segment the reference gradient carries the 1e4-amplified fp32 noise of its rank-deficient
     # regularised solve (primitive_forward.py:803 -> fitting_utils.py:52-64); only the loss value is compared there
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 1
+def test_cfg1_open_spline_control_point_solve_vs_reference(golden_dir):
+    """open-spline fit only: 30x30 samples of a random 20x20 control grid -> control points.  Golden = the unmodified
+    reference's approximation.fit_bezier_surface / fit_bezier_surface_fit_kronecker (float64, numpy).  The solve runs
+    in float64 on the device like the reference: 1e-9 relative.  With fp32 SAMPLES the rounding of the input alone is
+    amplified by ||Nu^+||_1 ||Nv^+||_1 ~ 8e4 to ~3e-4 (measured in float64 numpy on the rounded samples), so that case
+    is checked against exact arithmetic on the same rounded samples (1e-6) and at 1e-3 against the golden."""
+    from pnb200.fitting import fit_control_points_grid, spline_eval
+    from src import approximation as AP
+    g = _g(golden_dir, "cfg1.npz")
+    nu, nv, cp, S = g["nu"], g["nv"], g["cp"], g["S"]
+    pu = np.linalg.inv(nu.T @ nu) @ nu.T
+    pv = np.linalg.inv(nv.T @ nv) @ nv.T
+    Sd = torch.from_numpy(S.reshape(2, 30, 30, 3)).cuda().requires_grad_()                        # float64
+    rec = fit_control_points_grid(Sd, nu, nv)
+    assert rec.dtype == torch.float64
+    _close(rec, g["rec"], rtol=1e-9, name="cfg1 control points vs reference")
+    _close(rec, cp, rtol=1e-9, name="cfg1 control-point residual")
+    # fp32 samples
+    S32 = S.reshape(2, 30, 30, 3).astype(np.float32)
+    rec32 = fit_control_points_grid(torch.from_numpy(S32).cuda(), nu, nv)
+    assert rec32.dtype == torch.float32
+    _close(rec32, np.einsum("iu,buvc,jv->bijc", pu, S32.astype(np.float64), pv), rtol=1e-6, name="cfg1 fp32 samples, exact arithmetic")
+    _close(rec32, g["rec"], rtol=1e-3, name="cfg1 fp32 samples vs reference")
+    # numpy-in / numpy-out drop-in and the noisy (genuinely least-squares) case
+    rec_np = AP.fit_bezier_surface(g["Sn"][0].reshape(30, 30, 3), nu, nv)
+    assert isinstance(rec_np, np.ndarray) and rec_np.shape == (20, 20, 3) and rec_np.dtype == np.float64
+    _close(torch.from_numpy(rec_np), g["rec_n"][0], rtol=1e-9, name="cfg1 noisy samples vs reference")
+    # scattered-sample (Kronecker) solve
+    A_u, A_v = np.repeat(nu, 30, axis=0), np.tile(nv, (30, 1))
+    rec_k = AP.fit_bezier_surface_fit_kronecker(S[0], A_u, A_v)
+    _close(torch.from_numpy(rec_k), g["rec_k"], rtol=1e-6, name="cfg1 kronecker solve vs reference")
+    # round trip through the evaluation kernel and gradient w.r.t. the samples (linear map: grad = pinv^T (.) pinv)
+    back = spline_eval(rec, torch.from_numpy(nu).cuda(), torch.from_numpy(nv).cuda())
+    assert back.dtype == torch.float64
+    _close(back, S, rtol=1e-9, name="cfg1 re-evaluated surface")
+    w = torch.randn(rec.shape, generator=torch.Generator().manual_seed(0), dtype=torch.float64).cuda()
+    (rec * w).sum().backward()
+    gref = np.einsum("iu,bijc,jv->buvc", pu, w.cpu().numpy(), pv)
+    _close(Sd.grad, gref.reshape(2, 30, 30, 3), rtol=1e-9, name="cfg1 gradient w.r.t. samples")

@@ -106,3 +106,18 @@ def test_meanshift_port_matches_reference(golden_dir, case):
     w = torch.randn(center.shape, generator=gen); w2 = torch.randn(newX.shape, generator=gen) * 0.01
     ((center * w).sum() + (newX * w2).sum()).backward()
     np.testing.assert_allclose(X.grad.numpy(), g[case + "_gradX"], rtol=1e-4, atol=1e-6)
+
+
+def test_cfg1_control_point_solve_restatement_vs_reference_golden(golden_dir):
+    """BASELINE config 1 on the CPU: the pseudo-inverse restatement P = Nu^+ S (Nv^+)^T of the reference's gridded
+    solve (src/approximation.py:308-334) reproduces the reference's float64 output and recovers the control grid."""
+    import numpy as np
+    import os
+    g = np.load(os.path.join(golden_dir, "cfg1.npz"))
+    nu, nv = g["nu"], g["nv"]
+    pu, pv = np.linalg.inv(nu.T @ nu) @ nu.T, np.linalg.inv(nv.T @ nv) @ nv.T
+    for S, want in ((g["S"], g["rec"]), (g["Sn"], g["rec_n"])):
+        rec = np.einsum("iu,buvc,jv->bijc", pu, S.reshape(2, 30, 30, 3), pv)
+        assert np.abs(rec - want).max() < 1e-10
+    assert np.abs(g["rec"] - g["cp"]).max() < 1e-10 and np.abs(g["rec_k"] - g["cp"][0]).max() < 1e-10
+    assert abs(np.linalg.cond(nu) - 162.52) < 0.01             # SURVEY 8c
