@@ -29,6 +29,7 @@ BATCH_PER_GPU = 16
 KNN_K = 80
 EMB = 128
 N_PRIM = 10
+N_PATCHES = 8          # per shape: plane, sphere, cylinder, cone, open spline, closed spline, plane, sphere
 
 
 def peaks():
@@ -88,8 +89,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ workload
 def make_host_batch(B, N, seed):
-    from oracle.port import common  # synthetic generator only (no oracle math on the product path)
-    pts, nrm, lab, prim = common.synth_cloud(B, N, seed=seed, n_patches=8)
+    from tools.synth import ALL_KINDS, synth_cloud   # plain numpy generator (not oracle code)
+    pts, nrm, lab, prim = synth_cloud(B, N, seed=seed, n_patches=N_PATCHES, kinds=ALL_KINDS)
     x = np.concatenate([pts, nrm], 2).transpose(0, 2, 1).copy()       # (B,6,N) as the reference feeds it
     return (torch.from_numpy(x).pin_memory(), torch.from_numpy(lab).pin_memory(),
             torch.from_numpy(prim).pin_memory())
@@ -196,6 +197,9 @@ def run_ours(args):
         cabi.TIMED["pn_ms_iter_bwd_tc"] = []
     barrier()
     cabi.reset_launch_count()
+    from src.primitive_forward import STATS as fit_stats
+    for k in fit_stats:
+        fit_stats[k] = 0
     t_wall0 = time.time()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -206,6 +210,7 @@ def run_ours(args):
     barrier()
     ms_res = ev0.elapsed_time(ev1)
     launches = cabi.launch_count()
+    fits_per_step = {k: v / args.steps for k, v in fit_stats.items()}
     kern_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop(dominant)]
     bwd_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop("pn_ms_iter_bwd_tc", [])]
     # ---- timed: end to end (H2D of inputs + D2H of the loss inside the region)
@@ -270,10 +275,11 @@ def run_ours(args):
         "value": value, "unit": "shapes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "train_parsenet.py step (config 4 shape: 16 x 10k pts + normals, k=80, mode 5): "
-                               "seg-net fwd + triplet/NLL" + (" + Evaluation.fitting_loss (mean-shift %d it, match, primitive/"
-                               "spline fit, residual)" % MS_ITERS if FIT_STAGE else "") + " + bwd + Adam; random-init "
-                               "weights (seg net and SplineNets)",
+        "config": {"workload": "train_parsenet_e2e.py step (BASELINE config 5 call sequence at the config-4 batch: 16 x 10k "
+                               "pts + normals per GPU, k=80, mode 5): seg-net fwd + triplet/NLL" + (" + Evaluation.fitting_loss "
+                               "(mean-shift %d it, match, primitive + open/closed SplineNet fit, residual / Chamfer)" % MS_ITERS
+                               if FIT_STAGE else "") + " + bwd + Adam; shapes = 8 patches (plane, sphere, cylinder, cone, "
+                               "open spline, closed spline, ...); random-init weights (seg net and SplineNets)",
                    "per_gpu_batch": B, "global_batch": B * world, "n_points": N_POINTS, "knn_k": KNN_K,
                    "parallelism": f"dp{world}", "l2": "256 MB flush write between timed steps; per-step working set "
                                                       ">> 126 MB L2"},
@@ -284,6 +290,7 @@ def run_ours(args):
         "roofline": roof,
     }
     out["config"]["mean_clusters_per_shape_last"] = (float(np.mean(hp.clusters[-4:])) if hp.clusters else None)
+    out["config"]["fitted_segments_per_step"] = fits_per_step
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
@@ -300,10 +307,11 @@ def cpu_baseline(max_seconds=None):
     nms), membership weights, backward through everything.  The per-segment fit/residual stage is not in the port's
     timed sample (a few % of the reference's CPU time), i.e. the CPU figure is slightly optimistic."""
     import torch.nn.functional as F
-    from oracle.port import common, meanshift as pms, segnet as port
+    from oracle.port import meanshift as pms, segnet as port
+    from tools.synth import ALL_KINDS, synth_cloud
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    pts, nrm, lab, prim = common.synth_cloud(1, N_POINTS, seed=0, n_patches=8)
+    pts, nrm, lab, prim = synth_cloud(1, N_POINTS, seed=0, n_patches=N_PATCHES, kinds=ALL_KINDS)
     x = torch.from_numpy(np.concatenate([pts, nrm], 2)).permute(0, 2, 1).contiguous()
     from src.PointNet import PrimitivesEmbeddingDGCNGn
     torch.manual_seed(0)

@@ -32,7 +32,12 @@ struct Bars {
     uint64_t x_full[NSTAGE], x_empty[NSTAGE], s_full[2], s_empty[2], p_full, p_empty, o_flush, o_done;
 };
 
-template <int MODE>
+// LITE: the gradient-side operand P (= gS, resp. [gS^T | K^T]) of the second product is rounded to tf32 (round to nearest)
+// instead of split, i.e. 2 instead of 3 MMAs per k-step for P.X (the streamed operand keeps its exact split).  The
+// exponent argument S and G = Gn.X^T (a cancellation against gd) keep the full 3-MMA split.  Simulated effect on the
+// gradients (float64 model with the same rounding, tests/test_cpu_host_logic.py): 1-4e-4 of the largest entry.
+// Opt-in (PN_MS_BWD_LITE=1); the default is the exact split.
+template <int MODE, bool LITE>
 __global__ void __launch_bounds__(NT, 1)
 ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, const float* __restrict__ Gn,
                  const float* __restrict__ gd, int N, const float* __restrict__ cinv, float* __restrict__ out,
@@ -147,7 +152,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                         e = fminf(fmaxf(e, -CL2), CL2);
                         float kk = ex2_approx(e);
                         float p = (!cl && (j0 + u < N)) ? (g + gd_row) * kk * c : 0.f;
-                        float big = tf32_hi(p);
+                        float big = LITE ? to_tf32(p) : tf32_hi(p);
                         pb[u] = __float_as_uint(big);
                         ps[u] = __float_as_uint(p - big);
                     }
@@ -169,7 +174,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                     e = fminf(fmaxf(e, -CL2), CL2);
                     float kk = iv ? ex2_approx(e) : 0.f;
                     float p1 = (!cl && iv) ? (__uint_as_float(g8[u]) + gdi) * kk * c : 0.f;
-                    float b1 = tf32_hi(p1), b2 = tf32_hi(kk);
+                    float b1 = LITE ? to_tf32(p1) : tf32_hi(p1), b2 = LITE ? to_tf32(kk) : tf32_hi(kk);
                     pb[u] = __float_as_uint(b1);       ps[u] = __float_as_uint(p1 - b1);       // gS^T -> cols 8h..
                     pb[8 + u] = __float_as_uint(b2);   ps[8 + u] = __float_as_uint(kk - b2);   // K^T  -> cols 16+8h..
                 }
@@ -195,7 +200,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
             if (MODE == MODE_ROWS) {
                 if (q < 2) {
                     tmem_st16(tb + la + C_PB + 16 * h, pb);
-                    tmem_st16(tb + la + C_PS + 16 * h, ps);
+                    if (!LITE) tmem_st16(tb + la + C_PS + 16 * h, ps);
                     tmem_st_wait();
                 }
             } else {
@@ -204,10 +209,12 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                 for (int u = 0; u < 8; ++u) { a[u] = pb[u]; d[u] = pb[8 + u]; }
                 tmem_st8(tb + la + C_PB + 8 * h, a);
                 tmem_st8(tb + la + C_PB + 16 + 8 * h, d);
+                if (!LITE) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { a[u] = ps[u]; d[u] = ps[8 + u]; }
-                tmem_st8(tb + la + C_PS + 8 * h, a);
-                tmem_st8(tb + la + C_PS + 16 + 8 * h, d);
+                    for (int u = 0; u < 8; ++u) { a[u] = ps[u]; d[u] = ps[8 + u]; }
+                    tmem_st8(tb + la + C_PS + 8 * h, a);
+                    tmem_st8(tb + la + C_PS + 16 + 8 * h, d);
+                }
                 tmem_st_wait();
             }
             tc_fence_before();
@@ -331,8 +338,12 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                 for (int ks = 0; ks < BN / 8; ++ks) {
                     const uint64_t db = db0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
                     const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
-                    mma_tf32_ts(tb + C_O, tb + C_PS + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
-                    mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, ds, idesc_o, 1);
+                    if (LITE) {
+                        mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, ds, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                    } else {
+                        mma_tf32_ts(tb + C_O, tb + C_PS + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                        mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, ds, idesc_o, 1);
+                    }
                     mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, db, idesc_o, 1);
                 }
                 mma_commit(&bars.x_empty[u % NSTAGE]);
@@ -413,16 +424,18 @@ extern "C" int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const flo
     mstcb::ms_bwd_prep_tc_kernel<<<cdiv(rows, 8), 256, 0, st>>>(gout, Ynew, den, unorm, rows, ws_Gn, ws_gd);
     PN_COUNT_LAUNCH();
     size_t sm = mstcb::NSTAGE * mstcb::STAGE_BYTES + 2 * 64 * 32 * sizeof(float) + 1024;
-    PN_CUDA(cudaFuncSetAttribute(mstcb::ms_bwd_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    PN_CUDA(cudaFuncSetAttribute(mstcb::ms_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    static const bool lite = [] { const char* e = getenv("PN_MS_BWD_LITE"); return e && e[0] == '1'; }();
+    auto rows_k = lite ? mstcb::ms_bwd_tc_kernel<0, true> : mstcb::ms_bwd_tc_kernel<0, false>;
+    auto cols_k = lite ? mstcb::ms_bwd_tc_kernel<1, true> : mstcb::ms_bwd_tc_kernel<1, false>;
+    PN_CUDA(cudaFuncSetAttribute(rows_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_CUDA(cudaFuncSetAttribute(cols_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const char* dbg = getenv("PN_MS_BWD_TC_ONLY");      // bring-up switch: "rows" / "cols" run a single kernel
     if (!dbg || dbg[0] == 'r') {
-        mstcb::ms_bwd_tc_kernel<0><<<dim3(cdiv(N, 64), B), mstcb::NT, sm, st>>>(Yprev, X, ws_Gn, ws_gd, N, cinv, gYprev, 0);
+        rows_k<<<dim3(cdiv(N, 64), B), mstcb::NT, sm, st>>>(Yprev, X, ws_Gn, ws_gd, N, cinv, gYprev, 0);
         PN_COUNT_LAUNCH();
     }
     if (!dbg || dbg[0] == 'c') {
-        mstcb::ms_bwd_tc_kernel<1><<<dim3(cdiv(N, 128), B), mstcb::NT, sm, st>>>(Yprev, X, ws_Gn, ws_gd, N, cinv, gX,
-                                                                                  accumulate_gX);
+        cols_k<<<dim3(cdiv(N, 128), B), mstcb::NT, sm, st>>>(Yprev, X, ws_Gn, ws_gd, N, cinv, gX, accumulate_gX);
         PN_COUNT_LAUNCH();
     }
     PN_LAUNCH_CHECK("ms_bwd_tc kernels");

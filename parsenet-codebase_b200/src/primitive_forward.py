@@ -11,6 +11,7 @@ from src.guard import guard_sqrt
 
 EPS = float(np.finfo(np.float32).eps)
 CLOSED_IDS, OPEN_IDS = (0, 6, 7, 9), (2, 8)
+STATS = {"analytic_fits": 0, "open_spline_fits": 0, "closed_spline_fits": 0}   # host counters (bench.py reports them)
 
 
 # ------------------------------------------------------------------------------------------------ SplineNet passes
@@ -198,11 +199,14 @@ def fit_one_shape_torch(data, fitter, weights, bw, eval=False, sample_points=Fal
             w_h = W[0::2, col:col + 1] + EPS
             if prim in CLOSED_IDS:
                 rec = fitter.forward_pass_closed_spline(pts_h, weights=w_h, ids=label_index, if_optimize=False)
+                STATS["closed_spline_fits"] += 1
             else:
                 rec = fitter.forward_pass_open_spline(pts_h, weights=w_h, ids=label_index, if_optimize=False)
+                STATS["open_spline_fits"] += 1
             recon.append(rec)
         else:
             fitter.fitting.parameters[label_index] = fits[col]
+            STATS["analytic_fits"] += 1
             recon.append(None)
         gt_points[label_index] = d[3]
     return gt_points, recon

@@ -213,3 +213,44 @@ def test_gram_svd_backward_is_finite_on_rank_deficient_gram_matrices():
     # well-separated spectrum: unchanged by the floor, and the gradient matches the closed form of the reference
     sv = torch.tensor([[3.0, 2.0, 1.0]], dtype=torch.float64)
     assert torch.equal(floor_singular_values(sv), sv)
+
+
+def test_ms_bwd_lite_rounding_model_stays_within_gradient_tolerance():
+    """float64 model of PN_MS_BWD_LITE (csrc/meanshift_tc_bwd.cu): the gradient-side operand of the second tile product
+    (gS for dY, [gS^T | K^T] for dX) rounded to tf32 (round to nearest), the streamed operand exact.  The error of the
+    gradients of one mean-shift iteration stays below the 1e-3 gradient tolerance; rounding BOTH operands (a single
+    tf32 MMA) would not keep a 2x margin, which is why that variant does not exist."""
+    import torch
+
+    def rna(x):
+        i = x.float().contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1fff).view(torch.float32).double()
+
+    def trunc(x):
+        return (x.float().contiguous().view(torch.int32) & ~0x1fff).view(torch.float32).double()
+
+    g0 = torch.Generator().manual_seed(1)
+    N = 300
+    X = torch.nn.functional.normalize(torch.randn(N, 128, generator=g0), dim=1).double()
+    Y = torch.nn.functional.normalize(X + 0.05 * torch.randn(N, 128, generator=g0).double(), dim=1)
+    g = torch.randn(N, 128, generator=g0).double()
+    worst_lite, worst_single = 0.0, 0.0
+    for bw in (0.8, 0.5, 1.2):
+        c = 1 / bw ** 2
+        K = torch.exp(torch.clamp((Y @ X.t() - 1.0) * c, -75, 75))
+        den = K.sum(1)
+        M = (K @ X) / den[:, None]
+        nr = M.norm(dim=1)
+        Yn = M / nr[:, None]
+        gu = (g - Yn * (g * Yn).sum(1, keepdim=True)) / nr[:, None]
+        Gn = gu / den[:, None]
+        gd = -((gu * Yn).sum(1) * nr) / den
+        gS = (Gn @ X.t() + gd[:, None]) * K * c
+        exact = (gS @ X, gS.t() @ Y + K.t() @ Gn)
+        lite = (rna(gS) @ X, rna(gS).t() @ Y + rna(K).t() @ Gn)
+        single = (rna(gS) @ trunc(X), rna(gS).t() @ trunc(Y) + rna(K).t() @ trunc(Gn))
+        for e, l, s in zip(exact, lite, single):
+            worst_lite = max(worst_lite, ((e - l).abs().max() / e.abs().max()).item())
+            worst_single = max(worst_single, ((e - s).abs().max() / e.abs().max()).item())
+    assert 1e-6 < worst_lite < 5e-4, worst_lite
+    assert worst_single > worst_lite

@@ -119,3 +119,40 @@ def test_tc_argsel_matches_fp32_pipe(B, Ma, Nb):
                 da, db = torch.gather(dist, 2, a.unsqueeze(2)).squeeze(2), torch.gather(dist, 2, b.unsqueeze(2)).squeeze(2)
                 near = torch.minimum((da - thr.double().view(B, 1)).abs(), (db - thr.double().view(B, 1)).abs())
                 assert ((va == vb) | (near < 1e-5))[diff].all()
+
+
+def test_tc_backward_lite_variant_within_gradient_tolerance():
+    """PN_MS_BWD_LITE=1 (P operand of the second product rounded to tf32 instead of split: 2 MMAs instead of 3) is read
+    once per process, so it is exercised in a child process: gradients stay within 1e-3 of the fp32-pipe kernels."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, "parsenet-codebase_b200"); sys.path.insert(0, "tests")
+from test_gpu_meanshift_tc import _setup, _fwd
+from pnb200.cabi import call
+worst = 0.0
+for B, N in ((1, 64), (2, 200), (3, 1111)):
+    X, Y, cinv = _setup(B, N, 1)
+    Yn, den, un = _fwd("pn_ms_iter_fwd", X, Y, cinv)
+    g = torch.randn_like(X)
+    outs = []
+    for name in ("pn_ms_iter_bwd", "pn_ms_iter_bwd_tc"):
+        Gn = torch.empty_like(X); gd = torch.empty(B, N, device="cuda")
+        gY = torch.empty_like(X); gX = torch.zeros_like(X) + 0.5
+        call(name, g.data_ptr(), Yn.data_ptr(), Y.data_ptr(), X.data_ptr(), den.data_ptr(), un.data_ptr(), B, N, 128,
+             cinv.data_ptr(), Gn.data_ptr(), gd.data_ptr(), gY.data_ptr(), gX.data_ptr(), 1,
+             torch.cuda.current_stream().cuda_stream)
+        outs.append((gY, gX))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.isfinite(b).all()
+        worst = max(worst, ((a - b).abs().max() / a.abs().max()).item())
+print("LITE_WORST", worst)
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PN_MS_BWD_LITE="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split("LITE_WORST")[-1])
+    assert 1e-6 < worst < 1e-3, worst          # > 1e-6: the variant really ran (the exact split sits at ~1e-6)
