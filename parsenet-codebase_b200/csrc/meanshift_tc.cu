@@ -15,6 +15,12 @@
 #include "common.cuh"
 #include "tc05.cuh"
 
+// Loader lane mapping (all tcgen05 mean-shift kernels): at step `it` a loader warp covers an 8-row x 4-float4 block of the
+// 32 x 128 tile: row j = 8*lw + (lane & 7), float4 column c4 = 4*it + (lane >> 3).  A warp-wide LDG then touches 8
+// 128-byte lines (64 contiguous bytes per row) instead of 32 (lane = row, one 16-byte piece of 32 different rows), the
+// XA store stays at its 4-wavefront minimum and the transposed XB store drops from 8 to 4 wavefronts.  ncu before the
+// change: l1tex LSU data pipe 79-81 % busy (the limiter), 1024 of ~1900 LSU wavefronts per tile were those global loads.
+
 namespace pn {
 namespace mstc {
 using namespace tc05;
@@ -184,9 +190,10 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
     } else if (warp < MMA_WARP) {
         // =============================================================================== loader warps
         const int lw = warp - LOAD_WARP0;        // 0..3
-        const int j = lane;                      // row inside the tile
-        const int l4 = lane & 3;
-        const int jg = lane >> 2;                // 4-row group for the transposed copy
+        const int j = 8 * lw + (lane & 7);       // row inside the tile (8-row block per warp)
+        const int cq = lane >> 3;                // float4 column inside the 4-column block of step `it`
+        const int l4 = lane & 3;                 // == j & 3
+        const int jg = j >> 2;                   // 4-row group for the transposed copy
         // software prefetch: the global loads of tile t+1 are issued before tile t is processed / before the stage
         // of tile t+1 is known to be free, so only the split + shared-memory stores sit on the stage-release path
         float4 vin[8], vnx[8];
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
             const bool ok0 = j < N;
 #pragma unroll
             for (int it = 0; it < 8; ++it)
-                vin[it] = ok0 ? *reinterpret_cast<const float4*>(Xb + (long long)j * D + 4 * (lw + 4 * it))
+                vin[it] = ok0 ? *reinterpret_cast<const float4*>(Xb + (long long)j * D + 4 * (4 * it + cq))
                               : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll 1
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                 const bool okn = (t + 1 < ntiles) && (jn < N);
 #pragma unroll
                 for (int it = 0; it < 8; ++it)
-                    vnx[it] = okn ? *reinterpret_cast<const float4*>(Xb + (long long)jn * D + 4 * (lw + 4 * it))
+                    vnx[it] = okn ? *reinterpret_cast<const float4*>(Xb + (long long)jn * D + 4 * (4 * it + cq))
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             mbar_wait(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
             unsigned char* xb_s = st + 2 * XA_BYTES + XB_BYTES;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int c4 = lw + 4 * it;      // float4 column 0..31
+                const int c4 = 4 * it + cq;      // float4 column 0..31
                 float f0 = vin[it].x, f1 = vin[it].y, f2 = vin[it].z, f3 = vin[it].w;
                 // XA: chunk (j, c4) as is
                 {

@@ -117,7 +117,7 @@ ms_argsel_tc_kernel(const float* __restrict__ A, long long a_stride, int Ma, con
         }
     } else if (warp < MMA_WARP) {
         const int lw = warp - LOAD_WARP0;
-        const int j = lane;
+        const int j = 8 * lw + (lane & 7), cq = lane >> 3;       // coalesced 8-row x 4-float4 mapping, see meanshift_tc.cu
         float4 vin[8], vnx[8];
         auto load_tile = [&](int t, float4 (&v)[8]) {
             const int r = t * BN + j;
@@ -125,7 +125,7 @@ ms_argsel_tc_kernel(const float* __restrict__ A, long long a_stride, int Ma, con
             const float* p = Bb + (long long)(ok ? r : 0) * D;
 #pragma unroll
             for (int it = 0; it < 8; ++it)
-                v[it] = ok ? *reinterpret_cast<const float4*>(p + 4 * (lw + 4 * it)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[it] = ok ? *reinterpret_cast<const float4*>(p + 4 * (4 * it + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         load_tile(0, vin);
 #pragma unroll 1
@@ -137,7 +137,7 @@ ms_argsel_tc_kernel(const float* __restrict__ A, long long a_stride, int Ma, con
             unsigned char* xa_s = xa_b + XA_BYTES;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int c4 = lw + 4 * it;
+                const int c4 = 4 * it + cq;
                 const float f0 = vin[it].x, f1 = vin[it].y, f2 = vin[it].z, f3 = vin[it].w;
                 const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
                 const uint32_t oa = (uint32_t)(c4 * XA_LBO + (j >> 3) * 128 + (j & 7) * 16);

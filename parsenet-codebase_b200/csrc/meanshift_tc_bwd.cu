@@ -248,7 +248,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
     } else if (warp < MMA_WARP) {
         // =============================================================================== loader warps
         const int lw = warp - LOAD_WARP0;
-        const int j = lane, l4 = lane & 3, jg = lane >> 2;
+        const int j = 8 * lw + (lane & 7), cq = lane >> 3, l4 = lane & 3, jg = j >> 2;   // see meanshift_tc.cu
         auto src_row = [&](int t) -> const float* {
             if (MODE == MODE_ROWS) {
                 const int r = t * 32 + j;
@@ -263,7 +263,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
             const float* p = src_row(0);
 #pragma unroll
             for (int it = 0; it < 8; ++it)
-                vin[it] = p ? *reinterpret_cast<const float4*>(p + 4 * (lw + 4 * it)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vin[it] = p ? *reinterpret_cast<const float4*>(p + 4 * (4 * it + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
@@ -272,7 +272,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                 const float* p = src_row(t + 1);
 #pragma unroll
                 for (int it = 0; it < 8; ++it)
-                    vnx[it] = p ? *reinterpret_cast<const float4*>(p + 4 * (lw + 4 * it)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vnx[it] = p ? *reinterpret_cast<const float4*>(p + 4 * (4 * it + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             DBG(warp, t * 10 + 1);
             mbar_wait(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
@@ -284,7 +284,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
             unsigned char* xb_s = st + 2 * XA_BYTES + XB_BYTES;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int c4 = lw + 4 * it;
+                const int c4 = 4 * it + cq;
                 float f0 = vin[it].x, f1 = vin[it].y, f2 = vin[it].z, f3 = vin[it].w;
                 {
                     const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);

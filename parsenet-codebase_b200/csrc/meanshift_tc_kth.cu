@@ -161,7 +161,7 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
         }
     } else if (warp < MMA_WARP) {
         const int lw = warp - LOAD_WARP0;
-        const int j = lane;
+        const int j = 8 * lw + (lane & 7), cq = lane >> 3;       // coalesced 8-row x 4-float4 mapping, see meanshift_tc.cu
         float4 vin[8], vnx[8];
         auto load_tile = [&](int tt, float4 (&v)[8]) {
             const int t = tt % ntiles;
@@ -170,7 +170,7 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
             const float* p = ok ? row_ptr(r) : nullptr;
 #pragma unroll
             for (int it = 0; it < 8; ++it)
-                v[it] = ok ? *reinterpret_cast<const float4*>(p + 4 * (lw + 4 * it)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[it] = ok ? *reinterpret_cast<const float4*>(p + 4 * (4 * it + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         load_tile(0, vin);
 #pragma unroll 1
@@ -182,7 +182,7 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
             unsigned char* xa_s = xa_b + XA_BYTES;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int c4 = lw + 4 * it;
+                const int c4 = 4 * it + cq;
                 const float f0 = vin[it].x, f1 = vin[it].y, f2 = vin[it].z, f3 = vin[it].w;
                 const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
                 const uint32_t oa = (uint32_t)(c4 * XA_LBO + (j >> 3) * 128 + (j & 7) * 16);
