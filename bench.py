@@ -177,16 +177,30 @@ def run_ours(args):
         np.random.seed(i)
         return hp.step(x, host_np[i % 2][0], host_np[i % 2][1], lab, prim)
 
-    def e2e_step(i):
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+    losses = []
+
+    def e2e_step(i, last=False):
+        """public-API step with HOST inputs: pinned H2D of the batch, the step, D2H of its loss.  The loss of step i is
+        copied asynchronously and consumed after step i+1 has been enqueued (lagged logging, like a production loop), so
+        the host keeps one step of launch work ahead of the device; the last step's loss is read inside the region."""
         hx, hl, hpm = host[i % 2]
         x = hx.to(dev, non_blocking=True); lab = hl.to(dev, non_blocking=True); prim = hpm.to(dev, non_blocking=True)
         np.random.seed(i)
         loss = hp.step(x, host_np[i % 2][0], host_np[i % 2][1], lab, prim)
-        return loss.item()                     # D2H read of the step's result
+        loss_host[i % 2:i % 2 + 1].copy_(loss.detach().reshape(1), non_blocking=True)     # D2H read of the step's result
+        loss_ready[i % 2].record()
+        if i > 0:
+            loss_ready[(i - 1) % 2].synchronize()
+            losses.append(float(loss_host[(i - 1) % 2]))
+        if last:
+            loss_ready[i % 2].synchronize()
+            losses.append(float(loss_host[i % 2]))
 
     for i in range(args.warmup):
         resident_step(i)
-        e2e_step(i)
+        e2e_step(i, last=True)
     # ---- timed: resident inputs
     sampler = ClockSampler(local)
     if rank == 0:
@@ -217,13 +231,18 @@ def run_ours(args):
     barrier()
     ev2 = torch.cuda.Event(enable_timing=True); ev3 = torch.cuda.Event(enable_timing=True)
     ev2.record()
+    mem0 = torch.cuda.memory_stats(dev)
     for i in range(args.steps):
         flush.zero_()
-        e2e_step(i)
+        e2e_step(i, last=(i == args.steps - 1))
     ev3.record()
     barrier()
     t_wall1 = time.time()
     ms_e2e = ev2.elapsed_time(ev3)
+    mem1 = torch.cuda.memory_stats(dev)
+    alloc = {"cudaMalloc_calls_in_e2e_region": int(mem1.get("num_device_alloc", 0) - mem0.get("num_device_alloc", 0)),
+             "alloc_retries_in_e2e_region": int(mem1.get("num_alloc_retries", 0) - mem0.get("num_alloc_retries", 0)),
+             "peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)}
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     if world > 1:
         import torch.distributed as dist
@@ -284,7 +303,8 @@ def run_ours(args):
                    "parallelism": f"dp{world}", "l2": "256 MB flush write between timed steps; per-step working set "
                                                       ">> 126 MB L2"},
         "e2e": {"value": e2e_v, "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "last_loss": (losses[-1] if losses else None),
+                "loss_read": "every step, lagged by one step (async D2H + event)", "allocator": alloc},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,

@@ -26,7 +26,11 @@ constexpr uint32_t XA_LBO = BN * 16, XB_LBO = D * 16, SBO = 128;
 enum { MODE_ROWS = 0, MODE_COLS = 1 };
 
 __device__ volatile int* g_dbg = nullptr;   // bring-up aid: host-mapped progress words (set by pn_debug_set_progress)
+#ifdef PN_MS_DEBUG
 #define DBG(slot, val) do { if (g_dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) { g_dbg[slot] = (val); __threadfence_system(); } } while (0)
+#else
+#define DBG(slot, val) do { } while (0)      // (each live DBG site costs an LDG of g_dbg on the critical path)
+#endif
 
 struct Bars {
     uint64_t x_full[NSTAGE], x_empty[NSTAGE], s_full[2], s_empty[2], p_full, p_empty, o_flush, o_done;
@@ -37,11 +41,16 @@ struct Bars {
 // exponent argument S and G = Gn.X^T (a cancellation against gd) keep the full 3-MMA split.  Simulated effect on the
 // gradients (float64 model with the same rounding, tests/test_cpu_host_logic.py): 1-4e-4 of the largest entry.
 // Opt-in (PN_MS_BWD_LITE=1); the default is the exact split.
-template <int MODE, bool LITE>
+// VAR bit 0 = LITE.  The other bits are TIMING-ONLY ablations (results are wrong by construction; tools/exp_ms_bwd.py):
+//   2 no exp in the epilogue, 4 loaders skip the "small" split stores, 8 no second-product MMAs, 16 one instead of three
+//   MMAs in the first product, 32 loaders skip the transposed copy, 64 epilogue skips the P stores to TMEM.
+template <int MODE, int VAR>
 __global__ void __launch_bounds__(NT, 1)
 ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, const float* __restrict__ Gn,
                  const float* __restrict__ gd, int N, const float* __restrict__ cinv, float* __restrict__ out,
                  int accumulate) {
+    constexpr bool LITE = (VAR & 1) != 0, A_NOEXP = (VAR & 2) != 0, A_NOSMALL = (VAR & 4) != 0, A_NOG2 = (VAR & 8) != 0,
+                   A_G1ONE = (VAR & 16) != 0, A_NOXB = (VAR & 32) != 0, A_NOPST = (VAR & 64) != 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ Bars bars;
     __shared__ uint32_t tmem_base_s;
@@ -150,7 +159,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                         float e = (__uint_as_float(sv[u]) - 1.0f) * c2;
                         const bool cl = (e > CL2) || (e < -CL2);
                         e = fminf(fmaxf(e, -CL2), CL2);
-                        float kk = ex2_approx(e);
+                        float kk = A_NOEXP ? e : ex2_approx(e);
                         float p = (!cl && (j0 + u < N)) ? (g + gd_row) * kk * c : 0.f;
                         float big = LITE ? to_tf32(p) : tf32_hi(p);
                         pb[u] = __float_as_uint(big);
@@ -172,7 +181,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                     float e = (__uint_as_float(s8[u]) - 1.0f) * c2;
                     const bool cl = (e > CL2) || (e < -CL2);
                     e = fminf(fmaxf(e, -CL2), CL2);
-                    float kk = iv ? ex2_approx(e) : 0.f;
+                    float kk = iv ? (A_NOEXP ? e : ex2_approx(e)) : 0.f;
                     float p1 = (!cl && iv) ? (__uint_as_float(g8[u]) + gdi) * kk * c : 0.f;
                     float b1 = LITE ? to_tf32(p1) : tf32_hi(p1), b2 = LITE ? to_tf32(kk) : tf32_hi(kk);
                     pb[u] = __float_as_uint(b1);       ps[u] = __float_as_uint(p1 - b1);       // gS^T -> cols 8h..
@@ -198,12 +207,12 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                 mbar_arrive(&bars.o_flush);
             }
             if (MODE == MODE_ROWS) {
-                if (q < 2) {
+                if (q < 2 && !A_NOPST) {
                     tmem_st16(tb + la + C_PB + 16 * h, pb);
                     if (!LITE) tmem_st16(tb + la + C_PS + 16 * h, ps);
                     tmem_st_wait();
                 }
-            } else {
+            } else if (!A_NOPST) {
                 uint32_t a[8], d[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { a[u] = pb[u]; d[u] = pb[8 + u]; }
@@ -290,9 +299,9 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                     const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
                     const uint32_t oa = (uint32_t)(c4 * XA_LBO + (j >> 3) * 128 + (j & 7) * 16);
                     *reinterpret_cast<float4*>(xa_b + oa) = make_float4(b0, b1, b2, b3);
-                    *reinterpret_cast<float4*>(xa_s + oa) = make_float4(f0 - b0, f1 - b1, f2 - b2, f3 - b3);
+                    if (!A_NOSMALL) *reinterpret_cast<float4*>(xa_s + oa) = make_float4(f0 - b0, f1 - b1, f2 - b2, f3 - b3);
                 }
-                {
+                if (!A_NOXB) {
                     const bool hi = (l4 & 2) != 0;
                     float sa = hi ? f0 : f2, sb = hi ? f1 : f3;
                     sa = __shfl_xor_sync(0xffffffffu, sa, 2);
@@ -304,12 +313,12 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                     sd = __shfl_xor_sync(0xffffffffu, sd, 1);
                     f0 = od ? sc : f0; f1 = od ? f1 : sc; f2 = od ? sd : f2; f3 = od ? f3 : sd;
                 }
-                {
+                if (!A_NOXB) {
                     const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
                     const int d = 4 * c4 + l4;
                     const uint32_t ob = (uint32_t)(jg * XB_LBO + (d >> 3) * 128 + (d & 7) * 16);
                     *reinterpret_cast<float4*>(xb_b + ob) = make_float4(b0, b1, b2, b3);
-                    *reinterpret_cast<float4*>(xb_s + ob) = make_float4(f0 - b0, f1 - b1, f2 - b2, f3 - b3);
+                    if (!A_NOSMALL) *reinterpret_cast<float4*>(xb_s + ob) = make_float4(f0 - b0, f1 - b1, f2 - b2, f3 - b3);
                 }
             }
             fence_async_smem();
@@ -335,7 +344,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
             const uint64_t ds0 = make_smem_desc(st + 2 * XA_BYTES + XB_BYTES, XB_LBO, SBO, 0);
             if (leader) {
 #pragma unroll
-                for (int ks = 0; ks < BN / 8; ++ks) {
+                for (int ks = 0; ks < (A_NOG2 ? 0 : BN / 8); ++ks) {
                     const uint64_t db = db0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
                     const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
                     if (LITE) {
@@ -373,6 +382,10 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                 for (int ks = 0; ks < D / 8; ++ks) {
                     const uint64_t db = db0 + (uint64_t)(ks * ((2 * XA_LBO) >> 4));
                     const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XA_LBO) >> 4));
+                    if (A_G1ONE) {
+                        mma_tf32_ts(d_s, tb + C_AB + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
+                        continue;
+                    }
                     mma_tf32_ts(d_s, tb + C_AS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
                     mma_tf32_ts(d_s, tb + C_AB + ks * 8, ds, idesc_s, 1);
                     mma_tf32_ts(d_s, tb + C_AB + ks * 8, db, idesc_s, 1);
@@ -425,8 +438,17 @@ extern "C" int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const flo
     PN_COUNT_LAUNCH();
     size_t sm = mstcb::NSTAGE * mstcb::STAGE_BYTES + 2 * 64 * 32 * sizeof(float) + 1024;
     static const bool lite = [] { const char* e = getenv("PN_MS_BWD_LITE"); return e && e[0] == '1'; }();
-    auto rows_k = lite ? mstcb::ms_bwd_tc_kernel<0, true> : mstcb::ms_bwd_tc_kernel<0, false>;
-    auto cols_k = lite ? mstcb::ms_bwd_tc_kernel<1, true> : mstcb::ms_bwd_tc_kernel<1, false>;
+    int var = lite ? 1 : 0;
+    if (const char* e = getenv("PN_MS_BWD_ABLATE")) var = atoi(e);          // timing-only ablations (wrong results)
+    using KernelT = void (*)(const float*, const float*, const float*, const float*, int, const float*, float*, int);
+    KernelT rows_k = nullptr, cols_k = nullptr;
+#define PN_VAR_CASE(V) case V: rows_k = mstcb::ms_bwd_tc_kernel<0, V>; cols_k = mstcb::ms_bwd_tc_kernel<1, V>; break;
+    switch (var) {
+        PN_VAR_CASE(0) PN_VAR_CASE(1) PN_VAR_CASE(2) PN_VAR_CASE(4) PN_VAR_CASE(8) PN_VAR_CASE(16) PN_VAR_CASE(32)
+        PN_VAR_CASE(64) PN_VAR_CASE(36) PN_VAR_CASE(24) PN_VAR_CASE(126)
+        default: PN_REQUIRE(false, "pn_ms_iter_bwd_tc: unknown PN_MS_BWD_ABLATE variant %d", var);
+    }
+#undef PN_VAR_CASE
     PN_CUDA(cudaFuncSetAttribute(rows_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     PN_CUDA(cudaFuncSetAttribute(cols_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const char* dbg = getenv("PN_MS_BWD_TC_ONLY");      // bring-up switch: "rows" / "cols" run a single kernel
