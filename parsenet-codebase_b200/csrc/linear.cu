@@ -12,6 +12,7 @@
 // v1 math: FP32 FMA pipe, 128x128x16 tiles, 256 threads x (8x8) register tile, double-buffered shared memory.
 // (fp32-exact products; the tcgen05 3xTF32 path replaces the main loop, the epilogues stay.)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace pn {
 namespace lin {
@@ -279,7 +280,10 @@ struct BwdDataArgs {
     int vecdY, vecW, vecdZ;
 };
 
-__global__ void __launch_bounds__(NT, 2) linear_bwd_data_kernel(BwdDataArgs p) {
+// MINB = resident CTAs per SM the register allocation is capped for: 2 -> 128 registers (bwd_data spills 108 B, bwd_weight
+// 584 B per thread), 1 -> no cap (159 / 207 registers, no spills, 8 warps per SM).  PN_LIN_BWD_OCC selects (default 1).
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) linear_bwd_data_kernel(BwdDataArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Tile& S = *reinterpret_cast<Tile*>(smem_raw);
     __shared__ float c1[BN], c2[BN];
@@ -405,7 +409,8 @@ struct BwdWArgs {
     int vecdY, vecA;
 };
 
-__global__ void __launch_bounds__(NT, 2) linear_bwd_weight_kernel(BwdWArgs p) {
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) linear_bwd_weight_kernel(BwdWArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Tile& S = *reinterpret_cast<Tile*>(smem_raw);
     const int n0 = blockIdx.x * BM;      // dW rows (Nout)
@@ -571,6 +576,11 @@ extern "C" int pn_linear_fwd(const float* A, long long lda, const float* W, long
     return PN_OK;
 }
 
+static int bwd_occ() {      // read per call: tools/exp_linear_bwd.py flips it inside one process
+    const char* e = getenv("PN_LIN_BWD_OCC");
+    return (e && e[0] == '2') ? 2 : 1;
+}
+
 extern "C" int pn_linear_bwd_data(const float* dY, long long lddy, const float* W, long long ldw, float* dZ,
                                   long long lddz, int accumulate, int finalize, const float* A, long long lda,
                                   const float* in_scale, const float* in_shift, int in_act, const float* gamma,
@@ -584,10 +594,11 @@ extern "C" int pn_linear_bwd_data(const float* dY, long long lddy, const float* 
     p.vecdY = aligned16(dY) && lddy % 4 == 0;
     p.vecW = aligned16(W) && ldw % 4 == 0;
     p.vecdZ = aligned16(dZ) && lddz % 4 == 0;
-    PN_REQUIRE(set_smem((const void*)linear_bwd_data_kernel) == 0, "pn_linear_bwd_data: smem attribute");
+    auto kern = bwd_occ() == 2 ? linear_bwd_data_kernel<2> : linear_bwd_data_kernel<1>;
+    PN_REQUIRE(set_smem((const void*)kern) == 0, "pn_linear_bwd_data: smem attribute");
     PN_REQUIRE((long long)cdiv(Np, BM) * B <= 65535, "pn_linear_bwd_data: too many row tiles (%d x %d)", cdiv(Np, BM), B);
     dim3 grid(cdiv(K, BN), cdiv(Np, BM) * B);
-    linear_bwd_data_kernel<<<grid, NT, sizeof(Tile), (cudaStream_t)stream>>>(p);
+    kern<<<grid, NT, sizeof(Tile), (cudaStream_t)stream>>>(p);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("linear_bwd_data_kernel");
     return PN_OK;
@@ -608,9 +619,10 @@ extern "C" int pn_linear_bwd_weight(const float* dY, long long lddy, const float
     rows = max(BK * 4, ((rows + BK - 1) / BK) * BK);
     p.rows_per_split = rows;
     p.splits_per_shape = cdiv(Np, rows);
-    PN_REQUIRE(set_smem((const void*)linear_bwd_weight_kernel) == 0, "pn_linear_bwd_weight: smem attribute");
+    auto kern = bwd_occ() == 2 ? linear_bwd_weight_kernel<2> : linear_bwd_weight_kernel<1>;
+    PN_REQUIRE(set_smem((const void*)kern) == 0, "pn_linear_bwd_weight: smem attribute");
     dim3 grid(cdiv(Nout, BM), cdiv(K, BN), p.splits_per_shape * B);
-    linear_bwd_weight_kernel<<<grid, NT, sizeof(Tile), (cudaStream_t)stream>>>(p);
+    kern<<<grid, NT, sizeof(Tile), (cudaStream_t)stream>>>(p);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("linear_bwd_weight_kernel");
     return PN_OK;

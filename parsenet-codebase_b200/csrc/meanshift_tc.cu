@@ -14,6 +14,7 @@
 // Issue order G1(0) G1(1) G2(0) G1(2) G2(1) ... so the exp of tile t overlaps the S-MMA of tile t+1.
 #include "common.cuh"
 #include "tc05.cuh"
+#include <stdlib.h>
 
 // Loader lane mapping (all tcgen05 mean-shift kernels): at step `it` a loader warp covers an 8-row x 4-float4 block of the
 // 32 x 128 tile: row j = 8*lw + (lane & 7), float4 column c4 = 4*it + (lane >> 3).  A warp-wide LDG then touches 8
@@ -39,12 +40,17 @@ constexpr int XB_BYTES = D * BN * 4;     // layout [j/4][d/8][8][16B]   LBO = D*
 constexpr int STAGE_BYTES = 2 * XA_BYTES + 2 * XB_BYTES;   // 64 KB
 constexpr uint32_t XA_LBO = BN * 16, XB_LBO = D * 16, SBO = 128;
 
+constexpr uint32_t C_PS2 = 320;   // PDB: P_small buffers [320,352), [352,384); P_big of tile t aliases S buffer t&1 (C_S0 + 32k)
+
 struct Bars {
     uint64_t x_full[NSTAGE], x_empty[NSTAGE], s_full[2], s_empty[2], p_full, p_empty, o_flush, o_done;
+    uint64_t p_full2[2], a_ready;    // PDB: per-buffer "P ready", separate "Y rows in TMEM"
 };
 
-// grid (ceil(N/BM), B)
-__global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restrict__ Y, const float* __restrict__ X, int N,
+// grid (ceil(N/BM), B).  PDB = double-buffered P (P_big written in place over the S columns the thread has just loaded,
+// see meanshift_tc_bwd.cu): the epilogue of tile t no longer waits for the second product of tile t-1.
+template <bool PDB>
+__global__ void __maxnreg__(152) ms_fwd_tc_kernel(const float* __restrict__ Y, const float* __restrict__ X, int N,
                                                           const float* __restrict__ cinv, float* __restrict__ Ynew,
                                                           float* __restrict__ den_out, float* __restrict__ unorm_out) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -64,6 +70,8 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
         for (int k = 0; k < 2; ++k) { mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); }
         mbar_init(&bars.p_full, EPI_THREADS); mbar_init(&bars.p_empty, 1);
         mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
+        mbar_init(&bars.p_full2[0], EPI_THREADS); mbar_init(&bars.p_full2[1], EPI_THREADS);
+        mbar_init(&bars.a_ready, EPI_THREADS);
         mbar_fence_init();
     }
     tc_fence_before();
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars.p_full);          // phase 0 of p_full doubles as "Y is in TMEM" (consumed by the MMA warp)
+        mbar_arrive(PDB ? &bars.a_ready : &bars.p_full);   // (non-PDB: phase 0 of p_full doubles as "Y is in TMEM")
         float oacc[64];
 #pragma unroll
         for (int e = 0; e < 64; ++e) oacc[e] = 0.f;
@@ -127,10 +135,14 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                 pb[u] = __float_as_uint(big);
                 ps[u] = __float_as_uint(p - big);
             }
-            // P buffer free?  (G2 of tile t-1 finished)   p_empty completes once per tile; first wait passes (fresh)
-            mbar_wait(&bars.p_empty, (t & 1) ^ 1);
-            tc_fence_after();
-            if (t > 0 && (t % FLUSH) == 0) {
+            // non-PDB: P buffer free?  (G2 of tile t-1 finished)   p_empty completes once per tile; first wait passes (fresh)
+            // PDB: s_full(t) already implies G2(t-2) done; G2(t-1) only has to be complete before O is drained
+            const bool flush_now = (t > 0 && (t % FLUSH) == 0);
+            if (!PDB || flush_now) {
+                mbar_wait(&bars.p_empty, (t & 1) ^ 1);
+                tc_fence_after();
+            }
+            if (flush_now) {
                 // drain this thread's half of the O accumulator (sum over the previous FLUSH tiles) into registers
 #pragma unroll
                 for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -143,11 +155,11 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                 tc_fence_before();
                 mbar_arrive(&bars.o_flush);
             }
-            tmem_st16(tb + la + C_PB + 16 * h, pb);
-            tmem_st16(tb + la + C_PS + 16 * h, ps);
+            tmem_st16(tb + la + (PDB ? C_S0 + 32 * k : C_PB) + 16 * h, pb);
+            tmem_st16(tb + la + (PDB ? C_PS2 + 32 * k : C_PS) + 16 * h, ps);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bars.p_full);      // phase t+1
+            mbar_arrive(PDB ? &bars.p_full2[k] : &bars.p_full);      // (non-PDB: phase t+1)
         }
         // ---- final: last O chain, then u = y + (O/den - y), Y' = u/|u|
         mbar_wait(&bars.o_done, 0);
@@ -267,7 +279,9 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
         const uint32_t idesc_o = make_idesc(2, BM, D, 0, 0);
         const uint32_t sbase = smem_u32(smem);
         auto gemm2 = [&](int u) {
-            mbar_wait(&bars.p_full, (u + 1) & 1);              // phase u+1 (phase 0 was the Y-ready arrival)
+            if (PDB) mbar_wait(&bars.p_full2[u & 1], (u >> 1) & 1);
+            else mbar_wait(&bars.p_full, (u + 1) & 1);         // phase u+1 (phase 0 was the Y-ready arrival)
+            const uint32_t pb_col = PDB ? (C_S0 + 32 * (u & 1)) : C_PB, ps_col = PDB ? (C_PS2 + 32 * (u & 1)) : C_PS;
             const bool fresh = (u % FLUSH) == 0;
             if (u > 0 && fresh) mbar_wait(&bars.o_flush, ((u / FLUSH) - 1) & 1);
             tc_fence_after();
@@ -279,16 +293,16 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                 for (int ks = 0; ks < BN / 8; ++ks) {
                     const uint64_t db = db0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
                     const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
-                    mma_tf32_ts(tb + C_O, tb + C_PS + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
-                    mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, ds, idesc_o, 1);
-                    mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, db, idesc_o, 1);
+                    mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
+                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
                 }
                 mma_commit(&bars.x_empty[u % NSTAGE]);
                 mma_commit(&bars.p_empty);
             }
             __syncwarp();
         };
-        mbar_wait(&bars.p_full, 0);                             // Y rows are in TMEM
+        mbar_wait(PDB ? &bars.a_ready : &bars.p_full, 0);       // Y rows are in TMEM
         tc_fence_after();
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
@@ -332,9 +346,11 @@ extern "C" int pn_ms_iter_fwd_tc(const float* Y, const float* X, int B, int N, i
     PN_REQUIRE(Y && X && cinv && Ynew && den && unorm, "pn_ms_iter_fwd_tc: null pointer");
     PN_REQUIRE(d == mstc::D, "pn_ms_iter_fwd_tc: embedding width must be %d (got %d)", mstc::D, d);
     size_t sm = mstc::NSTAGE * mstc::STAGE_BYTES + 1024;
-    PN_CUDA(cudaFuncSetAttribute(mstc::ms_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    static const bool pdb = [] { const char* e = getenv("PN_MS_FWD_PDB"); return !(e && e[0] == '0'); }();
+    auto kern = pdb ? mstc::ms_fwd_tc_kernel<true> : mstc::ms_fwd_tc_kernel<false>;
+    PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(cdiv(N, mstc::BM), B);
-    mstc::ms_fwd_tc_kernel<<<grid, mstc::NT, sm, (cudaStream_t)stream>>>(Y, X, N, cinv, Ynew, den, unorm);
+    kern<<<grid, mstc::NT, sm, (cudaStream_t)stream>>>(Y, X, N, cinv, Ynew, den, unorm);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("ms_fwd_tc_kernel");
     return PN_OK;

@@ -32,8 +32,17 @@ __device__ volatile int* g_dbg = nullptr;   // bring-up aid: host-mapped progres
 #define DBG(slot, val) do { } while (0)      // (each live DBG site costs an LDG of g_dbg on the critical path)
 #endif
 
+// PDB (VAR bit 7, the default): P is double-buffered.  P_big of tile t is written IN PLACE over the S / G accumulator
+// columns of buffer t&1 (every epilogue thread overwrites exactly the columns it has just loaded), P_small has its own
+// two 32-column buffers.  The epilogue of tile t then only needs s_full(t) -- tcgen05.mma executes in issue order, so
+// "first product of tile t complete" implies "second product of tile t-2 complete" -- and no longer waits for the second
+// product of tile t-1 before it can hand over P(t): a whole tile step of slack on the MMA -> epilogue -> MMA round trip
+// (the ablation sweep in profiles/r01_ms_bwd_ablation_sweep.md showed the kernel bound by exactly that latency chain).
+constexpr uint32_t C_PS2 = 320;      // PDB: P_small buffers [320,352) and [352,384); P_big aliases C_D0 + 32k
+
 struct Bars {
     uint64_t x_full[NSTAGE], x_empty[NSTAGE], s_full[2], s_empty[2], p_full, p_empty, o_flush, o_done;
+    uint64_t p_full2[2], a_ready;    // PDB: per-buffer "P ready", separate "A operands in TMEM"
 };
 
 // LITE: the gradient-side operand P (= gS, resp. [gS^T | K^T]) of the second product is rounded to tf32 (round to nearest)
@@ -45,12 +54,12 @@ struct Bars {
 //   2 no exp in the epilogue, 4 loaders skip the "small" split stores, 8 no second-product MMAs, 16 one instead of three
 //   MMAs in the first product, 32 loaders skip the transposed copy, 64 epilogue skips the P stores to TMEM.
 template <int MODE, int VAR>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __maxnreg__(152)      // 13 warps x 152 regs fit the register file; (416,1) launch bounds cap at 128 and spill
 ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, const float* __restrict__ Gn,
                  const float* __restrict__ gd, int N, const float* __restrict__ cinv, float* __restrict__ out,
                  int accumulate) {
     constexpr bool LITE = (VAR & 1) != 0, A_NOEXP = (VAR & 2) != 0, A_NOSMALL = (VAR & 4) != 0, A_NOG2 = (VAR & 8) != 0,
-                   A_G1ONE = (VAR & 16) != 0, A_NOXB = (VAR & 32) != 0, A_NOPST = (VAR & 64) != 0;
+                   A_G1ONE = (VAR & 16) != 0, A_NOXB = (VAR & 32) != 0, A_NOPST = (VAR & 64) != 0, PDB = (VAR & 128) != 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ Bars bars;
     __shared__ uint32_t tmem_base_s;
@@ -74,6 +83,8 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
         for (int k = 0; k < 2; ++k) { mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); }
         mbar_init(&bars.p_full, EPI_THREADS); mbar_init(&bars.p_empty, 1);
         mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
+        mbar_init(&bars.p_full2[0], EPI_THREADS); mbar_init(&bars.p_full2[1], EPI_THREADS);
+        mbar_init(&bars.a_ready, EPI_THREADS);
         mbar_fence_init();
     }
     tc_fence_before();
@@ -120,12 +131,17 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
             uint32_t z[16];
 #pragma unroll
             for (int u = 0; u < 16; ++u) z[u] = 0u;
-            tmem_st16(tb + la + C_PB + 16 * h, z);
-            tmem_st16(tb + la + C_PS + 16 * h, z);
+            if (PDB) {                                           // (P_big of the virtual half is re-zeroed every tile)
+                tmem_st16(tb + la + C_PS2 + 16 * h, z);
+                tmem_st16(tb + la + C_PS2 + 32 + 16 * h, z);
+            } else {
+                tmem_st16(tb + la + C_PB + 16 * h, z);
+                tmem_st16(tb + la + C_PS + 16 * h, z);
+            }
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars.p_full);                               // phase 0: A operands are in TMEM
+        mbar_arrive(PDB ? &bars.a_ready : &bars.p_full);         // (non-PDB: phase 0 of p_full) A operands are in TMEM
         const bool owner = (MODE == MODE_COLS) || (q < 2);       // threads that own output rows
         float oacc[64];
 #pragma unroll
@@ -189,10 +205,13 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                 }
             }
             DBG(warp, t * 10 + 3);
-            mbar_wait(&bars.p_empty, (t & 1) ^ 1);
-            tc_fence_after();
+            const bool flush_now = (t > 0 && (t % FLUSH) == 0);
+            if (!PDB || flush_now) {                 // second product of tile t-1 complete (PDB: only needed to drain O)
+                mbar_wait(&bars.p_empty, (t & 1) ^ 1);
+                tc_fence_after();
+            }
             DBG(warp, t * 10 + 4);
-            if (t > 0 && (t % FLUSH) == 0) {
+            if (flush_now) {
                 if (owner) {
 #pragma unroll
                     for (int c0 = 0; c0 < 64; c0 += 16) {
@@ -206,28 +225,36 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                 tc_fence_before();
                 mbar_arrive(&bars.o_flush);
             }
+            const uint32_t pb_col = PDB ? (C_D0 + 32 * k) : C_PB, ps_col = PDB ? (C_PS2 + 32 * k) : C_PS;
             if (MODE == MODE_ROWS) {
                 if (q < 2 && !A_NOPST) {
-                    tmem_st16(tb + la + C_PB + 16 * h, pb);
-                    if (!LITE) tmem_st16(tb + la + C_PS + 16 * h, ps);
+                    tmem_st16(tb + la + pb_col + 16 * h, pb);
+                    if (!LITE) tmem_st16(tb + la + ps_col + 16 * h, ps);
+                    tmem_st_wait();
+                }
+                if (PDB && q >= 2) {                 // the G values of the virtual half must not act as P rows
+                    uint32_t z[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) z[u] = 0u;
+                    tmem_st16(tb + la + pb_col + 16 * h, z);
                     tmem_st_wait();
                 }
             } else if (!A_NOPST) {
                 uint32_t a[8], d[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) { a[u] = pb[u]; d[u] = pb[8 + u]; }
-                tmem_st8(tb + la + C_PB + 8 * h, a);
-                tmem_st8(tb + la + C_PB + 16 + 8 * h, d);
+                tmem_st8(tb + la + pb_col + 8 * h, a);
+                tmem_st8(tb + la + pb_col + 16 + 8 * h, d);
                 if (!LITE) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) { a[u] = ps[u]; d[u] = ps[8 + u]; }
-                    tmem_st8(tb + la + C_PS + 8 * h, a);
-                    tmem_st8(tb + la + C_PS + 16 + 8 * h, d);
+                    tmem_st8(tb + la + ps_col + 8 * h, a);
+                    tmem_st8(tb + la + ps_col + 16 + 8 * h, d);
                 }
                 tmem_st_wait();
             }
             tc_fence_before();
-            mbar_arrive(&bars.p_full);
+            mbar_arrive(PDB ? &bars.p_full2[k] : &bars.p_full);
         }
         mbar_wait(&bars.o_done, 0);
         tc_fence_after();
@@ -334,8 +361,10 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
         const uint32_t sbase = smem_u32(smem);
         auto gemm2 = [&](int u) {
             DBG(13, u * 10 + 1);
-            mbar_wait(&bars.p_full, (u + 1) & 1);
+            if (PDB) mbar_wait(&bars.p_full2[u & 1], (u >> 1) & 1);
+            else mbar_wait(&bars.p_full, (u + 1) & 1);
             DBG(13, u * 10 + 2);
+            const uint32_t pb_col = PDB ? (C_D0 + 32 * (u & 1)) : C_PB, ps_col = PDB ? (C_PS2 + 32 * (u & 1)) : C_PS;
             const bool fresh = (u % FLUSH) == 0;
             if (u > 0 && fresh) mbar_wait(&bars.o_flush, ((u / FLUSH) - 1) & 1);
             tc_fence_after();
@@ -348,12 +377,12 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                     const uint64_t db = db0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
                     const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
                     if (LITE) {
-                        mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, ds, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                        mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, (fresh && ks == 0) ? 0u : 1u);
                     } else {
-                        mma_tf32_ts(tb + C_O, tb + C_PS + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
-                        mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, ds, idesc_o, 1);
+                        mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                        mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
                     }
-                    mma_tf32_ts(tb + C_O, tb + C_PB + ks * 8, db, idesc_o, 1);
+                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
                 }
                 mma_commit(&bars.x_empty[u % NSTAGE]);
                 mma_commit(&bars.p_empty);
@@ -361,7 +390,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
             __syncwarp();
         };
         DBG(14, 1);
-        mbar_wait(&bars.p_full, 0);
+        mbar_wait(PDB ? &bars.a_ready : &bars.p_full, 0);
         DBG(14, 2);
         tc_fence_after();
 #pragma unroll 1
@@ -438,14 +467,15 @@ extern "C" int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const flo
     PN_COUNT_LAUNCH();
     size_t sm = mstcb::NSTAGE * mstcb::STAGE_BYTES + 2 * 64 * 32 * sizeof(float) + 1024;
     static const bool lite = [] { const char* e = getenv("PN_MS_BWD_LITE"); return e && e[0] == '1'; }();
-    int var = lite ? 1 : 0;
+    static const bool pdb = [] { const char* e = getenv("PN_MS_BWD_PDB"); return !(e && e[0] == '0'); }();
+    int var = (lite ? 1 : 0) | (pdb ? 128 : 0);
     if (const char* e = getenv("PN_MS_BWD_ABLATE")) var = atoi(e);          // timing-only ablations (wrong results)
     using KernelT = void (*)(const float*, const float*, const float*, const float*, int, const float*, float*, int);
     KernelT rows_k = nullptr, cols_k = nullptr;
 #define PN_VAR_CASE(V) case V: rows_k = mstcb::ms_bwd_tc_kernel<0, V>; cols_k = mstcb::ms_bwd_tc_kernel<1, V>; break;
     switch (var) {
         PN_VAR_CASE(0) PN_VAR_CASE(1) PN_VAR_CASE(2) PN_VAR_CASE(4) PN_VAR_CASE(8) PN_VAR_CASE(16) PN_VAR_CASE(32)
-        PN_VAR_CASE(64) PN_VAR_CASE(36) PN_VAR_CASE(24) PN_VAR_CASE(126)
+        PN_VAR_CASE(64) PN_VAR_CASE(36) PN_VAR_CASE(24) PN_VAR_CASE(126) PN_VAR_CASE(128) PN_VAR_CASE(129) PN_VAR_CASE(254)
         default: PN_REQUIRE(false, "pn_ms_iter_bwd_tc: unknown PN_MS_BWD_ABLATE variant %d", var);
     }
 #undef PN_VAR_CASE
