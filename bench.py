@@ -177,6 +177,7 @@ def run_ours(args):
         np.random.seed(i)
         return hp.step(x, host_np[i % 2][0], host_np[i % 2][1], lab, prim)
 
+    stage_in = [tuple(torch.empty_like(t, device=dev) for t in hb) for hb in host]
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
     losses = []
@@ -186,7 +187,8 @@ def run_ours(args):
         copied asynchronously and consumed after step i+1 has been enqueued (lagged logging, like a production loop), so
         the host keeps one step of launch work ahead of the device; the last step's loss is read inside the region."""
         hx, hl, hpm = host[i % 2]
-        x = hx.to(dev, non_blocking=True); lab = hl.to(dev, non_blocking=True); prim = hpm.to(dev, non_blocking=True)
+        x, lab, prim = stage_in[i % 2]                       # double-buffered device staging of the inputs
+        x.copy_(hx, non_blocking=True); lab.copy_(hl, non_blocking=True); prim.copy_(hpm, non_blocking=True)
         np.random.seed(i)
         loss = hp.step(x, host_np[i % 2][0], host_np[i % 2][1], lab, prim)
         loss_host[i % 2:i % 2 + 1].copy_(loss.detach().reshape(1), non_blocking=True)     # D2H read of the step's result
@@ -201,6 +203,10 @@ def run_ours(args):
     for i in range(args.warmup):
         resident_step(i)
         e2e_step(i, last=True)
+    # both timed loops start from the SAME model / optimizer state (the clustering, hence the number and kind of fitted
+    # segments, drifts with every Adam step: without this the two loops would time different workloads)
+    import copy
+    snap = (copy.deepcopy(hp.model.state_dict()), copy.deepcopy(hp.opt.state_dict()))
     # ---- timed: resident inputs
     sampler = ClockSampler(local)
     if rank == 0:
@@ -228,6 +234,7 @@ def run_ours(args):
     kern_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop(dominant)]
     bwd_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop("pn_ms_iter_bwd_tc", [])]
     # ---- timed: end to end (H2D of inputs + D2H of the loss inside the region)
+    hp.model.load_state_dict(snap[0]); hp.opt.load_state_dict(snap[1])
     barrier()
     ev2 = torch.cuda.Event(enable_timing=True); ev3 = torch.cuda.Event(enable_timing=True)
     ev2.record()
