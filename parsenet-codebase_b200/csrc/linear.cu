@@ -281,7 +281,7 @@ struct BwdDataArgs {
 };
 
 // MINB = resident CTAs per SM the register allocation is capped for: 2 -> 128 registers (bwd_data spills 108 B, bwd_weight
-// 584 B per thread), 1 -> no cap (159 / 207 registers, no spills, 8 warps per SM).  PN_LIN_BWD_OCC selects (default 1).
+// 584 B per thread), 1 -> no cap (159 / 207 registers, no spills, 8 warps per SM).  PN_LIN_BWD_OCC selects (default 2, measured faster: profiles/r01_linear_bwd_occupancy.md).
 template <int MINB>
 __global__ void __launch_bounds__(NT, MINB) linear_bwd_data_kernel(BwdDataArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -578,7 +578,7 @@ extern "C" int pn_linear_fwd(const float* A, long long lda, const float* W, long
 
 static int bwd_occ() {      // read per call: tools/exp_linear_bwd.py flips it inside one process
     const char* e = getenv("PN_LIN_BWD_OCC");
-    return (e && e[0] == '2') ? 2 : 1;
+    return (e && e[0] == '1') ? 1 : 2;      // measured: 2 is faster (bwd_data 8.2 vs 11.9 ms, bwd_weight equal)
 }
 
 extern "C" int pn_linear_bwd_data(const float* dY, long long lddy, const float* W, long long ldw, float* dZ,

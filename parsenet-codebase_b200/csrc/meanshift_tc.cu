@@ -50,7 +50,7 @@ struct Bars {
 // grid (ceil(N/BM), B).  PDB = double-buffered P (P_big written in place over the S columns the thread has just loaded,
 // see meanshift_tc_bwd.cu): the epilogue of tile t no longer waits for the second product of tile t-1.
 template <bool PDB>
-__global__ void __maxnreg__(152) ms_fwd_tc_kernel(const float* __restrict__ Y, const float* __restrict__ X, int N,
+__global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restrict__ Y, const float* __restrict__ X, int N,
                                                           const float* __restrict__ cinv, float* __restrict__ Ynew,
                                                           float* __restrict__ den_out, float* __restrict__ unorm_out) {
     extern __shared__ __align__(1024) unsigned char smem[];

@@ -54,7 +54,9 @@ struct Bars {
 //   2 no exp in the epilogue, 4 loaders skip the "small" split stores, 8 no second-product MMAs, 16 one instead of three
 //   MMAs in the first product, 32 loaders skip the transposed copy, 64 epilogue skips the P stores to TMEM.
 template <int MODE, int VAR>
-__global__ void __maxnreg__(152)      // 13 warps x 152 regs fit the register file; (416,1) launch bounds cap at 128 and spill
+// (13 warps are allocated as 16: 128 registers per thread is the hardware ceiling for this CTA shape -- __maxnreg__(144/152)
+// fails to launch; lifting it needs setmaxnreg re-balancing between the loader / MMA and the epilogue warpgroups)
+__global__ void __launch_bounds__(NT, 1)
 ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, const float* __restrict__ Gn,
                  const float* __restrict__ gd, int N, const float* __restrict__ cinv, float* __restrict__ out,
                  int accumulate) {
