@@ -49,9 +49,7 @@ struct Bars {
 
 // grid (ceil(N/BM), B).  PDB = double-buffered P (P_big written in place over the S columns the thread has just loaded,
 // see meanshift_tc_bwd.cu): the epilogue of tile t no longer waits for the second product of tile t-1.
-// MNB (opt-in PN_MS_FWD_MNB=1|2, unvalidated candidate, see the VAR notes in meanshift_tc_bwd.cu): O += P.X reads the XA
-// tile through an MN-major descriptor instead of the transposed XB copy, which the loaders then skip; 2 swaps LBO / SBO.
-template <bool PDB, int MNB>
+template <bool PDB>
 __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restrict__ Y, const float* __restrict__ X, int N,
                                                           const float* __restrict__ cinv, float* __restrict__ Ynew,
                                                           float* __restrict__ den_out, float* __restrict__ unorm_out) {
@@ -248,7 +246,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                 }
                 // branch-free 4x4 transpose inside each group of 4 lanes (two butterfly steps):
                 // afterwards lane (jg, l4) holds X[4jg + 0..3][4c4 + l4]
-                if (MNB == 0) {
+                {
                     const bool hi = (l4 & 2) != 0;
                     float sa = hi ? f0 : f2, sb = hi ? f1 : f3;
                     sa = __shfl_xor_sync(0xffffffffu, sa, 2);
@@ -260,7 +258,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
                     sd = __shfl_xor_sync(0xffffffffu, sd, 1);
                     f0 = od ? sc : f0; f1 = od ? f1 : sc; f2 = od ? sd : f2; f3 = od ? f3 : sd;
                 }
-                if (MNB == 0) {
+                {
                     const float b0 = tf32_hi(f0), b1 = tf32_hi(f1), b2 = tf32_hi(f2), b3 = tf32_hi(f3);
                     const int d = 4 * c4 + l4;
                     const uint32_t ob = (uint32_t)(jg * XB_LBO + (d >> 3) * 128 + (d & 7) * 16);
@@ -278,7 +276,7 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
         // The whole warp runs this warp-uniform code (descriptors stay in uniform registers); one elected lane issues.
         const bool leader = elect_one();
         const uint32_t idesc_s = make_idesc(2, BM, BN, 0, 0);
-        const uint32_t idesc_o = make_idesc(2, BM, D, 0, MNB ? 1 : 0);
+        const uint32_t idesc_o = make_idesc(2, BM, D, 0, 0);
         const uint32_t sbase = smem_u32(smem);
         auto gemm2 = [&](int u) {
             if (PDB) mbar_wait(&bars.p_full2[u & 1], (u >> 1) & 1);
@@ -288,17 +286,13 @@ __global__ void __launch_bounds__(NT, 1) ms_fwd_tc_kernel(const float* __restric
             if (u > 0 && fresh) mbar_wait(&bars.o_flush, ((u / FLUSH) - 1) & 1);
             tc_fence_after();
             const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
-            constexpr uint32_t MN_LBO = (MNB == 2) ? XA_LBO : 128u, MN_SBO = (MNB == 2) ? 128u : XA_LBO;
-            const uint64_t db0 = MNB ? make_smem_desc(st, MN_LBO, MN_SBO, 0)
-                                     : make_smem_desc(st + 2 * XA_BYTES, XB_LBO, SBO, 0);
-            const uint64_t ds0 = MNB ? make_smem_desc(st + XA_BYTES, MN_LBO, MN_SBO, 0)
-                                     : make_smem_desc(st + 2 * XA_BYTES + XB_BYTES, XB_LBO, SBO, 0);
-            constexpr uint32_t KSTEP = MNB ? (128u >> 4) : ((2 * XB_LBO) >> 4);      // one K = 8 step of the B operand
+            const uint64_t db0 = make_smem_desc(st + 2 * XA_BYTES, XB_LBO, SBO, 0);
+            const uint64_t ds0 = make_smem_desc(st + 2 * XA_BYTES + XB_BYTES, XB_LBO, SBO, 0);
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < BN / 8; ++ks) {
-                    const uint64_t db = db0 + (uint64_t)(ks * KSTEP);
-                    const uint64_t ds = ds0 + (uint64_t)(ks * KSTEP);
+                    const uint64_t db = db0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
+                    const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
                     mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
                     mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
                     mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
@@ -353,11 +347,7 @@ extern "C" int pn_ms_iter_fwd_tc(const float* Y, const float* X, int B, int N, i
     PN_REQUIRE(d == mstc::D, "pn_ms_iter_fwd_tc: embedding width must be %d (got %d)", mstc::D, d);
     size_t sm = mstc::NSTAGE * mstc::STAGE_BYTES + 1024;
     static const bool pdb = [] { const char* e = getenv("PN_MS_FWD_PDB"); return !(e && e[0] == '0'); }();
-    const char* mnb_env = getenv("PN_MS_FWD_MNB");       // read per call: tools/exp_ms_mnb.py flips it inside one process
-    const int mnb = mnb_env ? atoi(mnb_env) : 0;
-    auto kern = pdb ? mstc::ms_fwd_tc_kernel<true, 0> : mstc::ms_fwd_tc_kernel<false, 0>;
-    if (mnb == 1) kern = mstc::ms_fwd_tc_kernel<true, 1>;
-    if (mnb == 2) kern = mstc::ms_fwd_tc_kernel<true, 2>;
+    auto kern = pdb ? mstc::ms_fwd_tc_kernel<true> : mstc::ms_fwd_tc_kernel<false>;
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(cdiv(N, mstc::BM), B);
     kern<<<grid, mstc::NT, sm, (cudaStream_t)stream>>>(Y, X, N, cinv, Ynew, den, unorm);

@@ -53,14 +53,6 @@ struct Bars {
 // VAR bit 0 = LITE.  The other bits are TIMING-ONLY ablations (results are wrong by construction; tools/exp_ms_bwd.py):
 //   2 no exp in the epilogue, 4 loaders skip the "small" split stores, 8 no second-product MMAs, 16 one instead of three
 //   MMAs in the first product, 32 loaders skip the transposed copy, 64 epilogue skips the P stores to TMEM.
-// VAR bit 8 (256, MNB) is NOT an ablation but an unvalidated candidate (opt-in, PN_MS_BWD_ABLATE=384): the second product
-//   reads the XA tile [d/4][j/8][8][16B] through an MN-major no-swizzle descriptor (N = d, K = j: a core matrix of XA is
-//   8 j-rows x 4 d-values = an MN-major core matrix; SBO = stride between 4-wide d chunks = XA_LBO, LBO = stride between
-//   8-row j groups = 128 B, one K = 8 step = +128 B) instead of the transposed XB copy, which the loaders then skip
-//   (half of their shared-memory stores; ablation 32 measured 10-16 %).  Same products in the same order => bit-identical
-//   results if the descriptor convention is right (CUTLASS make_umma_desc<Major::MN>, LayoutType::INTERLEAVE).  VAR bit 9
-//   (512) swaps LBO / SBO in that descriptor (the other possible reading of the convention); tools/tc_probe/probe.cu
-//   modes 2/3 test both on a single tile.
 template <int MODE, int VAR>
 // (13 warps are allocated as 16: 128 registers per thread is the hardware ceiling for this CTA shape -- __maxnreg__(144/152)
 // fails to launch; lifting it needs setmaxnreg re-balancing between the loader / MMA and the epilogue warpgroups)
@@ -69,8 +61,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
                  const float* __restrict__ gd, int N, const float* __restrict__ cinv, float* __restrict__ out,
                  int accumulate) {
     constexpr bool LITE = (VAR & 1) != 0, A_NOEXP = (VAR & 2) != 0, A_NOSMALL = (VAR & 4) != 0, A_NOG2 = (VAR & 8) != 0,
-                   A_G1ONE = (VAR & 16) != 0, MNB = (VAR & 256) != 0, MNB_SWAP = (VAR & 512) != 0,
-                   A_NOXB = (VAR & 32) != 0 || MNB, A_NOPST = (VAR & 64) != 0, PDB = (VAR & 128) != 0;
+                   A_G1ONE = (VAR & 16) != 0, A_NOXB = (VAR & 32) != 0, A_NOPST = (VAR & 64) != 0, PDB = (VAR & 128) != 0;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ Bars bars;
     __shared__ uint32_t tmem_base_s;
@@ -368,7 +359,7 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
         // =============================================================================== MMA warp (warp-uniform)
         const bool leader = elect_one();
         const uint32_t idesc_s = make_idesc(2, 128, BN, 0, 0);
-        const uint32_t idesc_o = make_idesc(2, 128, D, 0, MNB ? 1 : 0);
+        const uint32_t idesc_o = make_idesc(2, 128, D, 0, 0);
         const uint32_t sbase = smem_u32(smem);
         auto gemm2 = [&](int u) {
             DBG(13, u * 10 + 1);
@@ -380,17 +371,13 @@ ms_bwd_tc_kernel(const float* __restrict__ Yp, const float* __restrict__ X, cons
             if (u > 0 && fresh) mbar_wait(&bars.o_flush, ((u / FLUSH) - 1) & 1);
             tc_fence_after();
             const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
-            // default: transposed copy XB (K-major, K = j).  MNB: the XA tile itself, read MN-major (see the VAR notes)
-            const uint64_t db0 = MNB ? make_smem_desc(st, MNB_SWAP ? XA_LBO : 128u, MNB_SWAP ? 128u : XA_LBO, 0)
-                                     : make_smem_desc(st + 2 * XA_BYTES, XB_LBO, SBO, 0);
-            const uint64_t ds0 = MNB ? make_smem_desc(st + XA_BYTES, MNB_SWAP ? XA_LBO : 128u, MNB_SWAP ? 128u : XA_LBO, 0)
-                                     : make_smem_desc(st + 2 * XA_BYTES + XB_BYTES, XB_LBO, SBO, 0);
-            constexpr uint32_t KSTEP = MNB ? (128u >> 4) : ((2 * XB_LBO) >> 4);      // one K = 8 step of the B operand
+            const uint64_t db0 = make_smem_desc(st + 2 * XA_BYTES, XB_LBO, SBO, 0);
+            const uint64_t ds0 = make_smem_desc(st + 2 * XA_BYTES + XB_BYTES, XB_LBO, SBO, 0);
             if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < (A_NOG2 ? 0 : BN / 8); ++ks) {
-                    const uint64_t db = db0 + (uint64_t)(ks * KSTEP);
-                    const uint64_t ds = ds0 + (uint64_t)(ks * KSTEP);
+                    const uint64_t db = db0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
+                    const uint64_t ds = ds0 + (uint64_t)(ks * ((2 * XB_LBO) >> 4));
                     if (LITE) {
                         mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, (fresh && ks == 0) ? 0u : 1u);
                     } else {
@@ -491,7 +478,6 @@ extern "C" int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const flo
     switch (var) {
         PN_VAR_CASE(0) PN_VAR_CASE(1) PN_VAR_CASE(2) PN_VAR_CASE(4) PN_VAR_CASE(8) PN_VAR_CASE(16) PN_VAR_CASE(32)
         PN_VAR_CASE(64) PN_VAR_CASE(36) PN_VAR_CASE(24) PN_VAR_CASE(126) PN_VAR_CASE(128) PN_VAR_CASE(129) PN_VAR_CASE(254)
-        PN_VAR_CASE(384) PN_VAR_CASE(896) PN_VAR_CASE(160)
         default: PN_REQUIRE(false, "pn_ms_iter_bwd_tc: unknown PN_MS_BWD_ABLATE variant %d", var);
     }
 #undef PN_VAR_CASE

@@ -20,8 +20,7 @@ Gn = torch.empty_like(X); gd = torch.empty(B, N, device="cuda"); gY = torch.empt
 NAMES = {0: "exact (3+3 MMAs)", 1: "LITE (P rounded, 3+2)", 2: "no exp", 4: "no small-part stores", 8: "no 2nd-product MMAs",
          16: "1 of 3 MMAs in 1st product", 32: "no transposed copy", 64: "no P stores", 36: "no small + no transposed",
          24: "1of3 + no 2nd product", 126: "all ablations", 128: "double-buffered P (default)", 129: "double-buffered P + LITE",
-         254: "double-buffered P + all ablations", 160: "double-buffered P, no transposed copy (timing bound for 384)",
-         384: "double-buffered P + MN-major B operand (candidate)", 896: "as 384 with LBO/SBO swapped"}
+         254: "double-buffered P + all ablations"}
 VARS = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else (0, 1, 2, 4, 32, 36, 64, 8, 16, 24, 126, 128, 129, 254)
 
 
