@@ -110,3 +110,8 @@ class PrimitivesEmbeddingDGCNGn(nn.Module):
         else:
             embed_loss = torch.zeros(1, device=points.device)
         return embedding, primitives_log_prob, embed_loss
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

@@ -41,3 +41,8 @@ def fit_bezier_surface_fit_kronecker(points, basis_u, basis_v):
     ctrl = torch.linalg.pinv(G, hermitian=True) @ (A.t() @ P)
     ctrl = ctrl.reshape(U.shape[1], V.shape[1], 3)
     return ctrl if isinstance(points, torch.Tensor) else ctrl.cpu().numpy()
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

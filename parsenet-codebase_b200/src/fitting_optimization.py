@@ -62,3 +62,8 @@ class FittingModule:
         self.fitting.parameters[ids] = ["sphere", center, radius]
         if sample_points:
             raise NotImplementedError("surface sampling is eval-only (outside the hot path)")
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

@@ -140,3 +140,8 @@ def sample_points_from_control_points_(nu, nv, outputs, batch_size, input_size_u
     """(B, cu*cv, 3) control points -> (B, g*g, 3) surface samples Nu P Nv^T"""
     P = outputs.reshape(outputs.shape[0], input_size_u, input_size_v, 3)
     return spline_eval(P, nu.to(P.device), nv.to(P.device))
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

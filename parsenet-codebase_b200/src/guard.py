@@ -14,3 +14,8 @@ def guard_exp(x, max_value=EXP_CLAMP, min_value=-EXP_CLAMP):
 
 def guard_sqrt(x, minimum=SQRT_FLOOR):
     return torch.sqrt(x.clamp(min=minimum))
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

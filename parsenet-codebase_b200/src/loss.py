@@ -103,3 +103,8 @@ def laplacian_loss(output, gt, dist_type="l2"):
     li = F.conv2d(gt.permute(0, 3, 1, 2), w, padding=1)
     d = (lo - li) ** 2 if dist_type == "l2" else (lo - li).abs()
     return d.sum(1).mean()
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

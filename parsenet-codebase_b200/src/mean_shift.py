@@ -57,3 +57,8 @@ class MeanShift:
 
     def pdist(self, x, y):
         return ((x.unsqueeze(1) - y.unsqueeze(0)) ** 2).sum(2)
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

@@ -85,3 +85,8 @@ class DGCNNControlPoints(nn.Module):
                     bn.running_var.mul_(0.9).add_(0.1 * var_unb.float())
                     bn.num_batches_tracked += 1
         return out.view(B, self.controlpoints * self.controlpoints, 3)
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

@@ -210,3 +210,8 @@ def fit_one_shape_torch(data, fitter, weights, bw, eval=False, sample_points=Fal
             recon.append(None)
         gt_points[label_index] = d[3]
     return gt_points, recon
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

@@ -107,3 +107,8 @@ class ResidualLoss:
                 v = parameters[k]
                 out[k] = [v[0], self.routines[v[0]](points=Points[k], params=v[1:], sqrt=sqrt)]
         return {k: out[k] for k in keys}
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

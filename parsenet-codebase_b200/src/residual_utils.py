@@ -161,3 +161,8 @@ class Evaluation:
             g = float(g) if g is not None else None
             sp = float(sp) if sp is not None else None
         return [loss, g, sp]
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

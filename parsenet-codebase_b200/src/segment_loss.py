@@ -43,3 +43,8 @@ def evaluate_miou(gt_labels, pred_labels):
 def primitive_loss(pred, gt):
     """NLL of (B,P,N) log-probabilities against (B,N) integer types (reference :151)."""
     return NllFn.apply(pred, gt)
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

@@ -119,3 +119,8 @@ def SIOU_matched_segments(target, pred_labels, primitives_pred, primitives, weig
     s_iou, p_iou, pairs = mean_IOU_primitive_segment(matching, pred_labels[None], target[None], prim_pred_seg[None],
                                                      primitives[None])
     return s_iou, p_iou, matching, pairs
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

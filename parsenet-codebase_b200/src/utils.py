@@ -59,3 +59,8 @@ def rescale_input_outputs(scales, output, points, control_points, batch_size):
 def grad_norm(model):
     total = sum(p.grad.data.norm(2) for p in model.parameters()).item()
     return bool(np.isnan(total) or np.isinf(total))
+
+
+from src._fallthrough import module_getattr as _module_getattr  # noqa: E402
+
+__getattr__ = _module_getattr(__name__)     # non-hot-path names: reference module of the same name (opt-in, see _fallthrough.py)

@@ -104,3 +104,88 @@ def test_two_process_gloo_gradient_average(tmp_path):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert p.stdout.count("OK") == 2
+
+
+# ------------------------------------------------------------------------------------------ drop-in completeness
+_FALLTHROUGH_SCRIPT = r"""
+import os, sys
+from unittest.mock import MagicMock
+ROOT, PKG, REF = sys.argv[1:4]
+sys.path.insert(0, PKG)
+# the deployment environment of the reference has these wheels; this container does not
+for name in ["open3d", "open3d.utility", "open3d.geometry", "open3d.visualization", "lap", "lapsolver", "geomdl",
+             "geomdl.fitting", "geomdl.BSpline", "geomdl.utilities", "geomdl.tessellate", "geomdl.visualization",
+             "geomdl.visualization.VisMPL", "geomdl.exchange", "geomdl.operations", "geomdl.NURBS", "geomdl.helpers",
+             "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "mpl_toolkits", "mpl_toolkits.mplot3d", "h5py",
+             "configobj", "trimesh", "transforms3d", "transforms3d.affines", "transforms3d.euler",
+             "tensorboard_logger", "ipdb", "skimage", "skimage.measure"]:
+    m = MagicMock(name=name); m.__name__ = name; m.__all__ = []; m.__path__ = []
+    sys.modules[name] = m
+o3d = sys.modules["open3d"]; o3d.__all__ = ["utility", "geometry", "visualization"]      # `from open3d import *`
+o3d.utility, o3d.geometry, o3d.visualization = (sys.modules["open3d." + n] for n in o3d.__all__)
+os.environ["PARSENET_REFERENCE_SRC"] = os.path.join(REF, "src")
+import src
+assert os.path.realpath(src.__path__[0]).startswith(os.path.realpath(PKG)), src.__path__
+# 1. modules the drop-in does not provide come from the reference's files
+from src.dataset import generator_iter
+from src.dataset_segments import Dataset
+import src.dataset, src.augment_utils
+assert os.path.realpath(src.dataset.__file__).startswith(os.path.realpath(REF)), src.dataset.__file__
+# 2. hot-path names are the drop-in's, whatever the variable says
+from src.PointNet import PrimitivesEmbeddingDGCNGn, DGCNNEncoderGn
+from src.mean_shift import MeanShift
+from src.residual_utils import Evaluation
+from src.utils import chamfer_distance, grad_norm
+from src.segment_utils import to_one_hot, SIOU_matched_segments
+import src.PointNet, src.utils, src.mean_shift, src.segment_utils, src.residual_utils
+for mod in (src.PointNet, src.utils, src.mean_shift, src.segment_utils, src.residual_utils):
+    assert os.path.realpath(mod.__file__).startswith(os.path.realpath(PKG)), mod.__file__
+for obj in (PrimitivesEmbeddingDGCNGn, DGCNNEncoderGn, MeanShift, Evaluation, chamfer_distance, to_one_hot,
+            SIOU_matched_segments):
+    assert obj.__module__.startswith("src."), (obj, obj.__module__)            # not the private reference copy
+# 3. names outside the hot path fall through to the reference module of the same name
+from src.utils import visualize_uv_maps, visualize_fitted_surface, fit_surface_sample_points
+from src.segment_utils import cluster
+from src.primitives import SaveParameters
+from src.fitting_utils import up_sample_points_torch_in_range, remove_outliers
+assert visualize_uv_maps.__module__ == "_parsenet_reference_src.utils", visualize_uv_maps.__module__
+assert cluster.__module__ == "_parsenet_reference_src.segment_utils"
+# every import statement of the reference's training / inference scripts that targets `src.` now resolves
+import ast
+for script in ("train_parsenet.py", "train_parsenet_e2e.py", "train_open_splines.py", "train_closed_control_points.py",
+               "generate_predictions.py"):
+    path = os.path.join(REF, script)
+    if not os.path.exists(path):
+        continue
+    for node in ast.walk(ast.parse(open(path).read())):
+        if isinstance(node, ast.ImportFrom) and node.module and node.module.startswith("src."):
+            mod = __import__(node.module, fromlist=["x"])
+            for a in node.names:
+                assert hasattr(mod, a.name), (script, node.module, a.name)
+# 4. a name nobody defines is still an AttributeError
+try:
+    src.utils.no_such_function
+    raise SystemExit("expected AttributeError")
+except AttributeError:
+    pass
+print("FALLTHROUGH-OK")
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference checkout (build container only)")
+def test_drop_in_package_resolves_every_src_import_of_the_reference_scripts():
+    """`parsenet-codebase_b200/` first on sys.path + PARSENET_REFERENCE_SRC: hot-path names are ours, everything else the
+    reference's training / inference scripts import from `src.*` still resolves (drop-in for the callers)"""
+    import subprocess
+    r = subprocess.run([sys.executable, "-c", _FALLTHROUGH_SCRIPT, ROOT, os.path.join(ROOT, "parsenet-codebase_b200"),
+                        "/root/reference"], capture_output=True, text=True, timeout=300)
+    assert "FALLTHROUGH-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_missing_name_without_reference_is_attribute_error():
+    import subprocess
+    code = ("import sys, os; os.environ.pop('PARSENET_REFERENCE_SRC', None); sys.path.insert(0, sys.argv[1]); import src.utils\n"
+            "try:\n    src.utils.visualize_uv_maps\nexcept AttributeError as e:\n    print('OK', e)\n")
+    r = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "parsenet-codebase_b200")], capture_output=True,
+                       text=True, timeout=300)
+    assert r.stdout.startswith("OK") and "PARSENET_REFERENCE_SRC" in r.stdout, r.stdout + r.stderr[-2000:]
