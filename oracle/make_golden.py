@@ -16,6 +16,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 import ref_loader as rl  # noqa: E402
 from oracle.port import common  # noqa: E402
+from oracle.make_golden_helpers import prim_cloud  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -104,35 +105,12 @@ def gen_meanshift():
     np.savez_compressed(os.path.join(OUT, "meanshift.npz"), **out)
 
 
-def _prim_cloud(kind, m, seed):
-    """noisy samples of one analytic primitive + outward normals + random positive weights"""
-    rng = np.random.RandomState(seed)
-    u, v = rng.rand(m), rng.rand(m)
-    if kind == "plane":
-        p = np.stack([u - 0.5, v - 0.5, 0 * u], 1); n = np.tile([0, 0, 1.0], (m, 1))
-    elif kind == "sphere":
-        th, ph = 2 * np.pi * u, np.arccos(1 - 1.4 * v)
-        n = np.stack([np.sin(ph) * np.cos(th), np.sin(ph) * np.sin(th), np.cos(ph)], 1); p = 0.7 * n
-    elif kind == "cylinder":
-        th = 2 * np.pi * u * 0.8
-        n = np.stack([np.cos(th), np.sin(th), 0 * u], 1); p = 0.4 * n + np.stack([0 * u, 0 * u, 1.5 * (v - 0.5)], 1)
-    else:
-        a = np.pi / 5; th = 2 * np.pi * u * 0.9; h = 0.3 + 0.7 * v
-        p = np.stack([h * np.tan(a) * np.cos(th), h * np.tan(a) * np.sin(th), h], 1)
-        n = np.stack([np.cos(a) * np.cos(th), np.cos(a) * np.sin(th), -np.sin(a) * np.ones(m)], 1)
-    R, _ = np.linalg.qr(rng.randn(3, 3))
-    p = p @ R.T + rng.randn(3) * 0.3 + rng.randn(m, 3) * 0.004
-    n = n @ R.T
-    w = 0.15 + 0.85 * rng.rand(m, 1)
-    return p.astype(np.float32), n.astype(np.float32), w.astype(np.float32)
-
-
 def gen_fits():
     PF = rl.ref("src.primitive_forward"); PR = rl.ref("src.primitives")
     fit = PF.Fit(); cp = PR.ComputePrimitiveDistance(reduce=True)
     out = {}
     for kind, seed in [("plane", 1), ("sphere", 2), ("cylinder", 3), ("cone", 4)]:
-        p, n, w = _prim_cloud(kind, 900, seed)
+        p, n, w = prim_cloud(kind, 900, seed)
         P, Nn = torch.from_numpy(p), torch.from_numpy(n)
         W = torch.from_numpy(w).requires_grad_()
         res = getattr(fit, f"fit_{kind}_torch")(P, Nn, W)
@@ -144,7 +122,7 @@ def gen_fits():
             out[f"{kind}_out{i}"] = r.detach().numpy(); out[f"{kind}_coef{i}"] = coef[i].numpy()
         out[kind + "_gw"] = W.grad.numpy()
         # residual distance of a second sample of the same surface to the fitted primitive (+ grads wrt params)
-        q = torch.from_numpy(_prim_cloud(kind, 500, seed + 50)[0])
+        q = torch.from_numpy(prim_cloud(kind, 500, seed + 50)[0])
         if kind == "plane":
             params = [res[0].detach().reshape(3, 1), res[1].detach()]
         elif kind == "sphere":

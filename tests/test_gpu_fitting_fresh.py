@@ -1,0 +1,213 @@
+"""Fitting / loss stage on the GPU vs the oracle port (oracle/port/fitting.py, pinned against the reference's golden vectors
+in tests/test_oracle_golden.py) on FRESH seeded inputs: sizes and shapes the fixed fixtures do not cover (tiny and ragged
+segments, point counts that are not tile multiples, single-cluster weights, full-size Chamfer through properties).
+
+These tests were written after the GPU budget of round 1 was spent; their first execution on a B200 is the round-end run.
+They are therefore marked `xfail(strict=False)`: a pass shows up as XPASS, a failure as XFAIL with the assertion text,
+and the rest of the suite keeps running.  Promote them to hard tests (delete FIRST_RUN) once they have been seen green.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FIRST_RUN = pytest.mark.xfail(strict=False, reason="first GPU execution is the round-end run (written after the round's "
+                                                   "GPU budget was spent); promote to a hard test once seen green")
+
+
+def _close(got, want, rtol, name):
+    got = got.detach().cpu().double().numpy() if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = want.detach().cpu().double().numpy() if torch.is_tensor(want) else np.asarray(want, np.float64)
+    scale = np.abs(want).max() + 1e-30
+    err = np.abs(got.reshape(want.shape) - want).max()
+    assert err <= rtol * scale + 1e-9, f"{name}: err {err:.3e} scale {scale:.3e}"
+
+
+def _cu(a, grad=False):
+    t = torch.from_numpy(np.asarray(a)).cuda()
+    return t.requires_grad_() if grad else t
+
+
+def _cpu(a, grad=False):
+    t = torch.from_numpy(np.asarray(a))
+    return t.requires_grad_() if grad else t
+
+
+# ------------------------------------------------------------------------------------------------ primitive fits
+@FIRST_RUN
+@pytest.mark.parametrize("kind,m,seed", [("plane", 61, 11), ("plane", 4999, 12), ("sphere", 61, 13), ("sphere", 4999, 14),
+                                         ("cone", 300, 15), ("cone", 4999, 16), ("cylinder", 2500, 17)])
+def test_fits_on_fresh_clouds_vs_port(kind, m, seed):
+    """Fit.fit_*_torch on new noisy primitive samples (odd sizes) vs the port: parameters 2e-4, d/dweights 2e-3"""
+    from oracle.make_golden_helpers import prim_cloud
+    from oracle.port import fitting as OP
+    from src.primitive_forward import Fit
+    p, n, w = prim_cloud(kind, m, seed)
+    Wc = _cpu(w, True)
+    want = {"plane": lambda: OP.fit_plane(_cpu(p), Wc), "sphere": lambda: OP.fit_sphere(_cpu(p), Wc),
+            "cylinder": lambda: OP.fit_cylinder(_cpu(p), _cpu(n), Wc), "cone": lambda: OP.fit_cone(_cpu(p), _cpu(n), Wc)}[kind]()
+    Wg = _cu(w, True)
+    got = getattr(Fit(), f"fit_{kind}_torch")(_cu(p), _cu(n), Wg)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert tuple(a.shape) == tuple(b.shape), (kind, a.shape, b.shape)
+    sign = 1.0
+    if kind in ("plane", "cylinder"):          # eigenvector sign convention (LAPACK vs Jacobi), see DESIGN.md §4
+        sign = float(np.sign((got[0].detach().cpu().reshape(-1) * want[0].detach().reshape(-1)).sum()))
+    g = torch.Generator().manual_seed(seed)
+    coefs = [torch.randn(t.shape, generator=g) for t in want]
+    if kind == "cylinder":
+        # centre / radius carry the reference's along-axis fp32 noise (declared deviation): compare axis and the
+        # perpendicular centre component only
+        _close(got[0] * sign, want[0], 2e-4, "cylinder axis")
+        ax = want[0].detach().double().reshape(3)
+        perp = lambda c: c - (c * ax).sum() * ax
+        _close(perp(got[1].detach().cpu().double().reshape(3)), perp(want[1].detach().double().reshape(3)), 3e-2,
+               "cylinder centre (perpendicular)")
+        return
+    loss_g = loss_c = 0
+    for i, (a, b) in enumerate(zip(got, want)):
+        s = sign if (kind == "plane") else 1.0
+        _close(a * s, b, 2e-4, f"{kind} out{i}")
+        loss_g = loss_g + (a * s * coefs[i].cuda()).sum()
+        loss_c = loss_c + (b * coefs[i]).sum()
+    loss_g.backward(); loss_c.backward()
+    _close(Wg.grad, Wc.grad, 2e-3, f"{kind} d/dweights")
+
+
+@FIRST_RUN
+@pytest.mark.parametrize("m", [1, 17, 3001])
+def test_residual_distances_on_fresh_points_vs_port(m):
+    """ComputePrimitiveDistance.* for all four analytic kinds (ragged point counts down to a single point)"""
+    from oracle.port import fitting as OP
+    from src.primitives import ComputePrimitiveDistance
+    g = torch.Generator().manual_seed(100 + m)
+    q = torch.randn(m, 3, generator=g) * 0.5
+    unit = lambda v: v / v.norm()
+    params = {
+        "plane": [unit(torch.randn(3, 1, generator=g)), torch.tensor(0.13)],
+        "sphere": [torch.randn(1, 3, generator=g) * 0.2, torch.tensor(0.6)],
+        "cylinder": [unit(torch.randn(3, 1, generator=g)), torch.randn(1, 3, generator=g) * 0.2, torch.tensor(0.35)],
+        "cone": [torch.randn(1, 3, generator=g) * 0.2, unit(torch.randn(3, 1, generator=g)), torch.tensor(0.5)],
+    }
+    cp = ComputePrimitiveDistance(reduce=True)
+    for kind, ps in params.items():
+        pc = [t.clone().requires_grad_() for t in ps]
+        pg = [t.clone().cuda().requires_grad_() for t in ps]
+        want = OP.DISTANCES[kind](q, pc)
+        got = getattr(cp, "distance_from_" + kind)(points=q.cuda(), params=pg, sqrt=False)
+        _close(got, want, 1e-4, f"{kind} residual m={m}")
+        got.backward(); want.backward()
+        for i in range(len(ps)):
+            _close(pg[i].grad, pc[i].grad, 1e-3, f"{kind} dpar{i} m={m}")
+
+
+# ------------------------------------------------------------------------------------------------ Chamfer
+@FIRST_RUN
+@pytest.mark.parametrize("B,Np,M", [(1, 1, 1), (2, 7, 1030), (3, 1024, 1025), (1, 2500, 900)])
+def test_chamfer_ragged_sizes_vs_port(B, Np, M):
+    from oracle.port import fitting as OP
+    from src import utils as U
+    g = torch.Generator().manual_seed(B * 1000 + Np)
+    pred, gt = torch.randn(B, Np, 3, generator=g), torch.randn(B, M, 3, generator=g)
+    pc, gc = pred.clone().requires_grad_(), gt.clone().requires_grad_()
+    pg, gg = pred.clone().cuda().requires_grad_(), gt.clone().cuda().requires_grad_()
+    want = [OP.chamfer_distance(pc, gc), OP.chamfer_distance(pc, gc, sqrt=True), OP.chamfer_distance_one_side(pc, gc, 0),
+            OP.chamfer_distance_one_side(pc, gc, 1), OP.chamfer_distance_single_shape(pc[0], gc[0]),
+            OP.chamfer_distance_single_shape(pc[0], gc[0], one_side=True, sqrt=True)]
+    got = [U.chamfer_distance(pg, gg), U.chamfer_distance(pg, gg, sqrt=True), U.chamfer_distance_one_side(pg, gg, 0),
+           U.chamfer_distance_one_side(pg, gg, 1), U.chamfer_distance_single_shape(pg[0], gg[0]),
+           U.chamfer_distance_single_shape(pg[0], gg[0], one_side=True, sqrt=True)]
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert abs(a.item() - b.item()) <= 1e-4 * abs(b.item()) + 1e-9, (i, a.item(), b.item())
+    sum((i + 1) * a for i, a in enumerate(got)).backward()
+    sum((i + 1) * b for i, b in enumerate(want)).backward()
+    _close(pg.grad, pc.grad, 1e-4, "chamfer d/dpred"); _close(gg.grad, gc.grad, 1e-4, "chamfer d/dgt")
+    # per-point vectors (reduce=False) and numpy inputs (utils.py:280-284)
+    v_got = U.chamfer_distance_single_shape(pred[0].numpy(), gt[0].numpy(), one_side=True, reduce=False)
+    v_want = OP.chamfer_distance_single_shape(pred[0], gt[0], one_side=True, reduce=False)
+    assert v_got.shape == (M,)
+    _close(v_got, v_want, 1e-4, "per-point one-sided distances")
+
+
+@FIRST_RUN
+def test_chamfer_full_size_properties():
+    """cfg-3-scale clouds (36 x 2000 x 1600) and a 10^4 x 10^4 pair through size-independent properties: symmetry under
+    swapping the arguments, zero on identical clouds, invariance under a permutation of the points, exact value on a
+    translated copy of a lattice"""
+    from src import utils as U
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(36, 1600, 3, generator=g).cuda(); b = torch.randn(36, 2000, 3, generator=g).cuda()
+    ab, ba = U.chamfer_distance(a, b).item(), U.chamfer_distance(b, a).item()
+    assert abs(ab - ba) <= 1e-6 * abs(ab)
+    assert U.chamfer_distance(a, a).item() == 0.0
+    perm = torch.randperm(2000, generator=g).cuda()
+    assert abs(U.chamfer_distance(a, b[:, perm]).item() - ab) <= 1e-6 * abs(ab)
+    assert abs(U.chamfer_distance_one_side(a, b, 0).item() + U.chamfer_distance_one_side(a, b, 1).item() - 2 * ab) <= 1e-5 * ab
+    big = torch.randn(1, 10000, 3, generator=g).cuda()
+    assert U.chamfer_distance(big, big.flip(1)).item() == 0.0
+    # integer lattice shifted by 0.25 along x: every nearest neighbour is the own copy, squared distance 1/16 exactly
+    ax = torch.arange(22, dtype=torch.float32)
+    lat = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(1, -1, 3).cuda()      # 10 648 points
+    shifted = lat + torch.tensor([0.25, 0.0, 0.0]).cuda()
+    assert abs(U.chamfer_distance(lat, shifted).item() - 0.0625) <= 1e-7
+
+
+# ------------------------------------------------------------------------------------------------ splines
+@FIRST_RUN
+@pytest.mark.parametrize("B,grid", [(1, 30), (5, 40)])
+def test_spline_evaluation_and_losses_fresh_vs_port(B, grid):
+    from oracle.port import fitting as OP
+    from src import loss as L
+    from src.fitting_utils import sample_points_from_control_points_
+    g = torch.Generator().manual_seed(B + grid)
+    nu, nv = L.uniform_knot_bspline(20, 20, 3, 3, grid)
+    onu, onv = OP.uniform_knot_bspline(20, 20, 3, 3, grid)
+    np.testing.assert_allclose(nu, onu, rtol=0, atol=1e-13); np.testing.assert_allclose(nv, onv, rtol=0, atol=1e-13)
+    assert np.allclose(nu.sum(1), 1.0) and (np.count_nonzero(nu, axis=1) <= 4).all()
+    nuf, nvf = torch.from_numpy(nu.astype(np.float32)), torch.from_numpy(nv.astype(np.float32))
+    cp = torch.rand(B, 400, 3, generator=g) - 0.5
+    cc, cg = cp.clone().requires_grad_(), cp.clone().cuda().requires_grad_()
+    want = OP.sample_points_from_control_points_(nuf, nvf, cc, B)
+    got = sample_points_from_control_points_(nuf, nvf, cg, B)
+    _close(got, want, 1e-4, "surface points")
+    pts = torch.randn(B, 3, 777, generator=g) * 0.3
+    gtcp = torch.rand(B, 20, 20, 3, generator=g) - 0.5
+
+    class Cfg:
+        batch_size = B
+        grid_size = 20
+    w_cd, _ = OP.spline_reconstruction_loss_one_sided(nuf, nvf, cc, pts, B, 20)
+    w_cd2, _ = OP.spline_reconstruction_loss(nuf, nvf, cc, pts, B, sqrt=True)
+    w_reg, w_perm = OP.control_points_permute_reg_loss(cc, gtcp, 20)
+    w_lap = OP.laplacian_loss(cc.reshape(B, 20, 20, 3), w_perm)
+    w_closed, _ = OP.control_points_permute_closed_reg_loss(cc, gtcp, 20, 20)
+    g_cd, _ = L.spline_reconstruction_loss_one_sided(nuf, nvf, cg, pts.cuda(), Cfg)
+    g_cd2, _ = L.spline_reconstruction_loss(nuf, nvf, cg, pts.cuda(), Cfg, sqrt=True)
+    g_reg, g_perm = L.control_points_permute_reg_loss(cg, gtcp.cuda(), 20)
+    g_lap = L.laplacian_loss(cg.reshape(B, 20, 20, 3), g_perm)
+    g_closed, _ = L.control_points_permute_closed_reg_loss(cg, gtcp.cuda(), 20, 20)
+    for name, a, b in [("one-sided", g_cd, w_cd), ("two-sided sqrt", g_cd2, w_cd2), ("reg", g_reg, w_reg),
+                       ("laplacian", g_lap, w_lap), ("closed reg", g_closed, w_closed)]:
+        assert abs(a.item() - b.item()) <= 1e-4 * abs(b.item()), (name, a.item(), b.item())
+    _close(g_perm, w_perm, 1e-6, "best-matching permutation of the gt grid")
+    (g_cd + 0.5 * g_cd2 + 0.9 * g_reg + 0.1 * g_lap + 0.5 * g_closed).backward()
+    (w_cd + 0.5 * w_cd2 + 0.9 * w_reg + 0.1 * w_lap + 0.5 * w_closed).backward()
+    _close(cg.grad, cc.grad, 2e-4, "d/dcontrol points")
+
+
+@FIRST_RUN
+@pytest.mark.parametrize("K,N", [(1, 333), (7, 1000), (49, 10000)])
+def test_weights_normalize_fresh_vs_port(K, N):
+    """membership weights incl. the single-cluster early return (fitting_utils.py:318-319) and the 49-cluster maximum"""
+    from oracle.port import fitting as OP
+    from src.fitting_utils import weights_normalize
+    g = torch.Generator().manual_seed(K)
+    w = torch.rand(K, N, generator=g) * 2 - 1
+    wc, wg = w.clone().requires_grad_(), w.clone().cuda().requires_grad_()
+    want, got = OP.weights_normalize(wc, 0.31), weights_normalize(wg, 0.31)
+    _close(got, want, 1e-4, "weights")
+    coef = torch.randn(K, N, generator=g)
+    (got * coef.cuda()).sum().backward(); (want * coef).sum().backward()
+    _close(wg.grad, wc.grad, 2e-3, "d/dweights")

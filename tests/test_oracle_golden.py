@@ -121,3 +121,113 @@ def test_cfg1_control_point_solve_restatement_vs_reference_golden(golden_dir):
         assert np.abs(rec - want).max() < 1e-10
     assert np.abs(g["rec"] - g["cp"]).max() < 1e-10 and np.abs(g["rec_k"] - g["cp"][0]).max() < 1e-10
     assert abs(np.linalg.cond(nu) - 162.52) < 0.01
+
+
+# ------------------------------------------------------------------------------------------ fitting / loss stage
+def _t(a, grad=False):
+    t = torch.from_numpy(np.asarray(a))
+    return t.requires_grad_() if grad else t
+
+
+def _rel(got, want, rtol, name):
+    got = got.detach().double().numpy() if torch.is_tensor(got) else np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    err = np.abs(got.reshape(want.shape) - want).max()
+    assert err <= rtol * (np.abs(want).max() + 1e-30) + 1e-12, f"{name}: err {err:.3e} vs scale {np.abs(want).max():.3e}"
+
+
+@pytest.mark.parametrize("kind", ["plane", "sphere", "cylinder", "cone"])
+def test_fitting_port_matches_reference_fits_and_residuals(golden_dir, kind):
+    """oracle/port/fitting.py vs Fit.fit_*_torch / ComputePrimitiveDistance of the unmodified reference (same torch, same
+    CPU): outputs, gradient w.r.t. the membership weights through the custom SVD backward / regularised lstsq, residual
+    distances and their parameter gradients"""
+    from oracle.port import fitting as F
+    g = _load(golden_dir, "fits.npz")
+    P, Nn, W = _t(g[kind + "_p"]), _t(g[kind + "_n"]), _t(g[kind + "_w"], True)
+    res = {"plane": lambda: F.fit_plane(P, W), "sphere": lambda: F.fit_sphere(P, W),
+           "cylinder": lambda: F.fit_cylinder(P, Nn, W), "cone": lambda: F.fit_cone(P, Nn, W)}[kind]()
+    loss = 0
+    for i, r in enumerate(res):
+        _rel(r, g[f"{kind}_out{i}"], 2e-5, f"{kind} out{i}")
+        loss = loss + (r * _t(g[f"{kind}_coef{i}"]).reshape(r.shape)).sum()
+    loss.backward()
+    _rel(W.grad, g[kind + "_gw"], 1e-3, f"{kind} d/dweights")
+    params = [_t(g[f"{kind}_par{i}"], True) for i in range(len(res))]
+    d = F.DISTANCES[kind](_t(g[kind + "_q"]), params)
+    _rel(d, g[kind + "_dist"], 1e-5, f"{kind} residual")
+    d.backward()
+    for i, p in enumerate(params):
+        _rel(p.grad, g[f"{kind}_gpar{i}"], 1e-4, f"{kind} dpar{i}")
+
+
+def test_fitting_port_matches_reference_chamfer_spline_losses(golden_dir):
+    from oracle.port import fitting as F
+    g = _load(golden_dir, "losses.npz")
+    pred, gt = _t(g["pred"], True), _t(g["gt"], True)
+    vals = {"cd": F.chamfer_distance(pred, gt), "cds": F.chamfer_distance(pred, gt, sqrt=True),
+            "c0": F.chamfer_distance_one_side(pred, gt, 0), "c1": F.chamfer_distance_one_side(pred, gt, 1),
+            "s1": F.chamfer_distance_single_shape(pred[0], gt[0]),
+            "s2": F.chamfer_distance_single_shape(pred[0], gt[0], one_side=True)}
+    for k, v in vals.items():
+        assert abs(v.item() - float(g[k])) <= 1e-6 * abs(float(g[k])), k
+    (vals["cd"] + 2 * vals["cds"] + 3 * vals["c0"] + 4 * vals["c1"] + 5 * vals["s1"] + 6 * vals["s2"]).backward()
+    _rel(pred.grad, g["gpred"], 1e-5, "chamfer dpred"); _rel(gt.grad, g["ggt"], 1e-5, "chamfer dgt")
+    # basis matrices: a different evaluation scheme (in-place Cox-de Boor) than the reference's triangular table
+    nu, nv = F.uniform_knot_bspline(20, 20, 3, 3, 30)
+    np.testing.assert_allclose(nu, g["nu"], rtol=0, atol=1e-13); np.testing.assert_allclose(nv, g["nv"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(F.uniform_knot_bspline(20, 20, 3, 3, 40)[0], g["nu40"], rtol=0, atol=1e-13)
+    cpts = _t(g["cpts"], True)
+    rec = F.sample_points_from_control_points_(_t(nu.astype(np.float32)), _t(nv.astype(np.float32)), cpts, 2)
+    _rel(rec, g["rec"], 1e-5, "spline evaluation")
+    (rec * _t(g["recw"])).sum().backward()
+    _rel(cpts.grad, g["gcpts"], 1e-5, "spline evaluation grad")
+    # open / closed spline training losses (train_open_splines.py:158-178)
+    nu4 = _t(g["nu40"].astype(np.float32))
+    outp = _t(g["tl_out"], True)
+    cd1, _ = F.spline_reconstruction_loss_one_sided(nu4, nu4, outp, _t(g["tl_pts"]), 2, 20)
+    lreg, perm = F.control_points_permute_reg_loss(outp, _t(g["tl_gtcp"]), 20)
+    lap = F.laplacian_loss(outp.reshape(2, 20, 20, 3), perm)
+    lclosed, _ = F.control_points_permute_closed_reg_loss(outp, _t(g["tl_gtcp"]), 20, 20)
+    for k, v in [("tl_cd", cd1), ("tl_reg", lreg), ("tl_lap", lap), ("tl_closed", lclosed)]:
+        assert abs(v.item() - float(g[k])) <= 2e-6 * abs(float(g[k])), (k, v.item(), float(g[k]))
+    (0.9 * lreg + 0.1 * (cd1 + lap) + 0.5 * lclosed).backward()
+    _rel(outp.grad, g["tl_gout"], 1e-5, "spline loss grads")
+    wts = _t(g["wn_in"], True)
+    wn = F.weights_normalize(wts, 0.8)
+    _rel(wn, g["wn_out"], 1e-6, "weights_normalize")
+    (wn * _t(g["wn_w"])).sum().backward()
+    _rel(wts.grad, g["wn_g"], 1e-5, "weights_normalize grad")
+
+
+def test_fitting_port_known_answers_of_reference_test_sketches():
+    """the analytic refits sketched in the reference's src/test_fitting_utils.py:5-57 as real assertions: unit sphere at
+    the origin, cylinder r = 1 about (1,2,0)/sqrt 5, cone with half-angle pi/3 about (1,1,0)/sqrt 2; rank-deficient
+    lstsq takes the Tikhonov branch (fitting_utils.py:52-64)"""
+    from oracle.port import fitting as F
+    rng = np.random.RandomState(0)
+    n = rng.randn(2000, 3); n /= np.linalg.norm(n, axis=1, keepdims=True)
+    w = torch.ones(2000, 1)
+    c, r = F.fit_sphere(_t(n.astype(np.float32)), w)
+    assert c.abs().max() < 1e-3 and abs(float(r) - 1.0) < 1e-3
+    ax = np.array([1.0, 2.0, 0.0]) / np.sqrt(5.0)
+    e1 = np.cross(ax, [0, 0, 1.0]); e1 /= np.linalg.norm(e1); e2 = np.cross(ax, e1)
+    th, h = rng.rand(2000) * 2 * np.pi, rng.rand(2000) * 2 - 1
+    nrm = np.cos(th)[:, None] * e1 + np.sin(th)[:, None] * e2
+    pts = nrm + h[:, None] * ax
+    a, c, r = F.fit_cylinder(_t(pts.astype(np.float32)), _t(nrm.astype(np.float32)), w)
+    assert abs(abs(float((a.reshape(3) * _t(ax.astype(np.float32))).sum())) - 1.0) < 1e-4 and abs(float(r) - 1.0) < 2e-3
+    ang = np.pi / 3
+    axc = np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0)
+    f1 = np.cross(axc, [0, 0, 1.0]); f1 /= np.linalg.norm(f1); f2 = np.cross(axc, f1)
+    hh = 0.2 + rng.rand(2000)
+    radial = np.cos(th)[:, None] * f1 + np.sin(th)[:, None] * f2
+    ptc = hh[:, None] * (axc + np.tan(ang) * radial)
+    nc = np.cos(ang) * radial - np.sin(ang) * axc
+    apex, a, theta = F.fit_cone(_t(ptc.astype(np.float32)), _t(nc.astype(np.float32)), w)
+    assert apex.abs().max() < 1e-3 and abs(float(theta) - ang) < 1e-3
+    assert abs(float((a.reshape(3) * _t(axc.astype(np.float32))).sum()) - 1.0) < 1e-4          # axis points into the cone
+    # rank-2 system: solution of the regularised normal equations, finite and consistent in the row space
+    A = torch.randn(50, 2, generator=torch.Generator().manual_seed(0)) @ torch.tensor([[1.0, 0.0, 1.0], [0.0, 1.0, 1.0]])
+    x_true = torch.tensor([[0.3], [-0.2], [0.1]])
+    x = F.lstsq(A, A @ x_true)
+    assert torch.isfinite(x).all() and (A @ x - A @ x_true).abs().max() < 1e-2
