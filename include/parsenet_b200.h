@@ -91,6 +91,18 @@ int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const float* Yprev, 
 int pn_ms_kth_dist_tc(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K, float* kth, void* stream);
 /* replaces: MeanShift.nms arg-selects: src/mean_shift.py:146-149 (mode 0), :163-171 (mode 1) — same contract as pn_ms_argsel for modes 0 and 1; meanshift_tc_argsel.cu */
 int pn_ms_argsel_tc(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream);
+/* the two halves of pn_ms_iter_bwd_tc on their own: prep pass (Gn, gd) and the cols kernel (gX) */
+int pn_ms_bwd_prep_tc(const float* gout, const float* Ynew, const float* den, const float* unorm, int B, int N, int d, float* ws_Gn, float* ws_gd, void* stream);
+int pn_ms_bwd_cols_tc(const float* Yprev, const float* X, int B, int N, int d, const float* cinv, const float* ws_Gn, const float* ws_gd, float* gX, int accumulate_gX, void* stream);
+
+/* ---- meanshift_tma.cu (EXPERIMENTAL, opt-in PN_MS_TMA=1: streamed operand tiles fetched by TMA; not yet run on a GPU) ---- */
+/* once per MeanShift.mean_shift_ call (X is constant over the iterations, src/mean_shift.py:58-77):
+   Xs = X - tf32_hi(X) [B][N][128], Xt / Xst = transposes [B][128][Np], Np = N rounded up to a multiple of 32 */
+int pn_ms_prepare_operands(const float* X, int B, int N, int d, int Np, float* Xs, float* Xt, float* Xst, void* stream);
+/* replaces: MeanShift.mean_shift_ (one iteration): src/mean_shift.py:58-77 — contract of pn_ms_iter_fwd_tc + operand forms */
+int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* Xs, const float* Xt, const float* Xst, int B, int N, int d, int Np, const float* cinv, float* Ynew, float* den, float* unorm, void* stream);
+/* replaces: autograd of one mean-shift iteration — contract of pn_ms_iter_bwd_tc + operand forms */
+int pn_ms_iter_bwd_tma(const float* gout, const float* Ynew, const float* Yprev, const float* X, const float* Xs, const float* Xt, const float* Xst, const float* den, const float* unorm, int B, int N, int d, int Np, const float* cinv, float* ws_Gn, float* ws_gd, float* gYprev, float* gX, int accumulate_gX, void* stream);
 /* replaces: (debug aid, no reference counterpart: host-mapped progress words written by the tcgen05 pipelines; NULL disables) */
 int pn_debug_set_progress(int* host_mapped_words);
 

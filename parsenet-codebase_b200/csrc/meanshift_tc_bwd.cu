@@ -496,6 +496,32 @@ extern "C" int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const flo
     return PN_OK;
 }
 
+// The two halves of pn_ms_iter_bwd_tc as separate entry points (used by pn_ms_iter_bwd_tma in meanshift_tma.cu, which
+// replaces only the rows kernel): the prep pass, and the cols kernel (gX) in its default variant.
+extern "C" int pn_ms_bwd_prep_tc(const float* gout, const float* Ynew, const float* den, const float* unorm, int B, int N,
+                                 int d, float* ws_Gn, float* ws_gd, void* stream) {
+    PN_REQUIRE(gout && Ynew && den && unorm && ws_Gn && ws_gd, "pn_ms_bwd_prep_tc: null pointer");
+    PN_REQUIRE(d == mstcb::D, "pn_ms_bwd_prep_tc: embedding width must be %d (got %d)", mstcb::D, d);
+    long long rows = (long long)B * N;
+    mstcb::ms_bwd_prep_tc_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(gout, Ynew, den, unorm, rows, ws_Gn, ws_gd);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_bwd_prep_tc_kernel");
+    return PN_OK;
+}
+
+extern "C" int pn_ms_bwd_cols_tc(const float* Yprev, const float* X, int B, int N, int d, const float* cinv,
+                                 const float* ws_Gn, const float* ws_gd, float* gX, int accumulate_gX, void* stream) {
+    PN_REQUIRE(Yprev && X && cinv && ws_Gn && ws_gd && gX, "pn_ms_bwd_cols_tc: null pointer");
+    PN_REQUIRE(d == mstcb::D, "pn_ms_bwd_cols_tc: embedding width must be %d (got %d)", mstcb::D, d);
+    size_t sm = mstcb::NSTAGE * mstcb::STAGE_BYTES + 2 * 64 * 32 * sizeof(float) + 1024;
+    auto cols_k = mstcb::ms_bwd_tc_kernel<1, 128>;           // double-buffered P, exact split (the default variant)
+    PN_CUDA(cudaFuncSetAttribute(cols_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    cols_k<<<dim3(cdiv(N, 128), B), mstcb::NT, sm, (cudaStream_t)stream>>>(Yprev, X, ws_Gn, ws_gd, N, cinv, gX, accumulate_gX);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_bwd_tc_kernel<cols>");
+    return PN_OK;
+}
+
 extern "C" int pn_debug_set_progress(int* host_mapped_words) {
     PN_CUDA(cudaMemcpyToSymbol(pn::mstcb::g_dbg, &host_mapped_words, sizeof(int*)));
     return PN_OK;

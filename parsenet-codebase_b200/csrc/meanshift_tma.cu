@@ -1,0 +1,663 @@
+// EXPERIMENTAL (opt-in, PN_MS_TMA=1; written after the GPU budget of round 1 was spent, NOT yet run on a GPU):
+// mean-shift iteration kernels whose streamed operand tiles are fetched by TMA instead of being staged by loader warps.
+//
+// Why (profiles/r01_tc_probe.md, r01_ncu_meanshift_tc.md, r01_ms_bwd_ablation_sweep.md): in ms_fwd_tc_kernel /
+// ms_bwd_tc_kernel<rows> four loader warps LDG a 32 x 128 tile of X, split it into tf32 big / small parts and store it
+// in two layouts (as is for S = Y.X^T, transposed for O += P.X): 16 KB of LDG + 64 KB of STS + shuffle transposes per
+// tile, which ncu shows as the l1tex / LSU limiter (79-81 % busy, tensor pipe 50-57 %).  The probes established that
+//   * the tensor core TRUNCATES fp32 operands to tf32, so raw X *is* the "big" part (no masked copy needed),
+//   * a 128B-swizzled [rows][32 floats] slab as TMA writes it is read exactly by a K-major kind::tf32 descriptor
+//     (layout type 2, SBO = 1024, K step = +32 B inside the atom),
+//   * MN-major tf32 operands are not executed, i.e. the second product needs the tile in [d][j] order.
+// X is constant over all iterations of one mean_shift call (reference src/mean_shift.py:58-77 shifts new_X against the
+// fixed X), so ONE pass per call (ms_prep_operands_kernel) writes Xs = X - tf32_hi(X) and the transposes Xt, Xst, and
+// every tile step fetches its four operand tiles with 10 TMA box loads on one mbarrier.  Loader warps, their
+// global loads, shared-memory stores and shuffles are gone; the epilogue / MMA protocol is that of the PDB variant of
+// meanshift_tc.cu (double-buffered S and P in TMEM).  Every mbarrier wait is the watchdog version (trap after ~2 s): a
+// protocol or tensor-map mistake surfaces as a launch error, not as a hung GPU.
+//
+// Stage layout (64 KB, 1024-byte aligned):  XA_b | XA_s | XB_b | XB_s, 16 KB each
+//   XA_* : 4 slabs (d in [32 s, 32 s + 32)) of [32 j rows][128 B], TMA box {32 d, 32 j, 1} of X / Xs       (K = d)
+//   XB_* : 1 slab of [128 d rows][128 B = 32 j], TMA box {32 j, 128 d, 1} of Xt / Xst                      (K = j)
+#include "common.cuh"
+#include "tc05.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace pn {
+namespace mstma {
+using namespace tc05;
+
+constexpr int D = 128, BM = 128, BN = 32;
+constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9, NT = 320, EPI_THREADS = 256;
+constexpr int NSTAGE = 3, FLUSH = 16;
+constexpr float CLAMP = 75.f;
+constexpr uint32_t C_YB = 0, C_YS = 128, C_S0 = 256, C_PS2 = 320, C_O = 384, TMEM_COLS = 512;
+constexpr int PART_BYTES = BN * D * 4;            // 16 KB per operand part
+constexpr int SLAB_BYTES = BN * 128;              // one [32 rows][128 B] slab of XA
+constexpr int STAGE_BYTES = 4 * PART_BYTES;       // 64 KB
+constexpr uint32_t SW128 = 2, SBO128 = 1024;      // descriptor layout type / 8-row group stride of a 128B-swizzled slab
+
+struct Bars {
+    uint64_t x_full[NSTAGE], x_empty[NSTAGE], s_full[2], s_empty[2], p_full2[2], p_empty, o_flush, o_done, a_ready;
+};
+
+// ---------------------------------------------------------------------------------------------- operand preparation
+// X [B][N][128] -> Xs [B][N][128] (small split part), Xt / Xst [B][128][Np] (transposes of X / Xs, zero beyond N).
+// grid (Np / 32, B), 256 threads: one 32 x 128 tile, transposed through shared memory.
+__global__ void __launch_bounds__(256) ms_prep_operands_kernel(const float* __restrict__ X, int N, int Np,
+                                                               float* __restrict__ Xs, float* __restrict__ Xt,
+                                                               float* __restrict__ Xst) {
+    __shared__ float tb[32][D + 1], ts[32][D + 1];
+    const int b = blockIdx.y, j0 = blockIdx.x * 32, tid = threadIdx.x;
+    const float* Xb = X + (long long)b * N * D;
+    float* Xsb = Xs + (long long)b * N * D;
+    for (int e = tid; e < 32 * D; e += 256) {
+        const int r = e >> 7, c = e & 127, j = j0 + r;
+        const float v = (j < N) ? Xb[(long long)j * D + c] : 0.f;
+        const float sm = v - tf32_hi(v);
+        if (j < N) Xsb[(long long)j * D + c] = sm;
+        tb[r][c] = v;
+        ts[r][c] = sm;
+    }
+    __syncthreads();
+    float* Xtb = Xt + (long long)b * D * Np;
+    float* Xstb = Xst + (long long)b * D * Np;
+    for (int e = tid; e < D * 32; e += 256) {
+        const int dd = e >> 5, r = e & 31;
+        Xtb[(long long)dd * Np + j0 + r] = tb[r][dd];
+        Xstb[(long long)dd * Np + j0 + r] = ts[r][dd];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- forward iteration
+// grid (ceil(N / 128), B), 320 threads: warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issue.
+__global__ void __launch_bounds__(NT, 1)
+ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mXs,
+                  const __grid_constant__ CUtensorMap mXt, const __grid_constant__ CUtensorMap mXst,
+                  const float* __restrict__ Y, int N, const float* __restrict__ cinv, float* __restrict__ Ynew,
+                  float* __restrict__ den_out, float* __restrict__ unorm_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ Bars bars;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float part[4][BM];
+    // the dynamic segment is only guaranteed 16-byte aligned by the ABI: round up to the 1024 B the swizzle needs
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, i0 = blockIdx.x * BM;
+    const float* Yb = Y + (long long)b * N * D;
+    const int ntiles = (N + BN - 1) / BN;
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); mbar_init(&bars.p_full2[k], EPI_THREADS);
+        }
+        mbar_init(&bars.p_empty, 1); mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
+        mbar_init(&bars.a_ready, EPI_THREADS);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+
+    if (warp < EPI_WARPS) {
+        // =============================================================================== epilogue warps
+        // (identical to the PDB path of ms_fwd_tc_kernel: thread = (row, column half h); P_big(t) overwrites S(t) in place)
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t la = (uint32_t)(q * 32) << 16;
+        const bool ok = (i0 + row) < N;
+        const float c2 = cinv[b] * 1.4426950408889634f;
+        const float CL2 = CLAMP * 1.4426950408889634f;
+        const float* yr = Yb + (long long)(i0 + row) * D + 64 * h;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t vb[16], vs[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+                float4 v = ok ? *reinterpret_cast<const float4*>(yr + c0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float big = tf32_hi(f[u]);
+                    vb[e + u] = __float_as_uint(big);
+                    vs[e + u] = __float_as_uint(f[u] - big);
+                }
+            }
+            tmem_st16(tb + la + C_YB + 64 * h + c0, vb);
+            tmem_st16(tb + la + C_YS + 64 * h + c0, vs);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.a_ready);
+        float oacc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) oacc[e] = 0.f;
+        float den = 0.f;
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int k = t & 1;
+            const int j0 = t * BN + 16 * h;
+            mbar_wait_guarded(&bars.s_full[k], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[16], pb[16], ps[16];
+            tmem_ld16(tb + la + C_S0 + 32 * k + 16 * h, sv);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.s_empty[k]);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                float e = (__uint_as_float(sv[u]) - 1.0f) * c2;
+                e = fminf(fmaxf(e, -CL2), CL2);
+                float p = (j0 + u < N) ? ex2_approx(e) : 0.f;
+                den += p;
+                float big = tf32_hi(p);
+                pb[u] = __float_as_uint(big);
+                ps[u] = __float_as_uint(p - big);
+            }
+            const bool flush_now = (t > 0 && (t % FLUSH) == 0);
+            if (flush_now) {
+                mbar_wait_guarded(&bars.p_empty, (t & 1) ^ 1);       // second product of tile t-1 complete
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t ov[16];
+                    tmem_ld16(tb + la + C_O + 64 * h + c0, ov);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) oacc[c0 + e] += __uint_as_float(ov[e]);
+                }
+                tc_fence_before();
+                mbar_arrive(&bars.o_flush);
+            }
+            tmem_st16(tb + la + C_S0 + 32 * k + 16 * h, pb);
+            tmem_st16(tb + la + C_PS2 + 32 * k + 16 * h, ps);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.p_full2[k]);
+        }
+        mbar_wait_guarded(&bars.o_done, 0);
+        tc_fence_after();
+        part[h][row] = den;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float dn = part[0][row] + part[1][row];
+        const float dinv = 1.0f / dn;
+        float n2 = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t ov[16];
+            tmem_ld16(tb + la + C_O + 64 * h + c0, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                float o = oacc[c0 + e] + __uint_as_float(ov[e]);
+                float y = ok ? yr[c0 + e] : 0.f;
+                float m = o * dinv - y;
+                float uu = y + m;
+                oacc[c0 + e] = uu;
+                n2 = fmaf(uu, uu, n2);
+            }
+        }
+        part[2 + h][row] = n2;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float nr = sqrtf(part[2][row] + part[3][row]);
+        if (ok) {
+            float* dst = Ynew + ((long long)b * N + i0 + row) * D + 64 * h;
+#pragma unroll
+            for (int e = 0; e < 64; e += 4)
+                *reinterpret_cast<float4*>(dst + e) =
+                    make_float4(oacc[e] / nr, oacc[e + 1] / nr, oacc[e + 2] / nr, oacc[e + 3] / nr);
+            if (h == 0) {
+                den_out[(long long)b * N + i0 + row] = dn;
+                unorm_out[(long long)b * N + i0 + row] = nr;
+            }
+        }
+        tc_fence_before();
+    } else if (warp == TMA_WARP) {
+        // =============================================================================== TMA producer (one lane)
+        if (elect_one()) {
+            tma_prefetch_desc(&mX); tma_prefetch_desc(&mXs); tma_prefetch_desc(&mXt); tma_prefetch_desc(&mXst);
+#pragma unroll 1
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % NSTAGE;
+                mbar_wait_guarded(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
+                unsigned char* st = smem + s * STAGE_BYTES;
+                mbar_arrive_expect_tx(&bars.x_full[s], STAGE_BYTES);
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    tma_load_3d(st + sl * SLAB_BYTES, &mX, &bars.x_full[s], 32 * sl, t * BN, b);
+                    tma_load_3d(st + PART_BYTES + sl * SLAB_BYTES, &mXs, &bars.x_full[s], 32 * sl, t * BN, b);
+                }
+                tma_load_3d(st + 2 * PART_BYTES, &mXt, &bars.x_full[s], t * BN, 0, b);
+                tma_load_3d(st + 3 * PART_BYTES, &mXst, &bars.x_full[s], t * BN, 0, b);
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================================================================== MMA warp (warp-uniform)
+        const bool leader = elect_one();
+        const uint32_t idesc_s = make_idesc(2, BM, BN, 0, 0);
+        const uint32_t idesc_o = make_idesc(2, BM, D, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+        auto gemm2 = [&](int u) {
+            mbar_wait_guarded(&bars.p_full2[u & 1], (u >> 1) & 1);
+            const uint32_t pb_col = C_S0 + 32 * (u & 1), ps_col = C_PS2 + 32 * (u & 1);
+            const bool fresh = (u % FLUSH) == 0;
+            if (u > 0 && fresh) mbar_wait_guarded(&bars.o_flush, ((u / FLUSH) - 1) & 1);
+            tc_fence_after();
+            const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
+            const uint64_t db0 = make_smem_desc(st + 2 * PART_BYTES, 16, SBO128, SW128);
+            const uint64_t ds0 = make_smem_desc(st + 3 * PART_BYTES, 16, SBO128, SW128);
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < BN / 8; ++ks) {            // K = j: 4 steps of 8 inside the one 128 B atom row
+                    const uint64_t db = db0 + (uint64_t)((ks * 32) >> 4);
+                    const uint64_t ds = ds0 + (uint64_t)((ks * 32) >> 4);
+                    mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
+                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
+                }
+                mma_commit(&bars.x_empty[u % NSTAGE]);
+                mma_commit(&bars.p_empty);
+            }
+            __syncwarp();
+        };
+        mbar_wait_guarded(&bars.a_ready, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % NSTAGE, k = t & 1;
+            mbar_wait_guarded(&bars.x_full[s], (t / NSTAGE) & 1);
+            mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t st = sbase + s * STAGE_BYTES;
+            const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
+            const uint64_t ds0 = make_smem_desc(st + PART_BYTES, 16, SBO128, SW128);
+            const uint32_t d_s = tb + C_S0 + 32 * k;
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < D / 8; ++ks) {             // K = d: slab ks / 4, +32 B per step inside the slab
+                    const uint32_t off = (uint32_t)((ks >> 2) * SLAB_BYTES + (ks & 3) * 32);
+                    const uint64_t db = db0 + (uint64_t)(off >> 4);
+                    const uint64_t ds = ds0 + (uint64_t)(off >> 4);
+                    mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
+                }
+                mma_commit(&bars.s_full[k]);
+            }
+            __syncwarp();
+            if (t > 0) gemm2(t - 1);
+        }
+        gemm2(ntiles - 1);
+        if (leader) mma_commit(&bars.o_done);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------- backward, rows
+// gY_i = sum_j gS_ij x_j  with gS = (G + gd_i) K c (0 where clamped), S = Y X^T, K = exp(clamp((S-1)c)), G = Gn X^T.
+// Same math and epilogue as ms_bwd_tc_kernel<MODE_ROWS> with PDB (meanshift_tc_bwd.cu): the CTA owns 64 rows; TMEM lanes
+// 0-63 hold Y_i, lanes 64-127 hold Gn_i ("virtual rows"), so one MMA chain against the streamed X tile yields S and G.
+// The streamed tile is X (constant): its four operand forms come from TMA exactly as in the forward kernel.
+// grid (ceil(N / 64), B), 320 threads; dynamic smem = stages + [2][64][32] floats for the G hand-over.
+__global__ void __launch_bounds__(NT, 1)
+ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mXs,
+                       const __grid_constant__ CUtensorMap mXt, const __grid_constant__ CUtensorMap mXst,
+                       const float* __restrict__ Yp, const float* __restrict__ Gn, const float* __restrict__ gd, int N,
+                       const float* __restrict__ cinv, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ Bars bars;
+    __shared__ uint32_t tmem_base_s;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* exch = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const long long off = (long long)b * N * D;
+    const float* Ypb = Yp + off;
+    const float* Gb = Gn + off;
+    const float* gdb = gd + (long long)b * N;
+    const int r0 = blockIdx.x * 64;
+    const int ntiles = (N + BN - 1) / BN;
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
+        for (int k = 0; k < 2; ++k) {
+            mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); mbar_init(&bars.p_full2[k], EPI_THREADS);
+        }
+        mbar_init(&bars.p_empty, 1); mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
+        mbar_init(&bars.a_ready, EPI_THREADS);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+
+    if (warp < EPI_WARPS) {
+        // =============================================================================== epilogue warps
+        const int q = warp & 3, h = warp >> 2;
+        const int vrow = q * 32 + lane;                         // TMEM lane: 0-63 real rows (Y), 64-127 virtual rows (Gn)
+        const uint32_t la = (uint32_t)(q * 32) << 16;
+        const float c = cinv[b];
+        const float c2 = c * 1.4426950408889634f, CL2 = CLAMP * 1.4426950408889634f;
+        const int r = r0 + (vrow & 63);
+        const bool aok = r < N;
+        const float* arow = ((vrow < 64) ? Ypb : Gb) + (long long)r * D + 64 * h;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t vb[16], vs[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+                float4 v = aok ? *reinterpret_cast<const float4*>(arow + c0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float big = tf32_hi(f[u]);
+                    vb[e + u] = __float_as_uint(big);
+                    vs[e + u] = __float_as_uint(f[u] - big);
+                }
+            }
+            tmem_st16(tb + la + C_YB + 64 * h + c0, vb);
+            tmem_st16(tb + la + C_YS + 64 * h + c0, vs);
+        }
+        if (q >= 2) {                                           // P_small rows of the virtual half stay zero forever
+            uint32_t z[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) z[u] = 0u;
+            tmem_st16(tb + la + C_PS2 + 16 * h, z);
+            tmem_st16(tb + la + C_PS2 + 32 + 16 * h, z);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.a_ready);
+        const bool owner = q < 2;
+        float oacc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) oacc[e] = 0.f;
+        const float gd_row = (owner && aok) ? gdb[r0 + vrow] : 0.f;
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int k = t & 1;
+            mbar_wait_guarded(&bars.s_full[k], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t pb[16], ps[16], sv[16];
+            tmem_ld16(tb + la + C_S0 + 32 * k + 16 * h, sv);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.s_empty[k]);
+            float* ex = exch + (t & 1) * 64 * 32;
+            if (q >= 2) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) ex[(vrow - 64) * 32 + ((16 * h + u + vrow) & 31)] = __uint_as_float(sv[u]);
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (q < 2) {
+                const int j0 = t * 32 + 16 * h;
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    float g = ex[vrow * 32 + ((16 * h + u + vrow) & 31)];
+                    float e = (__uint_as_float(sv[u]) - 1.0f) * c2;
+                    const bool cl = (e > CL2) || (e < -CL2);
+                    e = fminf(fmaxf(e, -CL2), CL2);
+                    float kk = ex2_approx(e);
+                    float p = (!cl && (j0 + u < N)) ? (g + gd_row) * kk * c : 0.f;
+                    float big = tf32_hi(p);
+                    pb[u] = __float_as_uint(big);
+                    ps[u] = __float_as_uint(p - big);
+                }
+            }
+            const bool flush_now = (t > 0 && (t % FLUSH) == 0);
+            if (flush_now) {
+                mbar_wait_guarded(&bars.p_empty, (t & 1) ^ 1);
+                tc_fence_after();
+                if (owner) {
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 16) {
+                        uint32_t ov[16];
+                        tmem_ld16(tb + la + C_O + 64 * h + c0, ov);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) oacc[c0 + e] += __uint_as_float(ov[e]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bars.o_flush);
+            }
+            const uint32_t pb_col = C_S0 + 32 * k, ps_col = C_PS2 + 32 * k;
+            if (q < 2) {
+                tmem_st16(tb + la + pb_col + 16 * h, pb);
+                tmem_st16(tb + la + ps_col + 16 * h, ps);
+            } else {                                 // the G values of the virtual half must not act as P rows
+                uint32_t z[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) z[u] = 0u;
+                tmem_st16(tb + la + pb_col + 16 * h, z);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.p_full2[k]);
+        }
+        mbar_wait_guarded(&bars.o_done, 0);
+        tc_fence_after();
+        if (owner) {       // warp-uniform: tcgen05.ld is warp-collective, only the global stores are per-lane guarded
+            float* dst = out + off + (long long)(r0 + vrow) * D + 64 * h;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                uint32_t ov[16];
+                tmem_ld16(tb + la + C_O + 64 * h + c0, ov);
+                tmem_ld_wait();
+                if (aok) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4)
+                        *reinterpret_cast<float4*>(dst + c0 + e) =
+                            make_float4(oacc[c0 + e] + __uint_as_float(ov[e]), oacc[c0 + e + 1] + __uint_as_float(ov[e + 1]),
+                                        oacc[c0 + e + 2] + __uint_as_float(ov[e + 2]),
+                                        oacc[c0 + e + 3] + __uint_as_float(ov[e + 3]));
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == TMA_WARP) {
+        if (elect_one()) {
+            tma_prefetch_desc(&mX); tma_prefetch_desc(&mXs); tma_prefetch_desc(&mXt); tma_prefetch_desc(&mXst);
+#pragma unroll 1
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % NSTAGE;
+                mbar_wait_guarded(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
+                unsigned char* st = smem + s * STAGE_BYTES;
+                mbar_arrive_expect_tx(&bars.x_full[s], STAGE_BYTES);
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    tma_load_3d(st + sl * SLAB_BYTES, &mX, &bars.x_full[s], 32 * sl, t * BN, b);
+                    tma_load_3d(st + PART_BYTES + sl * SLAB_BYTES, &mXs, &bars.x_full[s], 32 * sl, t * BN, b);
+                }
+                tma_load_3d(st + 2 * PART_BYTES, &mXt, &bars.x_full[s], t * BN, 0, b);
+                tma_load_3d(st + 3 * PART_BYTES, &mXst, &bars.x_full[s], t * BN, 0, b);
+            }
+        }
+        __syncwarp();
+    } else {
+        const bool leader = elect_one();
+        const uint32_t idesc_s = make_idesc(2, 128, BN, 0, 0);
+        const uint32_t idesc_o = make_idesc(2, 128, D, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+        auto gemm2 = [&](int u) {
+            mbar_wait_guarded(&bars.p_full2[u & 1], (u >> 1) & 1);
+            const uint32_t pb_col = C_S0 + 32 * (u & 1), ps_col = C_PS2 + 32 * (u & 1);
+            const bool fresh = (u % FLUSH) == 0;
+            if (u > 0 && fresh) mbar_wait_guarded(&bars.o_flush, ((u / FLUSH) - 1) & 1);
+            tc_fence_after();
+            const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
+            const uint64_t db0 = make_smem_desc(st + 2 * PART_BYTES, 16, SBO128, SW128);
+            const uint64_t ds0 = make_smem_desc(st + 3 * PART_BYTES, 16, SBO128, SW128);
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < BN / 8; ++ks) {
+                    const uint64_t db = db0 + (uint64_t)((ks * 32) >> 4);
+                    const uint64_t ds = ds0 + (uint64_t)((ks * 32) >> 4);
+                    mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
+                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
+                }
+                mma_commit(&bars.x_empty[u % NSTAGE]);
+                mma_commit(&bars.p_empty);
+            }
+            __syncwarp();
+        };
+        mbar_wait_guarded(&bars.a_ready, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % NSTAGE, k = t & 1;
+            mbar_wait_guarded(&bars.x_full[s], (t / NSTAGE) & 1);
+            mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t st = sbase + s * STAGE_BYTES;
+            const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
+            const uint64_t ds0 = make_smem_desc(st + PART_BYTES, 16, SBO128, SW128);
+            const uint32_t d_s = tb + C_S0 + 32 * k;
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < D / 8; ++ks) {
+                    const uint32_t o2 = (uint32_t)((ks >> 2) * SLAB_BYTES + (ks & 3) * 32);
+                    const uint64_t db = db0 + (uint64_t)(o2 >> 4);
+                    const uint64_t ds = ds0 + (uint64_t)(o2 >> 4);
+                    mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
+                }
+                mma_commit(&bars.s_full[k]);
+            }
+            __syncwarp();
+            if (t > 0) gemm2(t - 1);
+        }
+        gemm2(ntiles - 1);
+        if (leader) mma_commit(&bars.o_done);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {       // resolved through the runtime: the library keeps no link dependency on libcuda
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// fp32 tensor [dim2][dim1][dim0] (dim0 contiguous), box {b0, b1, 1}, 128B swizzle, zero fill out of bounds
+static bool make_map(CUtensorMap* m, const float* base, uint64_t dim0, uint64_t dim1, uint64_t dim2, uint64_t pitch1_elems,
+                     uint64_t pitch2_elems, uint32_t b0, uint32_t b1) {
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {dim0, dim1, dim2};
+    cuuint64_t strides[2] = {pitch1_elems * 4, pitch2_elems * 4};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace mstma
+}  // namespace pn
+
+using namespace pn;
+
+// X [B][N][128] -> Xs [B][N][128], Xt / Xst [B][128][Np] with Np = N rounded up to a multiple of 32 (caller allocates).
+// Once per mean_shift call: X is constant over the iterations (reference src/mean_shift.py:58-77).
+extern "C" int pn_ms_prepare_operands(const float* X, int B, int N, int d, int Np, float* Xs, float* Xt, float* Xst,
+                                      void* stream) {
+    PN_REQUIRE(X && Xs && Xt && Xst, "pn_ms_prepare_operands: null pointer");
+    PN_REQUIRE(d == mstma::D, "pn_ms_prepare_operands: embedding width must be %d (got %d)", mstma::D, d);
+    PN_REQUIRE(Np >= N && Np % 32 == 0, "pn_ms_prepare_operands: Np must be N rounded up to a multiple of 32");
+    mstma::ms_prep_operands_kernel<<<dim3(Np / 32, B), 256, 0, (cudaStream_t)stream>>>(X, N, Np, Xs, Xt, Xst);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_prep_operands_kernel");
+    return PN_OK;
+}
+
+// same contract as pn_ms_iter_fwd_tc (one mean-shift iteration, reference src/mean_shift.py:58-77) with the operand
+// forms of pn_ms_prepare_operands
+extern "C" int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* Xs, const float* Xt, const float* Xst,
+                                  int B, int N, int d, int Np, const float* cinv, float* Ynew, float* den, float* unorm,
+                                  void* stream) {
+    PN_REQUIRE(Y && X && Xs && Xt && Xst && cinv && Ynew && den && unorm, "pn_ms_iter_fwd_tma: null pointer");
+    PN_REQUIRE(d == mstma::D, "pn_ms_iter_fwd_tma: embedding width must be %d (got %d)", mstma::D, d);
+    PN_REQUIRE(Np >= N && Np % 32 == 0, "pn_ms_iter_fwd_tma: Np must be N rounded up to a multiple of 32");
+    CUtensorMap mX, mXs, mXt, mXst;
+    const uint64_t n = (uint64_t)N, np = (uint64_t)Np, dd = (uint64_t)mstma::D;
+    bool ok = mstma::make_map(&mX, X, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
+              mstma::make_map(&mXs, Xs, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
+              mstma::make_map(&mXt, Xt, np, dd, (uint64_t)B, np, dd * np, 32, 128) &&
+              mstma::make_map(&mXst, Xst, np, dd, (uint64_t)B, np, dd * np, 32, 128);
+    if (!ok) {
+        set_error("pn_ms_iter_fwd_tma: cuTensorMapEncodeTiled failed or is unavailable");
+        return PN_ERR_CUDA;
+    }
+    size_t sm = mstma::NSTAGE * mstma::STAGE_BYTES + 1024;
+    PN_CUDA(cudaFuncSetAttribute(mstma::ms_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid(cdiv(N, mstma::BM), B);
+    mstma::ms_fwd_tma_kernel<<<grid, mstma::NT, sm, (cudaStream_t)stream>>>(mX, mXs, mXt, mXst, Y, N, cinv, Ynew, den,
+                                                                            unorm);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_fwd_tma_kernel");
+    return PN_OK;
+}
+
+// same contract as pn_ms_iter_bwd_tc (backward of one mean-shift iteration) with the operand forms of
+// pn_ms_prepare_operands: the rows kernel (gYprev) streams X through TMA; the prep and the cols kernel (gX), which stream
+// [Yprev; Gn] tiles that change every iteration, are the ones of meanshift_tc_bwd.cu (PN_MS_BWD_TC_ONLY=cols inside).
+extern "C" int pn_ms_bwd_prep_tc(const float* gout, const float* Ynew, const float* den, const float* unorm, int B, int N,
+                                 int d, float* ws_Gn, float* ws_gd, void* stream);
+extern "C" int pn_ms_bwd_cols_tc(const float* Yprev, const float* X, int B, int N, int d, const float* cinv,
+                                 const float* ws_Gn, const float* ws_gd, float* gX, int accumulate_gX, void* stream);
+
+extern "C" int pn_ms_iter_bwd_tma(const float* gout, const float* Ynew, const float* Yprev, const float* X,
+                                  const float* Xs, const float* Xt, const float* Xst, const float* den,
+                                  const float* unorm, int B, int N, int d, int Np, const float* cinv, float* ws_Gn,
+                                  float* ws_gd, float* gYprev, float* gX, int accumulate_gX, void* stream) {
+    PN_REQUIRE(gout && Ynew && Yprev && X && Xs && Xt && Xst && den && unorm && cinv && ws_Gn && ws_gd && gYprev && gX,
+               "pn_ms_iter_bwd_tma: null pointer");
+    PN_REQUIRE(d == mstma::D, "pn_ms_iter_bwd_tma: embedding width must be %d (got %d)", mstma::D, d);
+    PN_REQUIRE(Np >= N && Np % 32 == 0, "pn_ms_iter_bwd_tma: Np must be N rounded up to a multiple of 32");
+    int rc = pn_ms_bwd_prep_tc(gout, Ynew, den, unorm, B, N, d, ws_Gn, ws_gd, stream);
+    if (rc != PN_OK) return rc;
+    CUtensorMap mX, mXs, mXt, mXst;
+    const uint64_t n = (uint64_t)N, np = (uint64_t)Np, dd = (uint64_t)mstma::D;
+    bool ok = mstma::make_map(&mX, X, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
+              mstma::make_map(&mXs, Xs, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
+              mstma::make_map(&mXt, Xt, np, dd, (uint64_t)B, np, dd * np, 32, 128) &&
+              mstma::make_map(&mXst, Xst, np, dd, (uint64_t)B, np, dd * np, 32, 128);
+    if (!ok) {
+        set_error("pn_ms_iter_bwd_tma: cuTensorMapEncodeTiled failed or is unavailable");
+        return PN_ERR_CUDA;
+    }
+    size_t sm = mstma::NSTAGE * mstma::STAGE_BYTES + 2 * 64 * 32 * sizeof(float) + 1024;
+    PN_CUDA(cudaFuncSetAttribute(mstma::ms_bwd_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    mstma::ms_bwd_rows_tma_kernel<<<dim3(cdiv(N, 64), B), mstma::NT, sm, (cudaStream_t)stream>>>(
+        mX, mXs, mXt, mXst, Yprev, ws_Gn, ws_gd, N, cinv, gYprev);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_bwd_rows_tma_kernel");
+    return pn_ms_bwd_cols_tc(Yprev, X, B, N, d, cinv, ws_Gn, ws_gd, gX, accumulate_gX, stream);
+}

@@ -30,6 +30,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// same wait with a watchdog: traps (launch error instead of a hung GPU) when the phase has not completed after ~2 s.
+// For kernels that have not been brought up on hardware yet.
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+// arrive (count 1) and add `bytes` to the transaction count the barrier's current phase waits for (TMA completes them)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// ---- TMA (tiled tensor maps built on the host with cuTensorMapEncodeTiled, passed as __grid_constant__ kernel parameters)
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// box at coordinates (c0 = innermost element index, c1, c2) -> shared memory; completes `bytes of the box` on `bar`
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ---- proxy / tcgen05 fences
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -17,12 +17,27 @@ FWD_IMPL = os.environ.get("PN_MS_FWD", "tc")
 BWD_IMPL = os.environ.get("PN_MS_BWD", "tc")
 KTH_IMPL = os.environ.get("PN_MS_KTH", "tc")
 ARGSEL_IMPL = os.environ.get("PN_MS_ARGSEL", "tc")      # modes 0 / 1 of the nms arg-selects (mode 2 is always simt)
+# EXPERIMENTAL, opt-in: operand tiles of the forward / rows-backward kernels fetched by TMA (csrc/meanshift_tma.cu).
+# Written after the GPU budget of round 1 was spent: not yet run on a GPU, hence off by default.
+USE_TMA = os.environ.get("PN_MS_TMA", "0") == "1"
 _KTH = {"tc": "pn_ms_kth_dist_tc", "simt": "pn_ms_kth_dist"}
 
 
 def _argsel_entry(mode, d):
     return "pn_ms_argsel_tc" if (ARGSEL_IMPL == "tc" and mode in (0, 1) and d == 128) else "pn_ms_argsel"
 SQRT_FLOOR = 1e-6     # guard_sqrt(top_k, 1e-6), mean_shift.py:135
+
+
+def _operand_forms(X):
+    """TMA operand forms of the constant matrix X (B,N,128) of one mean_shift call: Xs = X - tf32_hi(X) and the
+    transposes Xt, Xst (B,128,Np), Np = N rounded up to 32 (csrc/meanshift_tma.cu)"""
+    B, N, d = X.shape
+    Np = (N + 31) // 32 * 32
+    Xs = torch.empty_like(X)
+    Xt = torch.empty((B, d, Np), dtype=torch.float32, device=X.device)
+    Xst = torch.empty((B, d, Np), dtype=torch.float32, device=X.device)
+    call("pn_ms_prepare_operands", _ptr(X), B, N, d, Np, _ptr(Xs), _ptr(Xt), _ptr(Xst), _stream())
+    return Xs, Xt, Xst, Np
 
 
 class MeanShiftItersFn(torch.autograd.Function):
@@ -36,12 +51,18 @@ class MeanShiftItersFn(torch.autograd.Function):
         B, N, d = X.shape
         cinv = cinv.detach().to(torch.float32).contiguous()
         Ys, dens, norms = [X], [], []
+        forms = _operand_forms(X) if (USE_TMA and FWD_IMPL == "tc" and d == 128 and iterations > 0) else None
         for _ in range(iterations):
             Yn = torch.empty_like(X)
             den = torch.empty((B, N), dtype=torch.float32, device=X.device)
             un = torch.empty((B, N), dtype=torch.float32, device=X.device)
-            call("pn_ms_iter_fwd_tc" if FWD_IMPL == "tc" else "pn_ms_iter_fwd", _ptr(Ys[-1]), _ptr(X), B, N, d,
-                 _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
+            if forms is not None:
+                Xs, Xt, Xst, Np = forms
+                call("pn_ms_iter_fwd_tma", _ptr(Ys[-1]), _ptr(X), _ptr(Xs), _ptr(Xt), _ptr(Xst), B, N, d, Np,
+                     _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
+            else:
+                call("pn_ms_iter_fwd_tc" if FWD_IMPL == "tc" else "pn_ms_iter_fwd", _ptr(Ys[-1]), _ptr(X), B, N, d,
+                     _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
             Ys.append(Yn); dens.append(den); norms.append(un)
         ctx.saved = (X, cinv, Ys, dens, norms)
         # (fresh view: an output object kept in ctx would form a reference cycle, see segnet.EncoderFn.forward)
@@ -55,10 +76,19 @@ class MeanShiftItersFn(torch.autograd.Function):
         gX = torch.zeros_like(X)
         Gn = torch.empty_like(X)
         gd = torch.empty((B, N), dtype=torch.float32, device=X.device)
+        # (the operand forms are recomputed here rather than kept alive between forward and backward: one 15 MB / shape
+        # pass against 10 iterations of N^2 work)
+        forms = _operand_forms(X) if (USE_TMA and BWD_IMPL == "tc" and d == 128 and len(dens) > 0) else None
         for it in range(len(dens) - 1, -1, -1):
             gprev = torch.empty_like(X)
-            call("pn_ms_iter_bwd_tc" if BWD_IMPL == "tc" else "pn_ms_iter_bwd", _ptr(g), _ptr(Ys[it + 1]), _ptr(Ys[it]), _ptr(X), _ptr(dens[it]),
-                 _ptr(norms[it]), B, N, d, _ptr(cinv), _ptr(Gn), _ptr(gd), _ptr(gprev), _ptr(gX), 1, _stream())
+            if forms is not None:
+                Xs, Xt, Xst, Np = forms
+                call("pn_ms_iter_bwd_tma", _ptr(g), _ptr(Ys[it + 1]), _ptr(Ys[it]), _ptr(X), _ptr(Xs), _ptr(Xt), _ptr(Xst),
+                     _ptr(dens[it]), _ptr(norms[it]), B, N, d, Np, _ptr(cinv), _ptr(Gn), _ptr(gd), _ptr(gprev), _ptr(gX), 1,
+                     _stream())
+            else:
+                call("pn_ms_iter_bwd_tc" if BWD_IMPL == "tc" else "pn_ms_iter_bwd", _ptr(g), _ptr(Ys[it + 1]), _ptr(Ys[it]), _ptr(X), _ptr(dens[it]),
+                     _ptr(norms[it]), B, N, d, _ptr(cinv), _ptr(Gn), _ptr(gd), _ptr(gprev), _ptr(gX), 1, _stream())
             g = gprev
         gX += g            # Y_0 = X.clone()
         return gX, None, None
