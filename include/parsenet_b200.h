@@ -101,8 +101,9 @@ int pn_ms_bwd_cols_tc(const float* Yprev, const float* X, int B, int N, int d, c
 int pn_ms_prepare_operands(const float* X, int B, int N, int d, int Np, float* Xs, float* Xt, float* Xst, void* stream);
 /* replaces: MeanShift.mean_shift_ (one iteration): src/mean_shift.py:58-77 — contract of pn_ms_iter_fwd_tc + operand forms */
 int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* Xs, const float* Xt, const float* Xst, int B, int N, int d, int Np, const float* cinv, float* Ynew, float* den, float* unorm, void* stream);
-/* replaces: autograd of one mean-shift iteration — contract of pn_ms_iter_bwd_tc + operand forms */
-int pn_ms_iter_bwd_tma(const float* gout, const float* Ynew, const float* Yprev, const float* X, const float* Xs, const float* Xt, const float* Xst, const float* den, const float* unorm, int B, int N, int d, int Np, const float* cinv, float* ws_Gn, float* ws_gd, float* gYprev, float* gX, int accumulate_gX, void* stream);
+/* replaces: autograd of one mean-shift iteration — contract of pn_ms_iter_bwd_tc + operand forms of X + workspace ws_C
+   (4 * B * 2 Nq * 128 floats, Nq = N rounded up to 16) for the forms of the interleaved [Yprev; Gn] tiles */
+int pn_ms_iter_bwd_tma(const float* gout, const float* Ynew, const float* Yprev, const float* X, const float* Xs, const float* Xt, const float* Xst, const float* den, const float* unorm, int B, int N, int d, int Np, const float* cinv, float* ws_Gn, float* ws_gd, float* ws_C, float* gYprev, float* gX, int accumulate_gX, void* stream);
 /* replaces: (debug aid, no reference counterpart: host-mapped progress words written by the tcgen05 pipelines; NULL disables) */
 int pn_debug_set_progress(int* host_mapped_words);
 

@@ -70,6 +70,104 @@ __global__ void __launch_bounds__(256) ms_prep_operands_kernel(const float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------- shared warp roles
+// TMA producer (one elected lane of its warp): per tile step 4 + 4 slab boxes of the row-major forms and one box each of
+// the transposed forms, all completing on x_full[stage].  `row0(t)` = first row of tile t in the row-major forms.
+__device__ __forceinline__ void tma_producer(unsigned char* smem, Bars& bars, const CUtensorMap* mA, const CUtensorMap* mAs,
+                                             const CUtensorMap* mT, const CUtensorMap* mTs, int ntiles, int b) {
+    if (elect_one()) {
+        tma_prefetch_desc(mA); tma_prefetch_desc(mAs); tma_prefetch_desc(mT); tma_prefetch_desc(mTs);
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % NSTAGE;
+            mbar_wait_guarded(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
+            unsigned char* st = smem + s * STAGE_BYTES;
+            mbar_arrive_expect_tx(&bars.x_full[s], STAGE_BYTES);
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+                tma_load_3d(st + sl * SLAB_BYTES, mA, &bars.x_full[s], 32 * sl, t * BN, b);
+                tma_load_3d(st + PART_BYTES + sl * SLAB_BYTES, mAs, &bars.x_full[s], 32 * sl, t * BN, b);
+            }
+            tma_load_3d(st + 2 * PART_BYTES, mT, &bars.x_full[s], t * BN, 0, b);
+            tma_load_3d(st + 3 * PART_BYTES, mTs, &bars.x_full[s], t * BN, 0, b);
+        }
+    }
+    __syncwarp();
+}
+
+// MMA issue warp (warp-uniform code, one elected lane issues): per tile the first product D(t) = A . tile^T (48 MMAs,
+// N = 32, K = d through the 4 slabs) and, one tile behind, the second product O += P(t-1) . tile (12 MMAs, N = 128, K = 32
+// tile rows), split-TF32 (small.big + big.small + big.big), A operands in TMEM.  Issue order G1(0) G1(1) G2(0) G1(2) ...
+__device__ __forceinline__ void mma_issuer(unsigned char* smem, Bars& bars, uint32_t tb, int ntiles) {
+    const bool leader = elect_one();
+    const uint32_t idesc_s = make_idesc(2, 128, BN, 0, 0);
+    const uint32_t idesc_o = make_idesc(2, 128, D, 0, 0);
+    const uint32_t sbase = smem_u32(smem);
+    auto gemm2 = [&](int u) {
+        mbar_wait_guarded(&bars.p_full2[u & 1], (u >> 1) & 1);
+        const uint32_t pb_col = C_S0 + 32 * (u & 1), ps_col = C_PS2 + 32 * (u & 1);
+        const bool fresh = (u % FLUSH) == 0;
+        if (u > 0 && fresh) mbar_wait_guarded(&bars.o_flush, ((u / FLUSH) - 1) & 1);
+        tc_fence_after();
+        const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
+        const uint64_t db0 = make_smem_desc(st + 2 * PART_BYTES, 16, SBO128, SW128);
+        const uint64_t ds0 = make_smem_desc(st + 3 * PART_BYTES, 16, SBO128, SW128);
+        if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < BN / 8; ++ks) {            // K = tile row: 4 steps of 8 inside the one 128 B atom row
+                const uint64_t db = db0 + (uint64_t)((ks * 32) >> 4);
+                const uint64_t ds = ds0 + (uint64_t)((ks * 32) >> 4);
+                mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
+                mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
+            }
+            mma_commit(&bars.x_empty[u % NSTAGE]);
+            mma_commit(&bars.p_empty);
+        }
+        __syncwarp();
+    };
+    mbar_wait_guarded(&bars.a_ready, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % NSTAGE, k = t & 1;
+        mbar_wait_guarded(&bars.x_full[s], (t / NSTAGE) & 1);
+        mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t st = sbase + s * STAGE_BYTES;
+        const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
+        const uint64_t ds0 = make_smem_desc(st + PART_BYTES, 16, SBO128, SW128);
+        const uint32_t d_s = tb + C_S0 + 32 * k;
+        if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < D / 8; ++ks) {             // K = d: slab ks / 4, +32 B per step inside the slab
+                const uint32_t off = (uint32_t)((ks >> 2) * SLAB_BYTES + (ks & 3) * 32);
+                const uint64_t db = db0 + (uint64_t)(off >> 4);
+                const uint64_t ds = ds0 + (uint64_t)(off >> 4);
+                mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
+                mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
+                mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
+            }
+            mma_commit(&bars.s_full[k]);
+        }
+        __syncwarp();
+        if (t > 0) gemm2(t - 1);
+    }
+    gemm2(ntiles - 1);
+    if (leader) mma_commit(&bars.o_done);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void init_bars(Bars& bars) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
+    for (int k = 0; k < 2; ++k) {
+        mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); mbar_init(&bars.p_full2[k], EPI_THREADS);
+    }
+    mbar_init(&bars.p_empty, 1); mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
+    mbar_init(&bars.a_ready, EPI_THREADS);
+    mbar_fence_init();
+}
+
 // ---------------------------------------------------------------------------------------------- forward iteration
 // grid (ceil(N / 128), B), 320 threads: warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issue.
 __global__ void __launch_bounds__(NT, 1)
@@ -90,15 +188,7 @@ ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant_
     const int ntiles = (N + BN - 1) / BN;
 
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
-        for (int k = 0; k < 2; ++k) {
-            mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); mbar_init(&bars.p_full2[k], EPI_THREADS);
-        }
-        mbar_init(&bars.p_empty, 1); mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
-        mbar_init(&bars.a_ready, EPI_THREADS);
-        mbar_fence_init();
-    }
+    if (tid == 0) init_bars(bars);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -218,84 +308,9 @@ ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant_
         }
         tc_fence_before();
     } else if (warp == TMA_WARP) {
-        // =============================================================================== TMA producer (one lane)
-        if (elect_one()) {
-            tma_prefetch_desc(&mX); tma_prefetch_desc(&mXs); tma_prefetch_desc(&mXt); tma_prefetch_desc(&mXst);
-#pragma unroll 1
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % NSTAGE;
-                mbar_wait_guarded(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
-                unsigned char* st = smem + s * STAGE_BYTES;
-                mbar_arrive_expect_tx(&bars.x_full[s], STAGE_BYTES);
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                    tma_load_3d(st + sl * SLAB_BYTES, &mX, &bars.x_full[s], 32 * sl, t * BN, b);
-                    tma_load_3d(st + PART_BYTES + sl * SLAB_BYTES, &mXs, &bars.x_full[s], 32 * sl, t * BN, b);
-                }
-                tma_load_3d(st + 2 * PART_BYTES, &mXt, &bars.x_full[s], t * BN, 0, b);
-                tma_load_3d(st + 3 * PART_BYTES, &mXst, &bars.x_full[s], t * BN, 0, b);
-            }
-        }
-        __syncwarp();
+        tma_producer(smem, bars, &mX, &mXs, &mXt, &mXst, ntiles, b);
     } else {
-        // =============================================================================== MMA warp (warp-uniform)
-        const bool leader = elect_one();
-        const uint32_t idesc_s = make_idesc(2, BM, BN, 0, 0);
-        const uint32_t idesc_o = make_idesc(2, BM, D, 0, 0);
-        const uint32_t sbase = smem_u32(smem);
-        auto gemm2 = [&](int u) {
-            mbar_wait_guarded(&bars.p_full2[u & 1], (u >> 1) & 1);
-            const uint32_t pb_col = C_S0 + 32 * (u & 1), ps_col = C_PS2 + 32 * (u & 1);
-            const bool fresh = (u % FLUSH) == 0;
-            if (u > 0 && fresh) mbar_wait_guarded(&bars.o_flush, ((u / FLUSH) - 1) & 1);
-            tc_fence_after();
-            const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
-            const uint64_t db0 = make_smem_desc(st + 2 * PART_BYTES, 16, SBO128, SW128);
-            const uint64_t ds0 = make_smem_desc(st + 3 * PART_BYTES, 16, SBO128, SW128);
-            if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < BN / 8; ++ks) {            // K = j: 4 steps of 8 inside the one 128 B atom row
-                    const uint64_t db = db0 + (uint64_t)((ks * 32) >> 4);
-                    const uint64_t ds = ds0 + (uint64_t)((ks * 32) >> 4);
-                    mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
-                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
-                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
-                }
-                mma_commit(&bars.x_empty[u % NSTAGE]);
-                mma_commit(&bars.p_empty);
-            }
-            __syncwarp();
-        };
-        mbar_wait_guarded(&bars.a_ready, 0);
-        tc_fence_after();
-#pragma unroll 1
-        for (int t = 0; t < ntiles; ++t) {
-            const int s = t % NSTAGE, k = t & 1;
-            mbar_wait_guarded(&bars.x_full[s], (t / NSTAGE) & 1);
-            mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t st = sbase + s * STAGE_BYTES;
-            const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
-            const uint64_t ds0 = make_smem_desc(st + PART_BYTES, 16, SBO128, SW128);
-            const uint32_t d_s = tb + C_S0 + 32 * k;
-            if (leader) {
-#pragma unroll
-                for (int ks = 0; ks < D / 8; ++ks) {             // K = d: slab ks / 4, +32 B per step inside the slab
-                    const uint32_t off = (uint32_t)((ks >> 2) * SLAB_BYTES + (ks & 3) * 32);
-                    const uint64_t db = db0 + (uint64_t)(off >> 4);
-                    const uint64_t ds = ds0 + (uint64_t)(off >> 4);
-                    mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
-                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
-                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
-                }
-                mma_commit(&bars.s_full[k]);
-            }
-            __syncwarp();
-            if (t > 0) gemm2(t - 1);
-        }
-        gemm2(ntiles - 1);
-        if (leader) mma_commit(&bars.o_done);
-        __syncwarp();
+        mma_issuer(smem, bars, tb, ntiles);
     }
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
@@ -328,15 +343,7 @@ ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_cons
     const int ntiles = (N + BN - 1) / BN;
 
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
-        for (int k = 0; k < 2; ++k) {
-            mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); mbar_init(&bars.p_full2[k], EPI_THREADS);
-        }
-        mbar_init(&bars.p_empty, 1); mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
-        mbar_init(&bars.a_ready, EPI_THREADS);
-        mbar_fence_init();
-    }
+    if (tid == 0) init_bars(bars);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -467,82 +474,192 @@ ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_cons
         }
         tc_fence_before();
     } else if (warp == TMA_WARP) {
-        if (elect_one()) {
-            tma_prefetch_desc(&mX); tma_prefetch_desc(&mXs); tma_prefetch_desc(&mXt); tma_prefetch_desc(&mXst);
-#pragma unroll 1
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % NSTAGE;
-                mbar_wait_guarded(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
-                unsigned char* st = smem + s * STAGE_BYTES;
-                mbar_arrive_expect_tx(&bars.x_full[s], STAGE_BYTES);
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                    tma_load_3d(st + sl * SLAB_BYTES, &mX, &bars.x_full[s], 32 * sl, t * BN, b);
-                    tma_load_3d(st + PART_BYTES + sl * SLAB_BYTES, &mXs, &bars.x_full[s], 32 * sl, t * BN, b);
-                }
-                tma_load_3d(st + 2 * PART_BYTES, &mXt, &bars.x_full[s], t * BN, 0, b);
-                tma_load_3d(st + 3 * PART_BYTES, &mXst, &bars.x_full[s], t * BN, 0, b);
-            }
-        }
-        __syncwarp();
+        tma_producer(smem, bars, &mX, &mXs, &mXt, &mXst, ntiles, b);
     } else {
-        const bool leader = elect_one();
-        const uint32_t idesc_s = make_idesc(2, 128, BN, 0, 0);
-        const uint32_t idesc_o = make_idesc(2, 128, D, 0, 0);
-        const uint32_t sbase = smem_u32(smem);
-        auto gemm2 = [&](int u) {
-            mbar_wait_guarded(&bars.p_full2[u & 1], (u >> 1) & 1);
-            const uint32_t pb_col = C_S0 + 32 * (u & 1), ps_col = C_PS2 + 32 * (u & 1);
-            const bool fresh = (u % FLUSH) == 0;
-            if (u > 0 && fresh) mbar_wait_guarded(&bars.o_flush, ((u / FLUSH) - 1) & 1);
-            tc_fence_after();
-            const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
-            const uint64_t db0 = make_smem_desc(st + 2 * PART_BYTES, 16, SBO128, SW128);
-            const uint64_t ds0 = make_smem_desc(st + 3 * PART_BYTES, 16, SBO128, SW128);
-            if (leader) {
+        mma_issuer(smem, bars, tb, ntiles);
+    }
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------- backward, cols
+// gX_j (+)= sum_i gS_ij y_i + K_ij Gn_i: the CTA owns 128 rows j of X (A operand, TMEM); the streamed 32-row tile is the
+// CONCATENATION of 16 rows of Y and the same 16 rows of Gn, so D[:, 0:16] = S^T, D[:, 16:32] = G^T, P = [gS^T | K^T] and the
+// second product with the same tile gives gS^T Y + K^T Gn in one chain (ms_bwd_tc_kernel<MODE_COLS>, meanshift_tc_bwd.cu).
+// [Y; Gn] changes every iteration: ms_prep_concat_kernel writes the interleaved matrix C (tile t = rows 32t..32t+31) and
+// its three other operand forms once per backward iteration (50 MB per shape against 7 N^2 d flop), after which the
+// streaming side is exactly that of the forward kernel.
+// grid (Nq / 16, B), 256 threads; Nq = N rounded up to 16; C, Cs [B][2 Nq][128]; Ct, Cst [B][128][2 Nq]
+__global__ void __launch_bounds__(256) ms_prep_concat_kernel(const float* __restrict__ Y, const float* __restrict__ Gn, int N,
+                                                             int Nq, float* __restrict__ C, float* __restrict__ Cs,
+                                                             float* __restrict__ Ct, float* __restrict__ Cst) {
+    __shared__ float tb[32][D + 1], ts[32][D + 1];
+    const int b = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+    const long long src_off = (long long)b * N * D;
+    const long long rows2 = 2LL * Nq;
+    float* Cb = C + (long long)b * rows2 * D;
+    float* Csb = Cs + (long long)b * rows2 * D;
+    for (int e = tid; e < 32 * D; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        const int i = 16 * t + (r & 15);
+        const float* src = (r < 16) ? Y : Gn;
+        const float v = (i < N) ? src[src_off + (long long)i * D + c] : 0.f;
+        const float sm = v - tf32_hi(v);
+        Cb[(32LL * t + r) * D + c] = v;
+        Csb[(32LL * t + r) * D + c] = sm;
+        tb[r][c] = v;
+        ts[r][c] = sm;
+    }
+    __syncthreads();
+    float* Ctb = Ct + (long long)b * D * rows2;
+    float* Cstb = Cst + (long long)b * D * rows2;
+    for (int e = tid; e < D * 32; e += 256) {
+        const int dd = e >> 5, r = e & 31;
+        Ctb[(long long)dd * rows2 + 32LL * t + r] = tb[r][dd];
+        Cstb[(long long)dd * rows2 + 32LL * t + r] = ts[r][dd];
+    }
+}
+
+// grid (ceil(N / 128), B), 320 threads
+__global__ void __launch_bounds__(NT, 1)
+ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_constant__ CUtensorMap mCs,
+                       const __grid_constant__ CUtensorMap mCt, const __grid_constant__ CUtensorMap mCst,
+                       const float* __restrict__ X, const float* __restrict__ gd, int N, const float* __restrict__ cinv,
+                       float* __restrict__ out, int accumulate) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ Bars bars;
+    __shared__ uint32_t tmem_base_s;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y;
+    const long long off = (long long)b * N * D;
+    const float* Xb = X + off;
+    const float* gdb = gd + (long long)b * N;
+    const int r0 = blockIdx.x * 128;
+    const int ntiles = (N + 15) / 16;
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) init_bars(bars);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+
+    if (warp < EPI_WARPS) {
+        const int q = warp & 3, h = warp >> 2;
+        const int vrow = q * 32 + lane;
+        const uint32_t la = (uint32_t)(q * 32) << 16;
+        const float c = cinv[b];
+        const float c2 = c * 1.4426950408889634f, CL2 = CLAMP * 1.4426950408889634f;
+        const bool aok = (r0 + vrow) < N;
+        const float* arow = Xb + (long long)(r0 + vrow) * D + 64 * h;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t vb[16], vs[16];
 #pragma unroll
-                for (int ks = 0; ks < BN / 8; ++ks) {
-                    const uint64_t db = db0 + (uint64_t)((ks * 32) >> 4);
-                    const uint64_t ds = ds0 + (uint64_t)((ks * 32) >> 4);
-                    mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
-                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
-                    mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
+            for (int e = 0; e < 16; e += 4) {
+                float4 v = aok ? *reinterpret_cast<const float4*>(arow + c0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float big = tf32_hi(f[u]);
+                    vb[e + u] = __float_as_uint(big);
+                    vs[e + u] = __float_as_uint(f[u] - big);
                 }
-                mma_commit(&bars.x_empty[u % NSTAGE]);
-                mma_commit(&bars.p_empty);
             }
-            __syncwarp();
-        };
-        mbar_wait_guarded(&bars.a_ready, 0);
-        tc_fence_after();
+            tmem_st16(tb + la + C_YB + 64 * h + c0, vb);
+            tmem_st16(tb + la + C_YS + 64 * h + c0, vs);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.a_ready);
+        float oacc[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) oacc[e] = 0.f;
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
-            const int s = t % NSTAGE, k = t & 1;
-            mbar_wait_guarded(&bars.x_full[s], (t / NSTAGE) & 1);
-            mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
+            const int k = t & 1;
+            mbar_wait_guarded(&bars.s_full[k], (t >> 1) & 1);
             tc_fence_after();
-            const uint32_t st = sbase + s * STAGE_BYTES;
-            const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
-            const uint64_t ds0 = make_smem_desc(st + PART_BYTES, 16, SBO128, SW128);
-            const uint32_t d_s = tb + C_S0 + 32 * k;
-            if (leader) {
+            uint32_t s8[8], g8[8], pb[16], ps[16];
+            tmem_ld8(tb + la + C_S0 + 32 * k + 8 * h, s8);              // S^T: tile rows 8h .. 8h+7 (Y half)
+            tmem_ld8(tb + la + C_S0 + 32 * k + 16 + 8 * h, g8);         // G^T: the same rows of the Gn half
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.s_empty[k]);
+            const int i0t = t * 16 + 8 * h;
 #pragma unroll
-                for (int ks = 0; ks < D / 8; ++ks) {
-                    const uint32_t o2 = (uint32_t)((ks >> 2) * SLAB_BYTES + (ks & 3) * 32);
-                    const uint64_t db = db0 + (uint64_t)(o2 >> 4);
-                    const uint64_t ds = ds0 + (uint64_t)(o2 >> 4);
-                    mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
-                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
-                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
-                }
-                mma_commit(&bars.s_full[k]);
+            for (int u = 0; u < 8; ++u) {
+                const bool iv = (i0t + u) < N;
+                const float gdi = iv ? gdb[i0t + u] : 0.f;
+                float e = (__uint_as_float(s8[u]) - 1.0f) * c2;
+                const bool cl = (e > CL2) || (e < -CL2);
+                e = fminf(fmaxf(e, -CL2), CL2);
+                float kk = iv ? ex2_approx(e) : 0.f;
+                float p1 = (!cl && iv) ? (__uint_as_float(g8[u]) + gdi) * kk * c : 0.f;
+                float b1 = tf32_hi(p1), b2 = tf32_hi(kk);
+                pb[u] = __float_as_uint(b1);       ps[u] = __float_as_uint(p1 - b1);       // gS^T -> cols 8h..
+                pb[8 + u] = __float_as_uint(b2);   ps[8 + u] = __float_as_uint(kk - b2);   // K^T  -> cols 16+8h..
             }
-            __syncwarp();
-            if (t > 0) gemm2(t - 1);
+            const bool flush_now = (t > 0 && (t % FLUSH) == 0);
+            if (flush_now) {
+                mbar_wait_guarded(&bars.p_empty, (t & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    uint32_t ov[16];
+                    tmem_ld16(tb + la + C_O + 64 * h + c0, ov);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) oacc[c0 + e] += __uint_as_float(ov[e]);
+                }
+                tc_fence_before();
+                mbar_arrive(&bars.o_flush);
+            }
+            const uint32_t pb_col = C_S0 + 32 * k, ps_col = C_PS2 + 32 * k;
+            {
+                uint32_t a[8], dd[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a[u] = pb[u]; dd[u] = pb[8 + u]; }
+                tmem_st8(tb + la + pb_col + 8 * h, a);
+                tmem_st8(tb + la + pb_col + 16 + 8 * h, dd);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a[u] = ps[u]; dd[u] = ps[8 + u]; }
+                tmem_st8(tb + la + ps_col + 8 * h, a);
+                tmem_st8(tb + la + ps_col + 16 + 8 * h, dd);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&bars.p_full2[k]);
         }
-        gemm2(ntiles - 1);
-        if (leader) mma_commit(&bars.o_done);
-        __syncwarp();
+        mbar_wait_guarded(&bars.o_done, 0);
+        tc_fence_after();
+        float* dst = out + off + (long long)(r0 + vrow) * D + 64 * h;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t ov[16];
+            tmem_ld16(tb + la + C_O + 64 * h + c0, ov);
+            tmem_ld_wait();
+            if (aok) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                    float4 v = make_float4(oacc[c0 + e] + __uint_as_float(ov[e]), oacc[c0 + e + 1] + __uint_as_float(ov[e + 1]),
+                                           oacc[c0 + e + 2] + __uint_as_float(ov[e + 2]),
+                                           oacc[c0 + e + 3] + __uint_as_float(ov[e + 3]));
+                    if (accumulate) {
+                        float4 a = *reinterpret_cast<const float4*>(dst + c0 + e);
+                        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                    }
+                    *reinterpret_cast<float4*>(dst + c0 + e) = v;
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == TMA_WARP) {
+        tma_producer(smem, bars, &mC, &mCs, &mCt, &mCst, ntiles, b);
+    } else {
+        mma_issuer(smem, bars, tb, ntiles);
     }
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
@@ -626,38 +743,50 @@ extern "C" int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* X
 }
 
 // same contract as pn_ms_iter_bwd_tc (backward of one mean-shift iteration) with the operand forms of
-// pn_ms_prepare_operands: the rows kernel (gYprev) streams X through TMA; the prep and the cols kernel (gX), which stream
-// [Yprev; Gn] tiles that change every iteration, are the ones of meanshift_tc_bwd.cu (PN_MS_BWD_TC_ONLY=cols inside).
+// pn_ms_prepare_operands for X and a workspace ws_C of 4 * B * 2 Nq * 128 floats (Nq = N rounded up to 16) for the
+// operand forms of the interleaved [Yprev; Gn] matrix, which are rebuilt here every iteration.
 extern "C" int pn_ms_bwd_prep_tc(const float* gout, const float* Ynew, const float* den, const float* unorm, int B, int N,
                                  int d, float* ws_Gn, float* ws_gd, void* stream);
-extern "C" int pn_ms_bwd_cols_tc(const float* Yprev, const float* X, int B, int N, int d, const float* cinv,
-                                 const float* ws_Gn, const float* ws_gd, float* gX, int accumulate_gX, void* stream);
 
 extern "C" int pn_ms_iter_bwd_tma(const float* gout, const float* Ynew, const float* Yprev, const float* X,
                                   const float* Xs, const float* Xt, const float* Xst, const float* den,
                                   const float* unorm, int B, int N, int d, int Np, const float* cinv, float* ws_Gn,
-                                  float* ws_gd, float* gYprev, float* gX, int accumulate_gX, void* stream) {
-    PN_REQUIRE(gout && Ynew && Yprev && X && Xs && Xt && Xst && den && unorm && cinv && ws_Gn && ws_gd && gYprev && gX,
+                                  float* ws_gd, float* ws_C, float* gYprev, float* gX, int accumulate_gX, void* stream) {
+    PN_REQUIRE(gout && Ynew && Yprev && X && Xs && Xt && Xst && den && unorm && cinv && ws_Gn && ws_gd && ws_C && gYprev && gX,
                "pn_ms_iter_bwd_tma: null pointer");
     PN_REQUIRE(d == mstma::D, "pn_ms_iter_bwd_tma: embedding width must be %d (got %d)", mstma::D, d);
     PN_REQUIRE(Np >= N && Np % 32 == 0, "pn_ms_iter_bwd_tma: Np must be N rounded up to a multiple of 32");
+    cudaStream_t st = (cudaStream_t)stream;
     int rc = pn_ms_bwd_prep_tc(gout, Ynew, den, unorm, B, N, d, ws_Gn, ws_gd, stream);
     if (rc != PN_OK) return rc;
-    CUtensorMap mX, mXs, mXt, mXst;
-    const uint64_t n = (uint64_t)N, np = (uint64_t)Np, dd = (uint64_t)mstma::D;
+    const int Nq = (N + 15) / 16 * 16;
+    const uint64_t n = (uint64_t)N, np = (uint64_t)Np, dd = (uint64_t)mstma::D, r2 = 2ull * (uint64_t)Nq;
+    const size_t form = (size_t)B * r2 * dd;
+    float *C = ws_C, *Cs = ws_C + form, *Ct = ws_C + 2 * form, *Cst = ws_C + 3 * form;
+    mstma::ms_prep_concat_kernel<<<dim3(Nq / 16, B), 256, 0, st>>>(Yprev, ws_Gn, N, Nq, C, Cs, Ct, Cst);
+    PN_COUNT_LAUNCH();
+    CUtensorMap mX, mXs, mXt, mXst, mC, mCs, mCt, mCst;
     bool ok = mstma::make_map(&mX, X, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
               mstma::make_map(&mXs, Xs, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
               mstma::make_map(&mXt, Xt, np, dd, (uint64_t)B, np, dd * np, 32, 128) &&
-              mstma::make_map(&mXst, Xst, np, dd, (uint64_t)B, np, dd * np, 32, 128);
+              mstma::make_map(&mXst, Xst, np, dd, (uint64_t)B, np, dd * np, 32, 128) &&
+              mstma::make_map(&mC, C, dd, r2, (uint64_t)B, dd, r2 * dd, 32, 32) &&
+              mstma::make_map(&mCs, Cs, dd, r2, (uint64_t)B, dd, r2 * dd, 32, 32) &&
+              mstma::make_map(&mCt, Ct, r2, dd, (uint64_t)B, r2, dd * r2, 32, 128) &&
+              mstma::make_map(&mCst, Cst, r2, dd, (uint64_t)B, r2, dd * r2, 32, 128);
     if (!ok) {
         set_error("pn_ms_iter_bwd_tma: cuTensorMapEncodeTiled failed or is unavailable");
         return PN_ERR_CUDA;
     }
     size_t sm = mstma::NSTAGE * mstma::STAGE_BYTES + 2 * 64 * 32 * sizeof(float) + 1024;
     PN_CUDA(cudaFuncSetAttribute(mstma::ms_bwd_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    mstma::ms_bwd_rows_tma_kernel<<<dim3(cdiv(N, 64), B), mstma::NT, sm, (cudaStream_t)stream>>>(
-        mX, mXs, mXt, mXst, Yprev, ws_Gn, ws_gd, N, cinv, gYprev);
+    PN_CUDA(cudaFuncSetAttribute(mstma::ms_bwd_cols_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    mstma::ms_bwd_rows_tma_kernel<<<dim3(cdiv(N, 64), B), mstma::NT, sm, st>>>(mX, mXs, mXt, mXst, Yprev, ws_Gn, ws_gd, N,
+                                                                               cinv, gYprev);
     PN_COUNT_LAUNCH();
-    PN_LAUNCH_CHECK("ms_bwd_rows_tma_kernel");
-    return pn_ms_bwd_cols_tc(Yprev, X, B, N, d, cinv, ws_Gn, ws_gd, gX, accumulate_gX, stream);
+    mstma::ms_bwd_cols_tma_kernel<<<dim3(cdiv(N, 128), B), mstma::NT, sm, st>>>(mC, mCs, mCt, mCst, X, ws_gd, N, cinv, gX,
+                                                                                accumulate_gX);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_bwd_*_tma kernels");
+    return PN_OK;
 }

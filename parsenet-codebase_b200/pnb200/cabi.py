@@ -54,7 +54,7 @@ SIGNATURES = {
     # meanshift_tma.cu (experimental, PN_MS_TMA=1)
     "pn_ms_prepare_operands": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
     "pn_ms_iter_fwd_tma": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
-    "pn_ms_iter_bwd_tma": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
+    "pn_ms_iter_bwd_tma": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     "pn_ms_kth_dist": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
     "pn_ms_kth_dist_tc": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
     "pn_ms_argsel": [c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p],

@@ -79,13 +79,14 @@ class MeanShiftItersFn(torch.autograd.Function):
         # (the operand forms are recomputed here rather than kept alive between forward and backward: one 15 MB / shape
         # pass against 10 iterations of N^2 work)
         forms = _operand_forms(X) if (USE_TMA and BWD_IMPL == "tc" and d == 128 and len(dens) > 0) else None
+        ws_C = torch.empty((4, B, 2 * ((N + 15) // 16 * 16), d), dtype=torch.float32, device=X.device) if forms else None
         for it in range(len(dens) - 1, -1, -1):
             gprev = torch.empty_like(X)
             if forms is not None:
                 Xs, Xt, Xst, Np = forms
                 call("pn_ms_iter_bwd_tma", _ptr(g), _ptr(Ys[it + 1]), _ptr(Ys[it]), _ptr(X), _ptr(Xs), _ptr(Xt), _ptr(Xst),
-                     _ptr(dens[it]), _ptr(norms[it]), B, N, d, Np, _ptr(cinv), _ptr(Gn), _ptr(gd), _ptr(gprev), _ptr(gX), 1,
-                     _stream())
+                     _ptr(dens[it]), _ptr(norms[it]), B, N, d, Np, _ptr(cinv), _ptr(Gn), _ptr(gd), _ptr(ws_C), _ptr(gprev),
+                     _ptr(gX), 1, _stream())
             else:
                 call("pn_ms_iter_bwd_tc" if BWD_IMPL == "tc" else "pn_ms_iter_bwd", _ptr(g), _ptr(Ys[it + 1]), _ptr(Ys[it]), _ptr(X), _ptr(dens[it]),
                      _ptr(norms[it]), B, N, d, _ptr(cinv), _ptr(Gn), _ptr(gd), _ptr(gprev), _ptr(gX), 1, _stream())

@@ -194,9 +194,10 @@ def test_tma_fed_kernels_match_default_tc_kernels(B, N):
     for tma in (False, True):
         Gn = torch.empty_like(X); gd = torch.empty(B, N, device="cuda"); gY = torch.empty_like(X); gX = torch.zeros_like(X)
         if tma:
+            wsC = torch.empty(4, B, 2 * ((N + 15) // 16 * 16), d, device="cuda")
             call("pn_ms_iter_bwd_tma", g.data_ptr(), Yn.data_ptr(), Y.data_ptr(), X.data_ptr(), Xs.data_ptr(), Xt.data_ptr(),
                  Xst.data_ptr(), den.data_ptr(), un.data_ptr(), B, N, d, Np, cinv.data_ptr(), Gn.data_ptr(), gd.data_ptr(),
-                 gY.data_ptr(), gX.data_ptr(), 0, st)
+                 wsC.data_ptr(), gY.data_ptr(), gX.data_ptr(), 0, st)
         else:
             call("pn_ms_iter_bwd_tc", g.data_ptr(), Yn.data_ptr(), Y.data_ptr(), X.data_ptr(), den.data_ptr(), un.data_ptr(),
                  B, N, d, cinv.data_ptr(), Gn.data_ptr(), gd.data_ptr(), gY.data_ptr(), gX.data_ptr(), 0, st)

@@ -65,10 +65,11 @@ def run(B, N):
 
     def bwd(tma):
         Gn = torch.empty_like(X); gd = torch.empty(B, N, device="cuda"); gY = torch.empty_like(X); gX = torch.zeros_like(X)
+        wsC = torch.empty(4, B, 2 * ((N + 15) // 16 * 16), d, device="cuda")
         if tma:
             f = lambda: call("pn_ms_iter_bwd_tma", g.data_ptr(), Yn.data_ptr(), Y.data_ptr(), X.data_ptr(), Xs.data_ptr(),
                              Xt.data_ptr(), Xst.data_ptr(), den.data_ptr(), un.data_ptr(), B, N, d, Np, cinv.data_ptr(),
-                             Gn.data_ptr(), gd.data_ptr(), gY.data_ptr(), gX.data_ptr(), 0, st)
+                             Gn.data_ptr(), gd.data_ptr(), wsC.data_ptr(), gY.data_ptr(), gX.data_ptr(), 0, st)
         else:
             f = lambda: call("pn_ms_iter_bwd_tc", g.data_ptr(), Yn.data_ptr(), Y.data_ptr(), X.data_ptr(), den.data_ptr(),
                              un.data_ptr(), B, N, d, cinv.data_ptr(), Gn.data_ptr(), gd.data_ptr(), gY.data_ptr(),
@@ -77,7 +78,7 @@ def run(B, N):
 
     ref, t0 = bwd(False)
     out, t1 = bwd(True)
-    report("backward (prep + rows + cols; only rows differs)", ref, out, t0, t1)
+    report("backward (prep + rows + cols)", ref, out, t0, t1)
 
 
 if len(sys.argv) > 2:
