@@ -34,7 +34,6 @@ constexpr int NSTAGE = 3, FLUSH = 16;
 constexpr float CLAMP = 75.f;
 constexpr uint32_t C_YB = 0, C_YS = 128, C_S0 = 256, C_PS2 = 320, C_O = 384, TMEM_COLS = 512;
 constexpr int PART_BYTES = BN * D * 4;            // 16 KB per operand part
-constexpr int SLAB_BYTES = BN * 128;              // one [32 rows][128 B] slab of XA
 constexpr int STAGE_BYTES = 4 * PART_BYTES;       // 64 KB
 constexpr uint32_t SW128 = 2, SBO128 = 1024;      // descriptor layout type / 8-row group stride of a 128B-swizzled slab
 
@@ -71,58 +70,106 @@ __global__ void __launch_bounds__(256) ms_prep_operands_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------- shared warp roles
+// CG = 1: one CTA per 128 rows.  CG = 2 (tcgen05 cta_group::2, cluster of 2 CTAs along x): the pair shares every streamed
+// tile -- each CTA stages HALF of both B operands (16 of the 32 tile rows for the first product, 64 of the 128 d rows for
+// the second), the leader (cluster rank 0) issues M = 256 MMAs that write S / O into the TMEM of both CTAs, and each CTA
+// runs its own epilogue on its own 128 rows.  Per CTA and tile: 32 KB instead of 64 KB of operand traffic into shared
+// memory and half of the MMA operand reads -- the shared-memory co-limiter of the 1-CTA kernels.
+// Barriers the MMA issuer waits on (s_empty, p_full2, o_flush, a_ready, x_full) live in the leader and collect the
+// arrivals of both CTAs; barriers the epilogues / producers wait on (s_full, p_empty, o_done, x_empty) are local and are
+// signalled in both CTAs by multicast commits.
+template <int CG>
+struct Geo {
+    static constexpr int ROWS = BN / CG;              // tile rows staged by one CTA (first product)
+    static constexpr int SLAB = ROWS * 128;           // one [ROWS][128 B] slab
+    static constexpr int PART = PART_BYTES / CG;      // one operand part per CTA
+    static constexpr int STAGE = 4 * PART;            // per-CTA stage
+    static constexpr int DROWS = D / CG;              // d rows staged by one CTA (second product)
+};
+
+template <int CG>
+__device__ __forceinline__ void arrive_to_issuer(uint64_t* bar) {
+    if (CG == 1) mbar_arrive(bar);
+    else mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+}
+
 // TMA producer (one elected lane of its warp): per tile step 4 + 4 slab boxes of the row-major forms and one box each of
-// the transposed forms, all completing on x_full[stage].  `row0(t)` = first row of tile t in the row-major forms.
+// the transposed forms, all completing on the leader's x_full[stage].
+template <int CG>
 __device__ __forceinline__ void tma_producer(unsigned char* smem, Bars& bars, const CUtensorMap* mA, const CUtensorMap* mAs,
-                                             const CUtensorMap* mT, const CUtensorMap* mTs, int ntiles, int b) {
+                                             const CUtensorMap* mT, const CUtensorMap* mTs, int ntiles, int b, int rank) {
+    using G = Geo<CG>;
     if (elect_one()) {
         tma_prefetch_desc(mA); tma_prefetch_desc(mAs); tma_prefetch_desc(mT); tma_prefetch_desc(mTs);
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
             const int s = t % NSTAGE;
             mbar_wait_guarded(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
-            unsigned char* st = smem + s * STAGE_BYTES;
-            mbar_arrive_expect_tx(&bars.x_full[s], STAGE_BYTES);
+            unsigned char* st = smem + s * G::STAGE;
+            if (rank == 0) mbar_arrive_expect_tx(&bars.x_full[s], STAGE_BYTES);      // bytes of BOTH CTAs' halves
+            const int row = t * BN + rank * G::ROWS;
+            if (CG == 1) {
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl) {
-                tma_load_3d(st + sl * SLAB_BYTES, mA, &bars.x_full[s], 32 * sl, t * BN, b);
-                tma_load_3d(st + PART_BYTES + sl * SLAB_BYTES, mAs, &bars.x_full[s], 32 * sl, t * BN, b);
+                for (int sl = 0; sl < 4; ++sl) {
+                    tma_load_3d(st + sl * G::SLAB, mA, &bars.x_full[s], 32 * sl, row, b);
+                    tma_load_3d(st + G::PART + sl * G::SLAB, mAs, &bars.x_full[s], 32 * sl, row, b);
+                }
+                tma_load_3d(st + 2 * G::PART, mT, &bars.x_full[s], t * BN, 0, b);
+                tma_load_3d(st + 3 * G::PART, mTs, &bars.x_full[s], t * BN, 0, b);
+            } else {
+                const uint32_t full = mapa_u32(smem_u32(&bars.x_full[s]), 0);
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    tma_load_3d_2sm(st + sl * G::SLAB, mA, full, 32 * sl, row, b);
+                    tma_load_3d_2sm(st + G::PART + sl * G::SLAB, mAs, full, 32 * sl, row, b);
+                }
+                tma_load_3d_2sm(st + 2 * G::PART, mT, full, t * BN, rank * G::DROWS, b);
+                tma_load_3d_2sm(st + 3 * G::PART, mTs, full, t * BN, rank * G::DROWS, b);
             }
-            tma_load_3d(st + 2 * PART_BYTES, mT, &bars.x_full[s], t * BN, 0, b);
-            tma_load_3d(st + 3 * PART_BYTES, mTs, &bars.x_full[s], t * BN, 0, b);
         }
     }
     __syncwarp();
 }
 
-// MMA issue warp (warp-uniform code, one elected lane issues): per tile the first product D(t) = A . tile^T (48 MMAs,
-// N = 32, K = d through the 4 slabs) and, one tile behind, the second product O += P(t-1) . tile (12 MMAs, N = 128, K = 32
-// tile rows), split-TF32 (small.big + big.small + big.big), A operands in TMEM.  Issue order G1(0) G1(1) G2(0) G1(2) ...
+// MMA issue warp of the leader (warp-uniform code, one elected lane issues): per tile the first product D(t) = A . tile^T
+// (48 MMAs, N = 32, K = d through the 4 slabs) and, one tile behind, the second product O += P(t-1) . tile (12 MMAs,
+// N = 128, K = 32 tile rows), split-TF32 (small.big + big.small + big.big), A operands in TMEM.
+// Issue order G1(0) G1(1) G2(0) G1(2) ...
+template <int CG>
 __device__ __forceinline__ void mma_issuer(unsigned char* smem, Bars& bars, uint32_t tb, int ntiles) {
+    using G = Geo<CG>;
     const bool leader = elect_one();
-    const uint32_t idesc_s = make_idesc(2, 128, BN, 0, 0);
-    const uint32_t idesc_o = make_idesc(2, 128, D, 0, 0);
+    const uint32_t idesc_s = make_idesc(2, 128 * CG, BN, 0, 0);
+    const uint32_t idesc_o = make_idesc(2, 128 * CG, D, 0, 0);
     const uint32_t sbase = smem_u32(smem);
+    auto mma = [&](uint32_t dcol, uint32_t acol, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+        if (CG == 1) mma_tf32_ts(dcol, acol, bdesc, idesc, acc);
+        else mma_tf32_ts2(dcol, acol, bdesc, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar) {
+        if (CG == 1) mma_commit(bar);
+        else mma_commit2_mc(bar, (uint16_t)3);
+    };
     auto gemm2 = [&](int u) {
         mbar_wait_guarded(&bars.p_full2[u & 1], (u >> 1) & 1);
         const uint32_t pb_col = C_S0 + 32 * (u & 1), ps_col = C_PS2 + 32 * (u & 1);
         const bool fresh = (u % FLUSH) == 0;
         if (u > 0 && fresh) mbar_wait_guarded(&bars.o_flush, ((u / FLUSH) - 1) & 1);
         tc_fence_after();
-        const uint32_t st = sbase + (u % NSTAGE) * STAGE_BYTES;
-        const uint64_t db0 = make_smem_desc(st + 2 * PART_BYTES, 16, SBO128, SW128);
-        const uint64_t ds0 = make_smem_desc(st + 3 * PART_BYTES, 16, SBO128, SW128);
+        const uint32_t st = sbase + (u % NSTAGE) * G::STAGE;
+        const uint64_t db0 = make_smem_desc(st + 2 * G::PART, 16, SBO128, SW128);
+        const uint64_t ds0 = make_smem_desc(st + 3 * G::PART, 16, SBO128, SW128);
         if (leader) {
 #pragma unroll
             for (int ks = 0; ks < BN / 8; ++ks) {            // K = tile row: 4 steps of 8 inside the one 128 B atom row
                 const uint64_t db = db0 + (uint64_t)((ks * 32) >> 4);
                 const uint64_t ds = ds0 + (uint64_t)((ks * 32) >> 4);
-                mma_tf32_ts(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
-                mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
-                mma_tf32_ts(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
+                mma(tb + C_O, tb + ps_col + ks * 8, db, idesc_o, (fresh && ks == 0) ? 0u : 1u);
+                mma(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
+                mma(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
             }
-            mma_commit(&bars.x_empty[u % NSTAGE]);
-            mma_commit(&bars.p_empty);
+            commit(&bars.x_empty[u % NSTAGE]);
+            commit(&bars.p_empty);
         }
         __syncwarp();
     };
@@ -134,42 +181,63 @@ __device__ __forceinline__ void mma_issuer(unsigned char* smem, Bars& bars, uint
         mbar_wait_guarded(&bars.x_full[s], (t / NSTAGE) & 1);
         mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t st = sbase + s * STAGE_BYTES;
+        const uint32_t st = sbase + s * G::STAGE;
         const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
-        const uint64_t ds0 = make_smem_desc(st + PART_BYTES, 16, SBO128, SW128);
+        const uint64_t ds0 = make_smem_desc(st + G::PART, 16, SBO128, SW128);
         const uint32_t d_s = tb + C_S0 + 32 * k;
         if (leader) {
 #pragma unroll
             for (int ks = 0; ks < D / 8; ++ks) {             // K = d: slab ks / 4, +32 B per step inside the slab
-                const uint32_t off = (uint32_t)((ks >> 2) * SLAB_BYTES + (ks & 3) * 32);
+                const uint32_t off = (uint32_t)((ks >> 2) * G::SLAB + (ks & 3) * 32);
                 const uint64_t db = db0 + (uint64_t)(off >> 4);
                 const uint64_t ds = ds0 + (uint64_t)(off >> 4);
-                mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
-                mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
-                mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
+                mma(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
+                mma(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
+                mma(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
             }
-            mma_commit(&bars.s_full[k]);
+            commit(&bars.s_full[k]);
         }
         __syncwarp();
         if (t > 0) gemm2(t - 1);
     }
     gemm2(ntiles - 1);
-    if (leader) mma_commit(&bars.o_done);
+    if (leader) commit(&bars.o_done);
     __syncwarp();
 }
 
+template <int CG>
 __device__ __forceinline__ void init_bars(Bars& bars) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
     for (int k = 0; k < 2; ++k) {
-        mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); mbar_init(&bars.p_full2[k], EPI_THREADS);
+        mbar_init(&bars.s_full[k], 1);
+        mbar_init(&bars.s_empty[k], CG * EPI_THREADS);
+        mbar_init(&bars.p_full2[k], CG * EPI_THREADS);
     }
-    mbar_init(&bars.p_empty, 1); mbar_init(&bars.o_flush, EPI_THREADS); mbar_init(&bars.o_done, 1);
-    mbar_init(&bars.a_ready, EPI_THREADS);
+    mbar_init(&bars.p_empty, 1); mbar_init(&bars.o_flush, CG * EPI_THREADS); mbar_init(&bars.o_done, 1);
+    mbar_init(&bars.a_ready, CG * EPI_THREADS);
     mbar_fence_init();
+}
+
+// kernel prologue / epilogue shared by the three kernels: TMEM allocation, barrier init, (cluster) sync
+template <int CG>
+__device__ __forceinline__ uint32_t prologue(Bars& bars, uint32_t* tmem_base_s, int warp, int tid) {
+    if (warp == MMA_WARP) { if (CG == 1) tmem_alloc(tmem_base_s, TMEM_COLS); else tmem_alloc2(tmem_base_s, TMEM_COLS); }
+    if (tid == 0) init_bars<CG>(bars);
+    tc_fence_before();
+    if (CG == 1) __syncthreads(); else cluster_sync_all();
+    tc_fence_after();
+    return *tmem_base_s;
+}
+template <int CG>
+__device__ __forceinline__ void finale(uint32_t tb, int warp) {
+    tc_fence_before();
+    if (CG == 1) __syncthreads(); else cluster_sync_all();      // the leader's MMAs read the peer's shared memory until o_done
+    if (warp == MMA_WARP) { if (CG == 1) tmem_dealloc(tb, TMEM_COLS); else tmem_dealloc2(tb, TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------- forward iteration
 // grid (ceil(N / 128), B), 320 threads: warps 0-7 epilogue, warp 8 TMA producer, warp 9 MMA issue.
+template <int CG>
 __global__ void __launch_bounds__(NT, 1)
 ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mXs,
                   const __grid_constant__ CUtensorMap mXt, const __grid_constant__ CUtensorMap mXst,
@@ -187,12 +255,8 @@ ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant_
     const float* Yb = Y + (long long)b * N * D;
     const int ntiles = (N + BN - 1) / BN;
 
-    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
-    if (tid == 0) init_bars(bars);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tb = tmem_base_s;
+    const int rank = (CG == 1) ? 0 : (int)cluster_ctarank();
+    const uint32_t tb = prologue<CG>(bars, &tmem_base_s, warp, tid);
 
     if (warp < EPI_WARPS) {
         // =============================================================================== epilogue warps
@@ -223,7 +287,7 @@ ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant_
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars.a_ready);
+        arrive_to_issuer<CG>(&bars.a_ready);
         float oacc[64];
 #pragma unroll
         for (int e = 0; e < 64; ++e) oacc[e] = 0.f;
@@ -238,7 +302,7 @@ ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant_
             tmem_ld16(tb + la + C_S0 + 32 * k + 16 * h, sv);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&bars.s_empty[k]);
+            arrive_to_issuer<CG>(&bars.s_empty[k]);
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
                 float e = (__uint_as_float(sv[u]) - 1.0f) * c2;
@@ -262,13 +326,13 @@ ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant_
                     for (int e = 0; e < 16; ++e) oacc[c0 + e] += __uint_as_float(ov[e]);
                 }
                 tc_fence_before();
-                mbar_arrive(&bars.o_flush);
+                arrive_to_issuer<CG>(&bars.o_flush);
             }
             tmem_st16(tb + la + C_S0 + 32 * k + 16 * h, pb);
             tmem_st16(tb + la + C_PS2 + 32 * k + 16 * h, ps);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bars.p_full2[k]);
+            arrive_to_issuer<CG>(&bars.p_full2[k]);
         }
         mbar_wait_guarded(&bars.o_done, 0);
         tc_fence_after();
@@ -308,12 +372,11 @@ ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant_
         }
         tc_fence_before();
     } else if (warp == TMA_WARP) {
-        tma_producer(smem, bars, &mX, &mXs, &mXt, &mXst, ntiles, b);
-    } else {
-        mma_issuer(smem, bars, tb, ntiles);
+        tma_producer<CG>(smem, bars, &mX, &mXs, &mXt, &mXst, ntiles, b, rank);
+    } else if (rank == 0) {
+        mma_issuer<CG>(smem, bars, tb, ntiles);
     }
-    __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+    finale<CG>(tb, warp);
 }
 
 // ---------------------------------------------------------------------------------------------- backward, rows
@@ -322,6 +385,7 @@ ms_fwd_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant_
 // 0-63 hold Y_i, lanes 64-127 hold Gn_i ("virtual rows"), so one MMA chain against the streamed X tile yields S and G.
 // The streamed tile is X (constant): its four operand forms come from TMA exactly as in the forward kernel.
 // grid (ceil(N / 64), B), 320 threads; dynamic smem = stages + [2][64][32] floats for the G hand-over.
+template <int CG>
 __global__ void __launch_bounds__(NT, 1)
 ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mXs,
                        const __grid_constant__ CUtensorMap mXt, const __grid_constant__ CUtensorMap mXst,
@@ -342,12 +406,8 @@ ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_cons
     const int r0 = blockIdx.x * 64;
     const int ntiles = (N + BN - 1) / BN;
 
-    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
-    if (tid == 0) init_bars(bars);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tb = tmem_base_s;
+    const int rank = (CG == 1) ? 0 : (int)cluster_ctarank();
+    const uint32_t tb = prologue<CG>(bars, &tmem_base_s, warp, tid);
 
     if (warp < EPI_WARPS) {
         // =============================================================================== epilogue warps
@@ -385,7 +445,7 @@ ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_cons
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars.a_ready);
+        arrive_to_issuer<CG>(&bars.a_ready);
         const bool owner = q < 2;
         float oacc[64];
 #pragma unroll
@@ -400,7 +460,7 @@ ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_cons
             tmem_ld16(tb + la + C_S0 + 32 * k + 16 * h, sv);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&bars.s_empty[k]);
+            arrive_to_issuer<CG>(&bars.s_empty[k]);
             float* ex = exch + (t & 1) * 64 * 32;
             if (q >= 2) {
 #pragma unroll
@@ -437,7 +497,7 @@ ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_cons
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&bars.o_flush);
+                arrive_to_issuer<CG>(&bars.o_flush);
             }
             const uint32_t pb_col = C_S0 + 32 * k, ps_col = C_PS2 + 32 * k;
             if (q < 2) {
@@ -451,7 +511,7 @@ ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_cons
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bars.p_full2[k]);
+            arrive_to_issuer<CG>(&bars.p_full2[k]);
         }
         mbar_wait_guarded(&bars.o_done, 0);
         tc_fence_after();
@@ -474,12 +534,11 @@ ms_bwd_rows_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_cons
         }
         tc_fence_before();
     } else if (warp == TMA_WARP) {
-        tma_producer(smem, bars, &mX, &mXs, &mXt, &mXst, ntiles, b);
-    } else {
-        mma_issuer(smem, bars, tb, ntiles);
+        tma_producer<CG>(smem, bars, &mX, &mXs, &mXt, &mXst, ntiles, b, rank);
+    } else if (rank == 0) {
+        mma_issuer<CG>(smem, bars, tb, ntiles);
     }
-    __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+    finale<CG>(tb, warp);
 }
 
 // ---------------------------------------------------------------------------------------------- backward, cols
@@ -521,6 +580,7 @@ __global__ void __launch_bounds__(256) ms_prep_concat_kernel(const float* __rest
 }
 
 // grid (ceil(N / 128), B), 320 threads
+template <int CG>
 __global__ void __launch_bounds__(NT, 1)
 ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_constant__ CUtensorMap mCs,
                        const __grid_constant__ CUtensorMap mCt, const __grid_constant__ CUtensorMap mCst,
@@ -539,12 +599,8 @@ ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_cons
     const int r0 = blockIdx.x * 128;
     const int ntiles = (N + 15) / 16;
 
-    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
-    if (tid == 0) init_bars(bars);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tb = tmem_base_s;
+    const int rank = (CG == 1) ? 0 : (int)cluster_ctarank();
+    const uint32_t tb = prologue<CG>(bars, &tmem_base_s, warp, tid);
 
     if (warp < EPI_WARPS) {
         const int q = warp & 3, h = warp >> 2;
@@ -573,7 +629,7 @@ ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_cons
         }
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bars.a_ready);
+        arrive_to_issuer<CG>(&bars.a_ready);
         float oacc[64];
 #pragma unroll
         for (int e = 0; e < 64; ++e) oacc[e] = 0.f;
@@ -587,7 +643,7 @@ ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_cons
             tmem_ld8(tb + la + C_S0 + 32 * k + 16 + 8 * h, g8);         // G^T: the same rows of the Gn half
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(&bars.s_empty[k]);
+            arrive_to_issuer<CG>(&bars.s_empty[k]);
             const int i0t = t * 16 + 8 * h;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -615,7 +671,7 @@ ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_cons
                     for (int e = 0; e < 16; ++e) oacc[c0 + e] += __uint_as_float(ov[e]);
                 }
                 tc_fence_before();
-                mbar_arrive(&bars.o_flush);
+                arrive_to_issuer<CG>(&bars.o_flush);
             }
             const uint32_t pb_col = C_S0 + 32 * k, ps_col = C_PS2 + 32 * k;
             {
@@ -631,7 +687,7 @@ ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_cons
                 tmem_st_wait();
             }
             tc_fence_before();
-            mbar_arrive(&bars.p_full2[k]);
+            arrive_to_issuer<CG>(&bars.p_full2[k]);
         }
         mbar_wait_guarded(&bars.o_done, 0);
         tc_fence_after();
@@ -657,12 +713,11 @@ ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_cons
         }
         tc_fence_before();
     } else if (warp == TMA_WARP) {
-        tma_producer(smem, bars, &mC, &mCs, &mCt, &mCst, ntiles, b);
-    } else {
-        mma_issuer(smem, bars, tb, ntiles);
+        tma_producer<CG>(smem, bars, &mC, &mCs, &mCt, &mCst, ntiles, b, rank);
+    } else if (rank == 0) {
+        mma_issuer<CG>(smem, bars, tb, ntiles);
     }
-    __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+    finale<CG>(tb, warp);
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -714,6 +769,41 @@ extern "C" int pn_ms_prepare_operands(const float* X, int B, int N, int d, int N
     return PN_OK;
 }
 
+// CTA-group size of the experimental kernels: PN_MS_TMA_CG=2 launches CTA pairs (cluster of 2, tcgen05 cta_group::2)
+static int cta_group() {      // read per call: tools/exp_ms_tma.py flips it inside one process
+    const char* e = getenv("PN_MS_TMA_CG");
+    return (e && e[0] == '2') ? 2 : 1;
+}
+
+// the four operand-form maps of a [rows][128] matrix M (row-major M, Ms; transposed Mt, Mst with row pitch `tp`), boxes
+// sized for one CTA of a group of `cg`
+static bool make_forms(CUtensorMap* m, const float* M, const float* Ms, const float* Mt, const float* Mst, uint64_t rows,
+                       uint64_t tp, uint64_t B, int cg) {
+    const uint64_t dd = (uint64_t)mstma::D;
+    return mstma::make_map(&m[0], M, dd, rows, B, dd, rows * dd, 32, 32 / cg) &&
+           mstma::make_map(&m[1], Ms, dd, rows, B, dd, rows * dd, 32, 32 / cg) &&
+           mstma::make_map(&m[2], Mt, tp, dd, B, tp, dd * tp, 32, 128 / cg) &&
+           mstma::make_map(&m[3], Mst, tp, dd, B, tp, dd * tp, 32, 128 / cg);
+}
+
+template <typename... Args>
+static cudaError_t launch(void (*kern)(Args...), dim3 grid, int cg, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    if (cg == 2) grid.x = (grid.x + 1) & ~1u;              // whole pairs; the padding CTA owns rows >= N only
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(mstma::NT);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // same contract as pn_ms_iter_fwd_tc (one mean-shift iteration, reference src/mean_shift.py:58-77) with the operand
 // forms of pn_ms_prepare_operands
 extern "C" int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* Xs, const float* Xt, const float* Xst,
@@ -722,21 +812,17 @@ extern "C" int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* X
     PN_REQUIRE(Y && X && Xs && Xt && Xst && cinv && Ynew && den && unorm, "pn_ms_iter_fwd_tma: null pointer");
     PN_REQUIRE(d == mstma::D, "pn_ms_iter_fwd_tma: embedding width must be %d (got %d)", mstma::D, d);
     PN_REQUIRE(Np >= N && Np % 32 == 0, "pn_ms_iter_fwd_tma: Np must be N rounded up to a multiple of 32");
-    CUtensorMap mX, mXs, mXt, mXst;
-    const uint64_t n = (uint64_t)N, np = (uint64_t)Np, dd = (uint64_t)mstma::D;
-    bool ok = mstma::make_map(&mX, X, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
-              mstma::make_map(&mXs, Xs, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
-              mstma::make_map(&mXt, Xt, np, dd, (uint64_t)B, np, dd * np, 32, 128) &&
-              mstma::make_map(&mXst, Xst, np, dd, (uint64_t)B, np, dd * np, 32, 128);
-    if (!ok) {
+    const int cg = cta_group();
+    CUtensorMap m[4];
+    if (!make_forms(m, X, Xs, Xt, Xst, (uint64_t)N, (uint64_t)Np, (uint64_t)B, cg)) {
         set_error("pn_ms_iter_fwd_tma: cuTensorMapEncodeTiled failed or is unavailable");
         return PN_ERR_CUDA;
     }
     size_t sm = mstma::NSTAGE * mstma::STAGE_BYTES + 1024;
-    PN_CUDA(cudaFuncSetAttribute(mstma::ms_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    dim3 grid(cdiv(N, mstma::BM), B);
-    mstma::ms_fwd_tma_kernel<<<grid, mstma::NT, sm, (cudaStream_t)stream>>>(mX, mXs, mXt, mXst, Y, N, cinv, Ynew, den,
-                                                                            unorm);
+    auto kern = (cg == 2) ? mstma::ms_fwd_tma_kernel<2> : mstma::ms_fwd_tma_kernel<1>;
+    PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_CUDA(launch(kern, dim3(cdiv(N, mstma::BM), B), cg, sm, (cudaStream_t)stream, m[0], m[1], m[2], m[3], Y, N, cinv, Ynew,
+                   den, unorm));
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("ms_fwd_tma_kernel");
     return PN_OK;
@@ -759,33 +845,29 @@ extern "C" int pn_ms_iter_bwd_tma(const float* gout, const float* Ynew, const fl
     cudaStream_t st = (cudaStream_t)stream;
     int rc = pn_ms_bwd_prep_tc(gout, Ynew, den, unorm, B, N, d, ws_Gn, ws_gd, stream);
     if (rc != PN_OK) return rc;
+    const int cg = cta_group();
     const int Nq = (N + 15) / 16 * 16;
-    const uint64_t n = (uint64_t)N, np = (uint64_t)Np, dd = (uint64_t)mstma::D, r2 = 2ull * (uint64_t)Nq;
-    const size_t form = (size_t)B * r2 * dd;
+    const uint64_t r2 = 2ull * (uint64_t)Nq;
+    const size_t form = (size_t)B * r2 * mstma::D;
     float *C = ws_C, *Cs = ws_C + form, *Ct = ws_C + 2 * form, *Cst = ws_C + 3 * form;
     mstma::ms_prep_concat_kernel<<<dim3(Nq / 16, B), 256, 0, st>>>(Yprev, ws_Gn, N, Nq, C, Cs, Ct, Cst);
     PN_COUNT_LAUNCH();
-    CUtensorMap mX, mXs, mXt, mXst, mC, mCs, mCt, mCst;
-    bool ok = mstma::make_map(&mX, X, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
-              mstma::make_map(&mXs, Xs, dd, n, (uint64_t)B, dd, n * dd, 32, 32) &&
-              mstma::make_map(&mXt, Xt, np, dd, (uint64_t)B, np, dd * np, 32, 128) &&
-              mstma::make_map(&mXst, Xst, np, dd, (uint64_t)B, np, dd * np, 32, 128) &&
-              mstma::make_map(&mC, C, dd, r2, (uint64_t)B, dd, r2 * dd, 32, 32) &&
-              mstma::make_map(&mCs, Cs, dd, r2, (uint64_t)B, dd, r2 * dd, 32, 32) &&
-              mstma::make_map(&mCt, Ct, r2, dd, (uint64_t)B, r2, dd * r2, 32, 128) &&
-              mstma::make_map(&mCst, Cst, r2, dd, (uint64_t)B, r2, dd * r2, 32, 128);
-    if (!ok) {
+    CUtensorMap mx[4], mc[4];
+    if (!make_forms(mx, X, Xs, Xt, Xst, (uint64_t)N, (uint64_t)Np, (uint64_t)B, cg) ||
+        !make_forms(mc, C, Cs, Ct, Cst, r2, r2, (uint64_t)B, cg)) {
         set_error("pn_ms_iter_bwd_tma: cuTensorMapEncodeTiled failed or is unavailable");
         return PN_ERR_CUDA;
     }
     size_t sm = mstma::NSTAGE * mstma::STAGE_BYTES + 2 * 64 * 32 * sizeof(float) + 1024;
-    PN_CUDA(cudaFuncSetAttribute(mstma::ms_bwd_rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    PN_CUDA(cudaFuncSetAttribute(mstma::ms_bwd_cols_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    mstma::ms_bwd_rows_tma_kernel<<<dim3(cdiv(N, 64), B), mstma::NT, sm, st>>>(mX, mXs, mXt, mXst, Yprev, ws_Gn, ws_gd, N,
-                                                                               cinv, gYprev);
+    auto rows_k = (cg == 2) ? mstma::ms_bwd_rows_tma_kernel<2> : mstma::ms_bwd_rows_tma_kernel<1>;
+    auto cols_k = (cg == 2) ? mstma::ms_bwd_cols_tma_kernel<2> : mstma::ms_bwd_cols_tma_kernel<1>;
+    PN_CUDA(cudaFuncSetAttribute(rows_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_CUDA(cudaFuncSetAttribute(cols_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_CUDA(launch(rows_k, dim3(cdiv(N, 64), B), cg, sm, st, mx[0], mx[1], mx[2], mx[3], Yprev, (const float*)ws_Gn,
+                   (const float*)ws_gd, N, cinv, gYprev));
     PN_COUNT_LAUNCH();
-    mstma::ms_bwd_cols_tma_kernel<<<dim3(cdiv(N, 128), B), mstma::NT, sm, st>>>(mC, mCs, mCt, mCst, X, ws_gd, N, cinv, gX,
-                                                                                accumulate_gX);
+    PN_CUDA(launch(cols_k, dim3(cdiv(N, 128), B), cg, sm, st, mc[0], mc[1], mc[2], mc[3], X, (const float*)ws_gd, N, cinv, gX,
+                   accumulate_gX));
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("ms_bwd_*_tma kernels");
     return PN_OK;

@@ -163,10 +163,13 @@ print("LITE_WORST", worst)
 @pytest.mark.skipif(os.environ.get("PN_RUN_EXPERIMENTAL") != "1",
                     reason="experimental kernels (csrc/meanshift_tma.cu) have not been brought up on a GPU yet; "
                            "opt in with PN_RUN_EXPERIMENTAL=1 (they trap instead of hanging, still run under a timeout)")
+@pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("B,N", [(2, 1000), (3, 4999)])
-def test_tma_fed_kernels_match_default_tc_kernels(B, N):
-    """TMA-fed forward / rows-backward kernels: same products in the same order as the default tcgen05 kernels"""
+def test_tma_fed_kernels_match_default_tc_kernels(B, N, cg, monkeypatch):
+    """TMA-fed forward / backward kernels (1 CTA, and CTA pairs with cta_group::2): same products in the same order as the
+    default tcgen05 kernels"""
     from pnb200.cabi import call
+    monkeypatch.setenv("PN_MS_TMA_CG", str(cg))
     d = 128
     torch.manual_seed(1)
     X = torch.nn.functional.normalize(torch.randn(B, N, d, device="cuda"), dim=2)

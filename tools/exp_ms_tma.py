@@ -5,6 +5,8 @@ after ~2 s instead of hanging, still: run under `timeout 300`.
 
     python tools/exp_ms_tma.py            # (2, 1000) then (16, 10000)
     python tools/exp_ms_tma.py 4 4999     # one size
+    PN_EXP_CGS=1 python tools/exp_ms_tma.py      # only the 1-CTA kernels (bring those up first; default "1,2":
+                                                 # CTA group 2 = CTA pairs, tcgen05 cta_group::2, half the operand traffic)
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,6 +15,7 @@ import torch
 from pnb200.cabi import call
 
 d = 128
+CGS = [int(c) for c in os.environ.get("PN_EXP_CGS", "1,2").split(",")]
 st = torch.cuda.current_stream().cuda_stream
 
 
@@ -58,8 +61,10 @@ def run(B, N):
         return (Yn, den, un), timed(f)
 
     ref, t0 = fwd(False)
-    out, t1 = fwd(True)
-    report("forward", ref, out, t0, t1)
+    for cg in CGS:
+        os.environ["PN_MS_TMA_CG"] = str(cg)
+        out, t1 = fwd(True)
+        report(f"forward, CTA group {cg}", ref, out, t0, t1)
     Yn, den, un = ref
     g = torch.randn_like(X)
 
@@ -77,8 +82,10 @@ def run(B, N):
         return (gY, gX), timed(f)
 
     ref, t0 = bwd(False)
-    out, t1 = bwd(True)
-    report("backward (prep + rows + cols)", ref, out, t0, t1)
+    for cg in CGS:
+        os.environ["PN_MS_TMA_CG"] = str(cg)
+        out, t1 = bwd(True)
+        report(f"backward (prep + rows + cols), CTA group {cg}", ref, out, t0, t1)
 
 
 if len(sys.argv) > 2:
