@@ -189,3 +189,28 @@ def test_missing_name_without_reference_is_attribute_error():
     r = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "parsenet-codebase_b200")], capture_output=True,
                        text=True, timeout=300)
     assert r.stdout.startswith("OK") and "PARSENET_REFERENCE_SRC" in r.stdout, r.stdout + r.stderr[-2000:]
+
+
+def test_product_package_never_imports_the_oracle_or_falls_back_to_cpu():
+    """the oracle is test infrastructure: no module of the product package may import it, and `bench.py`'s product arm
+    (everything outside cpu_baseline / run_reference) may not either"""
+    import ast
+    pkg = os.path.join(ROOT, "parsenet-codebase_b200")
+    offenders = []
+    for sub in ("src", "pnb200"):
+        for f in sorted(os.listdir(os.path.join(pkg, sub))):
+            if not f.endswith(".py"):
+                continue
+            tree = ast.parse(open(os.path.join(pkg, sub, f)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom) and node.module:
+                    names = [node.module]
+                offenders += [(sub, f, n) for n in names if n == "oracle" or n.startswith("oracle.")]
+    assert not offenders, offenders
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
+        uses = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and n.module and n.module.startswith("oracle")]
+        assert not uses or fn.name in ("cpu_baseline", "run_reference"), f"bench.py::{fn.name} imports the oracle"
