@@ -214,3 +214,39 @@ def test_product_package_never_imports_the_oracle_or_falls_back_to_cpu():
     for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
         uses = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and n.module and n.module.startswith("oracle")]
         assert not uses or fn.name in ("cpu_baseline", "run_reference"), f"bench.py::{fn.name} imports the oracle"
+
+
+@pytest.mark.parametrize("use_tma", [False, True])
+def test_meanshift_host_wiring_matches_abi_arity(monkeypatch, use_tma):
+    """dry run of the mean-shift autograd schedule on CPU tensors with a recording stand-in for the C-ABI call: every
+    call site (default path and the experimental TMA path) passes exactly the arguments include/parsenet_b200.h declares,
+    pointers where pointers are expected, and the forward / backward sequences have the expected shape"""
+    import ctypes
+    from pnb200 import cabi, meanshift as pms
+    calls = []
+
+    def fake_call(name, *args):
+        sig = cabi.SIGNATURES[name]
+        assert len(args) == len(sig), f"{name}: {len(args)} arguments, header declares {len(sig)}"
+        for i, (a, t) in enumerate(zip(args, sig)):
+            if t is ctypes.c_void_p:
+                assert a is None or isinstance(a, int), f"{name} arg {i}: expected a pointer"
+            elif t in (ctypes.c_int, ctypes.c_longlong):
+                assert isinstance(a, int) and not isinstance(a, bool), f"{name} arg {i}: expected an int, got {type(a)}"
+        calls.append(name)
+
+    monkeypatch.setattr(pms, "call", fake_call)
+    monkeypatch.setattr(pms, "_need_cuda", lambda *a: None)
+    monkeypatch.setattr(pms, "_stream", lambda: 0)
+    monkeypatch.setattr(pms, "USE_TMA", use_tma)
+    B, N, d, its = 2, 70, 128, 3
+    X = torch.nn.functional.normalize(torch.randn(B, N, d), dim=2).requires_grad_()
+    Y = pms.mean_shift_iters(X, torch.tensor([0.3, 0.5]), its)
+    assert Y.shape == (B, N, d)
+    Y.sum().backward()
+    assert X.grad is not None and X.grad.shape == X.shape
+    if use_tma:
+        assert calls == ["pn_ms_prepare_operands"] + ["pn_ms_iter_fwd_tma"] * its + ["pn_ms_prepare_operands"] + \
+            ["pn_ms_iter_bwd_tma"] * its
+    else:
+        assert calls == ["pn_ms_iter_fwd_tc"] * its + ["pn_ms_iter_bwd_tc"] * its
