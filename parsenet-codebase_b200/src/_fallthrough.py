@@ -73,3 +73,23 @@ def module_getattr(module_name):
         raise AttributeError(f"module {module_name!r} has no attribute {name!r}{hint}")
 
     return __getattr__
+
+
+class ReferenceMethods:
+    """Mixin for drop-in classes: methods the drop-in class does not define (e.g. `Fit.fit_*_numpy`, `Fit.sample_*`,
+    host-side numpy helpers outside the hot path) are taken from the reference class of the same name in the
+    reference module of the same name and bound to the drop-in instance.  Opt-in like everything here
+    (PARSENET_REFERENCE_SRC); methods the drop-in defines always win."""
+
+    _reference_module = None        # short module name, e.g. "primitive_forward"
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        cls = type(self)
+        ref = _load_reference_module(cls._reference_module) if cls._reference_module else None
+        ref_cls = getattr(ref, cls.__name__, None) if ref is not None else None
+        attr = getattr(ref_cls, name, None) if ref_cls is not None else None
+        if attr is None:
+            raise AttributeError(f"{cls.__name__!r} object has no attribute {name!r}")
+        return attr.__get__(self, cls) if hasattr(attr, "__get__") else attr

@@ -77,11 +77,16 @@ def initialize_closed_spline_model(modelname, mode):
     return _load_splinenet(modelname, mode)
 
 
+from src._fallthrough import ReferenceMethods as _ReferenceMethods  # noqa: E402
+
+
 # ------------------------------------------------------------------------------------------------ primitive fits
-class Fit:
+class Fit(_ReferenceMethods):
     """Weighted fits of plane / sphere / cylinder / cone to (points, normals, weights); same outputs as the
     reference.  Each call computes the weighted moments with pn_fit_moments_* and solves the 3x3 problems with the
-    reference's gradient conventions (pnb200.fitting)."""
+    reference's gradient conventions (pnb200.fitting).  The numpy fits and the surface samplers (`fit_*_numpy`,
+    `sample_*`, outside the hot path) resolve to the reference's own methods when PARSENET_REFERENCE_SRC is set."""
+    _reference_module = "primitive_forward"
 
     def __init__(self):
         self.lstsq = LeastSquares().lstsq

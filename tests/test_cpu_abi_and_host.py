@@ -162,6 +162,21 @@ for script in ("train_parsenet.py", "train_parsenet_e2e.py", "train_open_splines
             mod = __import__(node.module, fromlist=["x"])
             for a in node.names:
                 assert hasattr(mod, a.name), (script, node.module, a.name)
+# 3b. methods of a drop-in class outside the hot path bind to the drop-in instance (SURVEY 8b: Fit numpy variants)
+import numpy as np
+from src.primitive_forward import Fit
+f = Fit()
+assert type(f).__module__ == "src.primitive_forward"
+rng = np.random.RandomState(0)
+n = rng.randn(500, 3); n /= np.linalg.norm(n, axis=1, keepdims=True)
+c, r = f.fit_sphere_numpy(0.5 * n + 0.1, n, np.ones((500, 1)))
+assert np.allclose(c, 0.1, atol=1e-6) and abs(r - 0.5) < 1e-6, (c, r)
+assert f.fit_plane_torch.__func__.__module__ == "src.primitive_forward"          # hot-path methods stay ours
+try:
+    f.no_such_method
+    raise SystemExit("expected AttributeError")
+except AttributeError:
+    pass
 # 4. a name nobody defines is still an AttributeError
 try:
     src.utils.no_such_function
