@@ -267,3 +267,52 @@ def test_fitting_loss_fresh_shape_vs_port(N, seed):
             assert abs(d1 - d2) <= 1e-3 * d2, (kind, d1, d2)
     if "cylinder" not in [k for k, _ in ref]:
         assert abs(res[0].item() - want[0].item()) <= 1e-3 * abs(want[0].item())
+
+
+# ------------------------------------------------------------------------------------------------ config 3 training step
+@FIRST_RUN
+def test_open_spline_training_step_vs_port():
+    """one optimisation step of train_open_splines.py:143-178 on fresh patches (SplineNet in TRAIN mode: batch statistics,
+    one-sided spline reconstruction loss + permutation-invariant control-point regression + Laplacian loss, backward)
+    against the oracle port: losses 1e-4 relative (BASELINE config 3), parameter gradient norms 5e-3"""
+    from oracle.port import common, e2e as pe2e, fitting as OP
+    from src import loss as L
+    from src.model import DGCNNControlPoints
+    B, M = 4, 700
+    g = torch.Generator().manual_seed(3)
+    pts = torch.randn(B, 3, M, generator=g) * 0.3
+    gtcp = torch.rand(B, 20, 20, 3, generator=g) - 0.5
+    net = DGCNNControlPoints(20, num_points=10, mode=0)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = common.seeded_state_dict(shapes, seed=7)
+    for i in (1, 2, 3, 4, 5):
+        for s_ in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+            a, b = f"bn{i}.{s_}", f"conv{i}.1.{s_}"
+            if a in sd and b in sd:
+                sd[b] = sd[a]
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    nu, nv = L.uniform_knot_bspline(20, 20, 3, 3, 40)
+    nuf, nvf = torch.from_numpy(nu.astype(np.float32)), torch.from_numpy(nv.astype(np.float32))
+
+    class Cfg:
+        batch_size = B
+        grid_size = 20
+    out = net(pts.cuda())
+    cd, _ = L.spline_reconstruction_loss_one_sided(nuf, nvf, out, pts.cuda(), Cfg)
+    reg, perm = L.control_points_permute_reg_loss(out, gtcp.cuda(), 20)
+    lap = L.laplacian_loss(out.reshape(B, 20, 20, 3), perm)
+    (0.9 * reg + 0.1 * (cd + lap)).backward()
+    sdp = {k: (v.clone().requires_grad_() if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+    o_r = pe2e.splinenet_fwd(sdp, pts, 10, None, train=True)
+    cd_r, _ = OP.spline_reconstruction_loss_one_sided(nuf, nvf, o_r, pts, B, 20)
+    reg_r, perm_r = OP.control_points_permute_reg_loss(o_r, gtcp, 20)
+    lap_r = OP.laplacian_loss(o_r.reshape(B, 20, 20, 3), perm_r)
+    (0.9 * reg_r + 0.1 * (cd_r + lap_r)).backward()
+    _close(out, o_r, 3e-4, "control points (train mode)")
+    for name, a, b in (("chamfer", cd, cd_r), ("regression", reg, reg_r), ("laplacian", lap, lap_r)):
+        assert abs(a.item() - b.item()) <= 1e-4 * abs(b.item()), (name, a.item(), b.item())
+    params = dict(net.named_parameters())
+    for key in ("conv8.weight", "conv7.weight", "conv5.0.weight", "conv3.0.weight", "conv1.0.weight", "bn5.weight", "bn2.bias"):
+        got, want = params[key].grad.norm().item(), sdp[key].grad.norm().item()
+        assert abs(got - want) <= 5e-3 * want + 1e-9, (key, got, want)

@@ -1,0 +1,26 @@
+#!/bin/bash
+# First GPU call of round 2: everything that was written after the GPU budget of round 1 ran out, in order of risk, each
+# step under its own timeout, all output under gpurun_out/r02_first/.
+#   gpurun --timeout 1500 -- 'bash tools/r02_runbook.sh'
+# Reading order afterwards: 00_gpu_tests.txt (XPASS = promote the test, XFAIL = read the assertion), 10_tma_cg1.txt,
+# 11_tma_cg12.txt (bit-identical? faster?), 20_bench_default.json vs 21_bench_tma*.json.
+set -u
+OUT=gpurun_out/r02_first
+mkdir -p "$OUT"
+export PYTHONUNBUFFERED=1
+run() { name=$1; shift; echo "== $name: $*"; timeout "$TMO" "$@" > "$OUT/$name" 2>&1; echo "   rc=$? ($(tail -n 1 "$OUT/$name" | cut -c1-160))"; }
+
+TMO=900; run 00_gpu_tests.txt python -m pytest tests -m gpu -q -rxXs -x
+TMO=120; run 01_smoke.txt python -c "import __graft_entry__ as g; g.smoke()"
+# experimental kernels (they trap after ~2 s instead of hanging): 1-CTA TMA first, small then full size, then CTA pairs
+TMO=120; PN_EXP_CGS=1 run 10_tma_cg1_small.txt python tools/exp_ms_tma.py 2 1000
+TMO=180; PN_EXP_CGS=1 run 10_tma_cg1.txt python tools/exp_ms_tma.py 16 10000
+TMO=120; PN_EXP_CGS=2 run 11_tma_cg2_small.txt python tools/exp_ms_tma.py 2 1000
+TMO=180; PN_EXP_CGS=1,2 run 11_tma_cg12.txt python tools/exp_ms_tma.py 16 10000
+TMO=300; PN_RUN_EXPERIMENTAL=1 run 12_tma_tests.txt python -m pytest tests/test_gpu_meanshift_tc.py -q -k tma
+# the bench with and without them (same box, back to back)
+TMO=400; run 20_bench_default.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+TMO=400; PN_MS_TMA=1 run 21_bench_tma_cg1.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+TMO=400; PN_MS_TMA=1 PN_MS_TMA_CG=2 run 22_bench_tma_cg2.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+TMO=120; run 30_ms_bwd_sweep.txt python tools/exp_ms_bwd.py 0,128,160
+ls -la "$OUT"
