@@ -5,6 +5,8 @@ segments, point counts that are not tile multiples, single-cluster weights, full
 These tests were written after the GPU budget of round 1 was spent; their first execution on a B200 is the round-end run.
 They are therefore marked `xfail(strict=False)`: a pass shows up as XPASS, a failure as XFAIL with the assertion text,
 and the rest of the suite keeps running.  Promote them to hard tests (delete FIRST_RUN) once they have been seen green.
+The file name sorts last on purpose: should one of the edge sizes (1-point segments, 1 x 1 Chamfer) ever fault a kernel,
+the sticky CUDA error cannot take the established tests down with it.
 """
 import numpy as np
 import pytest
