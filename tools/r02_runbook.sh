@@ -23,4 +23,5 @@ TMO=400; run 20_bench_default.json python bench.py --steps 5 --warmup 3 --no-cpu
 TMO=400; PN_MS_TMA=1 run 21_bench_tma_cg1.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
 TMO=400; PN_MS_TMA=1 PN_MS_TMA_CG=2 run 22_bench_tma_cg2.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
 TMO=120; run 30_ms_bwd_sweep.txt python tools/exp_ms_bwd.py 0,128,160
+TMO=120; run 31_knn_cap.txt python tools/exp_knn_cap.py 16
 ls -la "$OUT"
