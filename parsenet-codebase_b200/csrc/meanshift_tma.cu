@@ -30,7 +30,7 @@ using namespace tc05;
 
 constexpr int D = 128, BM = 128, BN = 32;
 constexpr int EPI_WARPS = 8, TMA_WARP = 8, MMA_WARP = 9, NT = 320, EPI_THREADS = 256;
-constexpr int NSTAGE = 3, FLUSH = 16;
+constexpr int NSTAGE = 3, MAX_STAGES = 6, FLUSH = 16;      // NSTAGE: 64 KB stages of one CTA; pairs use 6 x 32 KB
 constexpr float CLAMP = 75.f;
 constexpr uint32_t C_YB = 0, C_YS = 128, C_S0 = 256, C_PS2 = 320, C_O = 384, TMEM_COLS = 512;
 constexpr int PART_BYTES = BN * D * 4;            // 16 KB per operand part
@@ -38,7 +38,7 @@ constexpr int STAGE_BYTES = 4 * PART_BYTES;       // 64 KB
 constexpr uint32_t SW128 = 2, SBO128 = 1024;      // descriptor layout type / 8-row group stride of a 128B-swizzled slab
 
 struct Bars {
-    uint64_t x_full[NSTAGE], x_empty[NSTAGE], s_full[2], s_empty[2], p_full2[2], p_empty, o_flush, o_done, a_ready;
+    uint64_t x_full[MAX_STAGES], x_empty[MAX_STAGES], s_full[2], s_empty[2], p_full2[2], p_empty, o_flush, o_done, a_ready;
 };
 
 // ---------------------------------------------------------------------------------------------- operand preparation
@@ -85,6 +85,7 @@ struct Geo {
     static constexpr int PART = PART_BYTES / CG;      // one operand part per CTA
     static constexpr int STAGE = 4 * PART;            // per-CTA stage
     static constexpr int DROWS = D / CG;              // d rows staged by one CTA (second product)
+    static constexpr int NSTG = NSTAGE * CG;          // pipeline depth (same shared-memory footprint per CTA)
 };
 
 template <int CG>
@@ -103,8 +104,8 @@ __device__ __forceinline__ void tma_producer(unsigned char* smem, Bars& bars, co
         tma_prefetch_desc(mA); tma_prefetch_desc(mAs); tma_prefetch_desc(mT); tma_prefetch_desc(mTs);
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
-            const int s = t % NSTAGE;
-            mbar_wait_guarded(&bars.x_empty[s], ((t / NSTAGE) & 1) ^ 1);
+            const int s = t % G::NSTG;
+            mbar_wait_guarded(&bars.x_empty[s], ((t / G::NSTG) & 1) ^ 1);
             unsigned char* st = smem + s * G::STAGE;
             if (rank == 0) mbar_arrive_expect_tx(&bars.x_full[s], STAGE_BYTES);      // bytes of BOTH CTAs' halves
             const int row = t * BN + rank * G::ROWS;
@@ -156,7 +157,7 @@ __device__ __forceinline__ void mma_issuer(unsigned char* smem, Bars& bars, uint
         const bool fresh = (u % FLUSH) == 0;
         if (u > 0 && fresh) mbar_wait_guarded(&bars.o_flush, ((u / FLUSH) - 1) & 1);
         tc_fence_after();
-        const uint32_t st = sbase + (u % NSTAGE) * G::STAGE;
+        const uint32_t st = sbase + (u % G::NSTG) * G::STAGE;
         const uint64_t db0 = make_smem_desc(st + 2 * G::PART, 16, SBO128, SW128);
         const uint64_t ds0 = make_smem_desc(st + 3 * G::PART, 16, SBO128, SW128);
         if (leader) {
@@ -168,7 +169,7 @@ __device__ __forceinline__ void mma_issuer(unsigned char* smem, Bars& bars, uint
                 mma(tb + C_O, tb + pb_col + ks * 8, ds, idesc_o, 1);
                 mma(tb + C_O, tb + pb_col + ks * 8, db, idesc_o, 1);
             }
-            commit(&bars.x_empty[u % NSTAGE]);
+            commit(&bars.x_empty[u % G::NSTG]);
             commit(&bars.p_empty);
         }
         __syncwarp();
@@ -177,8 +178,8 @@ __device__ __forceinline__ void mma_issuer(unsigned char* smem, Bars& bars, uint
     tc_fence_after();
 #pragma unroll 1
     for (int t = 0; t < ntiles; ++t) {
-        const int s = t % NSTAGE, k = t & 1;
-        mbar_wait_guarded(&bars.x_full[s], (t / NSTAGE) & 1);
+        const int s = t % G::NSTG, k = t & 1;
+        mbar_wait_guarded(&bars.x_full[s], (t / G::NSTG) & 1);
         mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t st = sbase + s * G::STAGE;
@@ -207,7 +208,7 @@ __device__ __forceinline__ void mma_issuer(unsigned char* smem, Bars& bars, uint
 
 template <int CG>
 __device__ __forceinline__ void init_bars(Bars& bars) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
+    for (int s = 0; s < Geo<CG>::NSTG; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
     for (int k = 0; k < 2; ++k) {
         mbar_init(&bars.s_full[k], 1);
         mbar_init(&bars.s_empty[k], CG * EPI_THREADS);
