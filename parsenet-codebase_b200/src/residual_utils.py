@@ -8,9 +8,15 @@ from scipy import stats
 from src.fitting_optimization import FittingModule
 from src.fitting_utils import match, to_one_hot, weights_normalize
 from src.mean_shift import MeanShift
-from src.primitive_forward import fit_one_shape_torch
+from src.primitive_forward import finish_one_shape, fit_one_shape_torch, plan_one_shape, solve_planned_shapes
 from src.primitives import ResidualLoss
 from src.segment_utils import SIOU_matched_segments, segment_types_device
+
+
+import os
+
+# EXPERIMENTAL, opt-in: cross-shape batching of the per-kind fit solves (src/primitive_forward.py); not yet run on a GPU
+FIT_BATCHED = os.environ.get("PN_FIT_BATCHED", "0") == "1"
 
 
 def convert_to_one_hot(data):
@@ -70,20 +76,36 @@ class Evaluation:
         self._stage.reset()
         out, lazies, metrics, matchings = [], [], [], []
         parameters, weights = None, None
+        batched = FIT_BATCHED and B > 1      # experimental: the (S,3,3) solves of all shapes in one call per kind
+        pending = []
         for b in range(B):
             center, bandwidth = shifted[b][ids[b]], float(bw_host[b])
             if np.unique(cluster_np[b]).shape[0] > 49:       # rare: grow the quantile for this shape only (ref :76-83)
                 center, bw_t, cl = self.guard_mean_shift(embedding[b], quantile * 1.2, iterations)
                 cluster_np[b], bandwidth = cl.data.cpu().numpy(), float(bw_t)
             weights = center @ embedding[b].t()
-            loss, parameters, _, rows, cols, distance = self.residual_train_mode(
-                points[b], normals[b], labels[b], cluster_np[b], primitives[b], weights, bandwidth, lamb=lamb,
-                lazy=True)
-            lazies.append(loss)
-            matchings.append((rows, cols))
+            if batched:
+                pending.append(self._plan_train_mode(points[b], normals[b], labels[b], cluster_np[b], primitives[b],
+                                                     weights, bandwidth))
+            else:
+                loss, parameters, _, rows, cols, distance = self.residual_train_mode(
+                    points[b], normals[b], labels[b], cluster_np[b], primitives[b], weights, bandwidth, lamb=lamb,
+                    lazy=True)
+                lazies.append(loss)
+                matchings.append((rows, cols))
+                out.append(loss[0])
             with torch.no_grad():
                 metrics.append(segment_types_device(prim_pred_dev[b], weights))
-            out.append(loss[0])
+        if batched:
+            solve_planned_shapes([p[0] for p in pending])
+            for state, rows, cols in pending:
+                gt_points, _ = finish_one_shape(state, self.fitter)
+                parameters = self.fitter.fitting.parameters
+                distance = self.res_loss.residual_loss(gt_points, parameters)
+                loss = self.separate_losses(distance, gt_points, lamb=lamb, lazy=True)
+                lazies.append(loss)
+                matchings.append((rows, cols))
+                out.append(loss[0])
         # ---- ONE read-back for every deferred statistic of the step
         flat = [t for l in lazies for t in l[1:] if t is not None] + metrics
         host = torch.cat([t.reshape(-1).double() for t in flat]).cpu().numpy() if flat else np.zeros(0)
@@ -104,6 +126,31 @@ class Evaluation:
                                                        prim_pred_seg=seg_type, matching=matchings[b])
             res = res + [out[b]] + lazies[b] + [s_iou, p_iou]
         return res, [parameters, cluster_np[B - 1], weights]
+
+    def _plan_train_mode(self, points, normals, labels, cluster_ids, primitives, weights, bw):
+        """first half of residual_train_mode for the cross-shape batched path (PN_FIT_BATCHED=1): matching, per-segment
+        data, membership weights and the moment pass; the solves follow for all shapes at once"""
+        rows, cols, unique_target, unique_pred = match(labels, cluster_ids)
+        stage = getattr(self, "_stage", None)
+        entries, chunks = [], []
+        for index, i in enumerate(unique_pred):
+            gt_i = labels == cols[i]
+            if gt_i.sum() == 0 or (cluster_ids == i).sum() == 0:
+                continue
+            l = np.bincount(primitives[gt_i]).argmax()
+            entries.append((l, (index, i)))
+            chunks.append(np.nonzero(gt_i)[0])
+        data = []
+        if entries:
+            allidx = np.concatenate(chunks).astype(np.int64)
+            idx_dev = stage.upload(allidx, points.device) if stage is not None else \
+                torch.from_numpy(allidx).to(points.device)
+            o = 0
+            for (l, key), ch in zip(entries, chunks):
+                data.append([points, normals, l, points[idx_dev[o:o + ch.shape[0]]], None, key])
+                o += ch.shape[0]
+        w = weights_normalize(weights, float(bw)).t()
+        return plan_one_shape(data, w), rows, cols
 
     def residual_train_mode(self, points, normals, labels, cluster_ids, primitives, weights, bw, lamb=1.0,
                             lazy=False):

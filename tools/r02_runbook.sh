@@ -18,10 +18,12 @@ TMO=180; PN_EXP_CGS=1 run 10_tma_cg1.txt python tools/exp_ms_tma.py 16 10000
 TMO=120; PN_EXP_CGS=2 run 11_tma_cg2_small.txt python tools/exp_ms_tma.py 2 1000
 TMO=180; PN_EXP_CGS=1,2 run 11_tma_cg12.txt python tools/exp_ms_tma.py 16 10000
 TMO=300; PN_RUN_EXPERIMENTAL=1 run 12_tma_tests.txt python -m pytest tests/test_gpu_meanshift_tc.py -q -k tma
+TMO=300; PN_RUN_EXPERIMENTAL=1 run 13_fit_batched_test.txt python -m pytest tests/test_gpu_zz_first_run.py -q -k batched
 # the bench with and without them (same box, back to back)
 TMO=400; run 20_bench_default.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
 TMO=400; PN_MS_TMA=1 run 21_bench_tma_cg1.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
 TMO=400; PN_MS_TMA=1 PN_MS_TMA_CG=2 run 22_bench_tma_cg2.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+TMO=400; PN_FIT_BATCHED=1 run 23_bench_fit_batched.json python bench.py --steps 5 --warmup 3 --no-cpu-baseline
 TMO=120; run 30_ms_bwd_sweep.txt python tools/exp_ms_bwd.py 0,128,160
 TMO=120; run 31_knn_cap.txt python tools/exp_knn_cap.py 16
 ls -la "$OUT"
