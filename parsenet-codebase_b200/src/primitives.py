@@ -39,13 +39,40 @@ def _pack(kind, params):
     return torch.cat([apex.reshape(3), a.reshape(3), th.reshape(1), z(1)])
 
 
+def _closed_form(kind, points, params, sqrt, reduce):
+    """squared point-to-primitive distances of reference src/primitives.py:100-195 (per point; optional guard_sqrt / mean)"""
+    if kind == "plane":
+        a, d = params
+        dist = ((points @ a.reshape(3, 1) - d) ** 2).sum(1)
+    elif kind == "sphere":
+        c, r = params
+        dist = (torch.norm(points - c.reshape(1, 3), p=2, dim=1) - r) ** 2
+    elif kind == "cylinder":
+        axis, c, r = params
+        v = points - c.reshape(1, 3)
+        radial2 = torch.clamp((v * v).sum(1) - (v @ axis.reshape(3, 1))[:, 0] ** 2, min=1e-5)
+        dist = (torch.sqrt(radial2) - r) ** 2
+    else:
+        apex, axis, theta = params
+        v = points - apex.reshape(1, 3) + 1e-8
+        mod = torch.norm(v, dim=1, p=2)
+        cosang = torch.clamp((v @ axis.reshape(3, 1))[:, 0] / (mod + 1e-7), min=-0.999, max=0.999)
+        off = torch.clamp((torch.acos(cosang) - theta).abs(), max=3.142 / 2.0)
+        dist = (mod * torch.sin(off)) ** 2
+    if sqrt:
+        dist = guard_sqrt(dist)
+    return dist.mean() if reduce else dist
+
+
 class ComputePrimitiveDistance:
     def __init__(self, reduce=True, one_side=False):
         self.reduce, self.one_side = reduce, one_side
 
     def _analytic(self, kind, points, params, sqrt):
         if sqrt or not self.reduce:
-            raise NotImplementedError("device residuals implement the training path (sqrt=False, reduce=True)")
+            # evaluation-time variants (per-point vectors, guarded square roots; reference :100-195 with sqrt / reduce
+            # flags): off the training hot path, closed forms as plain torch expressions on the caller's device
+            return _closed_form(kind, points, params, sqrt, self.reduce)
         par = _pack(kind, [p.float() for p in params]).unsqueeze(0)
         seg = torch.zeros((points.shape[0],), dtype=torch.int32, device=points.device)
         typ = torch.full((1,), TYPE_ID[kind], dtype=torch.int32, device=points.device)

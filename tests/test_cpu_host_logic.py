@@ -254,3 +254,24 @@ def test_ms_bwd_lite_rounding_model_stays_within_gradient_tolerance():
             worst_single = max(worst_single, ((e - s).abs().max() / e.abs().max()).item())
     assert 1e-6 < worst_lite < 5e-4, worst_lite
     assert worst_single > worst_lite
+
+
+@pytest.mark.parametrize("sqrt,reduce", [(True, True), (False, False), (True, False)])
+def test_eval_time_residual_variants_match_the_oracle_port(sqrt, reduce):
+    """ComputePrimitiveDistance with sqrt=True / reduce=False (evaluation-time flags, reference src/primitives.py:100-195):
+    plain torch closed forms, so they can be checked against the oracle port right here on CPU tensors"""
+    from oracle.port import fitting as OP
+    from src.primitives import ComputePrimitiveDistance
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(257, 3, generator=g) * 0.5
+    unit = lambda v: v / v.norm()
+    params = {"plane": [unit(torch.randn(3, 1, generator=g)), torch.tensor(0.13)],
+              "sphere": [torch.randn(1, 3, generator=g) * 0.2, torch.tensor(0.6)],
+              "cylinder": [unit(torch.randn(3, 1, generator=g)), torch.randn(1, 3, generator=g) * 0.2, torch.tensor(0.35)],
+              "cone": [torch.randn(1, 3, generator=g) * 0.2, unit(torch.randn(3, 1, generator=g)), torch.tensor(0.5)]}
+    cp = ComputePrimitiveDistance(reduce=reduce)
+    for kind, ps in params.items():
+        got = getattr(cp, "distance_from_" + kind)(points=q, params=ps, sqrt=sqrt)
+        want = OP.DISTANCES[kind](q, ps, sqrt=sqrt, reduce=reduce)
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-9), kind
