@@ -12,6 +12,7 @@ run() { name=$1; shift; echo "== $name: $*"; timeout "$TMO" "$@" > "$OUT/$name" 
 
 TMO=900; run 00_gpu_tests.txt python -m pytest tests -m gpu -q -rxXs -x
 TMO=120; run 01_smoke.txt python -c "import __graft_entry__ as g; g.smoke()"
+TMO=200; run 02_tc_probes.txt bash tools/tc_probe/run_all.sh
 # experimental kernels (they trap after ~2 s instead of hanging): 1-CTA TMA first, small then full size, then CTA pairs
 TMO=120; PN_EXP_CGS=1 run 10_tma_cg1_small.txt python tools/exp_ms_tma.py 2 1000
 TMO=180; PN_EXP_CGS=1 run 10_tma_cg1.txt python tools/exp_ms_tma.py 16 10000

@@ -5,6 +5,7 @@ set -u
 cd "$(dirname "$0")"
 cp ../../parsenet-codebase_b200/csrc/tc05.cuh tc05.cuh
 nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O2 -o probe probe.cu || exit 1
+nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O2 -o probe2 probe2.cu || exit 1
 echo "== validated encodings (must be exact): K-major SS / TS"
 timeout 20 ./probe 0; timeout 20 ./probe 1
 echo "== MN-major B, no swizzle (variant 0: LBO = K direction, SBO = MN direction; variant 1: swapped)"
@@ -14,3 +15,5 @@ timeout 20 ./probe 4; timeout 20 ./probe 5
 echo "== 128B-swizzled (TMA-style) B tile: K-major read, then the same kind of tile read MN-major"
 timeout 20 ./probe 8; timeout 20 ./probe 9
 for v in 0 1; do timeout 20 ./probe 10 $v; timeout 20 ./probe 11 $v; done
+echo "== CTA pair (tcgen05 cta_group::2): B staged by threads, then by 2-SM TMA loads completing on the leader barrier"
+timeout 20 ./probe2 0; timeout 20 ./probe2 1
