@@ -319,7 +319,11 @@ def run_ours(args):
     out["config"]["mean_clusters_per_shape_last"] = (float(np.mean(hp.clusters[-4:])) if hp.clusters else None)
     out["config"]["fitted_segments_per_step"] = fits_per_step
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline()
+        try:
+            out["cpu_baseline"] = cpu_baseline()
+        except Exception as exc:          # a failure of the CPU arm must not cost the measured GPU line
+            out["cpu_baseline"] = {"value": None, "unit": "shapes/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"failed: {type(exc).__name__}: {exc}"}
     print(json.dumps(out))
 
 
