@@ -354,3 +354,37 @@ def test_cross_shape_batched_fit_equals_per_shape_path(monkeypatch):
     for a, b in zip(results[0][0], results[1][0]):
         assert abs(a - b) <= 1e-6 * abs(a), (a, b)
     _close(results[1][1], results[0][1], 1e-5, "d loss / d embedding, batched vs per-shape")
+
+
+# ------------------------------------------------------------------------------------------------ inference path
+@FIRST_RUN
+def test_inference_clustering_path_vs_port():
+    """generate_predictions.py:131-156: normalised embedding -> Evaluation.guard_mean_shift (50 iterations, no grad) ->
+    one-hot weights -> SIOU_matched_segments.  Partition identical to the oracle port's, hence identical IoU metrics."""
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as oms
+    from src.residual_utils import Evaluation
+    from src.segment_utils import SIOU_matched_segments, to_one_hot
+    N = 2000
+    X, gt = clustered_embedding(N, 128, 7, 123, spread=0.25)
+    np.random.seed(9)
+    _, _, lab_r = oms.guard_mean_shift(X, 0.015, 50, num_samples=10000, growth=1.2)
+    ev = Evaluation.__new__(Evaluation)            # only the clustering half is exercised (no SplineNets needed)
+    from src.mean_shift import MeanShift
+    ev.ms = MeanShift()
+    np.random.seed(9)
+    with torch.no_grad():
+        _, _, cluster_ids = ev.guard_mean_shift(X.cuda(), 0.015, 50, kernel_type="gaussian")
+
+    def canon(l):
+        l = np.asarray(l)
+        _, first = np.unique(l, return_index=True)
+        m = {int(v): i for i, v in enumerate(l[np.sort(first)])}
+        return np.array([m[int(v)] for v in l])
+    got, want = canon(cluster_ids.cpu().numpy()), canon(lab_r.numpy())
+    np.testing.assert_array_equal(got, want)
+    prim = (gt.numpy() % 6).astype(np.int64)
+    w = to_one_hot(torch.from_numpy(got).cuda(), int(got.max()) + 1)
+    s_iou, p_iou, _, _ = SIOU_matched_segments(gt.numpy(), got, prim, prim, w)
+    s_iou_r, p_iou_r, _, _ = SIOU_matched_segments(gt.numpy(), want, prim, prim, w)
+    assert abs(s_iou - s_iou_r) < 1e-12 and abs(p_iou - p_iou_r) < 1e-12 and 0.0 <= s_iou <= 1.0
