@@ -82,6 +82,13 @@ int pn_ms_kth_dist(const float* X, const int* rows, int B, int S, long long shap
 /* replaces: MeanShift.nms: src/mean_shift.py:146-149 (mode 0), :163-171 (mode 1), :177-178 (mode 2) */
 int pn_ms_argsel(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream);
 
+/* EXPERIMENTAL (opt-in PN_MS_SPARSE_BWD=1, not yet run on a GPU): backward of one mean-shift iteration restricted to a compact
+   set of R = 64 rows per shape.  In Evaluation.fitting_loss the loss sees the shifted points only through the <= 49 cluster
+   centres (src/mean_shift.py:41 `center = new_X[indices]`, src/residual_utils.py:118), row i of Y_t depends on row i of
+   Y_{t-1} alone, so every other row of the autograd pass of src/mean_shift.py:58-77 contributes exactly zero.
+   gout / Ynew_R / Yprev_R [B][64][d], den_R / unorm_R [B][64], ws_part [B][ceil(N/64)][64][d]; gX is accumulated. */
+int pn_ms_rows_bwd(const float* gout, const float* Ynew_R, const float* Yprev_R, const float* den_R, const float* unorm_R, const float* X, int B, int R, int N, int d, const float* cinv, float* ws_Gn, float* ws_gd, float* ws_part, float* gYprev_R, float* gX, void* stream);
+
 /* ---- meanshift_tc.cu / meanshift_tc_bwd.cu / meanshift_tc_kth.cu (tcgen05 split-TF32 versions, d must be 128) ---- */
 /* replaces: MeanShift.mean_shift_ (one iteration): src/mean_shift.py:58-77 — same contract as pn_ms_iter_fwd */
 int pn_ms_iter_fwd_tc(const float* Y, const float* X, int B, int N, int d, const float* cinv, float* Ynew, float* den, float* unorm, void* stream);

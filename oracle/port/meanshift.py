@@ -69,3 +69,22 @@ def guard_mean_shift(X, quantile, iterations, num_samples=10000, growth=1.2, rng
         else:
             break
     return center, bw, labels
+
+
+def sparse_rows_backward(g_R, Ynew_R, Yprev_R, den_R, unorm_R, X, b):
+    """Closed-form backward of ONE mean-shift iteration for a subset R of the rows (the math of the product's
+    ms_bwd_sparse_kernel, written out with torch on the CPU; checked against autograd through mean_shift_iters in
+    tests/test_oracle_golden.py).  Row i of Y_t depends on row i of Y_{t-1} and on X only, so a gradient that is non-zero
+    in rows R stays in rows R.  Inputs: gradient w.r.t. rows R of Y_t, rows R of Y_t and Y_{t-1}, their kernel row sums
+    `den` and pre-normalisation norms `unorm`, all of X, bandwidth b.  Returns (grad w.r.t. rows R of Y_{t-1}, grad w.r.t. X).
+    u = K X / den ; Y_t = u / |u| ; K = exp(clamp((S - 1) / b^2)), S = Y_{t-1} X^T"""
+    c = 1.0 / (b * b)
+    g_u = (g_R - Ynew_R * (Ynew_R * g_R).sum(1, keepdim=True)) / unorm_R[:, None]
+    Gn = g_u / den_R[:, None]
+    gd = -((g_u * Ynew_R).sum(1) * unorm_R) / den_R
+    S = Yprev_R @ X.t()
+    e = (S - 1.0) * c
+    clamped = (e > 75.0) | (e < -75.0)
+    K = torch.exp(torch.clamp(e, -75.0, 75.0))
+    gS = torch.where(clamped, torch.zeros_like(S), (Gn @ X.t() + gd[:, None]) * K * c)
+    return gS @ X, gS.t() @ Yprev_R + K.t() @ Gn

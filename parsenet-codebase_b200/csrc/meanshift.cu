@@ -522,9 +522,127 @@ __global__ void __launch_bounds__(NT) ms_argsel_kernel(const float* __restrict__
     }
 }
 
+// ================================================================================================ sparse-row backward
+// EXPERIMENTAL (opt-in PN_MS_SPARSE_BWD=1, written after the GPU budget of round 1 was spent, not yet run on a GPU).
+// In Evaluation.fitting_loss the loss depends on the shifted points only through the <= 49 cluster centres
+// `center = new_X[indices]` (reference src/mean_shift.py:41, src/residual_utils.py:118): the gradient w.r.t. the last
+// iterate is non-zero in those rows only, and since row i of Y_t depends on row i of Y_{t-1} (and on X) alone, it stays
+// confined to the same rows through all iterations.  The reference (and the dense kernels above) spend 14 N^2 d flop per
+// iteration on rows whose contribution is exactly zero; this kernel does the same arithmetic for a compact set of R = 64
+// rows: 10 R N d flop, ~150x less.  Every (i, j) term is the dense kernels' term (same helpers, same order over d).
+//   grid (ceil(N/T), B): the CTA owns T rows j of X and the whole compact row set;
+//   gX[j] += sum_i gS_ij y_i + K_ij Gn_i     (exclusive owner: no atomics)
+//   part[b][blk][i] = sum_{j in block} gS_ij x_j, summed over the blocks in a fixed order by ms_rows_reduce_kernel.
+// Yp, Gn: [B][T][D] compact rows (slots beyond the real count carry a zero gradient: Gn = 0, gd = 0 -> zero terms).
+__global__ void __launch_bounds__(NT) ms_bwd_sparse_kernel(const float* __restrict__ Yp, const float* __restrict__ X,
+                                                           const float* __restrict__ Gn, const float* __restrict__ gd,
+                                                           int N, const float* __restrict__ cinv,
+                                                           float* __restrict__ gX, float* __restrict__ part) {
+    extern __shared__ __align__(16) float sm[];
+    float* Xt = sm;                   // phase A: [D][PK] own rows j (k-major)      phase B: Xr [T][PR]
+    float* Yt = Xt + D * PK;          // phase A: [D][PK] compact rows i            phase B: Yr [T][PR]
+    float* Gt = Yt + D * PK;          // phase A: [D][PK]                           phase B: Gr [T][PR]
+    float* P1 = Gt + D * PK;          // gS  [T i][PK j]
+    float* P2 = P1 + T * PK;          // K   [T i][PK j]
+    float* Ps = P2 + T * PK;          // gS  [T j][PK i]
+    __shared__ float gds[T];
+    const int b = blockIdx.y, j0 = blockIdx.x * T;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const long long off = (long long)b * N * D;
+    const long long offr = (long long)b * T * D;
+    const float c = cinv[b];
+    load_tile(X + off, D, j0, N, nullptr, Xt);
+    load_tile(Yp + offr, D, 0, T, nullptr, Yt);
+    load_tile(Gn + offr, D, 0, T, nullptr, Gt);
+    if (tid < T) gds[tid] = gd[(long long)b * T + tid];
+    __syncthreads();
+    {
+        // s[jj][ii] = x_j . y_i ; g[jj][ii] = x_j . Gn_i   (thread rows = owned j, thread columns = compact rows i)
+        float s[4][4], g[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s[i][j] = 0.f; g[i][j] = 0.f; }
+#pragma unroll 8
+        for (int kk = 0; kk < D; ++kk) {
+            float4 a = *reinterpret_cast<const float4*>(Xt + kk * PK + 4 * ty);
+            float4 y4 = *reinterpret_cast<const float4*>(Yt + kk * PK + 4 * tx);
+            float4 g4 = *reinterpret_cast<const float4*>(Gt + kk * PK + 4 * tx);
+            const float av[4] = {a.x, a.y, a.z, a.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w},
+                        gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    s[jj][ii] = fmaf(av[jj], yv[ii], s[jj][ii]);
+                    g[jj][ii] = fmaf(av[jj], gv[ii], g[jj][ii]);
+                }
+        }
+        float p1[4][4], p2[4][4];            // [jj][ii]
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const bool jv = (j0 + 4 * ty + jj) < N;
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                bool cl;
+                const float k = jv ? kernel_val(s[jj][ii], c, &cl) : 0.f;
+                p2[jj][ii] = k;
+                p1[jj][ii] = (jv && !cl) ? (g[jj][ii] + gds[4 * tx + ii]) * k * c : 0.f;
+            }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            *reinterpret_cast<float4*>(P1 + (4 * tx + ii) * PK + 4 * ty) = make_float4(p1[0][ii], p1[1][ii], p1[2][ii], p1[3][ii]);
+            *reinterpret_cast<float4*>(P2 + (4 * tx + ii) * PK + 4 * ty) = make_float4(p2[0][ii], p2[1][ii], p2[2][ii], p2[3][ii]);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+            *reinterpret_cast<float4*>(Ps + (4 * ty + jj) * PK + 4 * tx) = make_float4(p1[jj][0], p1[jj][1], p1[jj][2], p1[jj][3]);
+    }
+    __syncthreads();                  // all reads of the k-major tiles are done: reuse their space for the row-major ones
+    float* Xr = Xt; float* Yr = Yt; float* Gr = Gt;
+    load_tile(X + off, D, j0, N, Xr, nullptr);
+    load_tile(Yp + offr, D, 0, T, Yr, nullptr);
+    load_tile(Gn + offr, D, 0, T, Gr, nullptr);
+    __syncthreads();
+    float o[4][8], q[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { o[i][j] = 0.f; q[i][j] = 0.f; }
+    gemm_pr(P1, Yr, ty, tx, o);       // rows m = owned j:      sum_i gS_ij y_i
+    gemm_pr(P2, Gr, ty, tx, o);       //                      + sum_i K_ij Gn_i
+    gemm_pr(Ps, Xr, ty, tx, q);       // rows m = compact i:    sum_{j in block} gS_ij x_j
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = j0 + 4 * ty + i;
+        if (r < N) {
+            float* dst = gX + off + (long long)r * D;
+            float4 a0 = *reinterpret_cast<float4*>(dst + 4 * tx), a1 = *reinterpret_cast<float4*>(dst + 64 + 4 * tx);
+            a0.x += o[i][0]; a0.y += o[i][1]; a0.z += o[i][2]; a0.w += o[i][3];
+            a1.x += o[i][4]; a1.y += o[i][5]; a1.z += o[i][6]; a1.w += o[i][7];
+            *reinterpret_cast<float4*>(dst + 4 * tx) = a0;
+            *reinterpret_cast<float4*>(dst + 64 + 4 * tx) = a1;
+        }
+        float* pd = part + (((long long)b * gridDim.x + blockIdx.x) * T + 4 * ty + i) * D;
+        *reinterpret_cast<float4*>(pd + 4 * tx) = make_float4(q[i][0], q[i][1], q[i][2], q[i][3]);
+        *reinterpret_cast<float4*>(pd + 64 + 4 * tx) = make_float4(q[i][4], q[i][5], q[i][6], q[i][7]);
+    }
+}
+
+// gY[b][i][:] = sum over the column blocks (fixed order: deterministic);  grid (T, B), D threads
+__global__ void __launch_bounds__(D) ms_rows_reduce_kernel(const float* __restrict__ part, int nblk, float* __restrict__ gY) {
+    const int b = blockIdx.y, i = blockIdx.x, dd = threadIdx.x;
+    const float* src = part + ((long long)b * nblk * T + i) * D + dd;
+    float acc = 0.f;
+    for (int k = 0; k < nblk; ++k) acc += src[(long long)k * T * D];
+    gY[((long long)b * T + i) * D + dd] = acc;
+}
+
 static size_t smem_fwd() { return sizeof(float) * (2 * D * PK + T * PR + T * PK); }
 static size_t smem_rows() { return sizeof(float) * (3 * D * PK + T * PR + T * PK); }
 static size_t smem_cols() { return sizeof(float) * (3 * D * PK + 2 * T * PR + 2 * T * PK); }
+static size_t smem_sparse() { return sizeof(float) * (3 * D * PK + 3 * T * PK); }
 static size_t smem_kth() { return sizeof(float) * (2 * D * PK) + sizeof(unsigned) * T * 256; }
 
 }  // namespace ms
@@ -601,5 +719,30 @@ extern "C" int pn_ms_argsel(int mode, const float* A, long long a_stride, int Ma
     }
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("ms_argsel_kernel");
+    return PN_OK;
+}
+
+// Backward of one mean-shift iteration restricted to a compact set of R = 64 rows per shape (see ms_bwd_sparse_kernel):
+//   gout, Ynew_R, Yprev_R: [B][64][d] (gradient w.r.t. / values of rows R of Y_t, and rows R of Y_{t-1}); den_R, unorm_R: [B][64];
+//   X [B][N][d]; ws_Gn [B][64][d], ws_gd [B][64], ws_part [B][ceil(N/64)][64][d] workspaces;
+//   gYprev_R [B][64][d] (written), gX [B][N][d] (accumulated).
+extern "C" int pn_ms_rows_bwd(const float* gout, const float* Ynew_R, const float* Yprev_R, const float* den_R,
+                              const float* unorm_R, const float* X, int B, int R, int N, int d, const float* cinv,
+                              float* ws_Gn, float* ws_gd, float* ws_part, float* gYprev_R, float* gX, void* stream) {
+    PN_REQUIRE(gout && Ynew_R && Yprev_R && den_R && unorm_R && X && cinv && ws_Gn && ws_gd && ws_part && gYprev_R && gX,
+               "pn_ms_rows_bwd: null pointer");
+    PN_REQUIRE(d == D, "pn_ms_rows_bwd: embedding width must be %d (got %d)", D, d);
+    PN_REQUIRE(R == T, "pn_ms_rows_bwd: the compact row set is padded to exactly %d rows (got %d)", T, R);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)B * R;
+    ms_bwd_prep_kernel<<<cdiv(rows, 8), 256, 0, st>>>(gout, Ynew_R, den_R, unorm_R, rows, ws_Gn, ws_gd);
+    PN_COUNT_LAUNCH();
+    PN_CUDA(cudaFuncSetAttribute(ms_bwd_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sparse()));
+    const int nblk = cdiv(N, T);
+    ms_bwd_sparse_kernel<<<dim3(nblk, B), NT, smem_sparse(), st>>>(Yprev_R, X, ws_Gn, ws_gd, N, cinv, gX, ws_part);
+    PN_COUNT_LAUNCH();
+    ms_rows_reduce_kernel<<<dim3(T, B), D, 0, st>>>(ws_part, nblk, gYprev_R);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_bwd_sparse kernels");
     return PN_OK;
 }

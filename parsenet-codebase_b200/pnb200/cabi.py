@@ -49,6 +49,7 @@ SIGNATURES = {
     "pn_ms_iter_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     "pn_ms_iter_bwd_tc": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     "pn_debug_set_progress": [c_p],
+    "pn_ms_rows_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "pn_ms_bwd_prep_tc": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "pn_ms_bwd_cols_tc": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p],
     # meanshift_tma.cu (experimental, PN_MS_TMA=1)

@@ -95,6 +95,85 @@ class MeanShiftItersFn(torch.autograd.Function):
         return gX, None, None
 
 
+# ------------------------------------------------------------------------------------------------ sparse-row backward
+# EXPERIMENTAL (opt-in PN_MS_SPARSE_BWD=1; csrc/meanshift.cu::ms_bwd_sparse_kernel; not yet run on a GPU).
+SPARSE_BWD = os.environ.get("PN_MS_SPARSE_BWD", "0") == "1"
+SPARSE_ROWS = 64          # the compact row set is padded to exactly this many rows (>= the 49 clusters the guards allow)
+
+
+def mean_shift_iters_keep(X_bnd, bw_b, iterations):
+    """the forward iterations WITHOUT an autograd node: returns (Y_final, state); state feeds centers_sparse"""
+    X = X_bnd.detach().contiguous()
+    _need_cuda(X)
+    B, N, d = X.shape
+    bw = bw_b.detach().to(torch.float32)
+    cinv = (1.0 / (bw * bw)).contiguous()
+    Ys, dens, norms = [X], [], []
+    for _ in range(int(iterations)):
+        Yn = torch.empty_like(X)
+        den = torch.empty((B, N), dtype=torch.float32, device=X.device)
+        un = torch.empty((B, N), dtype=torch.float32, device=X.device)
+        call("pn_ms_iter_fwd_tc" if (FWD_IMPL == "tc" and d == 128) else "pn_ms_iter_fwd", _ptr(Ys[-1]), _ptr(X), B, N, d,
+             _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
+        Ys.append(Yn); dens.append(den); norms.append(un)
+    return Ys[-1], (cinv, Ys, dens, norms)
+
+
+class MeanShiftCentersFn(torch.autograd.Function):
+    """rows `ids` (B,R) of the last mean-shift iterate as a differentiable function of X: the forward is a gather from
+    the iterates computed by mean_shift_iters_keep, the backward runs every iteration for those R rows only (the
+    gradient of a loss that sees the shifted points through `center = new_X[indices]` never leaves these rows)"""
+
+    @staticmethod
+    def forward(ctx, X, ids, state):
+        cinv, Ys, dens, norms = state
+        B, N, d = Ys[0].shape
+        idx3 = ids.unsqueeze(2).expand(B, ids.shape[1], d)
+        ctx.saved = (X.detach().contiguous(), ids, idx3, cinv, Ys, dens, norms)
+        return torch.gather(Ys[-1], 1, idx3)
+
+    @staticmethod
+    def backward(ctx, g):
+        X, ids, idx3, cinv, Ys, dens, norms = ctx.saved
+        B, N, d = X.shape
+        R = ids.shape[1]
+        dev = X.device
+        g = g.contiguous()
+        gX = torch.zeros_like(X)
+        nblk = (N + 63) // 64
+        Gn = torch.empty((B, R, d), dtype=torch.float32, device=dev)
+        gd = torch.empty((B, R), dtype=torch.float32, device=dev)
+        part = torch.empty((B, nblk, R, d), dtype=torch.float32, device=dev)
+        for it in range(len(dens) - 1, -1, -1):
+            y_new = torch.gather(Ys[it + 1], 1, idx3)
+            y_prev = torch.gather(Ys[it], 1, idx3)
+            den_r = torch.gather(dens[it], 1, ids)
+            un_r = torch.gather(norms[it], 1, ids)
+            gprev = torch.empty_like(g)
+            call("pn_ms_rows_bwd", _ptr(g), _ptr(y_new), _ptr(y_prev), _ptr(den_r), _ptr(un_r), _ptr(X), B, R, N, d,
+                 _ptr(cinv), _ptr(Gn), _ptr(gd), _ptr(part), _ptr(gprev), _ptr(gX), _stream())
+            g = gprev
+        gX.scatter_add_(1, idx3, g)            # Y_0 = X: the remaining gradient belongs to the same rows of X
+        return gX, None, None
+
+
+def centers_sparse(X_bnd, state, ids_list):
+    """ids_list: per shape a (K_b,) int64 device tensor of kept rows (nms_batched) -> list of (K_b, d) centre tensors,
+    differentiable w.r.t. X through the sparse-row backward.  Slots beyond K_b repeat the shape's first id and are
+    sliced away, i.e. receive a zero gradient and contribute exactly zero."""
+    B = X_bnd.shape[0]
+    R = SPARSE_ROWS
+    rows = []
+    for b in range(B):
+        k = int(ids_list[b].shape[0])
+        # (more than R centres only happens when the caller is about to re-cluster this shape with a larger quantile --
+        # Evaluation.fitting_loss does so above 49 -- and discards these centres: truncate instead of failing)
+        rows.append(torch.cat([ids_list[b], ids_list[b][:1].expand(R - k)]) if k < R else ids_list[b][:R])
+    ids = torch.stack(rows, 0).contiguous()
+    centers = MeanShiftCentersFn.apply(X_bnd, ids, state)
+    return [centers[b, :min(int(ids_list[b].shape[0]), R)] for b in range(B)]
+
+
 def mean_shift_iters(X_bnd, bw_b, iterations):
     """X (B,N,d) unit rows, bw (B,) bandwidths -> shifted points (B,N,d)   [mean_shift.py:45-79, gaussian kernel]"""
     bw = bw_b.detach().to(torch.float32)

@@ -66,10 +66,15 @@ class Evaluation:
         prim_pred_dev = torch.max(primitives_log_prob, 1)[1]                          # (B,N), stays on the device
         with torch.no_grad():
             bws = torch.clamp(_ms.compute_bandwidth_batched(embedding, 10000, quantile), min=_ms.BW_FLOOR)
-        shifted = _ms.mean_shift_iters(embedding, bws, iterations)
+        sparse = _ms.SPARSE_BWD and embedding.shape[2] == 128      # experimental: backward over the centre rows only
+        if sparse:
+            shifted, ms_state = _ms.mean_shift_iters_keep(embedding, bws, iterations)
+        else:
+            shifted = _ms.mean_shift_iters(embedding, bws, iterations)
         with torch.no_grad():
             members = _ms.nearest_center_batched(embedding, shifted)
             ids, labels_dev, _ = _ms.nms_batched(shifted, embedding, bws, members)   # one blocking read-back
+        centers_b = _ms.centers_sparse(embedding, ms_state, ids) if sparse else None
         cluster_np = labels_dev.cpu().numpy()
         bw_host = bws.detach().cpu().numpy()
         self._stage = arena("fit", dev)
@@ -79,7 +84,7 @@ class Evaluation:
         batched = FIT_BATCHED and B > 1      # experimental: the (S,3,3) solves of all shapes in one call per kind
         pending = []
         for b in range(B):
-            center, bandwidth = shifted[b][ids[b]], float(bw_host[b])
+            center, bandwidth = (centers_b[b] if sparse else shifted[b][ids[b]]), float(bw_host[b])
             if np.unique(cluster_np[b]).shape[0] > 49:       # rare: grow the quantile for this shape only (ref :76-83)
                 center, bw_t, cl = self.guard_mean_shift(embedding[b], quantile * 1.2, iterations)
                 cluster_np[b], bandwidth = cl.data.cpu().numpy(), float(bw_t)

@@ -265,3 +265,36 @@ def test_meanshift_host_wiring_matches_abi_arity(monkeypatch, use_tma):
             ["pn_ms_iter_bwd_tma"] * its
     else:
         assert calls == ["pn_ms_iter_fwd_tc"] * its + ["pn_ms_iter_bwd_tc"] * its
+
+
+def test_sparse_row_backward_host_wiring_matches_abi_arity(monkeypatch):
+    """dry run (recording stand-in for the C-ABI) of the experimental sparse-row backward schedule: forward iterations
+    without an autograd node, centres gathered from the last iterate, backward = one pn_ms_rows_bwd per iteration"""
+    import ctypes
+    from pnb200 import cabi, meanshift as pms
+    calls = []
+
+    def fake_call(name, *args):
+        sig = cabi.SIGNATURES[name]
+        assert len(args) == len(sig), f"{name}: {len(args)} arguments, header declares {len(sig)}"
+        for i, (a, t) in enumerate(zip(args, sig)):
+            if t is ctypes.c_void_p:
+                assert a is None or isinstance(a, int), f"{name} arg {i}: expected a pointer"
+            elif t in (ctypes.c_int, ctypes.c_longlong):
+                assert isinstance(a, int) and not isinstance(a, bool), f"{name} arg {i}: expected an int, got {type(a)}"
+        calls.append(name)
+
+    monkeypatch.setattr(pms, "call", fake_call)
+    monkeypatch.setattr(pms, "_need_cuda", lambda *a: None)
+    monkeypatch.setattr(pms, "_stream", lambda: 0)
+    B, N, d, its = 2, 300, 128, 3
+    X = torch.nn.functional.normalize(torch.randn(B, N, d), dim=2).requires_grad_()
+    Y, state = pms.mean_shift_iters_keep(X, torch.tensor([0.3, 0.5]), its)
+    assert Y.shape == (B, N, d) and not Y.requires_grad
+    ids = [torch.tensor([5, 17, 200]), torch.tensor([0, 299])]
+    centers = pms.centers_sparse(X, state, ids)
+    assert [tuple(c.shape) for c in centers] == [(3, d), (2, d)]
+    assert torch.equal(centers[0], Y[0][ids[0]]) and torch.equal(centers[1], Y[1][ids[1]])
+    (centers[0].sum() + centers[1].sum()).backward()
+    assert X.grad is not None and X.grad.shape == X.shape
+    assert calls == ["pn_ms_iter_fwd_tc"] * its + ["pn_ms_rows_bwd"] * its

@@ -388,3 +388,40 @@ def test_inference_clustering_path_vs_port():
     s_iou, p_iou, _, _ = SIOU_matched_segments(gt.numpy(), got, prim, prim, w)
     s_iou_r, p_iou_r, _, _ = SIOU_matched_segments(gt.numpy(), want, prim, prim, w)
     assert abs(s_iou - s_iou_r) < 1e-12 and abs(p_iou - p_iou_r) < 1e-12 and 0.0 <= s_iou <= 1.0
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PN_RUN_EXPERIMENTAL") != "1",
+                    reason="experimental sparse-row mean-shift backward (PN_MS_SPARSE_BWD) not yet run on a GPU; opt in with "
+                           "PN_RUN_EXPERIMENTAL=1")
+@pytest.mark.parametrize("B,N,K", [(2, 1000, 5), (3, 4999, 49)])
+def test_sparse_row_backward_equals_dense_backward(B, N, K):
+    """gradient w.r.t. X of a loss that sees K rows of the last iterate: the sparse-row path (pn_ms_rows_bwd) must equal
+    the dense tcgen05 backward (which spends N^2 work on rows that contribute zero) and the oracle's closed form"""
+    from oracle.port import meanshift as oms
+    from pnb200 import meanshift as pms
+    d, its = 128, 4
+    g = torch.Generator().manual_seed(B * N)
+    X0 = torch.nn.functional.normalize(torch.randn(B, N, d, generator=g), dim=2)
+    bws = torch.tensor([0.3, 0.5, 0.8])[:B]
+    ids = [torch.randperm(N, generator=g)[:K].sort()[0] for _ in range(B)]
+    w = [torch.randn(K, d, generator=g) for _ in range(B)]
+    # dense
+    Xd = X0.clone().cuda().requires_grad_()
+    Y = pms.mean_shift_iters(Xd, bws.cuda(), its)
+    sum((Y[b][ids[b].cuda()] * w[b].cuda()).sum() for b in range(B)).backward()
+    # sparse
+    Xs = X0.clone().cuda().requires_grad_()
+    Yk, state = pms.mean_shift_iters_keep(Xs, bws.cuda(), its)
+    centers = pms.centers_sparse(Xs, state, [i.cuda() for i in ids])
+    sum((centers[b] * w[b].cuda()).sum() for b in range(B)).backward()
+    assert torch.equal(Yk, Y.detach())
+    _close(Xs.grad, Xd.grad, 1e-4, "sparse vs dense d loss / d X")
+    # oracle closed form for shape 0
+    Ys = [t[0].cpu() for t in state[1]]
+    gX = torch.zeros(N, d); gg = w[0].clone()
+    for t in range(its, 0, -1):
+        gg, gx = oms.sparse_rows_backward(gg, Ys[t][ids[0]], Ys[t - 1][ids[0]], state[2][t - 1][0].cpu()[ids[0]],
+                                          state[3][t - 1][0].cpu()[ids[0]], X0[0], float(bws[0]))
+        gX += gx
+    gX[ids[0]] += gg
+    _close(Xs.grad[0], gX, 1e-3, "sparse path vs oracle closed form")

@@ -310,3 +310,45 @@ def test_e2e_port_matches_reference_fitting_loss(golden_dir, variant):
     loss[0].backward()
     if variant == "e2e_nocyl":
         _rel(E.grad, g["gradE"][0], 1e-3, "d loss / d embedding")
+
+
+def test_sparse_row_backward_of_mean_shift_equals_dense_autograd():
+    """the argument behind the product's sparse-row backward (PN_MS_SPARSE_BWD): when the loss depends on K rows of the
+    last iterate only (`center = new_X[indices]`), autograd through ALL N x N kernel matrices gives exactly what the
+    closed-form per-iteration backward restricted to those K rows gives -- and the gradient never leaves those rows"""
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as oms
+    N, K, its, bw = 600, 9, 5, 0.35
+    X0, _ = clustered_embedding(N, 128, 5, 3)
+    rows = torch.tensor([3, 17, 99, 100, 101, 256, 400, 577, 599])
+    w = torch.randn(K, 128, generator=torch.Generator().manual_seed(1))
+    # dense autograd through every iterate (the iteration of oracle/port/meanshift.py::mean_shift_iters, unrolled so that
+    # the intermediate iterates and their gradients can be inspected)
+    X = X0.clone().requires_grad_()
+    Y = X.clone()
+    iterates, dens, norms = [Y], [], []
+    for _ in range(its):
+        Kmat = torch.exp(torch.clamp(-(2.0 - 2.0 * Y @ X.t()) / (bw ** 2) / 2, -75.0, 75.0))
+        den = Kmat.sum(1, keepdim=True)
+        u = Y + ((Kmat @ X) / den - Y)
+        nrm = torch.norm(u, dim=1, p=2, keepdim=True)
+        Y = u / nrm
+        Y.retain_grad()
+        iterates.append(Y); dens.append(den[:, 0].detach()); norms.append(nrm[:, 0].detach())
+    (iterates[-1][rows] * w).sum().backward()
+    mask = torch.ones(N, dtype=torch.bool); mask[rows] = False
+    for t in range(1, its + 1):
+        assert iterates[t].grad[mask].abs().max() == 0.0          # the gradient stays confined to the selected rows
+    # sparse: closed-form backward over the K rows only
+    Xd = X0
+    g = w.clone()
+    gX = torch.zeros_like(Xd)
+    for t in range(its, 0, -1):
+        y_new, y_prev = iterates[t].detach()[rows], iterates[t - 1].detach()[rows]
+        g, gx = oms.sparse_rows_backward(g, y_new, y_prev, dens[t - 1][rows], norms[t - 1][rows], Xd, bw)
+        gX += gx
+        want = iterates[t - 1].grad[rows] if t > 1 else None
+        if want is not None:
+            assert ((g - want).abs().max() / want.abs().max()).item() < 1e-4, t
+    gX[rows] += g                                               # Y_0 = X
+    assert ((gX - X.grad).abs().max() / X.grad.abs().max()).item() < 1e-4
