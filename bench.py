@@ -215,6 +215,8 @@ def run_ours(args):
     cabi.TIMED[dominant] = []
     if FIT_STAGE:
         cabi.TIMED["pn_ms_iter_bwd_tc"] = []
+        cabi.TIMED["pn_ms_iter_fwd_tma"] = []       # experimental variants (PN_MS_TMA=1): timed under the same roofline entry
+        cabi.TIMED["pn_ms_iter_bwd_tma"] = []
     barrier()
     cabi.reset_launch_count()
     from src.primitive_forward import STATS as fit_stats
@@ -231,8 +233,8 @@ def run_ours(args):
     ms_res = ev0.elapsed_time(ev1)
     launches = cabi.launch_count()
     fits_per_step = {k: v / args.steps for k, v in fit_stats.items()}
-    kern_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop(dominant)]
-    bwd_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop("pn_ms_iter_bwd_tc", [])]
+    kern_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop(dominant) + cabi.TIMED.pop("pn_ms_iter_fwd_tma", [])]
+    bwd_ms = [a.elapsed_time(b) for a, b in cabi.TIMED.pop("pn_ms_iter_bwd_tc", []) + cabi.TIMED.pop("pn_ms_iter_bwd_tma", [])]
     # ---- timed: end to end (H2D of inputs + D2H of the loss inside the region)
     hp.model.load_state_dict(snap[0]); hp.opt.load_state_dict(snap[1])
     barrier()
@@ -289,6 +291,15 @@ def run_ours(args):
                             "launches_timed": len(kern_ms), "achieved": fwd_ach, "unit": "TFLOP/s",
                             "frac": (fwd_ach / pk["tf_sustained"]) if fwd_ach else None, "traffic": 127.8e6,
                             "note": "algorithmic flop = 4*N^2*d per shape per iteration; ncu: tensor pipe active 57 %"}}
+        if bwd_launch is None and fwd_ach is not None:
+            # the dense backward did not run (PN_MS_SPARSE_BWD=1: the backward only visits the centre rows): the
+            # dominant kernel of the step is then the forward iteration
+            fw = roof["forward"]
+            roof = {"kernel": fw["kernel"] + ": one fused mean-shift iteration, tcgen05 split-TF32, batch of %d shapes "
+                              "(the dense backward is replaced by the sparse-row backward in this run)" % B,
+                    "bound": "tensor", "achieved": fw["achieved"], "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": fw["frac"], "traffic": fw["traffic"], "peak_source": pk["source"] + " (cuBLAS bf16 dense, sustained)",
+                    "note": fw["note"], "launch_ms": fw["launch_ms"], "launches_timed": fw["launches_timed"]}
     else:
         alg_bytes = B * (N_POINTS * 64 * 4 + N_POINTS * KNN_K * 4)
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else None
