@@ -1,0 +1,113 @@
+"""CPU model of the thread / shared-memory index arithmetic of csrc/meanshift.cu::ms_bwd_sparse_kernel (the experimental
+sparse-row mean-shift backward, written without GPU access): the 256 threads of one CTA are replayed in Python with the
+SAME index expressions as the CUDA source (tile loaders, register-tile orientation, the three P tiles, gemm_pr, the
+partial-sum layout), and the result is compared with the closed form of oracle/port/meanshift.py.  A transposed tile or a
+swapped (i, j) in the kernel's indexing shows up here as a wrong gradient."""
+import numpy as np
+import torch
+
+D, T, NT, PK, PR = 128, 64, 256, 68, 132
+
+
+def load_tile(g, r0, nrows, want_R, want_Kt):
+    """csrc/meanshift.cu::load_tile: thread t loads row r0 + (t & 63), float4 column groups (t >> 6) + 4 i"""
+    R = np.zeros((T, PR), np.float32) if want_R else None
+    Kt = np.zeros((D, PK), np.float32) if want_Kt else None
+    for t in range(NT):
+        r = t & 63
+        ok = (r0 + r) < nrows
+        for i in range(8):
+            c4 = (t >> 6) + 4 * i
+            v = g[r0 + r, 4 * c4:4 * c4 + 4] if ok else np.zeros(4, np.float32)
+            if R is not None:
+                R[r, 4 * c4:4 * c4 + 4] = v
+            if Kt is not None:
+                for u in range(4):
+                    Kt[4 * c4 + u, r] = v[u]
+    return R, Kt
+
+
+def gemm_pr(P, R, ty, tx, acc):
+    """acc[4][8] += P[kk][4ty + i] * R[kk][4tx + j | 64 + 4tx + j - 4]"""
+    for kk in range(T):
+        a = P[kk, 4 * ty:4 * ty + 4]
+        b = np.concatenate([R[kk, 4 * tx:4 * tx + 4], R[kk, 64 + 4 * tx:64 + 4 * tx + 4]])
+        acc += np.outer(a, b)
+
+
+def sparse_cta(Yp, Gn, gd, X, N, c, j0):
+    """one CTA of ms_bwd_sparse_kernel: owns rows j0 .. j0+63 of X; returns (gX rows of the block, partial gY [64][128])"""
+    _, Xt = load_tile(X, j0, N, False, True)
+    _, Yt = load_tile(Yp, 0, T, False, True)
+    _, Gt = load_tile(Gn, 0, T, False, True)
+    P1 = np.zeros((T, PK), np.float32); P2 = np.zeros((T, PK), np.float32); Ps = np.zeros((T, PK), np.float32)
+    for tid in range(NT):
+        ty, tx = tid >> 4, tid & 15
+        s = np.zeros((4, 4), np.float32); g = np.zeros((4, 4), np.float32)          # [jj][ii]
+        for kk in range(D):
+            av = Xt[kk, 4 * ty:4 * ty + 4]; yv = Yt[kk, 4 * tx:4 * tx + 4]; gv = Gt[kk, 4 * tx:4 * tx + 4]
+            s += np.outer(av, yv); g += np.outer(av, gv)
+        p1 = np.zeros((4, 4), np.float32); p2 = np.zeros((4, 4), np.float32)
+        for jj in range(4):
+            jv = (j0 + 4 * ty + jj) < N
+            for ii in range(4):
+                e = (s[jj, ii] - 1.0) * c
+                cl = (e > 75.0) or (e < -75.0)
+                k = np.exp(np.float32(min(max(e, -75.0), 75.0))) if jv else 0.0
+                p2[jj, ii] = k
+                p1[jj, ii] = (g[jj, ii] + gd[4 * tx + ii]) * k * c if (jv and not cl) else 0.0
+        for ii in range(4):
+            P1[4 * tx + ii, 4 * ty:4 * ty + 4] = p1[:, ii]
+            P2[4 * tx + ii, 4 * ty:4 * ty + 4] = p2[:, ii]
+        for jj in range(4):
+            Ps[4 * ty + jj, 4 * tx:4 * tx + 4] = p1[jj, :]
+    Xr, _ = load_tile(X, j0, N, True, False)
+    Yr, _ = load_tile(Yp, 0, T, True, False)
+    Gr, _ = load_tile(Gn, 0, T, True, False)
+    gX = np.zeros((T, D), np.float32); part = np.zeros((T, D), np.float32)
+    for tid in range(NT):
+        ty, tx = tid >> 4, tid & 15
+        o = np.zeros((4, 8), np.float32); q = np.zeros((4, 8), np.float32)
+        gemm_pr(P1, Yr, ty, tx, o); gemm_pr(P2, Gr, ty, tx, o); gemm_pr(Ps, Xr, ty, tx, q)
+        for i in range(4):
+            gX[4 * ty + i, 4 * tx:4 * tx + 4] = o[i, :4]; gX[4 * ty + i, 64 + 4 * tx:64 + 4 * tx + 4] = o[i, 4:]
+            part[4 * ty + i, 4 * tx:4 * tx + 4] = q[i, :4]; part[4 * ty + i, 64 + 4 * tx:64 + 4 * tx + 4] = q[i, 4:]
+    return gX, part
+
+
+def test_sparse_backward_kernel_index_model_matches_closed_form():
+    from oracle.port import meanshift as oms
+    g = torch.Generator().manual_seed(0)
+    N, K, bw = 150, 7, 0.45                      # 3 column blocks, the last one ragged (150 = 2 * 64 + 22)
+    X = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+    rows = torch.tensor([2, 5, 63, 64, 100, 128, 149])
+    Yprev = torch.nn.functional.normalize(X[rows] + 0.05 * torch.randn(K, D, generator=g), dim=1)
+    # one forward iteration for those rows (values the product keeps from the forward kernel)
+    Kmat = torch.exp(torch.clamp((Yprev @ X.t() - 1.0) / bw ** 2, -75.0, 75.0))
+    den = Kmat.sum(1)
+    u = (Kmat @ X) / den[:, None]
+    un = u.norm(dim=1)
+    Ynew = u / un[:, None]
+    gout = torch.randn(K, D, generator=g)
+    want_gY, want_gX = oms.sparse_rows_backward(gout, Ynew, Yprev, den, un, X, bw)
+    # compact 64-row arrays exactly as the host layer builds them: slots beyond K repeat row 0 with a zero gradient
+    pad = lambda t: torch.cat([t, t[:1].expand(T - K, *t.shape[1:])], 0)
+    gpad = torch.cat([gout, torch.zeros(T - K, D)], 0)
+    Yn_p, Yp_p, den_p, un_p = pad(Ynew), pad(Yprev), pad(den), pad(un)
+    # prep (ms_bwd_prep_kernel)
+    dot = (gpad * Yn_p).sum(1, keepdim=True)
+    gu = (gpad - Yn_p * dot) / un_p[:, None]
+    Gn = (gu / den_p[:, None]).numpy().astype(np.float32)
+    gd = (-((gu * Yn_p).sum(1) * un_p) / den_p).numpy().astype(np.float32)
+    c = np.float32(1.0 / bw ** 2)
+    gX = np.zeros((N, D), np.float32); gY = np.zeros((T, D), np.float32)
+    for blk in range((N + T - 1) // T):
+        gx_blk, part = sparse_cta(Yp_p.numpy(), Gn, gd, X.numpy(), N, c, blk * T)
+        n = min(T, N - blk * T)
+        gX[blk * T:blk * T + n] += gx_blk[:n]
+        assert np.abs(gx_blk[n:]).max(initial=0.0) == 0.0            # rows beyond N contribute nothing
+        gY += part
+    assert np.abs(gY[K:]).max() == 0.0                               # padded slots: exactly zero
+    rel = lambda a, b: np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+    assert rel(gY[:K], want_gY.numpy()) < 1e-5
+    assert rel(gX, want_gX.numpy()) < 1e-5
