@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2: everything that was written after the GPU budget of round 1 ran out, in order of risk, each
 # step under its own timeout, all output under gpurun_out/r02_first/.
-#   gpurun --timeout 1500 -- 'bash tools/r02_runbook.sh'
+#   gpurun --timeout 2400 -- 'bash tools/r02_runbook.sh'      (typically ~20 min: tests 5, six bench runs 9, the rest 5)
 # The big one is 24_bench_sparse_bwd.json: the mean-shift backward (55 % of the device time of a step) only has to run for
 # the <= 49 centre rows the loss actually sees (exact).
 # Reading order afterwards: 00_gpu_tests.txt (XPASS = promote the test, XFAIL = read the assertion), 10_tma_cg1.txt,
