@@ -111,3 +111,82 @@ def test_sparse_backward_kernel_index_model_matches_closed_form():
     rel = lambda a, b: np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
     assert rel(gY[:K], want_gY.numpy()) < 1e-5
     assert rel(gX, want_gX.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ TMA-fed operand addressing
+# Model of what the tensor core reads in csrc/meanshift_tma.cu, built from the two layout facts the B200 probes established
+# (profiles/r01_tc_probe.md): (1) a TMA box with CU_TENSOR_MAP_SWIZZLE_128B lands as rows of 128 B whose 16-byte chunk index
+# is XOR-ed with bits 7..9 of the shared-memory address; (2) a K-major kind::tf32 descriptor with layout type 2 / SBO 1024
+# reads row n of a K = 8 step at start + (n >> 3) * 1024 + (n & 7) * 128 + k * 4 with the same XOR applied to the address.
+# The producer's TMA coordinates / destinations and the issuer's descriptor offsets are transcribed from the kernel source;
+# the check is that every MMA of both products sees exactly the rows / columns of the streamed tile it is meant to see,
+# for one CTA and for CTA pairs (each CTA staging half of both operands).
+BN = 32
+PART_BYTES = BN * D * 4
+
+
+def _swz(addr):
+    return addr ^ (((addr >> 7) & 7) << 4)
+
+
+def tma_box(smem, dst, tensor, c0, c1, box0, box1):
+    """tensor [rows][cols] (cols contiguous), box {box0 cols, box1 rows} at (c0, c1) -> smem bytes at dst (zero fill OOB)"""
+    assert dst % 1024 == 0 or (dst % 128 == 0)
+    for r in range(box1):
+        for cc in range(box0):
+            rr, col = c1 + r, c0 + cc
+            v = tensor[rr, col] if (rr < tensor.shape[0] and col < tensor.shape[1]) else 0.0
+            smem[_swz(dst + r * box0 * 4 + cc * 4) // 4] = v
+
+
+def umma_b(smem, start, nrows):
+    """the [nrows][8] B operand of one K = 8 MMA step whose descriptor start address is `start`"""
+    out = np.zeros((nrows, 8), np.float32)
+    for n in range(nrows):
+        for k in range(8):
+            out[n, k] = smem[_swz(start + (n >> 3) * 1024 + (n & 7) * 128 + k * 4) // 4]
+    return out
+
+
+def _check_stream(cg, N, t, X, Xs):
+    rows, slab, part, drows = BN // cg, (BN // cg) * 128, PART_BYTES // cg, D // cg
+    stage = 4 * part
+    Xt, Xst = np.ascontiguousarray(X.T), np.ascontiguousarray(Xs.T)
+    smems = []
+    for rank in range(cg):                                   # tma_producer<CG>
+        smem = np.full(stage // 4, np.nan, np.float32)
+        row = t * BN + rank * rows
+        for sl in range(4):
+            tma_box(smem, sl * slab, X, 32 * sl, row, 32, rows)
+            tma_box(smem, part + sl * slab, Xs, 32 * sl, row, 32, rows)
+        tma_box(smem, 2 * part, Xt, t * BN, rank * drows, 32, drows)
+        tma_box(smem, 3 * part, Xst, t * BN, rank * drows, 32, drows)
+        assert not np.isnan(smem).any()                      # the boxes tile the stage exactly
+        smems.append(smem)
+    tile = np.zeros((BN, D), np.float32); tile_s = np.zeros((BN, D), np.float32)
+    n_valid = max(0, min(BN, N - t * BN))
+    tile[:n_valid] = X[t * BN:t * BN + n_valid]; tile_s[:n_valid] = Xs[t * BN:t * BN + n_valid]
+    for ks in range(D // 8):                                 # first product: N = 32 tile rows, K = d
+        off = (ks >> 2) * slab + (ks & 3) * 32
+        big = np.concatenate([umma_b(s, off, rows) for s in smems], 0)
+        small = np.concatenate([umma_b(s, part + off, rows) for s in smems], 0)
+        assert np.array_equal(big, tile[:, ks * 8:ks * 8 + 8]) and np.array_equal(small, tile_s[:, ks * 8:ks * 8 + 8]), ks
+    for ks in range(BN // 8):                                # second product: N = 128 d rows, K = tile row
+        off = ks * 32
+        big = np.concatenate([umma_b(s, 2 * part + off, drows) for s in smems], 0)
+        small = np.concatenate([umma_b(s, 3 * part + off, drows) for s in smems], 0)
+        assert np.array_equal(big, tile[ks * 8:ks * 8 + 8].T) and np.array_equal(small, tile_s[ks * 8:ks * 8 + 8].T), ks
+
+
+def test_tma_fed_operand_addressing_one_cta_and_cta_pairs():
+    rs = np.random.RandomState(0)
+    N = 150                                                  # 4.7 tiles: the last one is ragged (TMA zero fill)
+    X = rs.randn(N, D).astype(np.float32)
+    Xs = (X - (X.view(np.int32) & -8192).view(np.float32)).astype(np.float32)
+    Np = (N + 31) // 32 * 32
+    Xp = np.zeros((Np, D), np.float32); Xp[:N] = X           # transposed forms are written for Np columns (zeros beyond N)
+    Xsp = np.zeros((Np, D), np.float32); Xsp[:N] = Xs
+    for cg in (1, 2):
+        for t in (0, 3, 4):
+            # (the zero rows of Xp beyond N stand for TMA's out-of-bounds zero fill of the N-row row-major forms)
+            _check_stream(cg, N, t, Xp, Xsp)
