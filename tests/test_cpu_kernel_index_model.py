@@ -190,3 +190,57 @@ def test_tma_fed_operand_addressing_one_cta_and_cta_pairs():
         for t in (0, 3, 4):
             # (the zero rows of Xp beyond N stand for TMA's out-of-bounds zero fill of the N-row row-major forms)
             _check_stream(cg, N, t, Xp, Xsp)
+
+
+# ------------------------------------------------------------------------------------------------ kNN selection algorithm
+def _stream_select(d, k, cap, tau0, lo, hi):
+    """the per-row selection of csrc/knn.cu over candidates lo..hi-1 in tiles of 128 / warps of 32: a candidate is admitted
+    when d > tau; when a ballot would overflow the buffer it is compacted to the best k (value desc, index asc) and tau
+    becomes the k-th best.  Returns (buffer of (value, index), tau)."""
+    buf, tau = [], tau0
+    for j0 in range(lo, hi, 32):
+        js = [j for j in range(j0, min(j0 + 32, hi)) if d[j] > tau]
+        if not js:
+            continue
+        if len(buf) + len(js) > cap:
+            buf.sort(key=lambda e: (-e[0], e[1]))
+            buf = buf[:k]
+            if len(buf) == k:
+                tau = buf[-1][0]
+        buf += [(d[j], j) for j in js]          # (admission was decided with the tau of before the compaction, like the kernel)
+    return buf, tau
+
+
+def _knn_row(d, k, cap, sampled_r=0, sample_m=1024):
+    n = len(d)
+    tau0 = -np.inf
+    if sampled_r:
+        buf, _ = _stream_select(d, sampled_r, cap, -np.inf, 0, min(n, sample_m))
+        buf.sort(key=lambda e: (-e[0], e[1]))
+        tau0 = buf[sampled_r - 1][0] if len(buf) >= sampled_r else -np.inf
+    buf, _ = _stream_select(d, k, cap, tau0, 0, n)
+    if len(buf) < k:                                          # third phase of the kernel: exact re-run from -inf
+        buf, _ = _stream_select(d, k, cap, -np.inf, 0, n)
+    buf.sort(key=lambda e: (-e[0], e[1]))
+    return [j for _, j in buf[:k]]
+
+
+def test_knn_selection_is_exact_for_every_capacity_and_with_the_sampled_threshold():
+    """streaming admission + compaction gives exactly the k best (ties to the lower index) whatever the buffer capacity,
+    and also when the main pass starts from the sampled threshold (PN_KNN_SAMPLE) -- including rows full of duplicates,
+    where the sampled threshold admits fewer than k candidates and the exact re-run has to kick in"""
+    rs = np.random.RandomState(1)
+    k = 80
+    rows = [(-rs.rand(6000)).astype(np.float32),                                   # generic
+            (-np.round(rs.rand(6000) * 40) / 40).astype(np.float32),               # heavy ties
+            np.concatenate([np.zeros(3000, np.float32), -np.ones(3000, np.float32)]),   # two values only
+            (-np.abs(rs.randn(6000)) ** 3).astype(np.float32)]                     # many near-zero distances
+    admitted_fewer = 0
+    for d in rows:
+        want = sorted(range(len(d)), key=lambda j: (-d[j], j))[:k]
+        for cap in (128, 256):
+            assert _knn_row(d, k, cap) == want
+            assert _knn_row(d, k, cap, sampled_r=25) == want
+        buf, _ = _stream_select(d, k, 256, sorted(d[:1024])[-25], 0, len(d))
+        admitted_fewer += len(buf) < k
+    assert admitted_fewer >= 1          # the duplicate-heavy rows do exercise the fallback
