@@ -733,6 +733,7 @@ extern "C" int pn_ms_rows_bwd(const float* gout, const float* Ynew_R, const floa
                "pn_ms_rows_bwd: null pointer");
     PN_REQUIRE(d == D, "pn_ms_rows_bwd: embedding width must be %d (got %d)", D, d);
     PN_REQUIRE(R == T, "pn_ms_rows_bwd: the compact row set is padded to exactly %d rows (got %d)", T, R);
+    PN_REQUIRE(B > 0 && N > 0, "pn_ms_rows_bwd: empty batch (B=%d, N=%d)", B, N);
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * R;
     ms_bwd_prep_kernel<<<cdiv(rows, 8), 256, 0, st>>>(gout, Ynew_R, den_R, unorm_R, rows, ws_Gn, ws_gd);

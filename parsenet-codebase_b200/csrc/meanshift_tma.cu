@@ -763,6 +763,7 @@ extern "C" int pn_ms_prepare_operands(const float* X, int B, int N, int d, int N
                                       void* stream) {
     PN_REQUIRE(X && Xs && Xt && Xst, "pn_ms_prepare_operands: null pointer");
     PN_REQUIRE(d == mstma::D, "pn_ms_prepare_operands: embedding width must be %d (got %d)", mstma::D, d);
+    PN_REQUIRE(B > 0 && N > 0, "pn_ms_prepare_operands: empty batch (B=%d, N=%d)", B, N);
     PN_REQUIRE(Np >= N && Np % 32 == 0, "pn_ms_prepare_operands: Np must be N rounded up to a multiple of 32");
     mstma::ms_prep_operands_kernel<<<dim3(Np / 32, B), 256, 0, (cudaStream_t)stream>>>(X, N, Np, Xs, Xt, Xst);
     PN_COUNT_LAUNCH();
@@ -812,7 +813,10 @@ extern "C" int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* X
                                   void* stream) {
     PN_REQUIRE(Y && X && Xs && Xt && Xst && cinv && Ynew && den && unorm, "pn_ms_iter_fwd_tma: null pointer");
     PN_REQUIRE(d == mstma::D, "pn_ms_iter_fwd_tma: embedding width must be %d (got %d)", mstma::D, d);
+    PN_REQUIRE(B > 0 && N > 0, "pn_ms_iter_fwd_tma: empty batch (B=%d, N=%d)", B, N);
     PN_REQUIRE(Np >= N && Np % 32 == 0, "pn_ms_iter_fwd_tma: Np must be N rounded up to a multiple of 32");
+    PN_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xs) | reinterpret_cast<uintptr_t>(Xt) |
+                reinterpret_cast<uintptr_t>(Xst)) % 16 == 0, "pn_ms_iter_fwd_tma: operand forms must be 16-byte aligned (TMA)");
     const int cg = cta_group();
     CUtensorMap m[4];
     if (!make_forms(m, X, Xs, Xt, Xst, (uint64_t)N, (uint64_t)Np, (uint64_t)B, cg)) {
@@ -842,7 +846,11 @@ extern "C" int pn_ms_iter_bwd_tma(const float* gout, const float* Ynew, const fl
     PN_REQUIRE(gout && Ynew && Yprev && X && Xs && Xt && Xst && den && unorm && cinv && ws_Gn && ws_gd && ws_C && gYprev && gX,
                "pn_ms_iter_bwd_tma: null pointer");
     PN_REQUIRE(d == mstma::D, "pn_ms_iter_bwd_tma: embedding width must be %d (got %d)", mstma::D, d);
+    PN_REQUIRE(B > 0 && N > 0, "pn_ms_iter_bwd_tma: empty batch (B=%d, N=%d)", B, N);
     PN_REQUIRE(Np >= N && Np % 32 == 0, "pn_ms_iter_bwd_tma: Np must be N rounded up to a multiple of 32");
+    PN_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xs) | reinterpret_cast<uintptr_t>(Xt) |
+                reinterpret_cast<uintptr_t>(Xst) | reinterpret_cast<uintptr_t>(ws_C)) % 16 == 0,
+               "pn_ms_iter_bwd_tma: operand forms / workspace must be 16-byte aligned (TMA)");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = pn_ms_bwd_prep_tc(gout, Ynew, den, unorm, B, N, d, ws_Gn, ws_gd, stream);
     if (rc != PN_OK) return rc;
