@@ -244,3 +244,62 @@ def test_knn_selection_is_exact_for_every_capacity_and_with_the_sampled_threshol
         buf, _ = _stream_select(d, k, 256, sorted(d[:1024])[-25], 0, len(d))
         admitted_fewer += len(buf) < k
     assert admitted_fewer >= 1          # the duplicate-heavy rows do exercise the fallback
+
+
+# ------------------------------------------------------------------------------------------------ operand preparation
+def _tf32_small(v):
+    return (v - (v.view(np.int32) & -8192).view(np.float32)).astype(np.float32)
+
+
+def test_operand_preparation_kernels_index_model():
+    """csrc/meanshift_tma.cu::ms_prep_operands_kernel / ms_prep_concat_kernel replayed thread by thread: small split parts,
+    transposes with zero padding, and the interleaved [16 rows of Y | 16 rows of Gn] tiles of the cols-backward kernel"""
+    rs = np.random.RandomState(0)
+    N = 75
+    Np, Nq = (N + 31) // 32 * 32, (N + 15) // 16 * 16
+    X = rs.randn(N, D).astype(np.float32); Y = rs.randn(N, D).astype(np.float32); G = rs.randn(N, D).astype(np.float32)
+    # ---- ms_prep_operands_kernel: grid (Np / 32), 256 threads
+    Xs = np.full((N, D), np.nan, np.float32); Xt = np.full((D, Np), np.nan, np.float32); Xst = np.full((D, Np), np.nan, np.float32)
+    for blk in range(Np // 32):
+        j0 = blk * 32
+        tb = np.zeros((32, D + 1), np.float32); ts = np.zeros((32, D + 1), np.float32)
+        for tid in range(256):
+            for e in range(tid, 32 * D, 256):
+                r, c = e >> 7, e & 127
+                j = j0 + r
+                v = X[j, c] if j < N else np.float32(0)
+                sm = _tf32_small(np.array([v], np.float32))[0]
+                if j < N:
+                    Xs[j, c] = sm
+                tb[r, c] = v; ts[r, c] = sm
+        for tid in range(256):
+            for e in range(tid, D * 32, 256):
+                dd, r = e >> 5, e & 31
+                Xt[dd, j0 + r] = tb[r, dd]; Xst[dd, j0 + r] = ts[r, dd]
+    want_s = _tf32_small(X)
+    assert np.array_equal(Xs, want_s)
+    assert np.array_equal(Xt[:, :N], X.T) and np.array_equal(Xst[:, :N], want_s.T)
+    assert (Xt[:, N:] == 0).all() and (Xst[:, N:] == 0).all()
+    # ---- ms_prep_concat_kernel: grid (Nq / 16), 256 threads
+    rows2 = 2 * Nq
+    C = np.full((rows2, D), np.nan, np.float32); Ct = np.full((D, rows2), np.nan, np.float32)
+    for t in range(Nq // 16):
+        tb = np.zeros((32, D + 1), np.float32)
+        for tid in range(256):
+            for e in range(tid, 32 * D, 256):
+                r, c = e >> 7, e & 127
+                i = 16 * t + (r & 15)
+                src = Y if r < 16 else G
+                v = src[i, c] if i < N else np.float32(0)
+                C[32 * t + r, c] = v
+                tb[r, c] = v
+        for tid in range(256):
+            for e in range(tid, D * 32, 256):
+                dd, r = e >> 5, e & 31
+                Ct[dd, 32 * t + r] = tb[r, dd]
+    assert not np.isnan(C).any() and np.array_equal(Ct, C.T)
+    for t in range(Nq // 16):
+        n = max(0, min(16, N - 16 * t))
+        assert np.array_equal(C[32 * t:32 * t + n], Y[16 * t:16 * t + n])                 # tile rows 0..15: Y   -> S^T columns
+        assert np.array_equal(C[32 * t + 16:32 * t + 16 + n], G[16 * t:16 * t + n])       # tile rows 16..31: Gn -> G^T columns
+        assert (C[32 * t + n:32 * t + 16] == 0).all() and (C[32 * t + 16 + n:32 * t + 32] == 0).all()
