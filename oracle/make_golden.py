@@ -296,7 +296,41 @@ def gen_cfg1():
     np.savez_compressed(os.path.join(OUT, "cfg1.npz"), cp=cp, S=S, rec=rec, rec_k=rec_k, Sn=Sn, rec_n=rec_n, nu=nu, nv=nv)
 
 
-GENS = {"cfg1": gen_cfg1, "knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
+def gen_guard():
+    """the retry loops around mean_shift (more than 49 clusters -> larger quantile): Evaluation.guard_mean_shift
+    (residual_utils.py:69-84, x1.2, 10000 samples) and MeanShift.guard_mean_shift (mean_shift.py:81-96, x2, 5000 samples)
+    on an embedding with 60 tight clusters, so that the first attempts do exceed 49"""
+    from oracle.make_golden_helpers import clustered_embedding
+    RU = rl.ref("src.residual_utils"); MS = rl.ref("src.mean_shift")
+    X, _ = clustered_embedding(1500, 128, 60, 11, spread=0.05)
+    # (the input is regenerated from its seed by the tests: clustered_embedding(1500, 128, 60, 11, spread=0.05))
+    out = {"x_checksum": np.array(float(X.double().sum())), "quantile": np.array(0.002), "iterations": np.array(10),
+           "seed": np.array(4)}
+    ev = RU.Evaluation.__new__(RU.Evaluation); ev.ms = MS.MeanShift()
+    calls = {"n": 0}
+    orig = ev.ms.mean_shift
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return orig(*a, **k)
+
+    ev.ms.mean_shift = counting
+    np.random.seed(4)
+    c, bw, lab = ev.guard_mean_shift(X, 0.002, 10, kernel_type="gaussian")
+    out.update(ev_center=c.numpy(), ev_bw=bw.numpy(), ev_labels=lab.numpy(), ev_attempts=np.array(calls["n"]))
+    m = MS.MeanShift()
+    calls["n"] = 0
+    orig2 = m.mean_shift
+    m.mean_shift = lambda *a, **k: (calls.__setitem__("n", calls["n"] + 1), orig2(*a, **k))[1]
+    np.random.seed(4)
+    c, bw, lab = m.guard_mean_shift(X, 0.002, 10, kernel_type="gaussian")
+    out.update(ms_center=c.numpy(), ms_bw=bw.numpy(), ms_labels=lab.numpy(), ms_attempts=np.array(calls["n"]))
+    print("guard: Evaluation attempts", int(out["ev_attempts"]), "clusters", len(np.unique(out["ev_labels"])),
+          "| MeanShift attempts", int(out["ms_attempts"]), "clusters", len(np.unique(out["ms_labels"])))
+    np.savez_compressed(os.path.join(OUT, "guard.npz"), **out)
+
+
+GENS = {"guard": gen_guard, "cfg1": gen_cfg1, "knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
         "splinenet": gen_splinenet, "e2e": gen_e2e, "e2e_nocyl": lambda: gen_e2e(True, "e2e_nocyl.npz")}
 
 if __name__ == "__main__":

@@ -425,3 +425,29 @@ def test_sparse_row_backward_equals_dense_backward(B, N, K):
         gX += gx
     gX[ids[0]] += gg
     _close(Xs.grad[0], gX, 1e-3, "sparse path vs oracle closed form")
+
+
+@FIRST_RUN
+def test_guard_mean_shift_retry_loops_vs_reference(golden_dir):
+    """the retry loops (more than 49 clusters -> larger quantile) of Evaluation.guard_mean_shift and
+    MeanShift.guard_mean_shift against the unmodified reference's run (tests/golden/guard.npz: three attempts each)"""
+    import os
+    from oracle.make_golden_helpers import clustered_embedding
+    from src.mean_shift import MeanShift
+    from src.residual_utils import Evaluation
+    g = np.load(os.path.join(golden_dir, "guard.npz"))
+    X, _ = clustered_embedding(1500, 128, 60, 11, spread=0.05)
+
+    def canon(l):
+        l = np.asarray(l)
+        _, first = np.unique(l, return_index=True)
+        m = {int(v): i for i, v in enumerate(l[np.sort(first)])}
+        return np.array([m[int(v)] for v in l])
+    ev = Evaluation.__new__(Evaluation)
+    ev.ms = MeanShift()
+    for prefix, fn in (("ev", ev.guard_mean_shift), ("ms", MeanShift().guard_mean_shift)):
+        np.random.seed(int(g["seed"]))
+        with torch.no_grad():
+            c, bw, lab = fn(X.cuda(), float(g["quantile"]), int(g["iterations"]), kernel_type="gaussian")
+        assert abs(float(bw) - float(g[prefix + "_bw"])) <= 1e-5 * float(g[prefix + "_bw"]), prefix
+        np.testing.assert_array_equal(canon(lab.cpu().numpy()), canon(g[prefix + "_labels"]))

@@ -352,3 +352,21 @@ def test_sparse_row_backward_of_mean_shift_equals_dense_autograd():
             assert ((g - want).abs().max() / want.abs().max()).item() < 1e-4, t
     gX[rows] += g                                               # Y_0 = X
     assert ((gX - X.grad).abs().max() / X.grad.abs().max()).item() < 1e-4
+
+
+def test_meanshift_port_retry_loops_match_reference(golden_dir):
+    """more than 49 clusters -> the quantile grows (x1.2 with 10000 samples in Evaluation.guard_mean_shift,
+    residual_utils.py:69-84; x2 with 5000 samples in MeanShift.guard_mean_shift, mean_shift.py:81-96): same number of
+    attempts is implied by the same final bandwidth; labels and centres identical"""
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as oms
+    g = _load(golden_dir, "guard.npz")
+    X, _ = clustered_embedding(1500, 128, 60, 11, spread=0.05)
+    assert abs(float(X.double().sum()) - float(g["x_checksum"])) < 1e-9
+    for prefix, kw in (("ev", dict(num_samples=10000, growth=1.2)), ("ms", dict(num_samples=5000, growth=2))):
+        np.random.seed(int(g["seed"]))
+        c, bw, lab = oms.guard_mean_shift(X, float(g["quantile"]), int(g["iterations"]), **kw)
+        assert abs(float(bw) - float(g[prefix + "_bw"])) <= 1e-6 * float(g[prefix + "_bw"])
+        np.testing.assert_array_equal(lab.numpy(), g[prefix + "_labels"])
+        _rel(c, g[prefix + "_center"], 1e-5, prefix + " centres")
+        assert int(g[prefix + "_attempts"]) >= 2          # the fixture does exercise the retry
