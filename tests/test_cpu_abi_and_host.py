@@ -298,3 +298,63 @@ def test_sparse_row_backward_host_wiring_matches_abi_arity(monkeypatch):
     (centers[0].sum() + centers[1].sum()).backward()
     assert X.grad is not None and X.grad.shape == X.shape
     assert calls == ["pn_ms_iter_fwd_tc"] * its + ["pn_ms_rows_bwd"] * its
+
+
+def test_sparse_row_backward_host_schedule_is_numerically_right_with_reference_kernels(monkeypatch):
+    """the Python half of the experimental sparse-row backward (forward without an autograd node, gather of the centre
+    rows, per-iteration backward over the compact row set, padding slots, final scatter into the rows of X) driven on the
+    CPU by stand-in kernels that implement the C-ABI contracts with the oracle's formulas, writing through the raw
+    pointers they are given: the gradient must equal dense autograd through the port's iteration"""
+    import ctypes
+    from oracle.port import meanshift as oms
+    from pnb200 import meanshift as pms
+
+    def arr(ptr, *shape):
+        n = int(np.prod(shape))
+        return np.ctypeslib.as_array((ctypes.c_float * n).from_address(ptr)).reshape(shape)
+
+    def fake_call(name, *a):
+        if name == "pn_ms_iter_fwd_tc":
+            Yp, Xp, B, N, d, cp, Ynp, dnp, unp, _ = a
+            Y, X, c = arr(Yp, B, N, d), arr(Xp, B, N, d), arr(cp, B)
+            Yn, dn, un = arr(Ynp, B, N, d), arr(dnp, B, N), arr(unp, B, N)
+            for b in range(B):
+                y, x = torch.from_numpy(Y[b].copy()), torch.from_numpy(X[b].copy())
+                K = torch.exp(torch.clamp((y @ x.t() - 1.0) * float(c[b]), -75.0, 75.0))
+                den = K.sum(1)
+                u = y + ((K @ x) / den[:, None] - y)
+                nr = u.norm(dim=1)
+                Yn[b], dn[b], un[b] = (u / nr[:, None]).numpy(), den.numpy(), nr.numpy()
+        elif name == "pn_ms_rows_bwd":
+            gp, ynp, ypp, dnp, unp, Xp, B, R, N, d, cp, _, _, _, gyp, gxp, _ = a
+            g, yn, yp = arr(gp, B, R, d), arr(ynp, B, R, d), arr(ypp, B, R, d)
+            dn, un, X, c = arr(dnp, B, R), arr(unp, B, R), arr(Xp, B, N, d), arr(cp, B)
+            gy, gx = arr(gyp, B, R, d), arr(gxp, B, N, d)
+            for b in range(B):
+                t = [torch.from_numpy(v[b].copy()) for v in (g, yn, yp, dn, un, X)]
+                gyb, gxb = oms.sparse_rows_backward(*t, float(c[b]) ** -0.5)
+                gy[b] = gyb.numpy()
+                gx[b] += gxb.numpy()
+        else:
+            raise AssertionError(name)
+
+    monkeypatch.setattr(pms, "call", fake_call)
+    monkeypatch.setattr(pms, "_need_cuda", lambda *a: None)
+    monkeypatch.setattr(pms, "_stream", lambda: 0)
+    gen = torch.Generator().manual_seed(0)
+    B, N, d, its = 2, 90, 128, 3
+    X0 = torch.nn.functional.normalize(torch.randn(B, N, d, generator=gen), dim=2)
+    bws = torch.tensor([0.4, 0.7])
+    ids = [torch.tensor([1, 40, 41, 89]), torch.tensor([0, 7])]
+    w = [torch.randn(len(i), d, generator=gen) for i in ids]
+    X = X0.clone().requires_grad_()
+    Yfin, state = pms.mean_shift_iters_keep(X, bws, its)
+    centers = pms.centers_sparse(X, state, ids)
+    sum((c * wi).sum() for c, wi in zip(centers, w)).backward()
+    for b in range(B):                                  # dense autograd through the port's iteration
+        xr = X0[b].clone().requires_grad_()
+        yr = oms.mean_shift_iters(xr, bws[b], its)
+        assert ((yr.detach() - Yfin[b]).abs().max() / yr.abs().max()).item() < 1e-5
+        (yr[ids[b]] * w[b]).sum().backward()
+        err = ((X.grad[b] - xr.grad).abs().max() / xr.grad.abs().max()).item()
+        assert err < 1e-4, (b, err)
