@@ -120,19 +120,70 @@ def reset_launch_count():
     lib.pn_reset_launch_count()
 
 
+# ---- device of a launch.  Every pointer argument goes through ops._ptr (which calls note_device) and the stream
+# argument through ops._stream (which calls close_device_set): one launch = one device, and `call` makes that device
+# current for the duration of the launch.  Kernels launched under another current device than the one owning their
+# pointers / stream fail with an invalid-resource-handle error (or, with peer access, race with the torch ops queued on
+# the owning device's stream).
+import threading
+
+_tls = threading.local()
+
+
+def note_device(device):
+    if device.type != "cuda":
+        raise PnError("parsenet_b200 ops need CUDA tensors (there is no CPU fallback)")
+    seen = getattr(_tls, "seen", None)
+    if seen is None:
+        _tls.seen = device.index
+    elif seen != device.index:
+        _tls.mixed = (seen, device.index)
+
+
+def close_device_set():
+    """-> device index shared by the pointers noted since the previous launch (None = no tensor argument)"""
+    dev = getattr(_tls, "seen", None)
+    mixed = getattr(_tls, "mixed", None)
+    _tls.seen = None
+    _tls.mixed = None
+    if mixed is not None:
+        raise PnError("pointer arguments of one launch live on different devices: cuda:%d and cuda:%d" % mixed)
+    _tls.launch_dev = dev
+    return dev
+
+
+def _take_launch_device():
+    dev = getattr(_tls, "launch_dev", None)
+    _tls.launch_dev = None
+    _tls.seen = None            # (a launch without a stream argument must not leak its pointers into the next one)
+    _tls.mixed = None
+    return dev
+
+
 # ---- optional per-entry-point device timing (bench.py uses it for the roofline of the dominant kernel)
 TIMED = {}          # name -> list of (start_event, end_event); register a name to start collecting
 
 
 def call(name, *args):
     fn = getattr(lib, name)
+    dev = _take_launch_device()
+    if dev is not None:
+        import torch
+        if torch.cuda.current_device() != dev:
+            with torch.cuda.device(dev):
+                return _call_on_current(name, fn, args, dev)
+    return _call_on_current(name, fn, args, dev)
+
+
+def _call_on_current(name, fn, args, dev):
     ev = TIMED.get(name)
     if ev is not None:
         import torch
+        st = torch.cuda.current_stream(dev)
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-        a.record()
+        a.record(st)
         rc = fn(*args)
-        b.record()
+        b.record(st)
         ev.append((a, b))
     else:
         rc = fn(*args)

@@ -8,11 +8,20 @@ from .cabi import lib, check, call
 
 
 def _ptr(t):
-    return None if t is None else t.data_ptr()
+    """raw device pointer of a tensor argument; remembers the tensor's device for the launch that follows"""
+    if t is None:
+        return None
+    cabi.note_device(t.device)
+    return t.data_ptr()
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """stream of the launch being assembled = torch's current stream ON THE DEVICE OF ITS POINTER ARGUMENTS (not of
+    torch.cuda.current_device(): the reference's scripts keep tensors on cuda:alt_gpu while the current device is 0,
+    train_parsenet_e2e.py:58).  Must be the last argument evaluated: it closes the argument list of one launch; cabi.call
+    then runs the entry point under that device.  Raises when the pointers of one launch live on different devices."""
+    dev = cabi.close_device_set()
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 def _need_cuda(*ts):

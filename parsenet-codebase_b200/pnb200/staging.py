@@ -38,8 +38,10 @@ class PinnedArena:
         view.numpy()[...] = arr
         self.off += (n + 63) & ~63
         out = view.to(device, non_blocking=True)
+        # (the copy runs on the current stream of the DESTINATION device; record the recycle event there, not on the
+        # stream of torch.cuda.current_device())
         self.last = torch.cuda.Event()
-        self.last.record()
+        self.last.record(torch.cuda.current_stream(out.device))
         return out
 
 

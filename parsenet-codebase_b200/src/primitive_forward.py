@@ -64,7 +64,16 @@ def _load_splinenet(modelname, mode):
     net = DGCNNControlPoints(20, num_points=10, mode=mode)
     state = torch.load(modelname, map_location="cpu")
     net.load_state_dict({k[len("module."):] if k.startswith("module.") else k: v for k, v in state.items()})
-    net.cuda(1 if torch.cuda.device_count() > 1 else 0)
+    # The reference parks both SplineNets on cuda:1 whenever a second GPU exists (primitive_forward.py:100, :411) because
+    # its training script keeps the fit stage on `alt_gpu`.  Under one-process-per-GPU data parallelism that would pile
+    # every rank's copy onto GPU 1 and hand cuda:<rank> activations to cuda:1 weights, so the default here is the
+    # process's current device; Evaluation.fitting_loss moves the decoders to the device of its inputs if they differ.
+    # PN_SPLINENET_DEVICE=reference restores the reference placement.
+    import os
+    if os.environ.get("PN_SPLINENET_DEVICE", "") == "reference":
+        net.cuda(1 if torch.cuda.device_count() > 1 else 0)
+    else:
+        net.cuda(torch.cuda.current_device())
     net.eval()
     return net
 

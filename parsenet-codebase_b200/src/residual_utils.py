@@ -62,6 +62,12 @@ class Evaluation:
         from pnb200.staging import arena
         B = embedding.shape[0]
         dev = embedding.device
+        for t in (points, normals, primitives_log_prob):
+            if isinstance(t, torch.Tensor) and t.device != dev:
+                raise ValueError(f"fitting_loss: inputs on different devices ({t.device} vs embedding on {dev})")
+        for net in (self.fitter.closed_control_decoder, self.fitter.open_control_decoder):
+            if next(net.parameters()).device != dev:       # frozen decoders follow the data (see _load_splinenet)
+                net.to(dev)
         embedding = l2_normalize(embedding)
         prim_pred_dev = torch.max(primitives_log_prob, 1)[1]                          # (B,N), stays on the device
         with torch.no_grad():

@@ -253,6 +253,7 @@ def test_meanshift_host_wiring_matches_abi_arity(monkeypatch, use_tma):
     monkeypatch.setattr(pms, "call", fake_call)
     monkeypatch.setattr(pms, "_need_cuda", lambda *a: None)
     monkeypatch.setattr(pms, "_stream", lambda: 0)
+    monkeypatch.setattr(pms, "_ptr", lambda t: None if t is None else t.data_ptr())     # (CPU tensors in a dry run)
     monkeypatch.setattr(pms, "USE_TMA", use_tma)
     B, N, d, its = 2, 70, 128, 3
     X = torch.nn.functional.normalize(torch.randn(B, N, d), dim=2).requires_grad_()
@@ -287,6 +288,7 @@ def test_sparse_row_backward_host_wiring_matches_abi_arity(monkeypatch):
     monkeypatch.setattr(pms, "call", fake_call)
     monkeypatch.setattr(pms, "_need_cuda", lambda *a: None)
     monkeypatch.setattr(pms, "_stream", lambda: 0)
+    monkeypatch.setattr(pms, "_ptr", lambda t: None if t is None else t.data_ptr())     # (CPU tensors in a dry run)
     B, N, d, its = 2, 300, 128, 3
     X = torch.nn.functional.normalize(torch.randn(B, N, d), dim=2).requires_grad_()
     Y, state = pms.mean_shift_iters_keep(X, torch.tensor([0.3, 0.5]), its)
@@ -341,6 +343,7 @@ def test_sparse_row_backward_host_schedule_is_numerically_right_with_reference_k
     monkeypatch.setattr(pms, "call", fake_call)
     monkeypatch.setattr(pms, "_need_cuda", lambda *a: None)
     monkeypatch.setattr(pms, "_stream", lambda: 0)
+    monkeypatch.setattr(pms, "_ptr", lambda t: None if t is None else t.data_ptr())     # (CPU tensors in a dry run)
     gen = torch.Generator().manual_seed(0)
     B, N, d, its = 2, 90, 128, 3
     X0 = torch.nn.functional.normalize(torch.randn(B, N, d, generator=gen), dim=2)
@@ -358,3 +361,19 @@ def test_sparse_row_backward_host_schedule_is_numerically_right_with_reference_k
         (yr[ids[b]] * w[b]).sum().backward()
         err = ((X.grad[b] - xr.grad).abs().max() / xr.grad.abs().max()).item()
         assert err < 1e-4, (b, err)
+
+
+def test_launch_device_bookkeeping_rejects_mixed_devices_and_cpu_pointers():
+    """every pointer of one launch must live on ONE cuda device; the launch then runs on that device's stream (ADVICE r1:
+    the reference's scripts keep the fit stage on cuda:alt_gpu while the current device is cuda:0)"""
+    from pnb200 import cabi
+    cabi.close_device_set()
+    cabi.note_device(torch.device("cuda", 1)); cabi.note_device(torch.device("cuda", 1))
+    assert cabi.close_device_set() == 1
+    assert cabi.close_device_set() is None                      # nothing noted since the last launch
+    cabi.note_device(torch.device("cuda", 0)); cabi.note_device(torch.device("cuda", 1))
+    with pytest.raises(cabi.PnError, match="different devices"):
+        cabi.close_device_set()
+    assert cabi.close_device_set() is None                      # the failed launch does not leak into the next one
+    with pytest.raises(cabi.PnError, match="no CPU fallback"):
+        cabi.note_device(torch.device("cpu"))
