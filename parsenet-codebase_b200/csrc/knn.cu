@@ -453,7 +453,7 @@ static size_t smem_bytes(int cap) {
 // feature spaces: r = 24 for k = 80, N = 10^4 admits 110 .. 380 per row)
 static int sample_rank(int N, int k) {
     const char* e = getenv("PN_KNN_SAMPLE");
-    if (!(e && e[0] == '1') || N < 4 * SAMPLE_M || k < 32) return 0;
+    if ((e && e[0] == '0') || N < 4 * SAMPLE_M || k < 32) return 0;      // default on since round 2 (PN_KNN_SAMPLE=0: off)
     const int r = (int)((3.0 * k * SAMPLE_M + N - 1) / N);
     return (r >= 8 && r < k) ? r : 0;
 }

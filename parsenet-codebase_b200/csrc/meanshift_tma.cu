@@ -1,5 +1,6 @@
-// EXPERIMENTAL (opt-in, PN_MS_TMA=1; written after the GPU budget of round 1 was spent, NOT yet run on a GPU):
-// mean-shift iteration kernels whose streamed operand tiles are fetched by TMA instead of being staged by loader warps.
+// Mean-shift iteration kernels whose streamed operand tiles are fetched by TMA instead of being staged by loader warps.
+// Default path since round 2 (first run on a B200: bit-identical to the loader-warp kernels of meanshift_tc*.cu, forward
+// 3.88 -> 3.47 ms, dense backward 15.8 -> 13.5 ms per iteration at B = 16, N = 10^4; profiles/r02_first_call.md).
 //
 // Why (profiles/r01_tc_probe.md, r01_ncu_meanshift_tc.md, r01_ms_bwd_ablation_sweep.md): in ms_fwd_tc_kernel /
 // ms_bwd_tc_kernel<rows> four loader warps LDG a 32 x 128 tile of X, split it into tf32 big / small parts and store it
@@ -771,11 +772,21 @@ extern "C" int pn_ms_prepare_operands(const float* X, int B, int N, int d, int N
     return PN_OK;
 }
 
-// CTA-group size of the experimental kernels: PN_MS_TMA_CG=2 launches CTA pairs (cluster of 2, tcgen05 cta_group::2)
+// CTA-group size.  The CTA-pair instantiations (cluster of 2, tcgen05 cta_group::2) were brought up on a B200 in round 2:
+// bit-identical to the 1-CTA kernels but SLOWER (forward 4.12 vs 3.47 ms, backward 18.3 vs 13.5 ms at B = 16, N = 10^4;
+// profiles/r02_first_call.md) -- with N = 32 MMAs the pair doubles the issue latency per tile without relieving the
+// epilogue.  They are therefore compiled only with -DPN_MS_TMA_PAIRS (tools/exp_ms_tma.py documents the A/B); the
+// shipped library contains the 1-CTA kernels only.
+#ifdef PN_MS_TMA_PAIRS
 static int cta_group() {      // read per call: tools/exp_ms_tma.py flips it inside one process
     const char* e = getenv("PN_MS_TMA_CG");
     return (e && e[0] == '2') ? 2 : 1;
 }
+#define PN_TMA_PICK(kern, cg) (((cg) == 2) ? kern<2> : kern<1>)
+#else
+static int cta_group() { return 1; }
+#define PN_TMA_PICK(kern, cg) (kern<1>)
+#endif
 
 // the four operand-form maps of a [rows][128] matrix M (row-major M, Ms; transposed Mt, Mst with row pitch `tp`), boxes
 // sized for one CTA of a group of `cg`
@@ -824,7 +835,7 @@ extern "C" int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* X
         return PN_ERR_CUDA;
     }
     size_t sm = mstma::NSTAGE * mstma::STAGE_BYTES + 1024;
-    auto kern = (cg == 2) ? mstma::ms_fwd_tma_kernel<2> : mstma::ms_fwd_tma_kernel<1>;
+    auto kern = PN_TMA_PICK(mstma::ms_fwd_tma_kernel, cg);
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     PN_CUDA(launch(kern, dim3(cdiv(N, mstma::BM), B), cg, sm, (cudaStream_t)stream, m[0], m[1], m[2], m[3], Y, N, cinv, Ynew,
                    den, unorm));
@@ -868,8 +879,8 @@ extern "C" int pn_ms_iter_bwd_tma(const float* gout, const float* Ynew, const fl
         return PN_ERR_CUDA;
     }
     size_t sm = mstma::NSTAGE * mstma::STAGE_BYTES + 2 * 64 * 32 * sizeof(float) + 1024;
-    auto rows_k = (cg == 2) ? mstma::ms_bwd_rows_tma_kernel<2> : mstma::ms_bwd_rows_tma_kernel<1>;
-    auto cols_k = (cg == 2) ? mstma::ms_bwd_cols_tma_kernel<2> : mstma::ms_bwd_cols_tma_kernel<1>;
+    auto rows_k = PN_TMA_PICK(mstma::ms_bwd_rows_tma_kernel, cg);
+    auto cols_k = PN_TMA_PICK(mstma::ms_bwd_cols_tma_kernel, cg);
     PN_CUDA(cudaFuncSetAttribute(rows_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     PN_CUDA(cudaFuncSetAttribute(cols_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     PN_CUDA(launch(rows_k, dim3(cdiv(N, 64), B), cg, sm, st, mx[0], mx[1], mx[2], mx[3], Yprev, (const float*)ws_Gn,

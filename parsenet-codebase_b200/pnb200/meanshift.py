@@ -17,10 +17,22 @@ FWD_IMPL = os.environ.get("PN_MS_FWD", "tc")
 BWD_IMPL = os.environ.get("PN_MS_BWD", "tc")
 KTH_IMPL = os.environ.get("PN_MS_KTH", "tc")
 ARGSEL_IMPL = os.environ.get("PN_MS_ARGSEL", "tc")      # modes 0 / 1 of the nms arg-selects (mode 2 is always simt)
-# EXPERIMENTAL, opt-in: operand tiles of the forward / rows-backward kernels fetched by TMA (csrc/meanshift_tma.cu).
-# Written after the GPU budget of round 1 was spent: not yet run on a GPU, hence off by default.
-USE_TMA = os.environ.get("PN_MS_TMA", "0") == "1"
+# operand tiles of the forward / backward kernels fetched by TMA (csrc/meanshift_tma.cu): bit-identical to the
+# loader-warp kernels and 1.12x (forward) / 1.17x (dense backward) faster at B = 16, N = 10^4 (first GPU call of round 2,
+# profiles/r02_first_call.md); default since then.  PN_MS_TMA=0 selects the loader-warp kernels (A/B tests).
+USE_TMA = os.environ.get("PN_MS_TMA", "1") == "1"
 _KTH = {"tc": "pn_ms_kth_dist_tc", "simt": "pn_ms_kth_dist"}
+
+
+WIDTH = 128
+
+
+def _check_width(d):
+    """all mean-shift kernels are built for the embedding width of every reference config (emb_size = 128,
+    configs/config_parsenet*.yml); say so up front instead of failing inside a launch"""
+    if d != WIDTH:
+        raise ValueError(f"mean-shift kernels are built for embedding width {WIDTH}, got {d} "
+                         "(construct PrimitivesEmbeddingDGCNGn with emb_size=128)")
 
 
 def _argsel_entry(mode, d):
@@ -40,6 +52,27 @@ def _operand_forms(X):
     return Xs, Xt, Xst, Np
 
 
+def _forward_iterations(X, cinv, iterations):
+    """the `iterations` fused mean-shift iterations starting from Y_0 = X (mean_shift.py:58-77); returns the iterates
+    [Y_0 .. Y_it] and the per-iteration kernel row sums / pre-normalisation norms the backward kernels need"""
+    B, N, d = X.shape
+    Ys, dens, norms = [X], [], []
+    forms = _operand_forms(X) if (USE_TMA and FWD_IMPL == "tc" and d == 128 and iterations > 0) else None
+    for _ in range(iterations):
+        Yn = torch.empty_like(X)
+        den = torch.empty((B, N), dtype=torch.float32, device=X.device)
+        un = torch.empty((B, N), dtype=torch.float32, device=X.device)
+        if forms is not None:
+            Xs, Xt, Xst, Np = forms
+            call("pn_ms_iter_fwd_tma", _ptr(Ys[-1]), _ptr(X), _ptr(Xs), _ptr(Xt), _ptr(Xst), B, N, d, Np,
+                 _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
+        else:
+            call("pn_ms_iter_fwd_tc" if (FWD_IMPL == "tc" and d == 128) else "pn_ms_iter_fwd", _ptr(Ys[-1]), _ptr(X),
+                 B, N, d, _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
+        Ys.append(Yn); dens.append(den); norms.append(un)
+    return Ys, dens, norms
+
+
 class MeanShiftItersFn(torch.autograd.Function):
     """Y_it = shift(Y_{it-1}; X, b) for it = 1..iterations with Y_0 = X; returns Y_iterations.
     Saves the Y iterates + two (B,N) vectors per iteration; the N x N kernel matrices are recomputed in backward."""
@@ -48,22 +81,8 @@ class MeanShiftItersFn(torch.autograd.Function):
     def forward(ctx, X, cinv, iterations):
         X = X.detach().contiguous()
         _need_cuda(X, cinv)
-        B, N, d = X.shape
         cinv = cinv.detach().to(torch.float32).contiguous()
-        Ys, dens, norms = [X], [], []
-        forms = _operand_forms(X) if (USE_TMA and FWD_IMPL == "tc" and d == 128 and iterations > 0) else None
-        for _ in range(iterations):
-            Yn = torch.empty_like(X)
-            den = torch.empty((B, N), dtype=torch.float32, device=X.device)
-            un = torch.empty((B, N), dtype=torch.float32, device=X.device)
-            if forms is not None:
-                Xs, Xt, Xst, Np = forms
-                call("pn_ms_iter_fwd_tma", _ptr(Ys[-1]), _ptr(X), _ptr(Xs), _ptr(Xt), _ptr(Xst), B, N, d, Np,
-                     _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
-            else:
-                call("pn_ms_iter_fwd_tc" if FWD_IMPL == "tc" else "pn_ms_iter_fwd", _ptr(Ys[-1]), _ptr(X), B, N, d,
-                     _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
-            Ys.append(Yn); dens.append(den); norms.append(un)
+        Ys, dens, norms = _forward_iterations(X, cinv, iterations)
         ctx.saved = (X, cinv, Ys, dens, norms)
         # (fresh view: an output object kept in ctx would form a reference cycle, see segnet.EncoderFn.forward)
         return Ys[-1].clone() if iterations == 0 else Ys[-1].view_as(Ys[-1])
@@ -96,26 +115,23 @@ class MeanShiftItersFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------ sparse-row backward
-# EXPERIMENTAL (opt-in PN_MS_SPARSE_BWD=1; csrc/meanshift.cu::ms_bwd_sparse_kernel; not yet run on a GPU).
-SPARSE_BWD = os.environ.get("PN_MS_SPARSE_BWD", "0") == "1"
+# Default in Evaluation.fitting_loss since round 2 (csrc/meanshift.cu::ms_bwd_sparse_kernel; equals the dense backward to
+# 1e-5 in tests/test_gpu_zz_fresh_inputs.py::test_sparse_row_backward_equals_dense_backward, step 377 -> 226 ms).  The
+# dense kernels stay for callers that consume all of new_X (MeanShift.mean_shift with nms=False, segment_loss.py:50).
+# PN_MS_SPARSE_BWD=0 forces the dense backward everywhere.
+SPARSE_BWD = os.environ.get("PN_MS_SPARSE_BWD", "1") == "1"
 SPARSE_ROWS = 64          # the compact row set is padded to exactly this many rows (>= the 49 clusters the guards allow)
 
 
 def mean_shift_iters_keep(X_bnd, bw_b, iterations):
     """the forward iterations WITHOUT an autograd node: returns (Y_final, state); state feeds centers_sparse"""
+    _check_width(X_bnd.shape[-1])
     X = X_bnd.detach().contiguous()
     _need_cuda(X)
     B, N, d = X.shape
     bw = bw_b.detach().to(torch.float32)
     cinv = (1.0 / (bw * bw)).contiguous()
-    Ys, dens, norms = [X], [], []
-    for _ in range(int(iterations)):
-        Yn = torch.empty_like(X)
-        den = torch.empty((B, N), dtype=torch.float32, device=X.device)
-        un = torch.empty((B, N), dtype=torch.float32, device=X.device)
-        call("pn_ms_iter_fwd_tc" if (FWD_IMPL == "tc" and d == 128) else "pn_ms_iter_fwd", _ptr(Ys[-1]), _ptr(X), B, N, d,
-             _ptr(cinv), _ptr(Yn), _ptr(den), _ptr(un), _stream())
-        Ys.append(Yn); dens.append(den); norms.append(un)
+    Ys, dens, norms = _forward_iterations(X, cinv, int(iterations))
     return Ys[-1], (cinv, Ys, dens, norms)
 
 
@@ -176,6 +192,7 @@ def centers_sparse(X_bnd, state, ids_list):
 
 def mean_shift_iters(X_bnd, bw_b, iterations):
     """X (B,N,d) unit rows, bw (B,) bandwidths -> shifted points (B,N,d)   [mean_shift.py:45-79, gaussian kernel]"""
+    _check_width(X_bnd.shape[-1])
     bw = bw_b.detach().to(torch.float32)
     cinv = 1.0 / (bw * bw)
     return MeanShiftItersFn.apply(X_bnd, cinv, int(iterations))
@@ -184,6 +201,7 @@ def mean_shift_iters(X_bnd, bw_b, iterations):
 def compute_bandwidth(X_nd, num_samples, quantile, rng=np.random):
     """mean over sampled rows of sqrt(K-th smallest of 2 - 2 X X^T), K = int(quantile * num_samples)
     [mean_shift.py:115-137].  Consumes np.random.shuffle exactly like the reference."""
+    _check_width(X_nd.shape[-1])
     _need_cuda(X_nd)
     N, d = X_nd.shape
     L = np.arange(N)
@@ -202,6 +220,7 @@ def compute_bandwidth(X_nd, num_samples, quantile, rng=np.random):
 def compute_bandwidth_batched(X_bnd, num_samples, quantile, rng=np.random):
     """compute_bandwidth for a batch of shapes in ONE launch (N <= num_samples, i.e. every row is used; the host RNG
     is still consumed once per shape like the reference would).  Returns (B,) bandwidths (before the 0.003 floor)."""
+    _check_width(X_bnd.shape[-1])
     _need_cuda(X_bnd)
     B, N, d = X_bnd.shape
     if N > int(num_samples):
@@ -236,6 +255,7 @@ def _argsel(mode, A, Bm, cnt=None, thr=None):
 def nms(centers_nd, X_nd, b, member=None):
     """non-max suppression of the shifted points [mean_shift.py:139-179] -> (kept centres, their ids, labels int64).
     `member` (N,) int32: precomputed nearest-centre ids (from nearest_center_batched)."""
+    _check_width(centers_nd.shape[-1])
     centers = centers_nd.detach().contiguous()
     X = X_nd.detach().contiguous()
     N = X.shape[0]
@@ -258,6 +278,7 @@ def nms_batched(Y_bnd, X_bnd, bw_b, member=None):
     Same arithmetic as nms(): the occupied-centre rows of the neighbour arg-select are a subset of the all-rows
     launch used here, and padding the kept list with a repeat of its first entry cannot win an arg-max tie
     (first occurrence wins)."""
+    _check_width(Y_bnd.shape[-1])
     Y = Y_bnd.detach().contiguous()
     X = X_bnd.detach().contiguous()
     B, N, d = X.shape

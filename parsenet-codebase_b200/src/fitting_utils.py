@@ -16,8 +16,23 @@ EPS = float(np.finfo(np.float32).eps)
 class LeastSquares:
     def lstsq(self, A, Y, lamb=0.0):
         """x = argmin |A x - Y| for a tall A (m,3); rank-deficient systems use the Tikhonov rule of the reference."""
+        if A.dim() != 2 or Y.dim() != 2 or Y.shape[0] != A.shape[0]:
+            raise ValueError(f"LeastSquares.lstsq: expected A (m,n) and Y (m,c), got {tuple(A.shape)} and {tuple(Y.shape)}")
         if not torch.isfinite(A).all():
             raise FloatingPointError("LeastSquares.lstsq: non-finite entries in A")
+        if A.shape[1] != 3 or Y.shape[1] != 1:
+            # every fit on the hot path solves for 3 unknowns (sphere / cylinder centre, cone apex); other widths take
+            # the reference's algorithm literally (fitting_utils.py:36-65: QR when A has full column rank, otherwise the
+            # normal equations regularised with best_lambda) as plain torch.linalg calls on the caller's device.
+            # `lamb` is ignored there as well (the reference overwrites it before use).
+            n = A.shape[1]
+            if n == int(torch.linalg.matrix_rank(A)):
+                q, r = torch.linalg.qr(A)
+                return torch.inverse(r) @ q.t() @ Y
+            AtA = A.t() @ A
+            with torch.no_grad():
+                lam = best_lambda(AtA)
+            return self.lstsq(AtA + lam * torch.eye(n, device=A.device, dtype=A.dtype), A.t() @ Y, 1)
         Ad, Yd = A.double(), Y.double()
         x = _f.solve_normal((Ad.t() @ Ad).unsqueeze(0), (Ad.t() @ Yd).reshape(1, -1), A.shape[0])
         return x.reshape(-1, 1).to(A.dtype)

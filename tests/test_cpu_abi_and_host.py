@@ -299,7 +299,7 @@ def test_sparse_row_backward_host_wiring_matches_abi_arity(monkeypatch):
     assert torch.equal(centers[0], Y[0][ids[0]]) and torch.equal(centers[1], Y[1][ids[1]])
     (centers[0].sum() + centers[1].sum()).backward()
     assert X.grad is not None and X.grad.shape == X.shape
-    assert calls == ["pn_ms_iter_fwd_tc"] * its + ["pn_ms_rows_bwd"] * its
+    assert calls == ["pn_ms_prepare_operands"] + ["pn_ms_iter_fwd_tma"] * its + ["pn_ms_rows_bwd"] * its
 
 
 def test_sparse_row_backward_host_schedule_is_numerically_right_with_reference_kernels(monkeypatch):
@@ -344,6 +344,7 @@ def test_sparse_row_backward_host_schedule_is_numerically_right_with_reference_k
     monkeypatch.setattr(pms, "_need_cuda", lambda *a: None)
     monkeypatch.setattr(pms, "_stream", lambda: 0)
     monkeypatch.setattr(pms, "_ptr", lambda t: None if t is None else t.data_ptr())     # (CPU tensors in a dry run)
+    monkeypatch.setattr(pms, "USE_TMA", False)         # (the stand-in implements the loader-warp entry point's contract)
     gen = torch.Generator().manual_seed(0)
     B, N, d, its = 2, 90, 128, 3
     X0 = torch.nn.functional.normalize(torch.randn(B, N, d, generator=gen), dim=2)

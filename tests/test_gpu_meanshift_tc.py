@@ -160,14 +160,11 @@ print("LITE_WORST", worst)
     assert 1e-6 < worst < 1e-3, worst          # > 1e-6: the variant really ran (the exact split sits at ~1e-6)
 
 
-@pytest.mark.skipif(os.environ.get("PN_RUN_EXPERIMENTAL") != "1",
-                    reason="experimental kernels (csrc/meanshift_tma.cu) have not been brought up on a GPU yet; "
-                           "opt in with PN_RUN_EXPERIMENTAL=1 (they trap instead of hanging, still run under a timeout)")
-@pytest.mark.parametrize("cg", [1, 2])
-@pytest.mark.parametrize("B,N", [(2, 1000), (3, 4999)])
+@pytest.mark.parametrize("cg", [1])
+@pytest.mark.parametrize("B,N", [(2, 1000), (3, 4999), (1, 33)])
 def test_tma_fed_kernels_match_default_tc_kernels(B, N, cg, monkeypatch):
-    """TMA-fed forward / backward kernels (1 CTA, and CTA pairs with cta_group::2): same products in the same order as the
-    default tcgen05 kernels"""
+    """TMA-fed forward / backward kernels (the default path) against the loader-warp tcgen05 kernels: same products in the
+    same order.  (The CTA-pair variant, cg = 2, lost the A/B on B200 and is compiled only with -DPN_MS_TMA_PAIRS.)"""
     from pnb200.cabi import call
     monkeypatch.setenv("PN_MS_TMA_CG", str(cg))
     d = 128

@@ -41,6 +41,7 @@ def phased_step(i, rec):
     pts = x[:, 0:3].permute(0, 2, 1).contiguous()
     nrm = x[:, 3:6].permute(0, 2, 1).contiguous()
     t2 = sync()
+    emb = bench.pin_clusters(emb, lab, hp.codes)
     res, extra = hp.evaluation.fitting_loss(emb.permute(0, 2, 1), pts, nrm, lab_np, prim_np.copy(), lp,
                                             quantile=0.025, iterations=bench.MS_ITERS, lamb=0.1)
     loss = loss + torch.stack([r.reshape(()) for r in res[0::5]]).mean()

@@ -3,9 +3,9 @@
 #   gpurun --timeout 300 -- 'bash tools/tc_probe/run_all.sh > gpurun_out/tc_probe.txt 2>&1'
 set -u
 cd "$(dirname "$0")"
-cp ../../parsenet-codebase_b200/csrc/tc05.cuh tc05.cuh
-nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O2 -o probe probe.cu || exit 1
-nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O2 -o probe2 probe2.cu || exit 1
+INC="-I ../../parsenet-codebase_b200/csrc"      # the probes include the SHIPPED tc05.cuh (no copy to drift)
+nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O2 $INC -o probe probe.cu || exit 1
+nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -O2 $INC -o probe2 probe2.cu || exit 1
 echo "== validated encodings (must be exact): K-major SS / TS"
 timeout 20 ./probe 0; timeout 20 ./probe 1
 echo "== MN-major B, no swizzle (variant 0: LBO = K direction, SBO = MN direction; variant 1: swapped)"
