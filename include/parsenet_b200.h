@@ -51,6 +51,18 @@ int pn_edge_bwd(const float* PQ, long long ldpq, const float* dy, const float* e
 int pn_fit_moments_fwd(const float* P, const float* Nr, const float* W, long long ldw, int S, int start, int step, int m, float eps, double* mom_zeroed, void* stream);
 /* replaces: autograd of the weighted reductions w.r.t. the membership weights */
 int pn_fit_moments_bwd(const float* P, const float* Nr, const float* W, long long ldw, int S, int start, int step, int m, float eps, const float* gmom, float* gW, long long ldg, void* stream);
+/* the same two kernels over all shapes of a step in one launch (gridDim.y = shape): P / Nr [B][N][3], W [B][N][ldw] with
+   column = segment slot, mom [B][S][55]; replaces the per-shape python loop of Evaluation.fitting_loss src/residual_utils.py:86-208 */
+int pn_fit_moments_fwd_batched(const float* P, const float* Nr, const float* W, long long ldw, int B, int N, int S, int start, int step, int m, float eps, double* mom_zeroed, void* stream);
+int pn_fit_moments_bwd_batched(const float* P, const float* Nr, const float* W, long long ldw, int B, int N, int S, int start, int step, int m, float eps, const float* gmom, float* gW, long long ldg, void* stream);
+
+/* ---- fitsolve.cu ---- */
+/* replaces: the per-segment 3x3 algebra of Fit.fit_{plane,sphere,cylinder,cone}_torch src/primitive_forward.py:708-831 +
+   LeastSquares.lstsq / best_lambda src/fitting_utils.py:36-85 + CustomSVD and its backward rule :385-455, for every segment
+   slot of every shape in ONE launch: mom [S][55] -> par [S][8] (residual-kernel layout) and jac [S][8][55] = d par / d mom
+   (forward mode; the backward is grad_mom = grad_par . jac); kind -1 none, 0 plane, 1 sphere, 2 cylinder, 3 cone;
+   bad[s] = 1 for a degenerate cone (cond > 1e5, :818-823) */
+int pn_fit_solve(const double* mom, const int* kind, int S, int rows, double* par, double* jac, float* bad, void* stream);
 
 /* ---- knn.cu ---- */
 /* replaces: src/PointNet.py:9-26 (knn), :29-69 (knn_points_normals); src/model.py:9-22 */
@@ -139,6 +151,8 @@ int pn_triplet_bwd(const float* E, long long lde, int D, const int* a_idx, const
 /* ---- primitives.cu ---- */
 /* replaces: ComputePrimitiveDistance.distance_from_{plane,sphere,cylinder,cone}: src/primitives.py:100-195 */
 int pn_residual_fwd(const float* P, const int* seg, int N, const int* type, const float* par, int S, float* sumf_zeroed, float* jac_zeroed, float* cnt_zeroed, void* stream);
+/* all shapes of a step in one launch: P [B][N][3], seg [B][N] = slot of the point's segment or -1, tables [B][S] by slot */
+int pn_residual_fwd_batched(const float* P, const int* seg, int B, int N, const int* type, const float* par, int S, float* sumf_zeroed, float* jac_zeroed, float* cnt_zeroed, void* stream);
 
 /* ---- small3.cu ---- */
 /* replaces: CustomSVD (torch.svd of the weighted (m,3) matrix, via the eigen-decomposition of its 3x3 Gram matrix): src/fitting_utils.py:420-455; torch.eig in pca_torch :585 */

@@ -42,11 +42,16 @@ __device__ __forceinline__ int wdeg(int k) { return k < 13 ? 1 : (k < 35 ? 2 : (
 
 // P, Nr: [N][3]; W: [N][ldw] (column s = segment); point set: n = start + i*step, i < m; w = W[n][s] + eps
 // mom: [S][NM] double (zero-initialised)
+// blockIdx.y = shape of a batch: P / Nr advance by sP floats, W by sW floats, mom by S * NM doubles per shape
 __global__ void __launch_bounds__(SEG_T) moments_fwd_kernel(const float* __restrict__ P, const float* __restrict__ Nr,
                                                             const float* __restrict__ W, long long ldw, int S,
                                                             int start, int step, int m, float eps,
-                                                            double* __restrict__ mom) {
+                                                            double* __restrict__ mom, long long sP, long long sW) {
     __shared__ float sp[PTS][3], sn[PTS][3];
+    P += blockIdx.y * sP;
+    if (Nr) Nr += blockIdx.y * sP;
+    W += blockIdx.y * sW;
+    mom += (long long)blockIdx.y * S * NM;
     const int s = threadIdx.x;
     const int i0 = blockIdx.x * PTS;
     const int cnt = min(PTS, m - i0);
@@ -82,8 +87,14 @@ __global__ void __launch_bounds__(SEG_T) moments_bwd_kernel(const float* __restr
                                                             const float* __restrict__ W, long long ldw, int S,
                                                             int start, int step, int m, float eps,
                                                             const float* __restrict__ gmom,
-                                                            float* __restrict__ gW, long long ldg) {
+                                                            float* __restrict__ gW, long long ldg, long long sP,
+                                                            long long sW, long long sG) {
     __shared__ float sp[PTS][3], sn[PTS][3];
+    P += blockIdx.y * sP;
+    if (Nr) Nr += blockIdx.y * sP;
+    W += blockIdx.y * sW;
+    gW += blockIdx.y * sG;
+    gmom += (long long)blockIdx.y * S * NM;
     const int s = threadIdx.x;
     const int i0 = blockIdx.x * PTS;
     const int cnt = min(PTS, m - i0);
@@ -125,7 +136,7 @@ extern "C" int pn_fit_moments_fwd(const float* P, const float* Nr, const float* 
     PN_REQUIRE(S > 0 && S <= fit::SEG_T, "pn_fit_moments_fwd: 1 <= segments <= %d (got %d)", fit::SEG_T, S);
     if (m <= 0) return PN_OK;
     fit::moments_fwd_kernel<<<cdiv(m, fit::PTS), fit::SEG_T, 0, (cudaStream_t)stream>>>(P, Nr, W, ldw, S, start, step, m,
-                                                                                        eps, mom_zeroed);
+                                                                                        eps, mom_zeroed, 0, 0);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("fit moments_fwd_kernel");
     return PN_OK;
@@ -138,8 +149,39 @@ extern "C" int pn_fit_moments_bwd(const float* P, const float* Nr, const float* 
     PN_REQUIRE(S > 0 && S <= fit::SEG_T, "pn_fit_moments_bwd: 1 <= segments <= %d (got %d)", fit::SEG_T, S);
     if (m <= 0) return PN_OK;
     fit::moments_bwd_kernel<<<cdiv(m, fit::PTS), fit::SEG_T, 0, (cudaStream_t)stream>>>(P, Nr, W, ldw, S, start, step, m,
-                                                                                        eps, gmom, gW, ldg);
+                                                                                        eps, gmom, gW, ldg, 0, 0, 0);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("fit moments_bwd_kernel");
+    return PN_OK;
+}
+
+// Batched over the shapes of a step (one launch instead of one per shape): P / Nr [B][N][3], W [B][N][ldw] (column = segment
+// slot), mom [B][S][NM] zero-initialised; gW [B][N][ldg] (rows outside the point set are left untouched).
+extern "C" int pn_fit_moments_fwd_batched(const float* P, const float* Nr, const float* W, long long ldw, int B, int N, int S,
+                                          int start, int step, int m, float eps, double* mom_zeroed, void* stream) {
+    PN_REQUIRE(P && W && mom_zeroed, "pn_fit_moments_fwd_batched: null pointer");
+    PN_REQUIRE(S > 0 && S <= fit::SEG_T, "pn_fit_moments_fwd_batched: 1 <= segments <= %d (got %d)", fit::SEG_T, S);
+    PN_REQUIRE(B > 0 && N > 0 && start >= 0 && step > 0 && start + (long long)(m - 1) * step < N,
+               "pn_fit_moments_fwd_batched: point set outside the shape (B=%d N=%d start=%d step=%d m=%d)", B, N, start, step, m);
+    if (m <= 0) return PN_OK;
+    fit::moments_fwd_kernel<<<dim3(cdiv(m, fit::PTS), B), fit::SEG_T, 0, (cudaStream_t)stream>>>(
+        P, Nr, W, ldw, S, start, step, m, eps, mom_zeroed, (long long)N * 3, (long long)N * ldw);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("fit moments_fwd_kernel (batched)");
+    return PN_OK;
+}
+
+extern "C" int pn_fit_moments_bwd_batched(const float* P, const float* Nr, const float* W, long long ldw, int B, int N, int S,
+                                          int start, int step, int m, float eps, const float* gmom, float* gW,
+                                          long long ldg, void* stream) {
+    PN_REQUIRE(P && W && gmom && gW, "pn_fit_moments_bwd_batched: null pointer");
+    PN_REQUIRE(S > 0 && S <= fit::SEG_T, "pn_fit_moments_bwd_batched: 1 <= segments <= %d (got %d)", fit::SEG_T, S);
+    PN_REQUIRE(B > 0 && N > 0 && start >= 0 && step > 0 && start + (long long)(m - 1) * step < N,
+               "pn_fit_moments_bwd_batched: point set outside the shape (B=%d N=%d start=%d step=%d m=%d)", B, N, start, step, m);
+    if (m <= 0) return PN_OK;
+    fit::moments_bwd_kernel<<<dim3(cdiv(m, fit::PTS), B), fit::SEG_T, 0, (cudaStream_t)stream>>>(
+        P, Nr, W, ldw, S, start, step, m, eps, gmom, gW, ldg, (long long)N * 3, (long long)N * ldw, (long long)N * ldg);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("fit moments_bwd_kernel (batched)");
     return PN_OK;
 }

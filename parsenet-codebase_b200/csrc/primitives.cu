@@ -18,20 +18,24 @@ constexpr int NT = 256;
 constexpr int MAXSEG = 64;
 
 // seg[n] in [0,S) or -1; type[s]; par[s][8].  Outputs (zero-initialised): sumf[S], jac[S][8], cnt[S]
-__global__ void __launch_bounds__(NT) residual_kernel(const float* __restrict__ P, const int* __restrict__ seg, int N,
-                                                      const int* __restrict__ type, const float* __restrict__ par,
-                                                      int S, float* __restrict__ sumf, float* __restrict__ jac,
-                                                      float* __restrict__ cnt) {
+__global__ void __launch_bounds__(NT) residual_kernel(const float* P, const int* seg, int N,
+                                                      const int* type, const float* par,
+                                                      int S, float* sumf, float* jac,
+                                                      float* cnt) {
     __shared__ float s_par[MAXSEG * NPAR];
     __shared__ int s_type[MAXSEG];
     __shared__ float s_sum[MAXSEG], s_cnt[MAXSEG], s_jac[MAXSEG * NPAR];
+    // blockIdx.y = shape of a batch (every table has S slots per shape, N points per shape)
+    P += (long long)blockIdx.y * N * 3; seg += (long long)blockIdx.y * N;
+    type += blockIdx.y * S; par += blockIdx.y * S * NPAR;
+    sumf += blockIdx.y * S; jac += blockIdx.y * S * NPAR; cnt += blockIdx.y * S;
     for (int e = threadIdx.x; e < S * NPAR; e += NT) { s_par[e] = par[e]; s_jac[e] = 0.f; }
     for (int e = threadIdx.x; e < S; e += NT) { s_type[e] = type[e]; s_sum[e] = 0.f; s_cnt[e] = 0.f; }
     __syncthreads();
     const int n = blockIdx.x * NT + threadIdx.x;
     if (n < N) {
         const int s = seg[n];
-        if (s >= 0 && s < S) {
+        if (s >= 0 && s < S && s_type[s] >= 0) {
             const float* q = s_par + s * NPAR;
             const float px = P[3 * n], py = P[3 * n + 1], pz = P[3 * n + 2];
             float f = 0.f, g[NPAR] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -118,5 +122,19 @@ extern "C" int pn_residual_fwd(const float* P, const int* seg, int N, const int*
                                                                                    jac_zeroed, cnt_zeroed);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("residual_kernel");
+    return PN_OK;
+}
+
+// Batched over the shapes of a step: P [B][N][3], seg [B][N] (slot of the point's segment or -1), type / par / outputs
+// [B][S](x8) indexed by slot (type -1 = unused slot; its points must carry seg = -1).
+extern "C" int pn_residual_fwd_batched(const float* P, const int* seg, int B, int N, const int* type, const float* par, int S,
+                                       float* sumf_zeroed, float* jac_zeroed, float* cnt_zeroed, void* stream) {
+    PN_REQUIRE(P && seg && type && par && sumf_zeroed && jac_zeroed && cnt_zeroed, "pn_residual_fwd_batched: null pointer");
+    PN_REQUIRE(S > 0 && S <= prim::MAXSEG, "pn_residual_fwd_batched: 1 <= slots <= %d (got %d)", prim::MAXSEG, S);
+    PN_REQUIRE(B > 0 && N > 0, "pn_residual_fwd_batched: empty batch (B=%d N=%d)", B, N);
+    prim::residual_kernel<<<dim3(cdiv(N, prim::NT), B), prim::NT, 0, (cudaStream_t)stream>>>(P, seg, N, type, par, S,
+                                                                                            sumf_zeroed, jac_zeroed, cnt_zeroed);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("residual_kernel (batched)");
     return PN_OK;
 }

@@ -70,6 +70,10 @@ SIGNATURES = {
     "pn_fit_moments_fwd": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p],
     "pn_fit_moments_bwd": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_ll, c_p],
     "pn_residual_fwd": [c_p, c_p, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
+    "pn_fit_moments_fwd_batched": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p],
+    "pn_fit_moments_bwd_batched": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_ll, c_p],
+    "pn_fit_solve": [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
+    "pn_residual_fwd_batched": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     # small3.cu
     "pn_sym3_eigh": [c_p, c_i, c_p, c_p, c_p],
     "pn_lstsq3": [c_p, c_p, c_i, c_i, c_d, c_p, c_p, c_p, c_p],

@@ -1,0 +1,136 @@
+"""Host twin of csrc/fitsolve.cuh (parameters of plane / sphere / cylinder / cone from the 55 weighted moments + forward-mode
+Jacobian) against the oracle port of the reference's fits run on the raw points with torch autograd:
+values to 2e-4 (the port computes in fp32 like the reference), gradient w.r.t. the membership weights to 2e-3."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EPS = float(np.finfo(np.float32).eps)
+KIND = {"plane": 0, "sphere": 1, "cylinder": 2, "cone": 3}
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("fitsolve") / "libfitsolve.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "parsenet-codebase_b200", "csrc"),
+                           "-o", out, os.path.join(ROOT, "tests", "c", "fitsolve_host.cpp")])
+    return ctypes.CDLL(out)
+
+
+def phi(p, n):
+    """(m,55) monomials of csrc/fit.cu eval_phi and the power of w multiplying each"""
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    a, b, c = n[:, 0], n[:, 1], n[:, 2]
+    one = np.ones_like(x)
+    npn = a * x + b * y + c * z
+    pp = [x * x, x * y, x * z, y * y, y * z, z * z]
+    cols = [one, x, y, z] + pp + [a, b, c] \
+        + [one, x, y, z] + pp + [a, b, c] + [a * a, a * b, a * c, b * b, b * c, c * c] + [npn * a, npn * b, npn * c] \
+        + pp + [x * x * x, x * x * y, x * x * z, x * y * y, x * y * z, x * z * z, y * y * y, y * y * z, y * z * z, z * z * z] \
+        + [a, b, c, one]
+    deg = np.array([1] * 13 + [2] * 22 + [3] * 16 + [0] * 4)
+    return np.stack(cols, 1), deg
+
+
+def moments(p, n, w):
+    P, deg = phi(p.astype(np.float64), n.astype(np.float64))
+    w = w.astype(np.float64).reshape(-1, 1)
+    return (w ** deg[None] * P).sum(0), P, deg
+
+
+def solve(lib, mom, kinds, rows):
+    S = mom.shape[0]
+    mom = np.ascontiguousarray(mom, np.float64)
+    kinds = np.ascontiguousarray(kinds, np.int32)
+    par, jac, bad = np.zeros((S, 8)), np.zeros((S, 8, 55)), np.zeros(S, np.int32)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.fitsolve_host(mom.ctypes.data_as(dp), kinds.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), S, int(rows),
+                      par.ctypes.data_as(dp), jac.ctypes.data_as(dp), bad.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    return par, jac, bad
+
+
+@pytest.mark.parametrize("kind,m,seed", [("plane", 61, 11), ("plane", 2500, 12), ("sphere", 61, 13), ("sphere", 2500, 14),
+                                         ("cone", 300, 15), ("cone", 2500, 16), ("cylinder", 2500, 17)])
+def test_solve_from_moments_matches_port_fit_and_autograd(lib, kind, m, seed):
+    from oracle.make_golden_helpers import prim_cloud
+    from oracle.port import fitting as OP
+    p, n, w = prim_cloud(kind, m, seed)
+    if kind == "cylinder":
+        # prim_cloud's normals are exact, i.e. exactly perpendicular to the axis: d axis / d weights is then rounding noise
+        # on both sides; jitter them so that the gradient is a number that can be compared
+        n = n + 0.03 * np.random.RandomState(seed).randn(m, 3).astype(np.float32)
+        n = n / np.linalg.norm(n, axis=1, keepdims=True)
+    mom, P, deg = moments(p, n, w)
+    par, jac, bad = solve(lib, mom[None], [KIND[kind]], m)
+    assert bad[0] == 0
+    par, jac = par[0], jac[0]
+    W = torch.from_numpy(w).requires_grad_()
+    tp, tn = torch.from_numpy(p), torch.from_numpy(n)
+    if kind == "plane":
+        a, d = OP.fit_plane(tp, W)
+        want = [a.reshape(3), d.reshape(1)]
+        slots = [slice(0, 3), slice(3, 4)]
+        sign = float(np.sign((par[0:3] * a.detach().numpy().reshape(3)).sum()))
+        signs = [sign, sign]
+    elif kind == "sphere":
+        c, r = OP.fit_sphere(tp, W)
+        want, slots, signs = [c.reshape(3), r.reshape(1)], [slice(0, 3), slice(3, 4)], [1.0, 1.0]
+    elif kind == "cylinder":
+        a, c, r = OP.fit_cylinder(tp, tn, W)
+        sign = float(np.sign((par[0:3] * a.detach().numpy().reshape(3)).sum()))
+        want, slots, signs = [a.reshape(3)], [slice(0, 3)], [sign]          # centre / radius: declared deviation
+    else:
+        apex, a, th = OP.fit_cone(tp, tn, W)
+        want, slots, signs = [apex.reshape(3), a.reshape(3)], [slice(0, 3), slice(3, 6)], [1.0, 1.0]
+    g = np.random.RandomState(seed).randn(8)
+    loss = 0
+    for wv, sl, sg in zip(want, slots, signs):
+        got = par[sl] * sg
+        ref = wv.detach().double().numpy()
+        assert np.abs(got - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1e-3), (kind, sl, got, ref)
+        loss = loss + (wv.double() * torch.from_numpy(g[sl] * sg)).sum()
+    loss.backward()
+    used = np.zeros(8)
+    for sl, sg in zip(slots, signs):
+        used[sl] = g[sl]
+    gmom = used @ jac                                           # (55,)
+    wd = w.astype(np.float64).reshape(-1, 1)
+    dmom_dw = np.where(deg[None] > 0, deg[None] * wd ** np.maximum(deg[None] - 1, 0), 0.0) * P      # (m,55)
+    gw = dmom_dw @ gmom
+    ref = W.grad.double().numpy().reshape(-1)
+    assert np.abs(gw - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-9, (kind, np.abs(gw - ref).max(), np.abs(ref).max())
+
+
+def test_jacobian_is_the_directional_derivative_where_the_rule_is_exact(lib):
+    """sphere fit (no SVD rule involved): the forward-mode Jacobian equals central finite differences of the solve"""
+    from oracle.make_golden_helpers import prim_cloud
+    p, n, w = prim_cloud("sphere", 400, 3)
+    mom, _, _ = moments(p, n, w)
+    par, jac, _ = solve(lib, mom[None], [1], 400)
+    rs = np.random.RandomState(0)
+    for _ in range(5):
+        d = rs.randn(55) * np.abs(mom) * 1e-6
+        pp, _, _ = solve(lib, (mom + d)[None], [1], 400)
+        pm, _, _ = solve(lib, (mom - d)[None], [1], 400)
+        fd = (pp[0] - pm[0]) / 2
+        an = jac[0] @ d
+        assert np.abs(fd - an).max() <= 1e-5 * np.abs(an).max() + 1e-14
+
+
+def test_degenerate_cone_and_empty_slot(lib):
+    """normals confined to a line -> cond(w n) = inf > 1e5 -> zero apex, x axis, no gradient (primitive_forward.py:818-823)"""
+    rs = np.random.RandomState(1)
+    m = 200
+    p = rs.randn(m, 3).astype(np.float32)
+    n = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (m, 1))
+    w = rs.rand(m, 1).astype(np.float32)
+    mom, _, _ = moments(p, n, w)
+    par, jac, bad = solve(lib, np.stack([mom, mom]), [3, -1], m)
+    assert bad[0] == 1 and bad[1] == 0
+    np.testing.assert_array_equal(par[0], [0, 0, 0, 1, 0, 0, 0, 0])
+    assert not jac.any() and not par[1].any()
