@@ -365,3 +365,87 @@ def fit_control_points_grid(S_bguv3, nu, nv):
     assert pu.shape[1] == gu and pv.shape[1] == gv, "basis matrices do not match the sample grid"
     out = SplineEvalFn.apply(S_bguv3.double(), pu, pv).view(B, pu.shape[0], pv.shape[0], 3)
     return out.to(S_bguv3.dtype)
+
+
+# ------------------------------------------------------------------------------------------------ batched fit stage
+# Slot-indexed versions of the three fit kernels for Evaluation.fitting_loss over a whole batch of shapes (fitstage.py):
+# every table is (B, S, .) with S = 64 weight columns ("slots") per shape; unused slots carry kind -1.
+KIND_NONE = -1
+
+
+class MomentsBatchedFn(torch.autograd.Function):
+    """W (B,N,S) membership weights -> (B,S,55) float64 moments of the point set {start + i*step, i < m} of every shape,
+    w = W + eps, in ONE launch (csrc/fit.cu, gridDim.y = shape)"""
+
+    @staticmethod
+    def forward(ctx, W, P, Nr, start, step, m, eps):
+        _need_cuda(W, P)
+        W = W.detach()
+        assert W.is_contiguous() and P.is_contiguous() and (Nr is None or Nr.is_contiguous())
+        B, N, S = W.shape
+        mom = torch.zeros((B, S, NM), dtype=torch.float64, device=W.device)
+        call("pn_fit_moments_fwd_batched", _ptr(P), _ptr(Nr), _ptr(W), S, B, N, S, start, step, m, float(eps), _ptr(mom),
+             _stream())
+        ctx.saved = (W, P, Nr, start, step, m, float(eps))
+        return mom
+
+    @staticmethod
+    def backward(ctx, gmom):
+        W, P, Nr, start, step, m, eps = ctx.saved
+        B, N, S = W.shape
+        gW = torch.zeros((B, N, S), dtype=torch.float32, device=W.device)
+        g32 = gmom.to(torch.float32).contiguous()
+        call("pn_fit_moments_bwd_batched", _ptr(P), _ptr(Nr), _ptr(W), S, B, N, S, start, step, m, eps, _ptr(g32),
+             _ptr(gW), S, _stream())
+        return gW, None, None, None, None, None, None
+
+
+class FitSolveFn(torch.autograd.Function):
+    """mom (S,55) float64, kind (S,) int32 -> par (S,8) float64 parameter rows (residual-kernel layout, cone angle slot
+    left 0) and bad (S,) float32 degenerate-cone flags, ONE launch for every segment of every shape (csrc/fitsolve.cu).
+    The kernel also returns d par / d mom (forward mode), so the backward is one small batched product."""
+
+    @staticmethod
+    def forward(ctx, mom, kind, rows):
+        _need_cuda(mom, kind)
+        mom = mom.detach().contiguous()
+        assert mom.dtype == torch.float64 and kind.dtype == torch.int32 and kind.is_contiguous()
+        S = mom.shape[0]
+        par = torch.empty((S, 8), dtype=torch.float64, device=mom.device)
+        jac = torch.empty((S, 8, NM), dtype=torch.float64, device=mom.device)
+        bad = torch.empty((S,), dtype=torch.float32, device=mom.device)
+        call("pn_fit_solve", _ptr(mom), _ptr(kind), S, int(rows), _ptr(par), _ptr(jac), _ptr(bad), _stream())
+        ctx.save_for_backward(jac)
+        ctx.mark_non_differentiable(bad)
+        return par, bad
+
+    @staticmethod
+    def backward(ctx, gpar, _gbad):
+        (jac,) = ctx.saved_tensors
+        return torch.bmm(gpar.unsqueeze(1), jac).squeeze(1), None, None
+
+
+class ResidualBatchedFn(torch.autograd.Function):
+    """mean squared point-to-primitive distance of every segment slot of every shape in ONE launch.
+    par (B,S,8) fp32, points (B,N,3), seg (B,N) int32 slot of every point or -1, kind (B,S) int32 -> (B,S)"""
+
+    @staticmethod
+    def forward(ctx, par, points, seg, kind):
+        _need_cuda(par, points)
+        par = par.detach().contiguous()
+        B, S, _ = par.shape
+        dev = par.device
+        assert points.is_contiguous() and seg.is_contiguous() and kind.is_contiguous()
+        sumf_c = torch.zeros((B, S), dtype=torch.float32, device=dev)
+        cnt_c = torch.zeros((B, S), dtype=torch.float32, device=dev)
+        jac_c = torch.zeros((B, S, 8), dtype=torch.float32, device=dev)
+        call("pn_residual_fwd_batched", _ptr(points), _ptr(seg), B, points.shape[1], _ptr(kind), _ptr(par), S,
+             _ptr(sumf_c), _ptr(jac_c), _ptr(cnt_c), _stream())
+        cnt_c = torch.clamp(cnt_c, min=1.0)
+        ctx.save_for_backward(jac_c, cnt_c)
+        return sumf_c / cnt_c
+
+    @staticmethod
+    def backward(ctx, g):
+        jac, cnt = ctx.saved_tensors
+        return jac * (g / cnt).unsqueeze(2), None, None, None

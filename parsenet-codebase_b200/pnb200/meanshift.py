@@ -173,19 +173,32 @@ class MeanShiftCentersFn(torch.autograd.Function):
         return gX, None, None
 
 
+def _padded_ids(ids_list, R):
+    rows = []
+    for ids_b in ids_list:
+        k = int(ids_b.shape[0])
+        # (more than R centres only happens when the caller is about to re-cluster this shape with a larger quantile --
+        # Evaluation.fitting_loss does so above 49 -- and discards these centres: truncate instead of failing)
+        rows.append(torch.cat([ids_b, ids_b[:1].expand(R - k)]) if k < R else ids_b[:R])
+    return torch.stack(rows, 0).contiguous()
+
+
+def centers_padded(X_bnd, state, ids_list, shifted=None):
+    """kept centres of every shape as ONE (B, SPARSE_ROWS, d) tensor (slots beyond K_b repeat the shape's first centre):
+    through the sparse-row backward when `state` is given, else gathered from the dense `shifted` (B,N,d)"""
+    ids = _padded_ids(ids_list, SPARSE_ROWS)
+    if state is not None:
+        return MeanShiftCentersFn.apply(X_bnd, ids, state)
+    return torch.gather(shifted, 1, ids.unsqueeze(2).expand(ids.shape[0], ids.shape[1], shifted.shape[2]))
+
+
 def centers_sparse(X_bnd, state, ids_list):
     """ids_list: per shape a (K_b,) int64 device tensor of kept rows (nms_batched) -> list of (K_b, d) centre tensors,
     differentiable w.r.t. X through the sparse-row backward.  Slots beyond K_b repeat the shape's first id and are
     sliced away, i.e. receive a zero gradient and contribute exactly zero."""
     B = X_bnd.shape[0]
     R = SPARSE_ROWS
-    rows = []
-    for b in range(B):
-        k = int(ids_list[b].shape[0])
-        # (more than R centres only happens when the caller is about to re-cluster this shape with a larger quantile --
-        # Evaluation.fitting_loss does so above 49 -- and discards these centres: truncate instead of failing)
-        rows.append(torch.cat([ids_list[b], ids_list[b][:1].expand(R - k)]) if k < R else ids_list[b][:R])
-    ids = torch.stack(rows, 0).contiguous()
+    ids = _padded_ids(ids_list, R)
     centers = MeanShiftCentersFn.apply(X_bnd, ids, state)
     return [centers[b, :min(int(ids_list[b].shape[0]), R)] for b in range(B)]
 

@@ -11,7 +11,7 @@ from src.guard import guard_sqrt
 
 EPS = float(np.finfo(np.float32).eps)
 CLOSED_IDS, OPEN_IDS = (0, 6, 7, 9), (2, 8)
-STATS = {"analytic_fits": 0, "open_spline_fits": 0, "closed_spline_fits": 0}   # host counters (bench.py reports them)
+from pnb200.fitstage import STATS          # host counters of fitted segments, shared with the batched path (bench.py reports them)
 
 
 # ------------------------------------------------------------------------------------------------ SplineNet passes
@@ -225,113 +225,6 @@ def fit_one_shape_torch(data, fitter, weights, bw, eval=False, sample_points=Fal
         gt_points[label_index] = d[3]
     return gt_points, recon
 
-
-
-# ------------------------------------------------------------------------------------------------ cross-shape batching
-# EXPERIMENTAL (opt-in PN_FIT_BATCHED=1, written after the GPU budget of round 1 was spent, not yet run on a GPU).
-# fit_one_shape_torch in three phases so that Evaluation.fitting_loss can run the (S,3,3) algebra of ALL shapes of a step
-# in one batched call per primitive kind: the per-shape fit glue is launch-bound (~4700 sub-10-us kernels per step,
-# DESIGN.md section 7).  Same kernels, same arithmetic per segment; only the launch grouping changes.
-def plan_one_shape(data, weights):
-    """phase 1: the segment plan of fit_one_shape_torch (training mode) + ONE moment pass; no solves"""
-    state = {"data": data, "plan": [], "analytic": [], "mom": None, "fits": {}}
-    if not data:
-        return state
-    points, normals = data[0][0].contiguous(), data[0][1].contiguous()
-    N = points.shape[0]
-    n_half = (N + 1) // 2
-    n_quarter = (n_half + 1) // 2
-    W = weights if (weights.shape[1] == 1 or weights.stride(1) == 1) else weights.contiguous()
-    spline_count = 0
-    for d in data:
-        prim = int(np.asarray(d[2]).reshape(-1)[0])
-        col, label_index = d[5]
-        if prim in CLOSED_IDS + OPEN_IDS:
-            spline_count += 1
-            if spline_count > 4:
-                state["plan"].append((None, d, col, label_index))
-                continue
-            m = n_half
-        else:
-            m = n_quarter
-        if m < 20 or (prim in CLOSED_IDS + OPEN_IDS and m < 100):
-            state["plan"].append((None, d, col, label_index))
-            continue
-        state["plan"].append((prim, d, col, label_index))
-    state.update(points=points, normals=normals, W=W, n_quarter=n_quarter)
-    state["analytic"] = [(prim, col) for prim, _, col, _ in state["plan"] if prim in (1, 3, 4, 5)]
-    if state["analytic"]:
-        state["mom"] = _f.MomentsFn.apply(W, points, normals, 0, 4, n_quarter, EPS)
-    return state
-
-
-def solve_planned_shapes(states):
-    """phase 2: one batched solve per primitive kind over the segments of ALL shapes (grouped by the decimated point
-    count, which enters the rank rule of the normal-equation solve); fills state['fits'][column]"""
-    groups = {}
-    for si, st in enumerate(states):
-        if st["analytic"]:
-            groups.setdefault(st["n_quarter"], []).append(si)
-    for n_quarter, members in groups.items():
-        for kind_id, fn in ((1, "plane"), (5, "sphere"), (4, "cylinder"), (3, "cone")):
-            where = [(si, c) for si in members for p, c in states[si]["analytic"] if p == kind_id]
-            if not where:
-                continue
-            sub = torch.stack([states[si]["mom"][c] for si, c in where], 0)
-            if fn == "plane":
-                a, dd = _f.fit_planes(sub)
-                for i, (si, c) in enumerate(where):
-                    states[si]["fits"][c] = ["plane", a[i].float().reshape(3, 1), dd[i].float()]
-            elif fn == "sphere":
-                ce, r = _f.fit_spheres(sub, n_quarter)
-                for i, (si, c) in enumerate(where):
-                    states[si]["fits"][c] = ["sphere", ce[i].float().reshape(1, 3), r[i].float()]
-            elif fn == "cylinder":
-                a, ce, r = _f.fit_cylinders(sub, n_quarter)
-                for i, (si, c) in enumerate(where):
-                    states[si]["fits"][c] = ["cylinder", a[i].float().reshape(3, 1), ce[i].float().reshape(1, 3),
-                                             r[i].float()]
-            else:
-                apex, axis, deg = _f.fit_cone_apex_axis(sub, n_quarter)
-                for i, (si, c) in enumerate(where):
-                    st = states[si]
-                    dev = st["points"].device
-                    x_axis = _f._dev_const("x_axis", torch.tensor([1.0, 0.0, 0.0]), dev)
-                    wq = (st["W"][0::4, c:c + 1] + EPS)
-                    th = _f.cone_theta(st["points"][0::4], wq, apex[i].float(), axis[i].float())
-                    bad = deg[i]
-                    ap = torch.where(bad, torch.zeros_like(apex[i]), apex[i]).float()
-                    ax = torch.where(bad, x_axis.to(axis.dtype), axis[i]).float()
-                    th = torch.where(bad, torch.zeros_like(th), th)
-                    st["fits"][c] = ["cone", ap.reshape(1, 3), ax.reshape(3, 1), th]
-
-
-def finish_one_shape(state, fitter):
-    """phase 3: spline segments through the SplineNets, parameter dictionary, gt points (as fit_one_shape_torch)"""
-    fitter.fitting.parameters = {}
-    gt_points, recon = {}, []
-    for prim, d, col, label_index in state["plan"]:
-        if prim is None:
-            recon.append(None)
-            gt_points[label_index] = None
-            fitter.fitting.parameters[label_index] = None
-            continue
-        if prim in CLOSED_IDS + OPEN_IDS:
-            pts_h = state["points"][0::2]
-            w_h = state["W"][0::2, col:col + 1] + EPS
-            if prim in CLOSED_IDS:
-                rec = fitter.forward_pass_closed_spline(pts_h, weights=w_h, ids=label_index, if_optimize=False)
-                STATS["closed_spline_fits"] += 1
-            else:
-                rec = fitter.forward_pass_open_spline(pts_h, weights=w_h, ids=label_index, if_optimize=False)
-                STATS["open_spline_fits"] += 1
-            recon.append(rec)
-        else:
-            fitter.fitting.parameters[label_index] = state["fits"][col]
-            STATS["analytic_fits"] += 1
-            recon.append(None)
-        gt_points[label_index] = d[3]
-    return gt_points, recon
 
 
 from src._fallthrough import module_getattr as _module_getattr  # noqa: E402

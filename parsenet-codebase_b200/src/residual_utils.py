@@ -8,15 +8,17 @@ from scipy import stats
 from src.fitting_optimization import FittingModule
 from src.fitting_utils import match, to_one_hot, weights_normalize
 from src.mean_shift import MeanShift
-from src.primitive_forward import finish_one_shape, fit_one_shape_torch, plan_one_shape, solve_planned_shapes
+from src.primitive_forward import fit_one_shape_torch
 from src.primitives import ResidualLoss
 from src.segment_utils import SIOU_matched_segments, segment_types_device
 
 
 import os
 
-# EXPERIMENTAL, opt-in: cross-shape batching of the per-kind fit solves (src/primitive_forward.py); not yet run on a GPU
-FIT_BATCHED = os.environ.get("PN_FIT_BATCHED", "0") == "1"
+# PN_FIT_STAGE: "batched" (default since round 2) = the fit half of fitting_loss runs for ALL shapes of the batch at once
+# (pnb200/fitstage.py: slot-indexed tables, one launch per stage); "loop" = the per-shape loop of round 1 (kept as the A/B
+# reference of the batched path, tests/test_gpu_fitstage.py, and used when a shape needs the >49-cluster retry).
+FIT_STAGE = os.environ.get("PN_FIT_STAGE", "batched")
 
 
 def convert_to_one_hot(data):
@@ -80,43 +82,30 @@ class Evaluation:
         with torch.no_grad():
             members = _ms.nearest_center_batched(embedding, shifted)
             ids, labels_dev, _ = _ms.nms_batched(shifted, embedding, bws, members)   # one blocking read-back
-        centers_b = _ms.centers_sparse(embedding, ms_state, ids) if sparse else None
         cluster_np = labels_dev.cpu().numpy()
         bw_host = bws.detach().cpu().numpy()
+        n_clusters = [np.unique(cluster_np[b]).shape[0] for b in range(B)]
+        if FIT_STAGE == "batched" and embedding.shape[2] == 128 and max(n_clusters) <= 49:
+            return self._fitting_loss_batched(embedding, ms_state if sparse else None, shifted, ids, bws, points, normals,
+                                              labels, primitives, prim_pred_dev, cluster_np, lamb)
+        centers_b = _ms.centers_sparse(embedding, ms_state, ids) if sparse else None
         self._stage = arena("fit", dev)
         self._stage.reset()
         out, lazies, metrics, matchings = [], [], [], []
         parameters, weights = None, None
-        batched = FIT_BATCHED and B > 1      # experimental: the (S,3,3) solves of all shapes in one call per kind
-        pending = []
         for b in range(B):
             center, bandwidth = (centers_b[b] if sparse else shifted[b][ids[b]]), float(bw_host[b])
             if np.unique(cluster_np[b]).shape[0] > 49:       # rare: grow the quantile for this shape only (ref :76-83)
                 center, bw_t, cl = self.guard_mean_shift(embedding[b], quantile * 1.2, iterations)
                 cluster_np[b], bandwidth = cl.data.cpu().numpy(), float(bw_t)
             weights = center @ embedding[b].t()
-            if batched:
-                pending.append(self._plan_train_mode(points[b], normals[b], labels[b], cluster_np[b], primitives[b],
-                                                     weights, bandwidth))
-            else:
-                loss, parameters, _, rows, cols, distance = self.residual_train_mode(
-                    points[b], normals[b], labels[b], cluster_np[b], primitives[b], weights, bandwidth, lamb=lamb,
-                    lazy=True)
-                lazies.append(loss)
-                matchings.append((rows, cols))
-                out.append(loss[0])
+            loss, parameters, _, rows, cols, distance = self.residual_train_mode(
+                points[b], normals[b], labels[b], cluster_np[b], primitives[b], weights, bandwidth, lamb=lamb, lazy=True)
+            lazies.append(loss)
+            matchings.append((rows, cols))
+            out.append(loss[0])
             with torch.no_grad():
                 metrics.append(segment_types_device(prim_pred_dev[b], weights))
-        if batched:
-            solve_planned_shapes([p[0] for p in pending])
-            for state, rows, cols in pending:
-                gt_points, _ = finish_one_shape(state, self.fitter)
-                parameters = self.fitter.fitting.parameters
-                distance = self.res_loss.residual_loss(gt_points, parameters)
-                loss = self.separate_losses(distance, gt_points, lamb=lamb, lazy=True)
-                lazies.append(loss)
-                matchings.append((rows, cols))
-                out.append(loss[0])
         # ---- ONE read-back for every deferred statistic of the step
         flat = [t for l in lazies for t in l[1:] if t is not None] + metrics
         host = torch.cat([t.reshape(-1).double() for t in flat]).cpu().numpy() if flat else np.zeros(0)
@@ -138,30 +127,35 @@ class Evaluation:
             res = res + [out[b]] + lazies[b] + [s_iou, p_iou]
         return res, [parameters, cluster_np[B - 1], weights]
 
-    def _plan_train_mode(self, points, normals, labels, cluster_ids, primitives, weights, bw):
-        """first half of residual_train_mode for the cross-shape batched path (PN_FIT_BATCHED=1): matching, per-segment
-        data, membership weights and the moment pass; the solves follow for all shapes at once"""
-        rows, cols, unique_target, unique_pred = match(labels, cluster_ids)
-        stage = getattr(self, "_stage", None)
-        entries, chunks = [], []
-        for index, i in enumerate(unique_pred):
-            gt_i = labels == cols[i]
-            if gt_i.sum() == 0 or (cluster_ids == i).sum() == 0:
-                continue
-            l = np.bincount(primitives[gt_i]).argmax()
-            entries.append((l, (index, i)))
-            chunks.append(np.nonzero(gt_i)[0])
-        data = []
-        if entries:
-            allidx = np.concatenate(chunks).astype(np.int64)
-            idx_dev = stage.upload(allidx, points.device) if stage is not None else \
-                torch.from_numpy(allidx).to(points.device)
-            o = 0
-            for (l, key), ch in zip(entries, chunks):
-                data.append([points, normals, l, points[idx_dev[o:o + ch.shape[0]]], None, key])
-                o += ch.shape[0]
-        w = weights_normalize(weights, float(bw)).t()
-        return plan_one_shape(data, w), rows, cols
+    def _fitting_loss_batched(self, embedding, ms_state, shifted, ids, bws, points, normals, labels, primitives,
+                              prim_pred_dev, cluster_np, lamb):
+        """fit half of fitting_loss for the whole batch (pnb200/fitstage.py); same return value as the per-shape loop"""
+        from pnb200 import fitstage, meanshift as _ms
+        from src.fitting_utils import rotation_matrix_a_to_b
+        from src.segment_utils import segment_types_batched
+        B = embedding.shape[0]
+        K = [int(i.shape[0]) for i in ids]
+        centers = _ms.centers_padded(embedding, ms_state, ids, shifted)
+        out = fitstage.run(self, embedding, centers, K, bws, points, normals, np.asarray(labels), np.asarray(primitives),
+                           cluster_np, lamb, match, rotation_matrix_a_to_b)
+        self.last_fit = out                                            # (fitstage.segment_distances(out, b) for debugging)
+        with torch.no_grad():
+            seg_types = segment_types_batched(prim_pred_dev, out["raw"])                 # (B, SLOTS) int64
+        # ---- ONE read-back for every statistic of the step
+        host = torch.cat([out["stats"].reshape(-1), seg_types.reshape(-1).double()]).cpu().numpy()
+        stats = host[:2 * B].reshape(B, 2)
+        types = host[2 * B:].reshape(B, -1).astype(np.int64)
+        res = []
+        for b in range(B):
+            rows, cols = out["plan"].matching[b]
+            s_iou, p_iou, _, _ = SIOU_matched_segments(labels[b], cluster_np[b], None, primitives[b], None,
+                                                       prim_pred_seg=types[b, :K[b]], matching=(rows, cols))
+            loss_b = out["loss"][b] if out["has_terms"][b] else torch.zeros(1, device=embedding.device)
+            res = res + [loss_b] + [None if np.isnan(v) else float(v) for v in stats[b]] + [s_iou, p_iou]
+        parameters = fitstage.parameters_of_shape(out, B - 1)
+        self.fitter.fitting.parameters = parameters
+        weights = out["raw"][B - 1, :, :K[B - 1]].t()
+        return res, [parameters, cluster_np[B - 1], weights]
 
     def residual_train_mode(self, points, normals, labels, cluster_ids, primitives, weights, bw, lamb=1.0,
                             lazy=False):

@@ -96,6 +96,22 @@ def segment_types_device(prim_pred_point, weights_kn):
     return torch.max(hot.t() @ weights_kn.t(), 0)[1]
 
 
+def segment_types_batched(prim_pred_bn, weights_bns):
+    """segment_types_device for a batch: per-point predicted ids (B,N) int64 + similarities (B,N,S) -> (B,S) majority type
+    of every weight column (one bmm for all shapes)"""
+    dev = weights_bns.device
+    lut = _MERGE_LUT.get(str(dev))
+    if lut is None:
+        table = np.arange(10)
+        for src, dst in _MERGE:
+            table[src] = dst
+        lut = _MERGE_LUT[str(dev)] = torch.from_numpy(table).to(dev)
+    merged = lut[prim_pred_bn]
+    B, N = merged.shape
+    hot = torch.zeros((B, N, 10), device=dev).scatter_(2, merged.unsqueeze(2), 1.0)
+    return torch.max(torch.bmm(hot.transpose(1, 2), weights_bns), 1)[1]
+
+
 def SIOU_matched_segments(target, pred_labels, primitives_pred, primitives, weights, prim_pred_seg=None,
                           matching=None):
     """segment IoU + primitive-type IoU over Hungarian-matched (predicted, gt) segments.

@@ -209,12 +209,16 @@ def _seeded_splinenet(mode, seed):
     return net.cuda().eval()
 
 
+@pytest.mark.parametrize("stage", ["batched", "loop"])
 @pytest.mark.parametrize("variant", ["e2e", "e2e_nocyl"])
-def test_evaluation_fitting_loss_vs_reference(golden_dir, variant):
+def test_evaluation_fitting_loss_vs_reference(golden_dir, variant, stage, monkeypatch):
     """Evaluation.fitting_loss (mean-shift -> match -> fit -> residual) on one synthetic shape with all six segment
-    kinds, against the reference run on the same inputs: loss within 1e-4 relative, same partition, same kinds."""
+    kinds, against the reference run on the same inputs: loss within 1e-4 relative, same partition, same kinds.
+    stage: the batched fit stage (default, pnb200/fitstage.py) and the per-shape loop of round 1."""
+    import src.residual_utils as RU
     from oracle.make_golden_helpers import e2e_inputs
     from src.residual_utils import Evaluation
+    monkeypatch.setattr(RU, "FIT_STAGE", stage)
     g = _g(golden_dir, variant + ".npz")
     N = int(g["N"])
     pts, nrm, lab, prim, emb, logp = e2e_inputs(N, 77, variant == "e2e_nocyl")
@@ -232,6 +236,10 @@ def test_evaluation_fitting_loss_vs_reference(golden_dir, variant):
     res, extra = ev.fitting_loss(E, torch.from_numpy(pts).cuda(), torch.from_numpy(nrm).cuda(), lab, prim.copy(),
                                  logp.cuda(), quantile=0.015, iterations=10, lamb=0.1)
     params, cluster_ids, weights = extra
+    if stage == "batched":
+        from pnb200 import fitstage
+        assert not captured, "the batched stage does not go through separate_losses"
+        captured.update({k: (v[0], float(v[1])) for k, v in fitstage.segment_distances(ev.last_fit, 0).items()})
     # partition identical (cluster numbering is representative-point dependent, see test_gpu_meanshift)
     def canon(l):
         _, first = np.unique(l, return_index=True)

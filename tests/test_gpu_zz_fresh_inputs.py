@@ -212,8 +212,9 @@ def test_weights_normalize_fresh_vs_port(K, N):
 
 
 # ------------------------------------------------------------------------------------------------ end to end
+@pytest.mark.parametrize("stage", ["batched", "loop"])
 @pytest.mark.parametrize("N,seed", [(1800, 91), (2600, 92)])
-def test_fitting_loss_fresh_shape_vs_port(N, seed):
+def test_fitting_loss_fresh_shape_vs_port(N, seed, stage, monkeypatch):
     """Evaluation.fitting_loss on a NEW synthetic shape (not the golden one) against the complete oracle port
     (oracle/port/e2e.py, pinned on CPU against the reference's own run): identical partition and segment kinds,
     per-segment residuals 1e-3 (cylinder excluded: declared deviation), loss 1e-3 when no cylinder is fitted"""
@@ -221,6 +222,8 @@ def test_fitting_loss_fresh_shape_vs_port(N, seed):
     from oracle.port import common, e2e as pe2e
     from src.model import DGCNNControlPoints
     from src.residual_utils import Evaluation
+    import src.residual_utils as RU
+    monkeypatch.setattr(RU, "FIT_STAGE", stage)
     pts, nrm, lab, prim, emb, logp = e2e_inputs(N, seed, True)
     nets, mods = {}, {}
     for name, mode, s in (("open", 0, 41), ("closed", 1, 42)):
@@ -256,6 +259,9 @@ def test_fitting_loss_fresh_shape_vs_port(N, seed):
         m = {int(v): i for i, v in enumerate(l[np.sort(first)])}
         return np.array([m[int(v)] for v in l])
     np.testing.assert_array_equal(canon(extra[1]), canon(wcl))
+    if stage == "batched":
+        from pnb200 import fitstage
+        captured.update({k: (v[0], float(v[1])) for k, v in fitstage.segment_distances(ev.last_fit, 0).items()})
     mine = sorted(captured.values())
     ref = sorted((v[0], float(v[1])) for v in wdist.values())
     assert [k for k, _ in mine] == [k for k, _ in ref]
@@ -312,40 +318,6 @@ def test_open_spline_training_step_vs_port():
     for key in ("conv8.weight", "conv7.weight", "conv5.0.weight", "conv3.0.weight", "conv1.0.weight", "bn5.weight", "bn2.bias"):
         got, want = params[key].grad.norm().item(), sdp[key].grad.norm().item()
         assert abs(got - want) <= 5e-3 * want + 1e-9, (key, got, want)
-
-
-# ------------------------------------------------------------------------------------------------ experimental paths
-def test_cross_shape_batched_fit_equals_per_shape_path(monkeypatch):
-    """PN_FIT_BATCHED: the (S,3,3) solves of all shapes of a step in one call per primitive kind must give the same
-    losses and the same gradient as the per-shape path (same kernels, same arithmetic per segment)"""
-    import src.residual_utils as RU
-    from oracle.make_golden_helpers import e2e_inputs
-    from oracle.port import common
-    from src.model import DGCNNControlPoints
-    nets = {}
-    for name, mode, s in (("open", 0, 41), ("closed", 1, 42)):
-        net = DGCNNControlPoints(20, num_points=10, mode=mode)
-        sd = common.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=s)
-        net.load_state_dict(sd)
-        nets[name] = net.cuda().eval()
-    shapes = [e2e_inputs(1400, 70 + i, False) for i in range(3)]
-    pts = torch.from_numpy(np.concatenate([s[0] for s in shapes])).cuda()
-    nrm = torch.from_numpy(np.concatenate([s[1] for s in shapes])).cuda()
-    lab = np.concatenate([s[2] for s in shapes]); prim = np.concatenate([s[3] for s in shapes])
-    emb = torch.cat([s[4] for s in shapes]); logp = torch.cat([s[5] for s in shapes]).cuda()
-    results = []
-    for flag in (False, True):
-        monkeypatch.setattr(RU, "FIT_BATCHED", flag)
-        ev = RU.Evaluation(open_decoder=nets["open"], closed_decoder=nets["closed"])
-        E = emb.clone().cuda().requires_grad_()
-        np.random.seed(5)
-        res, _ = ev.fitting_loss(E, pts, nrm, lab, prim.copy(), logp, quantile=0.015, iterations=10, lamb=0.1)
-        total = torch.stack([r.reshape(()) for r in res[0::5]]).sum()
-        total.backward()
-        results.append(([float(r) for r in res[0::5]], E.grad.clone()))
-    for a, b in zip(results[0][0], results[1][0]):
-        assert abs(a - b) <= 1e-6 * abs(a), (a, b)
-    _close(results[1][1], results[0][1], 1e-5, "d loss / d embedding, batched vs per-shape")
 
 
 # ------------------------------------------------------------------------------------------------ inference path (SURVEY 8f-2)
