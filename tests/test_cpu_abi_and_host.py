@@ -228,7 +228,8 @@ def test_product_package_never_imports_the_oracle_or_falls_back_to_cpu():
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
     for fn in [n for n in tree.body if isinstance(n, ast.FunctionDef)]:
         uses = [n for n in ast.walk(fn) if isinstance(n, ast.ImportFrom) and n.module and n.module.startswith("oracle")]
-        assert not uses or fn.name in ("cpu_baseline", "run_reference"), f"bench.py::{fn.name} imports the oracle"
+        assert not uses or fn.name in ("cpu_baseline", "run_reference", "_port_weights", "_port_one_shape",
+                                       "gpu_eager_baseline"), f"bench.py::{fn.name} imports the oracle"
 
 
 @pytest.mark.parametrize("use_tma", [False, True])
