@@ -388,8 +388,8 @@ FIT_STAGE = True
 MS_ITERS = 10
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel from the round's `ncu --set full` capture
 # (same command, B = 16): filled in from profiles/ when the capture exists, else null
-MS_FWD_TRAFFIC_BYTES = None
-MS_FWD_TRAFFIC_SOURCE = None
+MS_FWD_TRAFFIC_BYTES = 534.8e6
+MS_FWD_TRAFFIC_SOURCE = "profiles/r02_ncu_ms_fwd_tma.md (ncu --set full, B = 16, mean of two launches: 459.4 / 610.2 MB)"
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
