@@ -423,21 +423,25 @@ def _port_one_shape(seed, device=None):
         x, tp, tn, tprim, tlab, codes = (t.to(device) for t in (x, tp, tn, tprim, tlab, codes))
     sd = {n: v.detach().clone().requires_grad_(v.is_floating_point()) for n, v in sd.items()}
     sync = (lambda: torch.cuda.synchronize(device)) if device is not None else (lambda: None)
-    sync()
-    t0 = time.time()
-    emb, lp, _, _, _ = port.segnet_fwd(sd, x, KNN_K, 5)
-    np.random.seed(0)
-    el = port.triplet_loss(emb, lab, 1.0)
-    nll = F.nll_loss(lp, tprim)
-    sync()
-    t_seg = time.time() - t0
-    loss = el.sum() + nll
-    emb = pin_clusters(emb, tlab, codes)
-    fl, _, dist, cl = pe2e.fitting_loss(emb[0].t(), tp, tn, lab[0], prim[0].copy(), nets, 0.025, MS_ITERS, 0.1)
-    loss = loss + fl[0].reshape(())
-    loss.backward()
-    sync()
-    dt = time.time() - t0
+    import contextlib
+    # (inputs and seeded weights above are built on the CPU: their generators are CPU generators; only the port's own
+    # factory calls -- torch.zeros / eye / arange ... -- follow the device of the run)
+    with (torch.device(device) if device is not None else contextlib.nullcontext()):
+        sync()
+        t0 = time.time()
+        emb, lp, _, _, _ = port.segnet_fwd(sd, x, KNN_K, 5)
+        np.random.seed(0)
+        el = port.triplet_loss(emb, lab, 1.0)
+        nll = F.nll_loss(lp, tprim)
+        sync()
+        t_seg = time.time() - t0
+        loss = el.sum() + nll
+        emb = pin_clusters(emb, tlab, codes)
+        fl, _, dist, cl = pe2e.fitting_loss(emb[0].t(), tp, tn, lab[0], prim[0].copy(), nets, 0.025, MS_ITERS, 0.1)
+        loss = loss + fl[0].reshape(())
+        loss.backward()
+        sync()
+        dt = time.time() - t0
     kinds = sorted(v[0] for v in dist.values())
     return dt, (f"1 shape x {N_POINTS} pts, k={KNN_K}: seg-net fwd+losses ({t_seg:.1f} s), Evaluation.fitting_loss (mean-shift "
                 f"{MS_ITERS} it + nms, match, {len(dist)} segment fits {kinds}, residuals; {len(np.unique(cl))} clusters), bwd; "
@@ -494,7 +498,6 @@ def gpu_eager_baseline(dev):
             return torch.cat(outs, 0)
 
     saved = (port.knn_idx, torch.from_numpy, torch.Tensor.numpy)
-    torch.set_default_device(dev)
     try:
         port.knn_idx = knn_torch
         torch.from_numpy = lambda a: saved[1](a).to(dev)
@@ -503,7 +506,6 @@ def gpu_eager_baseline(dev):
         dt, sample = _port_one_shape(seed=0, device=dev)
     finally:
         port.knn_idx, torch.from_numpy, torch.Tensor.numpy = saved
-        torch.set_default_device("cpu")
     return {"value": 1.0 / dt, "unit": "shapes/s", "kind": "port on cuda (torch eager, reference formulation)", "sample": sample}
 
 

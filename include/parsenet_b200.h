@@ -64,6 +64,29 @@ int pn_fit_moments_bwd_batched(const float* P, const float* Nr, const float* W, 
    bad[s] = 1 for a degenerate cone (cond > 1e5, :818-823) */
 int pn_fit_solve(const double* mom, const int* kind, int S, int rows, double* par, double* jac, float* bad, void* stream);
 
+/* ---- weights.cu ---- */
+/* replaces: weights_normalize src/fitting_utils.py:306-325 (exp(clamp(w / bw^2 / 2)), normalise over the clusters of a point,
+   min-max over the points of a cluster; single-cluster early return :318-319) for all shapes of a step: raw / out [B][N][64]
+   (slots >= K[b] are padding), bw2 [B], K [B]; keys [2][B][64] u64 workspace (first half all-ones, second half zero on entry)
+   holding the packed (value, point) extrema for the backward */
+int pn_weights_normalize_fwd(const float* raw, const float* bw2, const int* K, int B, int N, int S, float* out, unsigned long long* keys, void* stream);
+/* replaces: autograd of the same expression (gradient of min / max goes to one point per cluster: lowest index among ties);
+   red [B][64][2] doubles zero-initialised workspace */
+int pn_weights_normalize_bwd(const float* raw, const float* g, const float* bw2, const int* K, int B, int N, int S, const unsigned long long* keys, double* red_zeroed, float* graw, void* stream);
+
+/* ---- gridloss.cu ---- */
+/* replaces: control_points_permute_reg_loss src/loss.py:76-97 (mode 0: 8 dihedral re-orderings of the target grid, all_permutations
+   :21) and control_points_permute_closed_reg_loss :100-124 (mode 1: g cyclic shifts along u (roll :60) x 4 flips,
+   all_permutations_half :41): out, gt [B][g][g][3] -> loss_b [B] = min_p sum (out - cand_p(gt))^2, pick [B], best [B][g][g][3] */
+int pn_grid_perm_fwd(const float* out, const float* gt, int B, int g, int mode, float* diff_ws, float* loss_b, int* pick, float* best, void* stream);
+/* replaces: autograd of the same (dout = 2 (out - best) * gscale[0] * inv) */
+int pn_grid_perm_bwd(const float* out, const float* best, long long n, const float* gscale, float inv, float* dout, void* stream);
+/* replaces: laplacian_loss src/loss.py:213-239 (two depthwise 3x3 convolutions with zero padding): l_ws [B][g][g][3] = lap(out) - lap(gt),
+   part [B] = sum l^2 (l1 = 0) or sum |l| (l1 = 1) */
+int pn_grid_laplacian_fwd(const float* out, const float* gt, int B, int g, int l1, float* l_ws, float* part, void* stream);
+/* replaces: autograd of the same (the zero-padded stencil is self-adjoint); dgt may be null */
+int pn_grid_laplacian_bwd(const float* l_ws, int B, int g, int l1, const float* gscale, float inv, float* dout, float* dgt, void* stream);
+
 /* ---- knn.cu ---- */
 /* replaces: src/PointNet.py:9-26 (knn), :29-69 (knn_points_normals); src/model.py:9-22 */
 int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, float* ws_norms, void* stream);

@@ -73,6 +73,12 @@ SIGNATURES = {
     "pn_fit_moments_fwd_batched": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p],
     "pn_fit_moments_bwd_batched": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_ll, c_p],
     "pn_fit_solve": [c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p],
+    "pn_grid_perm_fwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "pn_grid_perm_bwd": [c_p, c_p, c_ll, c_p, c_f, c_p, c_p],
+    "pn_grid_laplacian_fwd": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
+    "pn_grid_laplacian_bwd": [c_p, c_i, c_i, c_i, c_p, c_f, c_p, c_p, c_p],
+    "pn_weights_normalize_fwd": [c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
+    "pn_weights_normalize_bwd": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
     "pn_residual_fwd_batched": [c_p, c_p, c_i, c_i, c_p, c_p, c_i, c_p, c_p, c_p, c_p],
     # small3.cu
     "pn_sym3_eigh": [c_p, c_i, c_p, c_p, c_p],

@@ -86,7 +86,18 @@ def make_plan(labels, cluster_np, primitives, N, match_fn):
 def normalized_weights(raw, bws, K, stage):
     """weights_normalize (fitting_utils.py:306-325) for every shape: raw (B,N,SLOTS) centre . point similarities, columns
     >= K[b] are padding -> exp(clamp(raw / bw^2 / 2)), normalised over the clusters of a point, then min-max over the
-    points of a cluster (skipped for single-cluster shapes, :318-319).  Padded columns come out as exact zeros."""
+    points of a cluster (skipped for single-cluster shapes, :318-319).  Padded columns come out as exact zeros.
+    On the device this is csrc/weights.cu (2 launches forward, 2 backward); the torch expression below is its reference
+    (tests) and the path taken by CPU tensors (host-logic tests only)."""
+    if raw.is_cuda:
+        bw2 = (bws.detach().double() ** 2).float().contiguous()
+        Kd = stage.upload(np.asarray(K, np.int32), raw.device)
+        return F.WeightsNormalizeFn.apply(raw, bw2, Kd)
+    return normalized_weights_torch(raw, bws, K, stage)
+
+
+def normalized_weights_torch(raw, bws, K, stage):
+    """the same as ~12 torch expressions over (B,N,SLOTS) (+ ~25 autograd kernels)"""
     B, N, S = raw.shape
     dev = raw.device
     Kh = np.asarray(K, np.int64)

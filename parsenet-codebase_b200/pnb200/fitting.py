@@ -449,3 +449,34 @@ class ResidualBatchedFn(torch.autograd.Function):
     def backward(ctx, g):
         jac, cnt = ctx.saved_tensors
         return jac * (g / cnt).unsqueeze(2), None, None, None
+
+
+class WeightsNormalizeFn(torch.autograd.Function):
+    """weights_normalize (fitting_utils.py:306-325) for every shape of a batch: raw (B,N,64) centre . point similarities,
+    bw2 (B,) squared bandwidths, K (B,) int32 clusters per shape -> membership weights (B,N,64); 2 launches forward,
+    2 backward (csrc/weights.cu).  Padded slots (>= K[b]) come out as exact zeros and receive no gradient."""
+
+    @staticmethod
+    def forward(ctx, raw, bw2, K):
+        _need_cuda(raw, bw2, K)
+        raw = raw.detach().contiguous()
+        B, N, S = raw.shape
+        assert raw.dtype == torch.float32 and K.dtype == torch.int32 and bw2.dtype == torch.float32
+        out = torch.empty_like(raw)
+        keys = torch.empty((2, B, S), dtype=torch.int64, device=raw.device)
+        keys[0].fill_(-1)                   # all-ones = +inf for the running minima
+        keys[1].zero_()
+        call("pn_weights_normalize_fwd", _ptr(raw), _ptr(bw2), _ptr(K), B, N, S, _ptr(out), _ptr(keys), _stream())
+        ctx.saved = (raw, bw2, K, keys)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, bw2, K, keys = ctx.saved
+        B, N, S = raw.shape
+        g = g.contiguous()
+        red = torch.zeros((B, S, 2), dtype=torch.float64, device=raw.device)
+        graw = torch.empty_like(raw)
+        call("pn_weights_normalize_bwd", _ptr(raw), _ptr(g), _ptr(bw2), _ptr(K), B, N, S, _ptr(keys), _ptr(red), _ptr(graw),
+             _stream())
+        return graw, None, None

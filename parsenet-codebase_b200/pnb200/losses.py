@@ -146,3 +146,59 @@ class NllFn(torch.autograd.Function):
         dlp = torch.zeros((B, P, N), dtype=torch.float32, device=g.device)
         call("pn_nll_bwd", _ptr(ctx.tg), _ptr(g), B, N, P, _ptr(dlp), _stream())
         return dlp, None
+
+
+# ------------------------------------------------------------------------------------------------ control-grid losses
+class GridPermLossFn(torch.autograd.Function):
+    """min over the symmetric re-orderings of the target control grid of the squared error (csrc/gridloss.cu).
+    out, gt (B,g,g,3); mode 0 = the 8 dihedral candidates (open surfaces, loss.py:76-97), mode 1 = g cyclic shifts along u
+    x 4 flips (closed in u, loss.py:100-124) -> (mean_b min_p / (g*g*3), best-matching candidate of gt (B,g,g,3))."""
+
+    @staticmethod
+    def forward(ctx, out, gt, mode):
+        o = out.detach().contiguous().float()
+        t = gt.detach().contiguous().float()
+        B, g = o.shape[0], o.shape[1]
+        P = 8 if mode == 0 else 4 * g
+        dev = o.device
+        diff = torch.empty((B, P), dtype=torch.float32, device=dev)
+        loss_b = torch.empty((B,), dtype=torch.float32, device=dev)
+        pick = torch.empty((B,), dtype=torch.int32, device=dev)
+        best = torch.empty_like(t)
+        call("pn_grid_perm_fwd", _ptr(o), _ptr(t), B, g, int(mode), _ptr(diff), _ptr(loss_b), _ptr(pick), _ptr(best), _stream())
+        ctx.saved = (o, best, 1.0 / (B * g * g * 3))
+        ctx.mark_non_differentiable(best)
+        return loss_b.mean() / (g * g * 3), best
+
+    @staticmethod
+    def backward(ctx, gl, _gb):
+        o, best, inv = ctx.saved
+        dout = torch.empty_like(o)
+        gs = gl.reshape(1).float().contiguous()
+        call("pn_grid_perm_bwd", _ptr(o), _ptr(best), o.numel(), _ptr(gs), float(inv), _ptr(dout), _stream())
+        return dout, None, None
+
+
+class GridLaplacianLossFn(torch.autograd.Function):
+    """mean over cells of the channel-summed squared (or absolute) difference of the zero-padded 4-neighbour Laplacians of two
+    (B,g,g,3) grids (loss.py:213-239) as a 5-point stencil kernel instead of two cuDNN convolutions."""
+
+    @staticmethod
+    def forward(ctx, out, gt, l1):
+        o = out.detach().contiguous().float()
+        t = gt.detach().contiguous().float()
+        B, g = o.shape[0], o.shape[1]
+        l = torch.empty_like(o)
+        part = torch.empty((B,), dtype=torch.float32, device=o.device)
+        call("pn_grid_laplacian_fwd", _ptr(o), _ptr(t), B, g, int(l1), _ptr(l), _ptr(part), _stream())
+        ctx.saved = (l, B, g, int(l1), 1.0 / (B * g * g))
+        return part.sum() / (B * g * g)
+
+    @staticmethod
+    def backward(ctx, gl):
+        l, B, g, l1, inv = ctx.saved
+        dout = torch.empty_like(l)
+        dgt = torch.empty_like(l) if ctx.needs_input_grad[1] else None
+        gs = gl.reshape(1).float().contiguous()
+        call("pn_grid_laplacian_bwd", _ptr(l), B, g, l1, _ptr(gs), float(inv), _ptr(dout), _ptr(dgt), _stream())
+        return dout, dgt, None

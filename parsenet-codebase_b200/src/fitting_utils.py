@@ -76,7 +76,16 @@ customsvd = CustomSVD.apply
 
 
 def weights_normalize(weights, bw):
-    """(K,N) centre-point similarities -> per-point cluster probabilities, then per-cluster min-max to [0,1]"""
+    """(K,N) centre-point similarities -> per-point cluster probabilities, then per-cluster min-max to [0,1]
+    (reference :306-325).  Up to 64 clusters (the guards of the path allow 49) this is csrc/weights.cu through the batched
+    entry point with B = 1; wider inputs, which no caller on the path produces, take the same formula as torch expressions."""
+    K, N = weights.shape
+    if weights.is_cuda and K <= 64:
+        raw = torch.zeros((1, N, 64), dtype=torch.float32, device=weights.device)
+        raw[0, :, :K] = weights.t()
+        bw2 = torch.as_tensor(float(bw) ** 2, dtype=torch.float32, device=weights.device).reshape(1)
+        Kd = torch.full((1,), K, dtype=torch.int32, device=weights.device)
+        return _f.WeightsNormalizeFn.apply(raw, bw2, Kd)[0, :, :K].t()
     prob = guard_exp(weights / (bw ** 2) / 2)
     prob = prob / prob.sum(0, keepdim=True)
     if weights.shape[0] == 1:

@@ -2,9 +2,8 @@
 reconstruction losses (:142-187), permutation-invariant control-point regression (:76-124), Laplacian loss (:213)."""
 import numpy as np
 import torch
-import torch.nn.functional as F
-
 from pnb200.fitting import spline_eval
+from pnb200.losses import GridLaplacianLossFn, GridPermLossFn
 from src.utils import chamfer_distance, chamfer_distance_one_side
 
 
@@ -77,13 +76,18 @@ def _best_permutation(output, candidates, norm):
 
 
 def control_points_permute_reg_loss(output, control_points, grid_size):
-    """min over the 8 grid symmetries of the squared error; also returns the best-matching permuted target"""
+    """min over the 8 grid symmetries of the squared error; also returns the best-matching permuted target.
+    One kernel evaluates the 8 candidates as index maps (csrc/gridloss.cu); nothing is stacked."""
     out = output.view(output.shape[0], grid_size, grid_size, 3)
-    return _best_permutation(out, all_permutations(control_points), grid_size * grid_size * 3)
+    return GridPermLossFn.apply(out, control_points, 0)
 
 
 def control_points_permute_closed_reg_loss(output, control_points, grid_size_x, grid_size_y):
+    """closed in u: min over (cyclic shifts along u) x (4 flips)"""
     out = output.view(output.shape[0], grid_size_x, grid_size_y, 3)
+    if grid_size_x == grid_size_y:
+        return GridPermLossFn.apply(out, control_points, 1)
+    # (rectangular grids: no caller of the path; the reference's formulation as torch expressions)
     cands = torch.cat([all_permutations_half(roll(control_points, i, 1)) for i in range(grid_size_y)], 1)
     return _best_permutation(out, cands, grid_size_x * grid_size_y * 3)
 
@@ -94,15 +98,9 @@ def control_points_loss(output, control_points, grid_size):
 
 
 def laplacian_loss(output, gt, dist_type="l2"):
-    """difference of the 4-neighbour Laplacians (zero padding) of two (B,g,g,3) grids"""
-    k = torch.tensor([[0.0, -0.25, 0.0], [-0.25, 1.0, -0.25], [0.0, -0.25, 0.0]], device=gt.device)
-    w = torch.zeros(3, 3, 3, 3, device=gt.device)
-    for c in range(3):
-        w[c, c] = k
-    lo = F.conv2d(output.permute(0, 3, 1, 2), w, padding=1)
-    li = F.conv2d(gt.permute(0, 3, 1, 2), w, padding=1)
-    d = (lo - li) ** 2 if dist_type == "l2" else (lo - li).abs()
-    return d.sum(1).mean()
+    """difference of the 4-neighbour Laplacians (zero padding) of two (B,g,g,3) grids: 5-point stencil kernel
+    (csrc/gridloss.cu) instead of the reference's two 3x3 convolutions"""
+    return GridLaplacianLossFn.apply(output, gt, 0 if dist_type == "l2" else 1)
 
 
 from src._fallthrough import module_getattr as _module_getattr  # noqa: E402

@@ -189,3 +189,83 @@ def test_batched_fit_stage_single_cluster_and_unmatched_shapes():
     assert torch.isfinite(total)
     total.backward()
     assert torch.isfinite(E.grad).all()
+
+
+def test_weights_normalize_kernel_equals_torch_expression_and_port():
+    """csrc/weights.cu (2 launches forward, 2 backward) against the torch expression it replaces on padded (B,N,64) tables
+    (K = 1 single-cluster early return, K = 7, K = 49) and against the oracle port per shape; gradient incl. the min / max
+    routing"""
+    from oracle.port import fitting as OP
+    from pnb200 import fitstage as FS
+    from pnb200.staging import arena
+    g = torch.Generator().manual_seed(0)
+    B, N, S = 3, 5003, FS.SLOTS
+    K = [1, 7, 49]
+    bws = torch.tensor([0.31, 0.05, 0.8]).cuda()
+    raw0 = torch.rand(B, N, S, generator=g) * 2 - 1
+    coef = torch.randn(B, N, S, generator=g).cuda()
+    stage = arena("test", torch.device("cuda", 0))
+    a = raw0.clone().cuda().requires_grad_()
+    b = raw0.clone().cuda().requires_grad_()
+    Wk = FS.normalized_weights(a, bws, K, stage)
+    Wt = FS.normalized_weights_torch(b, bws, K, stage)
+    _close(Wk, Wt, 1e-6, "weights, kernel vs torch expression")
+    (Wk * coef).sum().backward(); (Wt * coef).sum().backward()
+    for i in range(B):
+        assert not Wk[i, :, K[i]:].any() and not a.grad[i, :, K[i]:].any()
+        if K[i] == 1:
+            bound = 8 * np.finfo(np.float32).eps * float(coef.abs().max()) / (2 * float(bws[i]) ** 2)
+            assert float(a.grad[i].abs().max()) <= bound
+        else:
+            _close(a.grad[i], b.grad[i], 2e-4, f"d/d similarities, shape {i}")
+        r = raw0[i, :, :K[i]].t().clone().requires_grad_()
+        want = OP.weights_normalize(r, float(bws[i]))
+        _close(Wk[i, :, :K[i]].t(), want, 1e-5, f"weights vs port, shape {i}")
+        if K[i] > 1:
+            (want * coef[i, :, :K[i]].t().cpu()).sum().backward()
+            _close(a.grad[i, :, :K[i]].t(), r.grad, 2e-3, f"d/d similarities vs port, shape {i}")
+
+
+def test_grid_loss_kernels_equal_reference_formulation():
+    """csrc/gridloss.cu against the reference's formulation written with torch ops (candidate stacks by flip / transpose /
+    roll, Laplacian as a 3x3 convolution): values 1e-6, chosen candidate identical, gradients 1e-5; L2 and L1 Laplacian"""
+    import torch.nn.functional as TF
+    from src import loss as L
+    gen = torch.Generator().manual_seed(4)
+    B, g = 5, 20
+    gt = torch.randn(B, g, g, 3, generator=gen).cuda()
+    # outputs close to a different symmetric copy of the target per shape, so that the arg-min is not always candidate 0
+    flips = [gt, gt.flip(1), gt.flip(2), gt.flip(1, 2)]
+    open_c = torch.stack(flips + [f.transpose(1, 2) for f in flips], 1)                                  # (B,8,g,g,3)
+    closed_c = torch.cat([torch.stack([r, r.flip(1), r.flip(2), r.flip(1, 2)], 1)
+                          for r in (torch.roll(gt, s, 1) for s in range(g))], 1)                         # (B,4g,g,g,3)
+    for mode, cands, pick in ((0, open_c, [0, 3, 5, 6, 7]), (1, closed_c, [0, 9, 38, 77, 79])):
+        base = torch.stack([cands[b, p] for b, p in enumerate(pick)])
+        out = (base + 0.05 * torch.randn(B, g, g, 3, generator=gen).cuda()).reshape(B, g * g, 3)
+        a = out.clone().requires_grad_(); b_ = out.clone().requires_grad_()
+        if mode == 0:
+            la, best = L.control_points_permute_reg_loss(a, gt, g)
+        else:
+            la, best = L.control_points_permute_closed_reg_loss(a, gt, g, g)
+        diff = ((b_.view(B, 1, g, g, 3) - cands) ** 2).sum((2, 3, 4))
+        lb, idx = diff.min(1)
+        assert idx.tolist() == pick
+        lb = lb.mean() / (g * g * 3)
+        assert abs(la.item() - lb.item()) <= 1e-6 * abs(lb.item())
+        torch.testing.assert_close(best, cands[torch.arange(B), idx], rtol=0, atol=0)
+        (3.0 * la).backward(); (3.0 * lb).backward()
+        _close(a.grad, b_.grad, 1e-5, f"d/d output, mode {mode}")
+    k = torch.tensor([[0.0, -0.25, 0.0], [-0.25, 1.0, -0.25], [0.0, -0.25, 0.0]]).cuda()
+    w = torch.zeros(3, 3, 3, 3).cuda()
+    for c in range(3):
+        w[c, c] = k
+    for dist_type in ("l2", "l1"):
+        o1 = torch.randn(B, g, g, 3, generator=gen).cuda().requires_grad_(); t1 = gt.clone().requires_grad_()
+        o2 = o1.detach().clone().requires_grad_(); t2 = gt.clone().requires_grad_()
+        la = L.laplacian_loss(o1, t1, dist_type)
+        d = TF.conv2d(o2.permute(0, 3, 1, 2), w, padding=1) - TF.conv2d(t2.permute(0, 3, 1, 2), w, padding=1)
+        lb = ((d ** 2) if dist_type == "l2" else d.abs()).sum(1).mean()
+        assert abs(la.item() - lb.item()) <= 2e-6 * abs(lb.item()), (dist_type, la.item(), lb.item())
+        (2.0 * la).backward(); (2.0 * lb).backward()
+        _close(o1.grad, o2.grad, 1e-5, "d laplacian / d output " + dist_type)
+        _close(t1.grad, t2.grad, 1e-5, "d laplacian / d target " + dist_type)
