@@ -269,3 +269,36 @@ def test_grid_loss_kernels_equal_reference_formulation():
         (2.0 * la).backward(); (2.0 * lb).backward()
         _close(o1.grad, o2.grad, 1e-5, "d laplacian / d output " + dist_type)
         _close(t1.grad, t2.grad, 1e-5, "d laplacian / d target " + dist_type)
+
+
+@pytest.mark.parametrize("branch", ["threshold", "topk"])
+def test_standardize_point_torch_vs_port(branch):
+    """SURVEY a27, direct: the SplineNet input frame (confident-subset mean, minor PCA axis onto x through LAPACK's
+    eigenvectors, per-axis extent of the weighted subset) on the device -- per-entry drop-in AND the batched stage version --
+    against the oracle port (fitting_utils.py:512-553): points 1e-4, extents 1e-4, mean 1e-5, rotation 1e-5"""
+    from oracle.port import e2e as PE
+    from pnb200 import fitstage as FS
+    from pnb200.staging import arena
+    from src.fitting_utils import rotation_matrix_a_to_b, standardize_point_torch
+    gen = torch.Generator().manual_seed(7 if branch == "topk" else 8)
+    n = 2500
+    P = torch.randn(n, 3, generator=gen) * torch.tensor([1.0, 0.45, 0.12]) + torch.tensor([0.3, -0.2, 0.1])
+    Rq, _ = torch.linalg.qr(torch.randn(3, 3, generator=gen))
+    P = P @ Rq.t()
+    w = torch.rand(n, 1, generator=gen)
+    if branch == "topk":
+        w = w * 0.6                               # nothing above 0.8 -> the top-N/2 fallback (:518-522)
+    else:
+        w[:1200] = 0.9 + 0.1 * w[:1200]
+    want_pts, want_std, want_mean, want_R = PE.standardize_point(P, w)
+    pts, std, mean, R = standardize_point_torch(P.cuda(), w.cuda())
+    _close(mean, want_mean, 1e-5, "mean")
+    _close(R, want_R, 1e-5, "rotation")
+    _close(std, want_std, 1e-4, "extents")
+    _close(pts, want_pts, 1e-4, "standardised points")
+    Ps, stdb, meanb, Rb, Rinv = FS.standardize_batched(P.cuda().unsqueeze(0), w.cuda().reshape(1, n), rotation_matrix_a_to_b,
+                                                       arena("test", torch.device("cuda", 0)))
+    _close(Ps[0], want_pts, 1e-4, "standardised points (batched stage)")
+    _close(stdb[0], want_std, 1e-4, "extents (batched stage)")
+    _close(Rb[0], want_R, 1e-5, "rotation (batched stage)")
+    _close(Rinv[0] @ Rb[0], torch.eye(3), 1e-5, "R^-1 R")

@@ -66,3 +66,40 @@ def test_knn_full_size_self_first_and_sorted():
             full = oknn.knn_row(x[b].numpy(), r, 0)
             order = np.lexsort((np.arange(10000), -full))[:80]
             np.testing.assert_array_equal(idx[b, r], order)
+
+
+def test_cfg2_encoder_graphs_at_full_size_bit_exact():
+    """BASELINE config 2 as written: DGCNN encoder forward on B = 8 synthetic 10k-point clouds (points + normals, k = 80);
+    the kNN graph of EVERY layer (positions+normals metric, then the two 64-channel feature spaces) is compared bit-exactly
+    with the C oracle on 512 sampled rows per shape and layer, each layer given the input the network itself fed it
+    (the strided channel slices of the concat buffer, exactly as EncoderFn passes them)."""
+    from oracle import knn as oknn
+    from oracle.port import common
+    from pnb200 import ops
+    from src.PointNet import PrimitivesEmbeddingDGCNGn
+    from tools.synth import ALL_KINDS, synth_cloud
+    B, N, k = 8, 10000, 80
+    pts, nrm, lab, prim = synth_cloud(B, N, seed=2024, n_patches=8, kinds=ALL_KINDS)
+    x = torch.from_numpy(np.concatenate([pts, nrm], 2)).cuda()                       # (B,N,6) point-major
+    m = PrimitivesEmbeddingDGCNGn(embedding=True, emb_size=128, primitives=True, num_primitives=10, loss_function=None,
+                                  mode=5, num_channels=6, nn_nb=k)
+    sd = common.seeded_state_dict({n_: tuple(v.shape) for n_, v in m.state_dict().items()}, seed=5)
+    for i in (1, 2, 3):
+        for s_ in ("weight", "bias"):
+            sd[f"encoder.conv{i}.1.{s_}"] = sd[f"encoder.bn{i}.{s_}"]
+    m.load_state_dict(sd)
+    m.cuda()
+    with torch.no_grad():
+        x4, xf = m.encoder(x.permute(0, 2, 1).contiguous())                          # xf (B,256,N) view of (B,N,256)
+    xf_pm = xf.permute(0, 2, 1)                                                       # point-major concat buffer
+    layer_inputs = [(x, 1), (xf_pm[:, :, 0:64], 0), (xf_pm[:, :, 64:128], 0)]
+    rs = np.random.RandomState(0)
+    for li, (inp, metric) in enumerate(layer_inputs):
+        idx = ops.knn_graph(inp, k, metric, out_dtype=torch.int64).cpu().numpy()
+        host = inp.contiguous().cpu().numpy()
+        assert (idx[:, :, 0] == np.arange(N)[None]).mean() > 0.999
+        for b in range(B):
+            for r in rs.choice(N, 512, replace=False):
+                full = oknn.knn_row(host[b], int(r), metric)
+                order = np.lexsort((np.arange(N), -full))[:k]
+                np.testing.assert_array_equal(idx[b, r], order, err_msg=f"layer {li + 1} shape {b} row {r}")

@@ -273,14 +273,15 @@ def test_fitting_loss_fresh_shape_vs_port(N, seed, stage, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ config 3 training step
-def test_open_spline_training_step_vs_port():
+@pytest.mark.parametrize("B,M", [(4, 700), (36, 1000)])
+def test_open_spline_training_step_vs_port(B, M):
     """one optimisation step of train_open_splines.py:143-178 on fresh patches (SplineNet in TRAIN mode: batch statistics,
     one-sided spline reconstruction loss + permutation-invariant control-point regression + Laplacian loss, backward)
-    against the oracle port: losses 1e-4 relative (BASELINE config 3), parameter gradient norms 5e-3"""
+    against the oracle port: losses 1e-4 relative (BASELINE config 3), parameter gradient norms 5e-3.
+    (36, 1000) is the batch size of configs/config_open_splines.yml at a patch size inside its 400..2000 range."""
     from oracle.port import common, e2e as pe2e, fitting as OP
     from src import loss as L
     from src.model import DGCNNControlPoints
-    B, M = 4, 700
     g = torch.Generator().manual_seed(3)
     pts = torch.randn(B, 3, M, generator=g) * 0.3
     gtcp = torch.rand(B, 20, 20, 3, generator=g) - 0.5
