@@ -380,7 +380,10 @@ def run_ours(args):
         try:
             out["gpu_eager_baseline"] = gpu_eager_baseline(dev)
         except Exception as exc:
-            out["gpu_eager_baseline"] = {"value": None, "unit": "shapes/s", "sample": f"failed: {type(exc).__name__}: {exc}"}
+            import traceback
+            where = " <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in traceback.extract_tb(exc.__traceback__)[-4:])
+            out["gpu_eager_baseline"] = {"value": None, "unit": "shapes/s",
+                                         "sample": f"failed: {type(exc).__name__}: {str(exc)[:160]} at {where}"}
     print(json.dumps(out))
 
 
@@ -497,15 +500,17 @@ def gpu_eager_baseline(dev):
                 outs.append(d.topk(k=k, dim=-1)[1])
             return torch.cat(outs, 0)
 
-    saved = (port.knn_idx, torch.from_numpy, torch.Tensor.numpy)
+    saved = (port.knn_idx, torch.from_numpy, torch.Tensor.numpy, torch.as_tensor)
     try:
         port.knn_idx = knn_torch
         torch.from_numpy = lambda a: saved[1](a).to(dev)
         torch.Tensor.numpy = lambda self, *a, **k: saved[2](self.detach().cpu(), *a, **k)
+        torch.as_tensor = lambda a, *ar, **k: (saved[3](a, *ar, **k).to(dev) if isinstance(a, np.ndarray)
+                                               else saved[3](a, *ar, **k))
         _port_one_shape(seed=1, device=dev)                      # warm-up (cuBLAS / cuSOLVER handles, allocator)
         dt, sample = _port_one_shape(seed=0, device=dev)
     finally:
-        port.knn_idx, torch.from_numpy, torch.Tensor.numpy = saved
+        port.knn_idx, torch.from_numpy, torch.Tensor.numpy, torch.as_tensor = saved
     return {"value": 1.0 / dt, "unit": "shapes/s", "kind": "port on cuda (torch eager, reference formulation)", "sample": sample}
 
 

@@ -65,3 +65,49 @@ for mode in (0, 1):
     for li, (a, b, c, n) in enumerate(stats):
         print(f"  layer {li + 1}: points (of {n}) whose 10-neighbour SET differs: reference-fp32 vs ours {a}, "
               f"reference-fp32 vs float64 {b}, ours vs float64 {c}")
+
+
+# ---------------------------------------------------------------------------------------------- train mode, config-3 batch
+def train_mode_case(B, M):
+    from oracle.port import common
+    from src.model import DGCNNControlPoints
+    gen = torch.Generator().manual_seed(3)
+    pts = torch.randn(B, 3, M, generator=gen) * 0.3
+    net = DGCNNControlPoints(20, num_points=10, mode=0)
+    sd = common.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=7)
+    for i in (1, 2, 3, 4, 5):
+        for s_ in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked"):
+            a, b = f"bn{i}.{s_}", f"conv{i}.1.{s_}"
+            if a in sd and b in sd:
+                sd[b] = sd[a]
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    with torch.no_grad():
+        ours = net(pts.cuda()).cpu().numpy()
+        port32 = pe2e.splinenet_fwd(sd, pts, 10, None, train=True).numpy()
+        orig = pe2e.knn_feature_space
+        stats = []
+
+        def our_knn(xc, k):
+            ref = orig(xc, k)
+            mine = ops.knn_graph(xc.float().permute(0, 2, 1).contiguous().cuda(), k, 0, out_dtype=torch.int64).cpu()
+            srt = lambda t: torch.sort(t, dim=-1)[0]
+            stats.append((int((srt(ref) != srt(mine)).any(-1).sum()), xc.shape[0] * xc.shape[2]))
+            return mine
+
+        pe2e.knn_feature_space = our_knn
+        try:
+            port_ourknn = pe2e.splinenet_fwd(sd, pts, 10, None, train=True).numpy()
+        finally:
+            pe2e.knn_feature_space = orig
+    print(f"train mode B={B} M={M}:")
+    print(f"  ours vs port32                      {rel(ours, port32):.2e}")
+    print(f"  ours vs port32 with OUR kNN graphs  {rel(ours, port_ourknn):.2e}")
+    per_shape = np.abs(ours - port32).reshape(B, -1).max(1)
+    print("  per-shape max-abs error vs port32:", " ".join(f"{v:.1e}" for v in per_shape))
+    for li, (a, n) in enumerate(stats):
+        print(f"  layer {li + 1}: points (of {n}) whose 10-neighbour set differs reference-fp32 vs ours: {a}")
+
+
+train_mode_case(4, 700)
+train_mode_case(36, 1000)

@@ -136,19 +136,39 @@ def test_batched_fit_stage_equals_per_shape_loop(monkeypatch, sparse):
     for stage in ("loop", "batched"):
         monkeypatch.setattr(RU, "FIT_STAGE", stage)
         ev = RU.Evaluation(open_decoder=nets["open"], closed_decoder=nets["closed"])
+        per_seg = []
+        orig_sep = ev.separate_losses
+
+        def sep(distance, gt_points, lamb=1.0, _orig=orig_sep, _rec=per_seg, **kw):
+            _rec.append({k: (v[0], float(v[1])) for k, v in distance.items()})
+            return _orig(distance, gt_points, lamb=lamb, **kw)
+
+        ev.separate_losses = sep
         E = emb.clone().cuda().requires_grad_()
         np.random.seed(5)
         res, extra = ev.fitting_loss(E, pts, nrm, lab, prim.copy(), logp, quantile=0.015, iterations=10, lamb=0.1)
         total = torch.stack([r.reshape(()) for r in res[0::5]]).sum()
         total.backward()
-        results[stage] = (res, extra, E.grad.clone(), ev)
-    (r0, x0, g0, _), (r1, x1, g1, ev1) = results["loop"], results["batched"]
+        if stage == "batched":
+            per_seg = [{k: (v[0], float(v[1])) for k, v in fitstage.segment_distances(ev.last_fit, b).items()} for b in range(3)]
+        results[stage] = (res, extra, E.grad.clone(), ev, per_seg)
+    (r0, x0, g0, _, s0), (r1, x1, g1, ev1, s1) = results["loop"], results["batched"]
     assert len(r0) == len(r1) == 15
+    # per segment: analytic primitives are a smooth function of the weights (2e-5); a spline segment goes through discrete
+    # decisions (confident-point mask w > 0.8, top-N/2 fallback, kNN graphs of the SplineNet, Chamfer arg-mins) on weights
+    # that differ by rounding between the per-shape GEMM and the batched GEMM: 1e-3 there
+    for b in range(3):
+        assert set(s0[b].keys()) == set(s1[b].keys()), (b, s0[b], s1[b])
+        for k in s0[b]:
+            (kind0, d0), (kind1, d1) = s0[b][k], s1[b][k]
+            assert kind0 == kind1
+            tol = 1e-3 if "spline" in kind0 else 2e-5
+            assert abs(d0 - d1) <= tol * abs(d0) + 1e-9, (b, k, kind0, d0, d1)
     for i, (a, b) in enumerate(zip(r0, r1)):
         if a is None or b is None:
             assert a is None and b is None, (i, a, b)
         else:
-            assert abs(float(a) - float(b)) <= 2e-5 * abs(float(a)) + 1e-9, (i, float(a), float(b))
+            assert abs(float(a) - float(b)) <= 3e-4 * abs(float(a)) + 1e-9, (i, float(a), float(b))
     np.testing.assert_array_equal(x0[1], x1[1])
     _close(x1[2], x0[2], 1e-5, "returned membership similarities of the last shape")
     p0, p1 = x0[0], x1[0]
@@ -161,7 +181,7 @@ def test_batched_fit_stage_equals_per_shape_loop(monkeypatch, sparse):
         for a, b in zip(p0[k][1:], p1[k][1:]):
             assert tuple(a.shape) == tuple(b.shape), (k, p0[k][0], a.shape, b.shape)
             _close(b, a, 2e-4, f"parameters of the last shape: {p0[k][0]}")
-    _close(g1, g0, 2e-4, "d loss / d embedding, batched stage vs per-shape loop")
+    _close(g1, g0, 2e-3, "d loss / d embedding, batched stage vs per-shape loop")
     # per-segment view used by the parity tests
     d = fitstage.segment_distances(ev1.last_fit, 0)
     assert sorted(v[0] for v in d.values()) == sorted(v[0] for v in p1.values() if v is not None) or len(d) > 0
@@ -201,7 +221,7 @@ def test_weights_normalize_kernel_equals_torch_expression_and_port():
     g = torch.Generator().manual_seed(0)
     B, N, S = 3, 5003, FS.SLOTS
     K = [1, 7, 49]
-    bws = torch.tensor([0.31, 0.05, 0.8]).cuda()
+    bws = torch.tensor([0.31, 0.2, 0.8]).cuda()
     raw0 = torch.rand(B, N, S, generator=g) * 2 - 1
     coef = torch.randn(B, N, S, generator=g).cuda()
     stage = arena("test", torch.device("cuda", 0))
@@ -302,3 +322,28 @@ def test_standardize_point_torch_vs_port(branch):
     _close(stdb[0], want_std, 1e-4, "extents (batched stage)")
     _close(Rb[0], want_R, 1e-5, "rotation (batched stage)")
     _close(Rinv[0] @ Rb[0], torch.eye(3), 1e-5, "R^-1 R")
+
+
+def test_weights_normalize_kernel_extreme_bandwidth_vs_float64():
+    """bandwidth 0.05 -> exponents clamp at +-75, e ~ 3.7e32: values and gradients stay finite and match a float64 evaluation
+    of the same expression (the fp32 torch expression itself produces non-finite gradients in this regime on the GPU)"""
+    from pnb200 import fitstage as FS
+    from pnb200.staging import arena
+    g = torch.Generator().manual_seed(1)
+    B, N, S, K = 1, 3001, FS.SLOTS, 7
+    raw0 = torch.rand(B, N, S, generator=g) * 2 - 1
+    coef = torch.randn(B, N, S, generator=g)
+    a = raw0.clone().cuda().requires_grad_()
+    Wk = FS.normalized_weights(a, torch.tensor([0.05]).cuda(), [K], arena("test", torch.device("cuda", 0)))
+    (Wk * coef.cuda()).sum().backward()
+    assert torch.isfinite(Wk).all() and torch.isfinite(a.grad).all()
+    r = raw0[0, :, :K].double().clone().requires_grad_()
+    bw2 = float(np.float32(0.05)) ** 2
+    x = torch.clamp(r / float(np.float32(bw2)) / 2, min=-75.0, max=75.0)
+    prob = torch.exp(x)
+    prob = prob / prob.sum(1, keepdim=True)
+    mm = prob - prob.min(0, keepdim=True)[0]
+    want = mm / (mm.max(0, keepdim=True)[0] + FS.EPS)
+    (want * coef[0, :, :K].double()).sum().backward()
+    _close(Wk[0, :, :K], want, 1e-5, "weights, clamp regime")
+    _close(a.grad[0, :, :K], r.grad, 1e-3, "d/d similarities, clamp regime")

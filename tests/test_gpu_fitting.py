@@ -161,7 +161,7 @@ def test_splinenet_eval_with_weights_vs_reference(golden_dir, mode):
     net = _spline_net(g, f"m{mode}", mode, 30 + mode).eval()
     w = _cu(g[f"m{mode}_w"], True)
     o = net(_cu(g[f"m{mode}_x"]), w.t())
-    _close(o, g[f"m{mode}_out"], rtol=2e-4, name="control points")
+    _close(o, g[f"m{mode}_out"], rtol=1e-5, name="control points")    # measured 0.9e-6 / 1.5e-6 (profiles/r02_parity_bounds.md)
     (o * _cu(g[f"m{mode}_c"])).sum().backward()
     _close(w.grad, g[f"m{mode}_gw"], rtol=2e-3, name="grad wrt weights")
 
