@@ -501,7 +501,21 @@ def gpu_eager_baseline(dev):
             return torch.cat(outs, 0)
 
     saved = (port.knn_idx, torch.from_numpy, torch.Tensor.numpy, torch.as_tensor)
+    # factory calls without a device argument follow the run's device -- patched on the torch module itself, because the
+    # backward of the port's autograd Functions runs on the autograd engine's thread, where a torch.device(...) context
+    # (thread-local) is not active
+    factories = {n: getattr(torch, n) for n in ("zeros", "ones", "eye", "full", "arange", "tensor", "empty", "linspace")}
+
+    def on_dev(fn):
+        def wrapped(*a, **k):
+            if k.get("device") is None:
+                k["device"] = dev
+            return fn(*a, **k)
+        return wrapped
+
     try:
+        for n, fn in factories.items():
+            setattr(torch, n, on_dev(fn))
         port.knn_idx = knn_torch
         torch.from_numpy = lambda a: saved[1](a).to(dev)
         torch.Tensor.numpy = lambda self, *a, **k: saved[2](self.detach().cpu(), *a, **k)
@@ -511,6 +525,8 @@ def gpu_eager_baseline(dev):
         dt, sample = _port_one_shape(seed=0, device=dev)
     finally:
         port.knn_idx, torch.from_numpy, torch.Tensor.numpy, torch.as_tensor = saved
+        for n, fn in factories.items():
+            setattr(torch, n, fn)
     return {"value": 1.0 / dt, "unit": "shapes/s", "kind": "port on cuda (torch eager, reference formulation)", "sample": sample}
 
 

@@ -88,17 +88,21 @@ class Evaluation:
         if FIT_STAGE == "batched" and embedding.shape[2] == 128 and max(n_clusters) <= 49:
             return self._fitting_loss_batched(embedding, ms_state if sparse else None, shifted, ids, bws, points, normals,
                                               labels, primitives, prim_pred_dev, cluster_np, lamb)
-        centers_b = _ms.centers_sparse(embedding, ms_state, ids) if sparse else None
+        # (similarities of ALL shapes by the same batched product the batched stage uses: the two paths then see bit-identical
+        # weights, so the discrete decisions of the spline fits -- confident-point masks, kNN graphs -- agree between them)
+        raw_all = torch.bmm(embedding, _ms.centers_padded(embedding, ms_state if sparse else None, ids, shifted).transpose(1, 2))
         self._stage = arena("fit", dev)
         self._stage.reset()
         out, lazies, metrics, matchings = [], [], [], []
         parameters, weights = None, None
         for b in range(B):
-            center, bandwidth = (centers_b[b] if sparse else shifted[b][ids[b]]), float(bw_host[b])
+            bandwidth = float(bw_host[b])
             if np.unique(cluster_np[b]).shape[0] > 49:       # rare: grow the quantile for this shape only (ref :76-83)
                 center, bw_t, cl = self.guard_mean_shift(embedding[b], quantile * 1.2, iterations)
                 cluster_np[b], bandwidth = cl.data.cpu().numpy(), float(bw_t)
-            weights = center @ embedding[b].t()
+                weights = center @ embedding[b].t()
+            else:
+                weights = raw_all[b, :, :int(ids[b].shape[0])].t()
             loss, parameters, _, rows, cols, distance = self.residual_train_mode(
                 points[b], normals[b], labels[b], cluster_np[b], primitives[b], weights, bandwidth, lamb=lamb, lazy=True)
             lazies.append(loss)

@@ -68,11 +68,15 @@ for mode in (0, 1):
 
 
 # ---------------------------------------------------------------------------------------------- train mode, config-3 batch
-def train_mode_case(B, M):
+def train_mode_case(B, M, patches=False):
     from oracle.port import common
     from src.model import DGCNNControlPoints
     gen = torch.Generator().manual_seed(3)
-    pts = torch.randn(B, 3, M, generator=gen) * 0.3
+    if patches:
+        from tools.synth import open_spline_batch
+        pts = torch.from_numpy(open_spline_batch(B, M, seed=3)[0])
+    else:
+        pts = torch.randn(B, 3, M, generator=gen) * 0.3
     net = DGCNNControlPoints(20, num_points=10, mode=0)
     sd = common.seeded_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=7)
     for i in (1, 2, 3, 4, 5):
@@ -100,7 +104,11 @@ def train_mode_case(B, M):
             port_ourknn = pe2e.splinenet_fwd(sd, pts, 10, None, train=True).numpy()
         finally:
             pe2e.knn_feature_space = orig
-    print(f"train mode B={B} M={M}:")
+        sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+        port64 = pe2e.splinenet_fwd(sd64, pts.double(), 10, None, train=True).numpy()
+    print(f"train mode B={B} M={M} {'smooth spline patches' if patches else 'gaussian point clouds'}:")
+    print(f"  port32 vs port64 (reference's own fp32 error) {rel(port32, port64):.2e}")
+    print(f"  ours   vs port64                              {rel(ours, port64):.2e}")
     print(f"  ours vs port32                      {rel(ours, port32):.2e}")
     print(f"  ours vs port32 with OUR kNN graphs  {rel(ours, port_ourknn):.2e}")
     per_shape = np.abs(ours - port32).reshape(B, -1).max(1)
@@ -111,3 +119,4 @@ def train_mode_case(B, M):
 
 train_mode_case(4, 700)
 train_mode_case(36, 1000)
+train_mode_case(36, 1000, patches=True)

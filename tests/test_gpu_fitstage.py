@@ -154,21 +154,21 @@ def test_batched_fit_stage_equals_per_shape_loop(monkeypatch, sparse):
         results[stage] = (res, extra, E.grad.clone(), ev, per_seg)
     (r0, x0, g0, _, s0), (r1, x1, g1, ev1, s1) = results["loop"], results["batched"]
     assert len(r0) == len(r1) == 15
-    # per segment: analytic primitives are a smooth function of the weights (2e-5); a spline segment goes through discrete
-    # decisions (confident-point mask w > 0.8, top-N/2 fallback, kNN graphs of the SplineNet, Chamfer arg-mins) on weights
-    # that differ by rounding between the per-shape GEMM and the batched GEMM: 1e-3 there
+    # per segment.  Both paths take the similarities from the same batched product, so the discrete decisions of a spline fit
+    # (confident-point mask w > 0.8, top-N/2 fallback, kNN graphs of the SplineNet, Chamfer arg-mins) agree; what differs is
+    # summation order (padded Chamfer means, batched SplineNet launches) and the fp64 solve kernel vs torch algebra
     for b in range(3):
         assert set(s0[b].keys()) == set(s1[b].keys()), (b, s0[b], s1[b])
         for k in s0[b]:
             (kind0, d0), (kind1, d1) = s0[b][k], s1[b][k]
             assert kind0 == kind1
-            tol = 1e-3 if "spline" in kind0 else 2e-5
+            tol = 1e-4 if "spline" in kind0 else 2e-5
             assert abs(d0 - d1) <= tol * abs(d0) + 1e-9, (b, k, kind0, d0, d1)
     for i, (a, b) in enumerate(zip(r0, r1)):
         if a is None or b is None:
             assert a is None and b is None, (i, a, b)
         else:
-            assert abs(float(a) - float(b)) <= 3e-4 * abs(float(a)) + 1e-9, (i, float(a), float(b))
+            assert abs(float(a) - float(b)) <= 5e-5 * abs(float(a)) + 1e-9, (i, float(a), float(b))
     np.testing.assert_array_equal(x0[1], x1[1])
     _close(x1[2], x0[2], 1e-5, "returned membership similarities of the last shape")
     p0, p1 = x0[0], x1[0]
@@ -181,7 +181,7 @@ def test_batched_fit_stage_equals_per_shape_loop(monkeypatch, sparse):
         for a, b in zip(p0[k][1:], p1[k][1:]):
             assert tuple(a.shape) == tuple(b.shape), (k, p0[k][0], a.shape, b.shape)
             _close(b, a, 2e-4, f"parameters of the last shape: {p0[k][0]}")
-    _close(g1, g0, 2e-3, "d loss / d embedding, batched stage vs per-shape loop")
+    _close(g1, g0, 2e-4, "d loss / d embedding, batched stage vs per-shape loop")
     # per-segment view used by the parity tests
     d = fitstage.segment_distances(ev1.last_fit, 0)
     assert sorted(v[0] for v in d.values()) == sorted(v[0] for v in p1.values() if v is not None) or len(d) > 0

@@ -283,8 +283,13 @@ def test_open_spline_training_step_vs_port(B, M):
     from src import loss as L
     from src.model import DGCNNControlPoints
     g = torch.Generator().manual_seed(3)
-    pts = torch.randn(B, 3, M, generator=g) * 0.3
-    gtcp = torch.rand(B, 20, 20, 3, generator=g) - 0.5
+    if B == 36:     # config 3 as SURVEY 8d describes it: smooth random bicubic patches with their control grids
+        from tools.synth import open_spline_batch
+        p_np, cp_np = open_spline_batch(B, M, seed=3)
+        pts, gtcp = torch.from_numpy(p_np), torch.from_numpy(cp_np)
+    else:
+        pts = torch.randn(B, 3, M, generator=g) * 0.3
+        gtcp = torch.rand(B, 20, 20, 3, generator=g) - 0.5
     net = DGCNNControlPoints(20, num_points=10, mode=0)
     shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
     sd = common.seeded_state_dict(shapes, seed=7)

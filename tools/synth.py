@@ -118,3 +118,27 @@ def synth_cloud(B, N, seed, n_patches=5, kinds=ANALYTIC_KINDS):
         pts[b] -= pts[b].mean(0, keepdims=True)
         pts[b] /= np.max(pts[b].max(0) - pts[b].min(0))
     return pts, nrm, lab, prim
+
+
+def open_spline_batch(B, M, seed):
+    """BASELINE config 3 input: B smooth random bicubic 20x20 control grids, M surface points each at random
+    (u, v), centred and scaled to unit max extent together with their control grid.
+    -> points (B,3,M) f32 (channel-major like train_open_splines.py feeds them), control grids (B,20,20,3) f32"""
+    rng = np.random.RandomState(seed)
+    pts = np.zeros((B, 3, M), np.float32)
+    cps = np.zeros((B, 20, 20, 3), np.float32)
+    g = np.linspace(-0.5, 0.5, 20)
+    gx, gy = np.meshgrid(g, g, indexing="ij")
+    for b in range(B):
+        a = rng.uniform(0.05, 0.15, 3); f = rng.uniform(0.5, 2.0, (3, 2)); ph = rng.uniform(0, 2 * np.pi, 3)
+        gz = sum(a[k] * np.sin(2 * np.pi * (f[k, 0] * gx + f[k, 1] * gy) + ph[k]) for k in range(3))
+        cp = np.stack([gx, gy, gz], 2)
+        R, _ = np.linalg.qr(rng.randn(3, 3))
+        cp = cp @ R.T
+        u, v = rng.rand(M) * (1 - 1e-9), rng.rand(M) * (1 - 1e-9)
+        p = np.einsum("mi,ijc,mj->mc", bspline_basis(20, 3, u), cp, bspline_basis(20, 3, v))
+        c = p.mean(0, keepdims=True)
+        s = np.max(p.max(0) - p.min(0))
+        pts[b] = ((p - c) / s).T
+        cps[b] = (cp - c.reshape(1, 1, 3)) / s
+    return pts, cps
