@@ -146,7 +146,11 @@ def standardize_batched(P, w, rotation_fn, stage):
     mean = (P * wm).sum(1) / (wm.sum(1) + EPS)                                        # (E,3)
     Pc = P - mean.unsqueeze(1)
     Xm = Pc * m
-    cov = (Xm.transpose(1, 2) @ Xm).cpu()                                             # THE read-back of the spline stage
+    # covariance accumulated in float64 and rounded once: its fp32 value then does not depend on how many point sets share
+    # the launch (a batched product sums in another order than a single one), so LAPACK sees the same matrix -- hence returns
+    # the same eigenvector SIGNS -- whether a segment is standardised alone or in a batch
+    Xd = Xm.double()
+    cov = (Xd.transpose(1, 2) @ Xd).float().cpu()                                     # THE read-back of the spline stage
     evals, evecs = torch.linalg.eig(cov)
     R_np = np.empty((E, 3, 3), np.float32)
     Rinv_np = np.empty((E, 3, 3), np.float32)
@@ -258,7 +262,7 @@ def run(evaluation, embedding, centers, K, bws, points, normals, labels, primiti
         values.append(d_spl)
         for e, s in enumerate(plan.splines):
             terms.append((s[0], off + e, float(lamb), True))
-    out = {"plan": plan, "raw": raw, "recs": recs, "par32": par32}
+    out = {"plan": plan, "raw": raw, "recs": recs, "par32": par32, "Wn": Wn}
     if not terms:
         out.update(loss=torch.zeros(B, device=dev), stats=torch.full((B, 2), float("nan"), dtype=torch.float64, device=dev),
                    has_terms=np.zeros(B, bool), D=None, terms=terms)

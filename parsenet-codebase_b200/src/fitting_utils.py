@@ -118,7 +118,8 @@ def rotation_matrix_a_to_b(A, B):
 def pca_torch(X):
     """eigen-decomposition of X^T X as (eigenvalues (3,2) real/imag, eigenvectors (3,3)); LAPACK geev on the host so
     that eigenvector signs are the reference's (torch.eig on a 3x3 runs on the CPU there as well)."""
-    cov = (X.t() @ X).detach().cpu()
+    Xd = X.detach().double()
+    cov = (Xd.t() @ Xd).float().cpu()       # (float64 accumulation, rounded once: see pnb200.fitstage.standardize_batched)
     w, v = torch.linalg.eig(cov)
     return torch.stack([w.real, w.imag], 1), v.real
 
