@@ -32,9 +32,11 @@ def test_fitting_loss_on_cuda1_while_current_device_is_cuda0():
         torch.cuda.synchronize(dev)
         out[dev_i] = (float(res[0]), E.grad.cpu().clone(), extra[1].copy())
         assert torch.cuda.current_device() == 0
-    assert out[0][0] == out[1][0], "same kernels, same inputs: the loss is bit-identical on either device"
+    # same kernels, same inputs; floating-point atomics (moment / statistics accumulation) order differently per run
+    assert abs(out[0][0] - out[1][0]) <= 1e-5 * abs(out[0][0]), (out[0][0], out[1][0])
     np.testing.assert_array_equal(out[0][2], out[1][2])
-    torch.testing.assert_close(out[0][1], out[1][1], rtol=0, atol=0)
+    scale = out[0][1].abs().max().item()
+    assert (out[0][1] - out[1][1]).abs().max().item() <= 1e-4 * scale
 
 
 @needs2
