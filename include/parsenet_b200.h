@@ -100,6 +100,10 @@ int pn_linear_fwd_tc(const float* A, long long lda, const float* W, long long ld
 int pn_linear_fwd_tc_supported(const float* A, long long lda, const float* W, long long ldw, const float* Y, long long ldy, int Np, int K, int Nout, int G, int has_stats);
 /* replaces: autograd of the same chains (torch built-in in the reference) */
 int pn_linear_bwd_data(const float* dY, long long lddy, const float* W, long long ldw, float* dZ, long long lddz, int accumulate, int finalize, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, const float* gamma, const float* mean_rstd, double* gsum, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream);
+/* the same backward on the tcgen05 tensor cores (split-TF32): the forward GEMM kernel with A = dY and the TRANSPOSED weight
+   Wt [K][Nout] as its row-major weight operand, finalize epilogue (activation mask + norm-backward sums) in the store phase */
+int pn_linear_bwd_data_tc_supported(const float* dY, long long lddy, const float* Wt, long long ldwt, const float* dZ, long long lddz, const float* A, long long lda, int Np, int K, int Nout, int G, int has_gamma);
+int pn_linear_bwd_data_tc(const float* dY, long long lddy, const float* Wt, long long ldwt, float* dZ, long long lddz, int accumulate, int finalize, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, const float* gamma, const float* mean_rstd, double* gsum, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream);
 /* replaces: autograd of the same chains (torch built-in in the reference) */
 int pn_linear_bwd_weight(const float* dY, long long lddy, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, float* dW, long long lddw, float* db, float* dsb, int B, int Np, int K, int Nout, void* stream);
 /* replaces: nn.GroupNorm / nn.BatchNorm statistics: src/PointNet.py:151-155,166-169; src/model.py:69-73,98-99 */

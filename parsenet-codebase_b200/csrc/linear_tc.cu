@@ -45,13 +45,28 @@ struct Args {
     float* Y; long long ldy;            // [B*Np][Nout]
     double* stats;                      // [S][G][2] or null
     int B, Np, K, Nout, G, stats_per_shape;
+    // ---- backward-data epilogue (BWD instantiation: A = dY, W = W^T of the layer, Y = dZ, Nout = input width of the layer)
+    int acc;                            // dZ += instead of overwrite
+    int fin;                            // multiply by act'(norm(fA)) and accumulate the norm-backward sums
+    const float* fA; long long fld;     // pre-norm input of the layer [B*Np][Nout]
+    const float* fsc; const float* fsh; int fact;      // producer scale / shift [B][Nout] (or null), activation
+    const float* fgamma;                // [Nout] norm weight of the producer, or null: mask only
+    const float* fmr;                   // [S][fG][2] mean / rstd of the producer
+    double* fgsum;                      // [S][fG][2]
+    int fG, fps;
 };
+__device__ __forceinline__ float act_grad(float pre, int act) {
+    if (act == ACT_RELU) return pre > 0.f ? 1.f : 0.f;
+    if (act == ACT_LRELU) return pre > 0.f ? 1.f : 0.2f;
+    return 1.f;
+}
 
 struct Bars { uint64_t full[NSTAGE], empty[NSTAGE], acc_full; };
 
 // grid (tiles_n, tiles_m * B): the column tiles of one row block are adjacent in launch order, so the A rows they share
 // are read from DRAM once and re-used out of L2 (with the row block outermost ncu showed A re-read once per column tile)
-__global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
+template <bool BWD>
+__global__ void __launch_bounds__(NT, 2) linear_tc_kernel(Args p) {
     extern __shared__ __align__(1024) unsigned char smem[];
     float* sc_s = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);      // [K] producer scale (or unused)
     float* sh_s = sc_s + p.K;                                                 // [K] producer shift
@@ -126,16 +141,69 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
                 }
             }
             __syncwarp();
+            [[maybe_unused]] float f1 = 0.f, f2 = 0.f;
+            [[maybe_unused]] float fmean = 0.f, frstd = 0.f;
+            if constexpr (BWD) {
+                if (p.fin && p.fgamma) {
+                    const int g = (n0 + c0) / (p.Nout / p.fG);
+                    const float* mr = p.fmr + ((long long)(p.fps ? b : 0) * p.fG + g) * 2;
+                    fmean = mr[0]; frstd = mr[1];
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int rr = sub_r + 4 * i;                    // row inside this warp's 32
                 const int gr = m0 + 32 * warp + rr;
                 if (gr < p.Np) {
-                    const float4 o = *reinterpret_cast<const float4*>(tr + rr * EPI_PITCH + sub_c);
-                    *reinterpret_cast<float4*>(p.Y + ((long long)b * p.Np + gr) * p.ldy + n0 + c0 + sub_c) = o;
+                    float4 o = *reinterpret_cast<const float4*>(tr + rr * EPI_PITCH + sub_c);
+                    const long long row = (long long)b * p.Np + gr;
+                    const int col = n0 + c0 + sub_c;
+                    float* dst = p.Y + row * p.ldy + col;
+                    if constexpr (BWD) {
+                        if (p.acc) {
+                            const float4 old = *reinterpret_cast<const float4*>(dst);
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        if (p.fin) {
+                            const float4 a = *reinterpret_cast<const float4*>(p.fA + row * p.fld + col);
+                            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.fsc) {
+                                sc = *reinterpret_cast<const float4*>(p.fsc + (long long)b * p.Nout + col);
+                                sh = *reinterpret_cast<const float4*>(p.fsh + (long long)b * p.Nout + col);
+                            }
+                            const float av[4] = {a.x, a.y, a.z, a.w};
+                            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+                            float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float pre = p.fsc ? fmaf(av[e], scv[e], shv[e]) : av[e];
+                                const float t = ov[e] * act_grad(pre, p.fact);
+                                if (p.fgamma) {
+                                    const float xh = (av[e] - fmean) * frstd;
+                                    const float gt = p.fgamma[col + e] * t;
+                                    f1 += gt;
+                                    f2 = fmaf(gt, xh, f2);
+                                }
+                                ov[e] = t;
+                            }
+                            o = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                        }
+                    }
+                    *reinterpret_cast<float4*>(dst) = o;
                 }
             }
             __syncwarp();
+            if constexpr (BWD) {
+                if (p.fin && p.fgamma) {
+                    const double d1 = warp_sum((double)f1), d2 = warp_sum((double)f2);
+                    if (lane == 0) {
+                        const int cpgf = p.Nout / p.fG;
+                        const int gl = (n0 + c0) / cpgf - n0 / cpgf;
+                        atomicAdd(&gacc[gl][0], d1);
+                        atomicAdd(&gacc[gl][1], d2);
+                    }
+                }
+            }
             if (p.stats) {
                 double ds = warp_sum((double)s), dq = warp_sum((double)q);
                 if (lane == 0) {
@@ -146,6 +214,18 @@ __global__ void __launch_bounds__(NT, 2) linear_fwd_tc_kernel(Args p) {
             }
         }
         tc_fence_before();
+        if constexpr (BWD) {
+            if (p.fin && p.fgamma) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid < MAXG * 2) {
+                    const int cpgf = p.Nout / p.fG;
+                    const int gl = tid >> 1;
+                    const int g = n0 / cpgf + gl;
+                    if (g < p.fG && (long long)g * cpgf < (long long)min(p.Nout, n0 + BN) && gacc[gl][tid & 1] != 0.0)
+                        atomicAdd(&p.fgsum[((long long)(p.fps ? b : 0) * p.fG + g) * 2 + (tid & 1)], gacc[gl][tid & 1]);
+                }
+            }
+        }
         if (p.stats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid < MAXG * 2) {
@@ -281,13 +361,59 @@ extern "C" int pn_linear_fwd_tc(const float* A, long long lda, const float* W, l
     PN_REQUIRE(pn_linear_fwd_tc_supported(A, lda, W, ldw, Y, ldy, Np, K, Nout, G, stats != nullptr),
                "pn_linear_fwd_tc: unsupported problem (K=%d Nout=%d G=%d; need 16-byte aligned rows, K %% 4 == 0, "
                "Nout %% 32 == 0, channels/group %% 32 == 0)", K, Nout, G);
-    Args p{A, lda, W, ldw, bias, sbias, in_scale, in_shift, in_act, Y, ldy, stats, B, Np, K, Nout, G, stats_per_shape};
+    Args p{};
+    p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.bias = bias; p.sbias = sbias; p.in_scale = in_scale; p.in_shift = in_shift;
+    p.in_act = in_act; p.Y = Y; p.ldy = ldy; p.stats = stats; p.B = B; p.Np = Np; p.K = K; p.Nout = Nout; p.G = G;
+    p.stats_per_shape = stats_per_shape;
     size_t sm = (size_t)NSTAGE * STAGE_BYTES + 2 * (size_t)K * sizeof(float) + 1024;
-    PN_CUDA(cudaFuncSetAttribute(linear_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_CUDA(cudaFuncSetAttribute(linear_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     PN_REQUIRE((long long)cdiv(Np, BM) * B <= 65535, "pn_linear_fwd_tc: too many row tiles (%d x %d)", cdiv(Np, BM), B);
     dim3 grid(cdiv(Nout, BN), cdiv(Np, BM) * B);
-    linear_fwd_tc_kernel<<<grid, NT, sm, (cudaStream_t)stream>>>(p);
+    linear_tc_kernel<false><<<grid, NT, sm, (cudaStream_t)stream>>>(p);
     PN_COUNT_LAUNCH();
-    PN_LAUNCH_CHECK("linear_fwd_tc_kernel");
+    PN_LAUNCH_CHECK("linear_tc_kernel<fwd>");
+    return PN_OK;
+}
+
+// Backward w.r.t. the layer input on the tensor cores: dZ[m][k] (+)= sum_n dY[m][n] W[n][k], same epilogue contract as
+// pn_linear_bwd_data (activation mask of the layer input + norm-backward sums).  It is the forward GEMM with A = dY and the
+// TRANSPOSED weight Wt [K][Nout] as the row-major "weight" operand (contraction over Nout), plus the finalize epilogue.
+extern "C" int pn_linear_bwd_data_tc_supported(const float* dY, long long lddy, const float* Wt, long long ldwt, const float* dZ,
+                                               long long lddz, const float* A, long long lda, int Np, int K, int Nout, int G,
+                                               int has_gamma) {
+    using namespace lintc;
+    if (!aligned16(dY) || !aligned16(Wt) || !aligned16(dZ) || lddy % 4 || ldwt % 4 || lddz % 4) return 0;
+    if (A && (!aligned16(A) || lda % 4)) return 0;
+    if (Nout % 4 || Nout < 16 || Nout > 4096 || K % 32 || K < 32 || Np < 1) return 0;
+    if (has_gamma && (G <= 0 || K % G || (K / G) % 32)) return 0;
+    return 1;
+}
+
+extern "C" int pn_linear_bwd_data_tc(const float* dY, long long lddy, const float* Wt, long long ldwt, float* dZ, long long lddz,
+                                     int accumulate, int finalize, const float* A, long long lda, const float* in_scale,
+                                     const float* in_shift, int in_act, const float* gamma, const float* mean_rstd,
+                                     double* gsum, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream) {
+    using namespace lintc;
+    PN_REQUIRE(dY && Wt && dZ, "pn_linear_bwd_data_tc: null pointer");
+    PN_REQUIRE(!finalize || A, "pn_linear_bwd_data_tc: finalize needs A");
+    PN_REQUIRE(!(finalize && gamma) || (mean_rstd && gsum), "pn_linear_bwd_data_tc: norm args");
+    PN_REQUIRE(B > 0 && Np > 0, "pn_linear_bwd_data_tc: bad shape");
+    PN_REQUIRE(pn_linear_bwd_data_tc_supported(dY, lddy, Wt, ldwt, dZ, lddz, finalize ? A : nullptr, lda, Np, K, Nout, G,
+                                               finalize && gamma),
+               "pn_linear_bwd_data_tc: unsupported problem (K=%d Nout=%d G=%d)", K, Nout, G);
+    Args p{};
+    p.A = dY; p.lda = lddy; p.W = Wt; p.ldw = ldwt; p.Y = dZ; p.ldy = lddz; p.B = B; p.Np = Np;
+    p.K = Nout;                  // contraction length of the GEMM
+    p.Nout = K;                  // output columns = input width of the layer
+    p.G = 1; p.stats_per_shape = 1;
+    p.acc = accumulate; p.fin = finalize; p.fA = A; p.fld = lda; p.fsc = in_scale; p.fsh = in_shift; p.fact = in_act;
+    p.fgamma = finalize ? gamma : nullptr; p.fmr = mean_rstd; p.fgsum = gsum; p.fG = G > 0 ? G : 1; p.fps = stats_per_shape;
+    size_t sm = (size_t)NSTAGE * STAGE_BYTES + 2 * (size_t)p.K * sizeof(float) + 1024;
+    PN_CUDA(cudaFuncSetAttribute(linear_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_REQUIRE((long long)cdiv(Np, BM) * B <= 65535, "pn_linear_bwd_data_tc: too many row tiles (%d x %d)", cdiv(Np, BM), B);
+    dim3 grid(cdiv(p.Nout, BN), cdiv(Np, BM) * B);
+    linear_tc_kernel<true><<<grid, NT, sm, (cudaStream_t)stream>>>(p);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("linear_tc_kernel<bwd_data>");
     return PN_OK;
 }

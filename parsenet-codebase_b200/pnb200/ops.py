@@ -53,6 +53,7 @@ def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
 ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 GN_EPS = 1e-5
 LINEAR_IMPL = os.environ.get("PN_LINEAR", "tc")
+LINEAR_BWD_IMPL = os.environ.get("PN_LINEAR_BWD", LINEAR_IMPL)       # "tc" | "simt" for the two backward GEMMs
 
 
 def _pitch(t):
@@ -130,6 +131,17 @@ def linear_bwd_data(dY, W, dZ=None, accumulate=False, fin_A=None, fin_norm=None,
             gsum = torch.zeros((mr.shape[0], G, 2), dtype=torch.float64, device=dY.device)
         else:
             act = fin_act if fin_act is not None else ACT_NONE
+    # tensor-core path (split-TF32, csrc/linear_tc.cu): the forward GEMM kernel on (dY, W^T) with the finalize epilogue;
+    # shapes it does not take (narrow layers, per-channel BatchNorm groups, M < 128) stay on the FP32-pipe kernel
+    if LINEAR_BWD_IMPL == "tc" and Np >= 128 and W.stride(1) == 1:
+        Wt = W.t().contiguous()
+        if lib.pn_linear_bwd_data_tc_supported(_ptr(dY), _pitch(dY), _ptr(Wt), Wt.stride(0), _ptr(dZ), _pitch(dZ),
+                                               _ptr(fin_A), _pitch(fin_A) if finalize else 0, Np, K, Nout, G,
+                                               1 if (finalize and gamma is not None) else 0):
+            call("pn_linear_bwd_data_tc", _ptr(dY), _pitch(dY), _ptr(Wt), Wt.stride(0), _ptr(dZ), _pitch(dZ),
+                 1 if accumulate else 0, 1 if finalize else 0, _ptr(fin_A), _pitch(fin_A) if finalize else 0, _ptr(sc),
+                 _ptr(sh), act, _ptr(gamma), _ptr(mr), _ptr(gsum), B, Np, K, Nout, G, per_shape, _stream())
+            return dZ, gsum
     call("pn_linear_bwd_data", _ptr(dY), _pitch(dY), _ptr(W), W.stride(0), _ptr(dZ), _pitch(dZ),
                                  1 if accumulate else 0, 1 if finalize else 0, _ptr(fin_A),
                                  _pitch(fin_A) if finalize else 0, _ptr(sc), _ptr(sh), act, _ptr(gamma), _ptr(mr),

@@ -70,3 +70,56 @@ def test_linear_dispatch_uses_tensor_cores_for_mlp_shapes():
     torch.cuda.synchronize()
     n_tc, n_simt = len(cabi.TIMED.pop("pn_linear_fwd_tc")), len(cabi.TIMED.pop("pn_linear_fwd"))
     assert (n_tc, n_simt) == ((1, 1) if ops.LINEAR_IMPL == "tc" else (0, 2))
+
+
+@pytest.mark.parametrize("B,Np,K,Nout,G,act,fin,acc", [
+    (2, 300, 256, 1024, 8, 1, True, False),      # mlp1: dZ over the 256-wide concat, GroupNorm(8)... of a 256-wide producer
+    (3, 1000, 512, 256, 8, 1, True, False),      # head conv2 <- conv1 (GroupNorm(8, 512), ReLU)
+    (2, 777, 256, 128, 4, 1, True, False),       # embedding layer
+    (1, 2113, 64, 128, 0, 0, False, True),       # edge-conv P/Q GEMM: accumulate into a concat-gradient slice, no finalize
+    (2, 500, 128, 256, 0, 2, True, True),        # mask only (no norm sums) + accumulate
+])
+def test_linear_bwd_data_tc_matches_simt_and_fp64(B, Np, K, Nout, G, act, fin, acc):
+    """dZ = dY W with the finalize epilogue (activation mask of the layer input, norm-backward sums) on the tensor cores
+    against the FP32-pipe kernel of the same contract and a float64 evaluation"""
+    from pnb200.cabi import call
+    g = torch.Generator().manual_seed(B * 100 + Np)
+    dY = torch.randn(B, Np, Nout, generator=g).cuda()
+    W = (torch.randn(Nout, K, generator=g) / Nout ** 0.5).cuda()
+    A = torch.randn(B, Np, K, generator=g).cuda()
+    sc = (torch.rand(B, K, generator=g) + 0.5).cuda() if fin else None
+    sh = torch.randn(B, K, generator=g).cuda() if fin else None
+    gamma = (torch.randn(K, generator=g) * 0.5 + 1).cuda() if (fin and G) else None
+    mr = torch.stack([torch.randn(B, max(G, 1), generator=g) * 0.1, torch.rand(B, max(G, 1), generator=g) + 0.5], 2).cuda()
+    base = torch.randn(B, Np, K, generator=g).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: None if t is None else t.data_ptr()
+    outs = []
+    for name, Wop in (("pn_linear_bwd_data", W), ("pn_linear_bwd_data_tc", W.t().contiguous())):
+        dZ = base.clone() if acc else torch.full((B, Np, K), float("nan"), device="cuda")
+        gsum = torch.zeros(B, max(G, 1), 2, dtype=torch.float64, device="cuda") if gamma is not None else None
+        call(name, p(dY), Nout, p(Wop), Wop.stride(0), p(dZ), K, 1 if acc else 0, 1 if fin else 0, p(A) if fin else None,
+             K if fin else 0, p(sc), p(sh), act, p(gamma), p(mr) if gamma is not None else None, p(gsum), B, Np, K, Nout,
+             max(G, 1), 1, st)
+        outs.append((dZ, gsum))
+    ref = dY.double() @ W.double()
+    if acc:
+        ref = ref + base.double()
+    if fin:
+        pre = A.double() * sc.double().unsqueeze(1) + sh.double().unsqueeze(1)
+        mask = (pre > 0).double() if act == 1 else (torch.where(pre > 0, 1.0, 0.2) if act == 2 else torch.ones_like(pre))
+        ref = ref * mask
+    scale = ref.abs().max().item()
+    err_s = (outs[0][0].double() - ref).abs().max().item() / scale
+    err_t = (outs[1][0].double() - ref).abs().max().item() / scale
+    print(f"rel err vs fp64: tc {err_t:.2e}, fp32 pipe {err_s:.2e}")
+    assert torch.isfinite(outs[1][0]).all() and err_t < 1e-5, err_t
+    if gamma is not None:
+        cpg = K // G
+        xh = (A.double() - mr[:, :, 0].double().repeat_interleave(cpg, 1).unsqueeze(1)) * \
+            mr[:, :, 1].double().repeat_interleave(cpg, 1).unsqueeze(1)
+        gt = ref * gamma.double()
+        want = torch.stack([gt.view(B, Np, G, cpg).sum((1, 3)), (gt * xh).view(B, Np, G, cpg).sum((1, 3))], 2)
+        mag = torch.stack([gt.abs().view(B, Np, G, cpg).sum((1, 3)), (gt * xh).abs().view(B, Np, G, cpg).sum((1, 3))], 2)
+        for o in outs:
+            assert ((o[1] - want).abs() / mag).max().item() < 1e-5
