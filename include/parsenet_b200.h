@@ -106,6 +106,10 @@ int pn_linear_bwd_data_tc_supported(const float* dY, long long lddy, const float
 int pn_linear_bwd_data_tc(const float* dY, long long lddy, const float* Wt, long long ldwt, float* dZ, long long lddz, int accumulate, int finalize, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, const float* gamma, const float* mean_rstd, double* gsum, int B, int Np, int K, int Nout, int G, int stats_per_shape, void* stream);
 /* replaces: autograd of the same chains (torch built-in in the reference) */
 int pn_linear_bwd_weight(const float* dY, long long lddy, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, float* dW, long long lddw, float* db, float* dsb, int B, int Np, int K, int Nout, void* stream);
+/* the same weight gradient on the tcgen05 tensor cores (split-TF32): D[n][k] += (dY tile)^T (act(norm(A)) tile), the loader warps
+   transpose 4 x 4 blocks in registers into the K-major operand layout; rows split over the grid, fp32 atomics into dW */
+int pn_linear_bwd_weight_tc_supported(const float* dY, long long lddy, const float* A, long long lda, int Np, int K, int Nout);
+int pn_linear_bwd_weight_tc(const float* dY, long long lddy, const float* A, long long lda, const float* in_scale, const float* in_shift, int in_act, float* dW, long long lddw, float* db, float* dsb, int B, int Np, int K, int Nout, void* stream);
 /* replaces: nn.GroupNorm / nn.BatchNorm statistics: src/PointNet.py:151-155,166-169; src/model.py:69-73,98-99 */
 int pn_norm_finalize(const double* stats, const float* gamma, const float* beta, int S, int G, int C, double count, float eps, float* mean_rstd, float* scale, float* shift, void* stream);
 /* replaces: autograd of nn.GroupNorm / nn.BatchNorm */

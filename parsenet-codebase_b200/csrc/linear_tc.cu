@@ -334,6 +334,214 @@ __global__ void __launch_bounds__(NT, 2) linear_tc_kernel(Args p) {
     if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
 }
 
+// ================================================================================================ backward: weight
+// dW[n][k] += sum_m dY[m][n] * act(norm(A))[m][k] on the tensor cores: D[128 n][128 k] += (dY tile)^T (X tile), contraction
+// over the rows m.  Both operands are row-major in HBM with the contraction index OUTERMOST, while tcgen05 wants it
+// innermost (K-major; MN-major tf32 operands are not executed, profiles/r01_tc_probe.md): the loader warps transpose 4 x 4
+// blocks in registers on the way from LDG.128 (4 consecutive n / k of one row) to STS.128 (4 consecutive m of one n / k).
+// 8-row groups are 144 B apart (SBO) so that a quarter-warp's eight 16-byte stores fall into eight different bank groups.
+// The rows of a shape are split over gridDim.z; partial tiles are accumulated with fp32 atomics like the FP32-pipe kernel.
+constexpr uint32_t W_SBO = 144, W_LBO = (BM / 8) * W_SBO;               // 2304 B per 4-row (m) chunk
+constexpr int W_OP_BYTES = (BK / 4) * W_LBO;                           // 9216
+constexpr int W_STAGE_BYTES = 4 * W_OP_BYTES;                          // dY big, dY small, X big, X small
+constexpr int W_NSTAGE = 2;                                            // 2 x 36 KB: two CTAs per SM (4 stages in flight per SM)
+
+struct WArgs {
+    const float* dY; long long lddy;    // [B*Np][Nout]
+    const float* A; long long lda;      // [B*Np][K]
+    const float* in_scale; const float* in_shift; int in_act;     // [B][K] or null
+    float* dW; long long lddw;          // [Nout][K]
+    float* db;                          // [Nout] or null
+    float* dsb;                         // [B][Nout] or null
+    int B, Np, K, Nout, rows_per_split, splits_per_shape;
+};
+
+__global__ void __launch_bounds__(NT, 2) linear_bwd_weight_tc_kernel(WArgs p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ Bars bars;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float colsum_s[4][BM];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * BM;                 // dW rows
+    const int k0 = blockIdx.y * BN;                 // dW columns
+    const int b = blockIdx.z / p.splits_per_shape;
+    const int r_begin = (blockIdx.z % p.splits_per_shape) * p.rows_per_split;
+    const int r_end = min(p.Np, r_begin + p.rows_per_split);
+    const int nch = (r_end - r_begin + BK - 1) / BK;          // >= 1 (host guarantees r_begin < Np)
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < W_NSTAGE; ++s) { mbar_init(&bars.full[s], LOAD_THREADS); mbar_init(&bars.empty[s], 1); }
+        mbar_init(&bars.acc_full, 1);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+
+    if (warp < 4) {
+        // =============================================================================== epilogue warps
+        const uint32_t la = (uint32_t)(32 * warp) << 16;
+        float* tr = reinterpret_cast<float*>(smem) + warp * 32 * EPI_PITCH;
+        const int sub_r = lane >> 3, sub_c = 4 * (lane & 7);
+        mbar_wait(&bars.acc_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (k0 + c0 >= p.K) break;
+            uint32_t v[32];
+            tmem_ld32(tb + la + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<float4*>(tr + lane * EPI_PITCH + e) =
+                    make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = sub_r + 4 * i;
+                const int n = n0 + 32 * warp + rr;
+                if (n < p.Nout) {
+                    const float4 o = *reinterpret_cast<const float4*>(tr + rr * EPI_PITCH + sub_c);
+                    float* dst = p.dW + (long long)n * p.lddw + k0 + c0 + sub_c;
+                    const int kk = k0 + c0 + sub_c;
+                    if (kk < p.K) atomicAdd(dst, o.x);
+                    if (kk + 1 < p.K) atomicAdd(dst + 1, o.y);
+                    if (kk + 2 < p.K) atomicAdd(dst + 2, o.z);
+                    if (kk + 3 < p.K) atomicAdd(dst + 3, o.w);
+                }
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    } else if (warp < MMA_WARP) {
+        // =============================================================================== loader warps (transposing)
+        const int lt = tid - LOAD_WARP0 * 32;          // 0..127
+        const int c4 = lt & 31;                        // columns 4 c4 .. 4 c4 + 3 of both tiles (n of dY, k of A)
+        const int mq = lt >> 5;                        // rows 4 mq .. 4 mq + 3 of the 16-row stage = k-chunk index of the stage
+        const float* dYb = p.dY + (long long)b * p.Np * p.lddy;
+        const float* Ab = p.A + (long long)b * p.Np * p.lda;
+        const int nn = n0 + 4 * c4, kk = k0 + 4 * c4;
+        const bool n_ok = nn < p.Nout, k_ok = kk < p.K;       // (Nout % 4 == 0 and K % 4 == 0: a 4-group is inside or outside)
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool has_norm = p.in_scale != nullptr;
+        if (has_norm && k_ok) {
+            sc = *reinterpret_cast<const float4*>(p.in_scale + (long long)b * p.K + kk);
+            sh = *reinterpret_cast<const float4*>(p.in_shift + (long long)b * p.K + kk);
+        }
+        const int act = p.in_act;
+        const bool want_cs = (p.db || p.dsb) && blockIdx.y == 0;
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 vy[4], va[4], ny[4], na[4];
+        auto fetch = [&](int kc, float4 (&xy)[4], float4 (&xa)[4]) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r_begin + kc * BK + 4 * mq + i;
+                const bool rin = (kc < nch) && (r < r_end);
+                xy[i] = (rin && n_ok) ? *reinterpret_cast<const float4*>(dYb + (long long)r * p.lddy + nn)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                xa[i] = (rin && k_ok) ? *reinterpret_cast<const float4*>(Ab + (long long)r * p.lda + kk)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        fetch(0, vy, va);
+#pragma unroll 1
+        for (int kc = 0; kc < nch; ++kc) {
+            const int s = kc % W_NSTAGE;
+            fetch(kc + 1, ny, na);
+            mbar_wait(&bars.empty[s], ((kc / W_NSTAGE) & 1) ^ 1);
+            unsigned char* st = smem + s * W_STAGE_BYTES;
+            // X = act(norm(A)); rows beyond the split stay exactly zero
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r_begin + kc * BK + 4 * mq + i;
+                if (r < r_end && k_ok) {
+                    float f0 = va[i].x, f1 = va[i].y, f2 = va[i].z, f3 = va[i].w;
+                    if (has_norm) {
+                        f0 = fmaf(f0, sc.x, sh.x); f1 = fmaf(f1, sc.y, sh.y); f2 = fmaf(f2, sc.z, sh.z); f3 = fmaf(f3, sc.w, sh.w);
+                    }
+                    va[i] = make_float4(act_fwd(f0, act), act_fwd(f1, act), act_fwd(f2, act), act_fwd(f3, act));
+                }
+            }
+            if (want_cs) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { cs[0] += vy[i].x; cs[1] += vy[i].y; cs[2] += vy[i].z; cs[3] += vy[i].w; }
+            }
+            // 4 x 4 register transpose: element e of the four rows -> one 16-byte chunk (4 consecutive m) of row (4 c4 + e)
+            const float ye[4][4] = {{vy[0].x, vy[1].x, vy[2].x, vy[3].x}, {vy[0].y, vy[1].y, vy[2].y, vy[3].y},
+                                    {vy[0].z, vy[1].z, vy[2].z, vy[3].z}, {vy[0].w, vy[1].w, vy[2].w, vy[3].w}};
+            const float ae[4][4] = {{va[0].x, va[1].x, va[2].x, va[3].x}, {va[0].y, va[1].y, va[2].y, va[3].y},
+                                    {va[0].z, va[1].z, va[2].z, va[3].z}, {va[0].w, va[1].w, va[2].w, va[3].w}};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int row = 4 * c4 + e;
+                const uint32_t o = (uint32_t)(mq * W_LBO + (row >> 3) * W_SBO + (row & 7) * 16);
+                {
+                    const float b0 = tf32_hi(ye[e][0]), b1 = tf32_hi(ye[e][1]), b2 = tf32_hi(ye[e][2]), b3 = tf32_hi(ye[e][3]);
+                    *reinterpret_cast<float4*>(st + o) = make_float4(b0, b1, b2, b3);
+                    *reinterpret_cast<float4*>(st + W_OP_BYTES + o) =
+                        make_float4(ye[e][0] - b0, ye[e][1] - b1, ye[e][2] - b2, ye[e][3] - b3);
+                }
+                {
+                    const float b0 = tf32_hi(ae[e][0]), b1 = tf32_hi(ae[e][1]), b2 = tf32_hi(ae[e][2]), b3 = tf32_hi(ae[e][3]);
+                    *reinterpret_cast<float4*>(st + 2 * W_OP_BYTES + o) = make_float4(b0, b1, b2, b3);
+                    *reinterpret_cast<float4*>(st + 3 * W_OP_BYTES + o) =
+                        make_float4(ae[e][0] - b0, ae[e][1] - b1, ae[e][2] - b2, ae[e][3] - b3);
+                }
+            }
+            fence_async_smem();
+            mbar_arrive(&bars.full[s]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { vy[i] = ny[i]; va[i] = na[i]; }
+        }
+        if (want_cs) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) colsum_s[mq][4 * c4 + e] = cs[e];
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            const int n = n0 + lt;
+            if (n < p.Nout) {
+                const float t = (colsum_s[0][lt] + colsum_s[1][lt]) + (colsum_s[2][lt] + colsum_s[3][lt]);
+                if (p.db) atomicAdd(&p.db[n], t);
+                if (p.dsb) atomicAdd(&p.dsb[(long long)b * p.Nout + n], t);
+            }
+        }
+    } else {
+        // =============================================================================== MMA warp
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc(2, BM, BN, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+#pragma unroll 1
+        for (int kc = 0; kc < nch; ++kc) {
+            const int s = kc % W_NSTAGE;
+            mbar_wait(&bars.full[s], (kc / W_NSTAGE) & 1);
+            tc_fence_after();
+            const uint32_t st = sbase + s * W_STAGE_BYTES;
+            const uint64_t dyb = make_smem_desc(st, W_LBO, W_SBO, 0);
+            const uint64_t dys = make_smem_desc(st + W_OP_BYTES, W_LBO, W_SBO, 0);
+            const uint64_t dab = make_smem_desc(st + 2 * W_OP_BYTES, W_LBO, W_SBO, 0);
+            const uint64_t das = make_smem_desc(st + 3 * W_OP_BYTES, W_LBO, W_SBO, 0);
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)(ks * ((2 * W_LBO) >> 4));
+                    mma_tf32_ss(tb, dys + adv, dab + adv, idesc, (kc | ks) ? 1u : 0u);
+                    mma_tf32_ss(tb, dyb + adv, das + adv, idesc, 1u);
+                    mma_tf32_ss(tb, dyb + adv, dab + adv, idesc, 1u);
+                }
+                mma_commit(&bars.empty[s]);
+            }
+            __syncwarp();
+        }
+        if (leader) mma_commit(&bars.acc_full);
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace lintc
@@ -415,5 +623,41 @@ extern "C" int pn_linear_bwd_data_tc(const float* dY, long long lddy, const floa
     linear_tc_kernel<true><<<grid, NT, sm, (cudaStream_t)stream>>>(p);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("linear_tc_kernel<bwd_data>");
+    return PN_OK;
+}
+
+
+// dW += dY^T act(norm(A)) (+ bias gradients) on the tensor cores; same contract as pn_linear_bwd_weight
+extern "C" int pn_linear_bwd_weight_tc_supported(const float* dY, long long lddy, const float* A, long long lda, int Np, int K,
+                                                 int Nout) {
+    using namespace lintc;
+    if (!aligned16(dY) || !aligned16(A) || lddy % 4 || lda % 4) return 0;
+    if (K % 4 || Nout % 4 || K < 32 || Nout < 32 || Np < 64) return 0;
+    return 1;
+}
+
+extern "C" int pn_linear_bwd_weight_tc(const float* dY, long long lddy, const float* A, long long lda, const float* in_scale,
+                                       const float* in_shift, int in_act, float* dW, long long lddw, float* db, float* dsb,
+                                       int B, int Np, int K, int Nout, void* stream) {
+    using namespace lintc;
+    PN_REQUIRE(dY && A && dW, "pn_linear_bwd_weight_tc: null pointer");
+    PN_REQUIRE(B > 0 && pn_linear_bwd_weight_tc_supported(dY, lddy, A, lda, Np, K, Nout),
+               "pn_linear_bwd_weight_tc: unsupported problem (K=%d Nout=%d Np=%d)", K, Nout, Np);
+    PN_REQUIRE(!in_scale || (aligned16(in_scale) && aligned16(in_shift)), "pn_linear_bwd_weight_tc: scale / shift alignment");
+    WArgs p{dY, lddy, A, lda, in_scale, in_shift, in_act, dW, lddw, db, dsb, B, Np, K, Nout, 0, 0};
+    // aim for ~2 waves of 296 CTAs; a split never straddles two shapes and is a multiple of the 16-row stage
+    const int tiles = cdiv(Nout, BM) * cdiv(K, BN);
+    const int want = max(1, (592 + tiles * B - 1) / (tiles * B));
+    int rows = cdiv(Np, want);
+    rows = max(BK * 8, ((rows + BK - 1) / BK) * BK);
+    p.rows_per_split = rows;
+    p.splits_per_shape = cdiv(Np, rows);
+    const size_t sm = (size_t)W_NSTAGE * W_STAGE_BYTES + 1024;
+    PN_CUDA(cudaFuncSetAttribute(linear_bwd_weight_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_REQUIRE((long long)p.splits_per_shape * B <= 65535, "pn_linear_bwd_weight_tc: too many row splits");
+    dim3 grid(cdiv(Nout, BM), cdiv(K, BN), p.splits_per_shape * B);
+    linear_bwd_weight_tc_kernel<<<grid, NT, sm, (cudaStream_t)stream>>>(p);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("linear_bwd_weight_tc_kernel");
     return PN_OK;
 }

@@ -25,6 +25,7 @@ SIGNATURES = {
     "pn_linear_bwd_data_tc": [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_p, c_ll, c_p, c_p, c_i, c_p, c_p, c_p,
                               c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "pn_linear_bwd_weight": [c_p, c_ll, c_p, c_ll, c_p, c_p, c_i, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
+    "pn_linear_bwd_weight_tc": [c_p, c_ll, c_p, c_ll, c_p, c_p, c_i, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_i, c_p],
     "pn_norm_finalize": [c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_f, c_p, c_p, c_p, c_p],
     "pn_norm_bwd_apply": [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_p, c_p, c_p],
     # edgeconv.cu
@@ -92,6 +93,7 @@ _SPECIAL = {
     "pn_reset_launch_count": (None, []),
     "pn_abi_version": (c_i, []),
     "pn_linear_fwd_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i]),
+    "pn_linear_bwd_weight_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_i, c_i, c_i]),
     "pn_linear_bwd_data_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i]),
 }
 

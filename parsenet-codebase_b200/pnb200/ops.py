@@ -175,7 +175,11 @@ def linear_bwd_weight(dY, A, in_norm=None, dW=None, want_bias=True, want_sbias=F
     if in_norm is not None:
         sc, sh, act = in_norm.scale, in_norm.shift, in_norm.act
     assert dW.stride(1) == 1
-    call("pn_linear_bwd_weight", _ptr(dY), _pitch(dY), _ptr(A), _pitch(A), _ptr(sc), _ptr(sh), act, _ptr(dW),
+    entry = "pn_linear_bwd_weight"
+    if LINEAR_BWD_IMPL == "tc" and lib.pn_linear_bwd_weight_tc_supported(_ptr(dY), _pitch(dY), _ptr(A), _pitch(A), Np, K, Nout) \
+            and (sc is None or (sc.data_ptr() % 16 == 0 and sh.data_ptr() % 16 == 0)):
+        entry = "pn_linear_bwd_weight_tc"
+    call(entry, _ptr(dY), _pitch(dY), _ptr(A), _pitch(A), _ptr(sc), _ptr(sh), act, _ptr(dW),
                                    dW.stride(0), _ptr(db), _ptr(dsb), B, Np, K, Nout, _stream())
     return dW, db, dsb
 

@@ -123,3 +123,47 @@ def test_linear_bwd_data_tc_matches_simt_and_fp64(B, Np, K, Nout, G, act, fin, a
         mag = torch.stack([gt.abs().view(B, Np, G, cpg).sum((1, 3)), (gt * xh).abs().view(B, Np, G, cpg).sum((1, 3))], 2)
         for o in outs:
             assert ((o[1] - want).abs() / mag).max().item() < 1e-5
+
+
+@pytest.mark.parametrize("B,Np,K,Nout,act,norm,bias", [
+    (2, 300, 256, 1024, 1, True, "b"),        # mlp1 (ragged row count, several row splits)
+    (3, 1000, 512, 256, 1, True, "b"),        # head conv2
+    (2, 777, 1280 - 1024, 512, 0, False, "sb"),   # head conv1 on the 256 local channels, per-shape bias gradient
+    (1, 2113, 64, 128, 0, False, ""),         # edge-conv P/Q GEMM (K = 64: half a column tile), no bias
+    (2, 4999, 128, 132, 2, True, "b"),        # Nout not a multiple of 32 (ragged last row tile)
+])
+def test_linear_bwd_weight_tc_matches_simt_and_fp64(B, Np, K, Nout, act, norm, bias):
+    """dW += dY^T act(norm(A)) (+ bias / per-shape bias gradients) on the tensor cores (transposing loaders, row splits, fp32
+    atomics) against the FP32-pipe kernel of the same contract and a float64 evaluation"""
+    from pnb200.cabi import call
+    g = torch.Generator().manual_seed(B * 100 + Np)
+    dY = torch.randn(B, Np, Nout, generator=g).cuda()
+    A = torch.randn(B, Np, K, generator=g).cuda()
+    sc = (torch.rand(B, K, generator=g) + 0.5).cuda() if norm else None
+    sh = torch.randn(B, K, generator=g).cuda() if norm else None
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: None if t is None else t.data_ptr()
+    outs = []
+    for name in ("pn_linear_bwd_weight", "pn_linear_bwd_weight_tc"):
+        dW = torch.zeros(Nout, K, device="cuda")
+        db = torch.zeros(Nout, device="cuda") if "b" in bias and bias != "sb" else None
+        dsb = torch.zeros(B, Nout, device="cuda") if bias == "sb" else None
+        call(name, p(dY), Nout, p(A), K, p(sc), p(sh), act, p(dW), K, p(db), p(dsb), B, Np, K, Nout, st)
+        outs.append((dW, db, dsb))
+    X = A.double()
+    if norm:
+        X = X * sc.double().unsqueeze(1) + sh.double().unsqueeze(1)
+    X = torch.relu(X) if act == 1 else (torch.where(X > 0, X, 0.2 * X) if act == 2 else X)
+    ref = torch.einsum("bmn,bmk->nk", dY.double(), X)
+    # magnitude the sums are made of (a weight-gradient entry can cancel to ~0)
+    mag = torch.einsum("bmn,bmk->nk", dY.double().abs(), X.abs()).max().item()
+    err_s = (outs[0][0].double() - ref).abs().max().item() / mag
+    err_t = (outs[1][0].double() - ref).abs().max().item() / mag
+    print(f"err / magnitude vs fp64: tc {err_t:.2e}, fp32 pipe {err_s:.2e}")
+    assert torch.isfinite(outs[1][0]).all() and err_t < 2e-6, err_t
+    if outs[1][1] is not None:
+        want = dY.double().sum((0, 1))
+        assert ((outs[1][1].double() - want).abs().max() / dY.double().abs().sum((0, 1)).max()).item() < 1e-6
+    if outs[1][2] is not None:
+        want = dY.double().sum(1)
+        assert ((outs[1][2].double() - want).abs().max() / dY.double().abs().sum(1).max()).item() < 1e-6
