@@ -90,6 +90,10 @@ int pn_grid_laplacian_bwd(const float* l_ws, int B, int g, int l1, const float* 
 /* ---- knn.cu ---- */
 /* replaces: src/PointNet.py:9-26 (knn), :29-69 (knn_points_normals); src/model.py:9-22 */
 int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, float* ws_norms, void* stream);
+/* the same graph build for the 32-channel-multiple feature spaces with TMA-staged point blocks (knn_tma.cu: cp.async.bulk.tensor
+   ring, row-major swizzled tiles, admission straight from registers); identical results, identical arguments */
+int pn_knn_tma_supported(const float* x, int N, int C, int ld, int k, int metric);
+int pn_knn_tma(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, float* ws_norms, void* stream);
 
 /* ---- linear.cu ---- */
 /* replaces: Conv1d/Conv2d(k=1) + GroupNorm/BatchNorm + ReLU chains: src/PointNet.py:157-165,194-196,274-284; src/model.py:74-99,155-176 */

@@ -17,6 +17,7 @@ c_ll = ctypes.c_longlong
 c_d = ctypes.c_double
 SIGNATURES = {
     "pn_knn": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p],
+    "pn_knn_tma": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p],
     # linear.cu
     "pn_linear_fwd": [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_i, c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
     "pn_linear_fwd_tc": [c_p, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_i, c_p, c_ll, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p],
@@ -92,6 +93,7 @@ _SPECIAL = {
     "pn_launch_count": (ctypes.c_ulonglong, []),
     "pn_reset_launch_count": (None, []),
     "pn_abi_version": (c_i, []),
+    "pn_knn_tma_supported": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i]),
     "pn_linear_fwd_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i]),
     "pn_linear_bwd_weight_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_i, c_i, c_i]),
     "pn_linear_bwd_data_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i]),

@@ -31,6 +31,9 @@ def _need_cuda(*ts):
 
 
 # --------------------------------------------------------------------------------------------- kNN
+KNN_IMPL = os.environ.get("PN_KNN", "tma")          # "tma" | "simt" (A/B tests)
+
+
 def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
     """x_bnc: (B,N,C) fp32 point-major, possibly a channel slice of a wider buffer (stride(1) = row pitch).
     Returns idx (B,N,k) sorted best-first.  metric 0: feature space (src/PointNet.py:9), 1: positions+normals,
@@ -43,8 +46,13 @@ def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
     idx = torch.empty((B, N, k), dtype=out_dtype, device=x_bnc.device)
     dist = torch.empty((B, N, k), dtype=torch.float32, device=x_bnc.device) if return_dist else None
     ws = torch.empty((B * N,), dtype=torch.float32, device=x_bnc.device)
+    # feature spaces with whole 32-channel chunks go through the TMA-staged kernel (csrc/knn_tma.cu); positions (+ normals),
+    # very large k or N >= 65536 through the loader-thread kernel (csrc/knn.cu).  Same results (both bit-exact vs the oracle).
+    entry = "pn_knn"
+    if KNN_IMPL == "tma" and lib.pn_knn_tma_supported(x_bnc.data_ptr(), N, C, ld, k, metric):
+        entry = "pn_knn_tma"
     with torch.cuda.device(x_bnc.device):
-        call("pn_knn", _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), 1 if out_dtype == torch.int64 else 0,
+        call(entry, _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), 1 if out_dtype == torch.int64 else 0,
                          _ptr(dist), _ptr(ws), _stream())
     return (idx, dist) if return_dist else idx
 

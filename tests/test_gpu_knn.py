@@ -103,3 +103,42 @@ def test_cfg2_encoder_graphs_at_full_size_bit_exact():
                 full = oknn.knn_row(host[b], int(r), metric)
                 order = np.lexsort((np.arange(N), -full))[:k]
                 np.testing.assert_array_equal(idx[b, r], order, err_msg=f"layer {li + 1} shape {b} row {r}")
+
+
+@pytest.mark.parametrize("B,N,C,k", [
+    (2, 1000, 64, 80),        # below the sampling size: single pass
+    (2, 5000, 64, 80),        # sampled admission threshold + main pass
+    (1, 5000, 128, 10),       # SplineNet layers (k = 10, 64-entry buffers, 3-stage ring)
+    (2, 4999, 256, 10),       # ragged tile, 8 channel chunks per tile
+    (1, 130, 32, 16),         # two candidate tiles, one chunk
+    (3, 10000, 64, 80),       # BASELINE size
+])
+def test_knn_tma_kernel_equals_loader_kernel(B, N, C, k):
+    """csrc/knn_tma.cu (TMA-staged tiles, admission from registers, 16-bit buffer indices) against csrc/knn.cu (itself
+    bit-exact vs the C oracle at every tested size): identical indices AND identical ranked values"""
+    from pnb200.cabi import call
+    x = _cloud(B, N, C, 99 + N + C, 0).cuda()
+    x[0, N // 2:N // 2 + 7] = x[0, 3:10]            # a few exact duplicates: ties must break to the lower index
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for name in ("pn_knn", "pn_knn_tma"):
+        idx = torch.full((B, N, k), -1, dtype=torch.int32, device="cuda")
+        dist = torch.full((B, N, k), float("nan"), device="cuda")
+        ws = torch.empty(B * N, device="cuda")
+        call(name, x.data_ptr(), B, N, C, C, k, 0, idx.data_ptr(), 0, dist.data_ptr(), ws.data_ptr(), st)
+        outs.append((idx, dist))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
+def test_knn_tma_strided_slice_and_int64():
+    """channel slice of a wider buffer (row pitch 256 floats, offset 64) as EncoderFn passes layer inputs; int64 output"""
+    from oracle import knn as oknn
+    from pnb200 import ops
+    full = _cloud(2, 1500, 256, 17, 0).cuda()
+    sl = full[:, :, 64:128]
+    want = oknn.knn(sl.cpu().contiguous().numpy(), 80, 0)
+    assert ops.lib.pn_knn_tma_supported(sl.data_ptr(), 1500, 64, 256, 80, 0) == 1
+    got = ops.knn_graph(sl, 80, 0, out_dtype=torch.int64)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
