@@ -39,9 +39,24 @@ static constexpr size_t smem_bytes() {
            2 * 4 * sizeof(uint64_t) + 1024;
 }
 
-// 16-byte chunk g (4 channels) of row r in a [rows][128 B] tile written by TMA with the 128-byte swizzle
-__device__ __forceinline__ float4 lds_chunk(const unsigned char* tile, int r, int g) {
-    return *reinterpret_cast<const float4*>(tile + r * 128 + ((g ^ (r & 7)) << 4));
+// ld.shared.v4.f32 at a 32-bit shared-window address + compile-time offset (explicit state space: a pointer re-derived
+// through integer arithmetic would compile to generic LD.E loads with 64-bit address math)
+template <int IMM>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(IMM));
+    return v;
+}
+// a tile written by TMA with the 128-byte swizzle is [rows][128 B] with the 16-byte chunk g (4 channels) of row r stored at
+// chunk position g ^ (r & 7)
+
+// full-barrier wait: the common case (data already landed) is one try_wait; the watchdog loop only runs while waiting
+__device__ __forceinline__ void wait_ready(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done) mbar_wait_guarded(bar, parity);
 }
 
 // out of line on purpose: the compaction's register arrays must not merge into the register allocation of the FMA loop
@@ -61,8 +76,10 @@ knn_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ C
                int N, int C, int k, int r_sample, IdxT* __restrict__ idx_out, float* __restrict__ dist_out) {
     constexpr int NST = Cfg<CAP>::NST;
     extern __shared__ unsigned char smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    unsigned char* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);          // (offset from the array: stays a shared pointer)
     unsigned char* stages = smem;                                                    // NST x (x tile | q tile)
+    const uint32_t stages_u32 = smem_u32(stages);
     float* bufv = reinterpret_cast<float*>(smem + NST * STAGE_BYTES);                // [TQ][CAP]
     BI* bufi = reinterpret_cast<BI*>(bufv + TQ * CAP);                               // [TQ][CAP]
     float* tau_s = reinterpret_cast<float*>(bufi + TQ * CAP);                        // [TQ]
@@ -77,6 +94,7 @@ knn_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ C
     const int tq = tid >> 4;            // queries 4 tq .. 4 tq + 3   (a warp: tq = 2 warp, 2 warp + 1 -> rows 8 warp .. 8 warp + 7)
     const int tc = tid & 15;            // candidates tc + 16 cc, cc = 0..7
     const int half = lane >> 4;         // which of the warp's two query groups this lane belongs to
+    const int kx = tc & 7, kq = 4 * (tq & 1);
     const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
     const unsigned lt_mask = ((1u << lane) - 1u) & hmask;         // lanes of my half below me
 
@@ -93,9 +111,9 @@ knn_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ C
 
     // per-thread copies of the state of its 4 query rows (identical in the 16 lanes of a half-warp)
     float tau[4];
-    int cnt[4];
+    int cnt[4], cnt_o[4];               // cnt: my half's rows; cnt_o: the other half's rows (every lane tracks both from the ballots)
 #pragma unroll
-    for (int a = 0; a < 4; ++a) { tau[a] = -INFINITY; cnt[a] = 0; }
+    for (int a = 0; a < 4; ++a) { tau[a] = -INFINITY; cnt[a] = 0; cnt_o[a] = 0; }
     float xq[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) xq[a] = xxq[4 * tq + a];
@@ -146,16 +164,21 @@ phase_begin:
                     ++issued; ++next;
                 }
                 const int s = consumed % NST;
-                mbar_wait_guarded(&full[s], (consumed / NST) & 1);
-                const unsigned char* xt = stages + s * STAGE_BYTES;
-                const unsigned char* qt = xt + X_BYTES;
+                wait_ready(&full[s], (consumed / NST) & 1);
+                // candidate rows tc + 16 cc (swizzle key tc & 7 for all of them), query rows 4 tq + a (key 4 (tq & 1) + a)
+                const uint32_t xrow = stages_u32 + s * STAGE_BYTES + tc * 128;
+                const uint32_t qrow = stages_u32 + s * STAGE_BYTES + X_BYTES + (4 * tq) * 128;
 #pragma unroll 2
                 for (int g = 0; g < KC / 4; ++g) {
                     float4 qv[4], xv[8];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) qv[a] = lds_chunk(qt, 4 * tq + a, g);
-#pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) xv[cc] = lds_chunk(xt, tc + 16 * cc, g);
+                    const uint32_t xa = xrow + (uint32_t)((g ^ kx) << 4);
+                    const uint32_t qa = qrow + (uint32_t)((g ^ kq) << 4);          // row a: chunk (g ^ kq) ^ a, kq has low bits 0
+                    qv[0] = lds128<0>(qa);
+                    qv[1] = lds128<128>(qa ^ 16u);
+                    qv[2] = lds128<256>(qa ^ 32u);
+                    qv[3] = lds128<384>(qa ^ 48u);
+                    xv[0] = lds128<0>(xa);         xv[1] = lds128<2048>(xa);   xv[2] = lds128<4096>(xa);   xv[3] = lds128<6144>(xa);
+                    xv[4] = lds128<8192>(xa);      xv[5] = lds128<10240>(xa);  xv[6] = lds128<12288>(xa);  xv[7] = lds128<14336>(xa);
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -188,19 +211,19 @@ phase_begin:
                     const unsigned m = __ballot_sync(FULL, pass);
                     if (m) {                                          // warp-uniform
                         const int c_lo = __popc(m & 0xffffu), c_hi = __popc(m >> 16);
-                        // overflow of either row: the whole warp compacts that row (rare), its state is re-broadcast
-                        const int n_lo = __shfl_sync(FULL, cnt[a], 0), n_hi = __shfl_sync(FULL, cnt[a], 16);
+                        // overflow of either row: the whole warp compacts that row (rare); the new state is warp-uniform
+                        const int n_lo = half ? cnt_o[a] : cnt[a], n_hi = half ? cnt[a] : cnt_o[a];
                         if (n_lo + c_lo > CAP) {
                             float t_new;
                             const int n_new = compact_rare<CAP>(bufv + (8 * warp + a) * CAP, bufi + (8 * warp + a) * CAP, n_lo, ksel, lane,
                                                                 &t_new);
-                            if (!half) { cnt[a] = n_new; tau[a] = t_new; }
+                            if (!half) { cnt[a] = n_new; tau[a] = t_new; } else cnt_o[a] = n_new;
                         }
                         if (n_hi + c_hi > CAP) {
                             float t_new;
                             const int n_new = compact_rare<CAP>(bufv + (8 * warp + 4 + a) * CAP, bufi + (8 * warp + 4 + a) * CAP, n_hi, ksel,
                                                                 lane, &t_new);
-                            if (half) { cnt[a] = n_new; tau[a] = t_new; }
+                            if (half) { cnt[a] = n_new; tau[a] = t_new; } else cnt_o[a] = n_new;
                         }
                         if (pass) {
                             const int pos = cnt[a] + __popc(m & lt_mask);
@@ -208,6 +231,7 @@ phase_begin:
                             bi[pos] = (BI)j;
                         }
                         cnt[a] += half ? c_hi : c_lo;
+                        cnt_o[a] += half ? c_lo : c_hi;
                         __syncwarp();
                     }
                 }
@@ -233,7 +257,7 @@ phase_begin:
             }
             __syncwarp();
 #pragma unroll
-            for (int a = 0; a < 4; ++a) { tau[a] = tau_s[4 * tq + a]; cnt[a] = 0; }
+            for (int a = 0; a < 4; ++a) { tau[a] = tau_s[4 * tq + a]; cnt[a] = 0; cnt_o[a] = 0; }
             phase = 1; ksel = k; jend = N;
             goto phase_begin;
         }
@@ -243,7 +267,7 @@ phase_begin:
             for (int r = 0; r < 8; ++r) short_rows |= (cnt_s[warp * 8 + r] < k) ? 1 : 0;
             if (__syncthreads_or(short_rows)) {             // rare: some row admitted fewer than k -> exact re-run from -inf
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { tau[a] = -INFINITY; cnt[a] = 0; }
+                for (int a = 0; a < 4; ++a) { tau[a] = -INFINITY; cnt[a] = 0; cnt_o[a] = 0; }
                 phase = 2;
                 goto phase_begin;
             }
