@@ -10,6 +10,9 @@
  * The reference ranks, per query row i, the fp32 value
  *   feature metric :  D[i][j] = (-xx[j] - inner[i][j]) - xx[i],  inner = -2 * <x_i, x_j>     (PointNet.py:15-17)
  *   pos+normal     :  D[i][j] = -( ((xx[j] - 2<p_i,p_j>) + xx[i]) * (1 + (2 - 2<n_i,n_j>)) )  (PointNet.py:44-52)
+ *   squared diff   :  D[i][j] = -(((dx*dx) + (dy*dy)) + (dz*dz)),  d = x_i - x_j  (metric 2: up_sample_points_torch,
+ *                     src/fitting_utils.py:150-163: torch.sum((p_i - p_j) ** 2, 2), topk(5, largest=False)); every square and
+ *                     every sum is its own fp32 rounding (no fma), summed in channel order
  * and takes torch.topk(k) along j (largest first) (PointNet.py:22,65).
  *
  * The reference leaves the accumulation order of the dot product to the BLAS it runs on (cuBLAS / MKL), so
@@ -53,6 +56,12 @@ static int cmp_best_first(const void *a, const void *b) {
     return 0;
 }
 
+static inline float sqdiff3(const float *a, const float *b) {
+    float acc = 0.0f;
+    for (int c = 0; c < 3; ++c) { float d = a[c] - b[c]; float q = d * d; acc = acc + q; }
+    return acc;
+}
+
 static inline float dotf(const float *a, const float *b, int c0, int c1) {
     float acc = 0.0f;
     for (int c = c0; c < c1; ++c) acc = fmaf(a[c], b[c], acc);
@@ -64,6 +73,7 @@ int pn_oracle_knn(const float *x, int B, int N, int C, int ld, int k, int metric
                   int32_t *idx_out, float *dist_out /* may be NULL, [B][N][k] */) {
     if (k > N || k <= 0) return 1;
     if (metric == 1 && C != 6) return 2;
+    if (metric == 2 && C != 3) return 2;
     int cx = (metric == 1) ? 3 : C;
     for (int b = 0; b < B; ++b) {
         const float *xb = x + (size_t)b * N * ld;
@@ -79,7 +89,9 @@ int pn_oracle_knn(const float *x, int B, int N, int C, int ld, int k, int metric
                 for (int j = 0; j < N; ++j) {
                     const float *xj = xb + (size_t)j * ld;
                     float D;
-                    if (metric == 0) {
+                    if (metric == 2) {
+                        D = -sqdiff3(xi, xj);
+                    } else if (metric == 0) {
                         float inner = -2.0f * dotf(xi, xj, 0, C);
                         D = (-xx[j] - inner) - xx[i];
                     } else {
@@ -116,7 +128,9 @@ int pn_oracle_knn_row(const float *x, int N, int C, int ld, int metric, int i, f
     for (int j = 0; j < N; ++j) {
         const float *xj = x + (size_t)j * ld;
         float xxj = dotf(xj, xj, 0, cx);
-        if (metric == 0) {
+        if (metric == 2) {
+            row_out[j] = -sqdiff3(xi, xj);
+        } else if (metric == 0) {
             float inner = -2.0f * dotf(xi, xj, 0, C);
             row_out[j] = (-xxj - inner) - xxi;
         } else {

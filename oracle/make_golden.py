@@ -330,7 +330,25 @@ def gen_guard():
     np.savez_compressed(os.path.join(OUT, "guard.npz"), **out)
 
 
-GENS = {"guard": gen_guard, "cfg1": gen_cfg1, "knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
+def gen_upsample():
+    """up_sample_points_torch (2 rounds), its memory-efficient variant (1 round) and up_sample_points_in_range
+    (np.random.seed(3)) of the unmodified reference on uniform random points"""
+    FU = rl.ref("src.fitting_utils")
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for name, n in (("a", 333), ("b", 1000)):
+        p = torch.rand(n, 3, generator=g)
+        out[name + "_p"] = p.numpy()
+        out[name + "_up2"] = FU.up_sample_points_torch(p.clone(), 2).numpy()
+        out[name + "_me1"] = FU.up_sample_points_torch_memory_efficient(p.clone(), 1).numpy()
+    p = torch.rand(700, 3, generator=g); w = torch.rand(700, 1, generator=g)
+    np.random.seed(3)
+    rp, rw = FU.up_sample_points_in_range(p.clone(), w.clone(), 1400, 1800)
+    out.update(r_p=p.numpy(), r_w=w.numpy(), r_out_p=rp.numpy(), r_out_w=rw.numpy())
+    np.savez_compressed(os.path.join(OUT, "upsample.npz"), **out)
+
+
+GENS = {"upsample": gen_upsample, "guard": gen_guard, "cfg1": gen_cfg1, "knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
         "splinenet": gen_splinenet, "e2e": gen_e2e, "e2e_nocyl": lambda: gen_e2e(True, "e2e_nocyl.npz")}
 
 if __name__ == "__main__":

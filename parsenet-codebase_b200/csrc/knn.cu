@@ -8,6 +8,8 @@
 // Arithmetic contract (bit-exact with oracle/c/knn_oracle.c): the ranked value is
 //   metric 0:  D = (-xx_j - (-2*dot(x_i,x_j))) - xx_i
 //   metric 1:  D = -(((xx_j - 2*dot(p_i,p_j)) + xx_i) * (1 + (2 - 2*dot(n_i,n_j))))
+//   metric 2:  D = -(((dx*dx) + (dy*dy)) + (dz*dz)), d = x_i - x_j, C == 3, every op its own fp32 rounding
+//              (up_sample_points_torch, reference src/fitting_utils.py:150-163: sum((p_i - p_j)**2, 2), 5 smallest)
 // dot / xx are fmaf chains over channels in increasing order starting from +0; ranking is D descending,
 // ties to the lower candidate index.  This stays on the FP32 FMA pipe on purpose: TF32/BF16 tensor-core
 // products would change near-tie ordering (north_star: indices bit-exact).
@@ -157,7 +159,23 @@ phase_begin:
                 xxc[tid] = (j < N) ? xxb[j] : 0.f;
             }
             __syncthreads();
-            if constexpr (METRIC == 0) {
+            if constexpr (METRIC == 2) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float4 qv = *reinterpret_cast<const float4*>(qs + c * TQ + 4 * tq);
+                    float4 xa = *reinterpret_cast<const float4*>(xs + c * TC + 4 * tc);
+                    float4 xc = *reinterpret_cast<const float4*>(xs + c * TC + 64 + 4 * tc);
+                    const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+                    const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int cc = 0; cc < 8; ++cc) {
+                            const float d = __fsub_rn(qa[a], xv[cc]);
+                            acc[a][cc] = __fadd_rn(acc[a][cc], __fmul_rn(d, d));
+                        }
+                }
+            } else if constexpr (METRIC == 0) {
 #pragma unroll 8
                 for (int c = 0; c < kc; ++c) {
                     float4 qv = *reinterpret_cast<const float4*>(qs + c * TQ + 4 * tq);
@@ -204,7 +222,9 @@ phase_begin:
                 for (int cc = 0; cc < 8; ++cc) {
                     int j = j0 + (cc < 4 ? 0 : 60) + 4 * tc + cc;
                     float D;
-                    if constexpr (METRIC == 0) {
+                    if constexpr (METRIC == 2) {
+                        D = -acc[a][cc];
+                    } else if constexpr (METRIC == 0) {
                         float inner = __fmul_rn(-2.0f, acc[a][cc]);
                         D = __fsub_rn(__fsub_rn(-xc8[cc], inner), xq[a]);
                     } else {
@@ -353,7 +373,8 @@ extern "C" int pn_knn(const float* x, int B, int N, int C, int ld, int k, int me
     PN_REQUIRE(x && idx_out && ws_norms, "pn_knn: null pointer");
     PN_REQUIRE(B > 0 && N > 0 && C > 0 && ld >= C, "pn_knn: bad shape B=%d N=%d C=%d ld=%d", B, N, C, ld);
     PN_REQUIRE(k > 0 && k <= N && k <= 224, "pn_knn: need 0 < k <= min(N,224), got k=%d N=%d", k, N);
-    PN_REQUIRE(metric == 0 || (metric == 1 && C == 6), "pn_knn: metric 1 needs C == 6");
+    PN_REQUIRE(metric == 0 || (metric == 1 && C == 6) || (metric == 2 && C == 3),
+               "pn_knn: metric 1 needs C == 6, metric 2 needs C == 3");
     cudaStream_t st = (cudaStream_t)stream;
     long long rows = (long long)B * N;
     knn::norms_kernel<<<cdiv(rows, 256), 256, 0, st>>>(x, rows, ld, 0, metric == 1 ? 3 : C, ws_norms);
@@ -362,6 +383,10 @@ extern "C" int pn_knn(const float* x, int B, int N, int C, int ld, int k, int me
     if (metric == 0) {
         return idx_is_i64 ? knn::dispatch_cap<0, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st)
                           : knn::dispatch_cap<0, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st);
+    }
+    if (metric == 2) {
+        return idx_is_i64 ? knn::dispatch_cap<2, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st)
+                          : knn::dispatch_cap<2, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st);
     }
     return idx_is_i64 ? knn::dispatch_cap<1, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st)
                       : knn::dispatch_cap<1, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st);

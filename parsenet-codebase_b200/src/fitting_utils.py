@@ -1,6 +1,6 @@
 """Drop-in for the hot-path part of reference src/fitting_utils.py: LeastSquares.lstsq (:36), best_lambda (:68),
 weights_normalize (:306), match (:362), customsvd (:420), standardize_point[s]_torch (:493-553), pca_torch (:585),
-rotation_matrix_a_to_b (:556), sample_points_from_control_points_ (:609).  Mesh / open3d / visualisation helpers of
+rotation_matrix_a_to_b (:556), sample_points_from_control_points_ (:609), up_sample_points_torch[_in_range] (:150-237).  Mesh / open3d / visualisation helpers of
 that file are out of scope."""
 import numpy as np
 import torch
@@ -159,6 +159,66 @@ def standardize_point_torch(point, weights):
 def standardize_points_torch(points, weights):
     outs = [standardize_point_torch(points[i], weights) for i in range(points.shape[0])]
     return torch.stack([o[0] for o in outs], 0), [o[1] for o in outs], [o[2] for o in outs], [o[3] for o in outs]
+
+
+# ------------------------------------------------------------------------------------------------ up-sampling
+def _nearest5(points):
+    """(N,3) -> (N,5) indices of the 5 smallest squared distances sum((p_i - p_j)**2), nearest (the point itself) first:
+    the kNN kernel with the squared-difference metric (csrc/knn.cu metric 2; ties to the lower index)"""
+    from pnb200 import ops
+    if points.shape[0] < 5:
+        raise ValueError("up-sampling needs at least 5 points")
+    return ops.knn_graph(points.detach().float().contiguous().unsqueeze(0), 5, 2, out_dtype=torch.int64)[0]
+
+
+def up_sample_points_torch(points, times=1):
+    """append, per point, the centroid of its 4 nearest other points (reference :150-163); N -> 2^times N points.
+    The reference materialises the (N,N,3) difference tensor and a full-row topk; here the graph comes from the kNN kernel."""
+    for _ in range(times):
+        idx = _nearest5(points)
+        points = torch.cat([points, torch.mean(points[idx[:, 1:]], 1)])
+    return points
+
+
+def up_sample_points_torch_memory_efficient(points, times=1):
+    """reference :166-189: centroid over all 5 nearest (the point included); rows beyond the last whole block of
+    min(N, 100) rows get no new point (the reference's block loop drops them)"""
+    for _ in range(times):
+        n = points.shape[0]
+        blk = min(n, 100)
+        m = (n // blk) * blk
+        idx = _nearest5(points)[:m]
+        points = torch.cat([points, torch.mean(points[idx], 1)])
+    return points
+
+
+def up_sample_points_in_range(points, weights, a_min, a_max):
+    """reference :202-219 (np.random.choice consumed in the same order)"""
+    N = points.shape[0]
+    if N > a_max:
+        L = np.random.choice(np.arange(N), a_max, replace=False)
+        return points[L], weights[L]
+    while True:
+        points = up_sample_points_torch(points)
+        weights = torch.cat([weights, weights], 0)
+        if points.shape[0] >= a_max:
+            break
+    L = np.random.choice(np.arange(points.shape[0]), a_max, replace=False)
+    return points[L], weights[L]
+
+
+def up_sample_points_torch_in_range(points, a_min, a_max):
+    """reference :222-237"""
+    N = points.shape[0]
+    if N > a_max:
+        L = np.random.choice(np.arange(N), a_max, replace=False)
+        return points[L]
+    while True:
+        points = up_sample_points_torch(points)
+        if points.shape[0] >= a_max:
+            break
+    L = np.random.choice(np.arange(points.shape[0]), a_max, replace=False)
+    return points[L]
 
 
 def sample_points_from_control_points_(nu, nv, outputs, batch_size, input_size_u=20, input_size_v=20):

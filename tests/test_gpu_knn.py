@@ -142,3 +142,40 @@ def test_knn_tma_strided_slice_and_int64():
     assert ops.lib.pn_knn_tma_supported(sl.data_ptr(), 1500, 64, 256, 80, 0) == 1
     got = ops.knn_graph(sl, 80, 0, out_dtype=torch.int64)
     np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("N", [5, 333, 4000])
+def test_knn_squared_difference_metric_bit_exact(N):
+    """metric 2 (up-sampling helpers): 5 smallest sum((p_i - p_j)**2) with every op its own fp32 rounding, vs the C oracle"""
+    from oracle import knn as oknn
+    from pnb200 import ops
+    g = torch.Generator().manual_seed(N)
+    x = torch.rand(2, N, 3, generator=g)
+    want, wd = oknn.knn(x.numpy(), 5, 2, return_dist=True)
+    got, gd = ops.knn_graph(x.cuda(), 5, 2, out_dtype=torch.int64, return_dist=True)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    np.testing.assert_array_equal(gd.cpu().numpy(), wd)
+
+
+def test_up_sampling_helpers_vs_reference(golden_dir):
+    """up_sample_points_torch (2 rounds), the memory-efficient variant and up_sample_points_in_range against the
+    unmodified reference's outputs (tests/golden/upsample.npz): same neighbours -> centroids equal to fp32 rounding"""
+    import os
+    from src.fitting_utils import (up_sample_points_in_range, up_sample_points_torch, up_sample_points_torch_in_range,
+                                   up_sample_points_torch_memory_efficient)
+    g = np.load(os.path.join(golden_dir, "upsample.npz"))
+    for name in ("a", "b"):
+        p = torch.from_numpy(g[name + "_p"]).cuda()
+        up = up_sample_points_torch(p, 2)
+        assert up.shape == g[name + "_up2"].shape
+        assert np.abs(up.cpu().numpy() - g[name + "_up2"]).max() <= 2e-7
+        me = up_sample_points_torch_memory_efficient(p, 1)
+        assert me.shape == g[name + "_me1"].shape
+        assert np.abs(me.cpu().numpy() - g[name + "_me1"]).max() <= 2e-7
+    np.random.seed(3)
+    op, ow = up_sample_points_in_range(torch.from_numpy(g["r_p"]).cuda(), torch.from_numpy(g["r_w"]).cuda(), 1400, 1800)
+    assert np.abs(op.cpu().numpy() - g["r_out_p"]).max() <= 2e-7
+    np.testing.assert_array_equal(ow.cpu().numpy(), g["r_out_w"])
+    np.random.seed(4)
+    assert up_sample_points_torch_in_range(torch.from_numpy(g["r_p"]).cuda(), 1000, 1500).shape == (1500, 3)
+    assert up_sample_points_torch_in_range(torch.from_numpy(g["b_p"]).cuda(), 100, 600).shape == (600, 3)

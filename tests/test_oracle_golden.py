@@ -370,3 +370,24 @@ def test_meanshift_port_retry_loops_match_reference(golden_dir):
         np.testing.assert_array_equal(lab.numpy(), g[prefix + "_labels"])
         _rel(c, g[prefix + "_center"], 1e-5, prefix + " centres")
         assert int(g[prefix + "_attempts"]) >= 2          # the fixture does exercise the retry
+
+
+def test_upsample_port_and_c_oracle_vs_reference(golden_dir):
+    """the port of up_sample_points_torch / _memory_efficient / _in_range reproduces the unmodified reference
+    exactly (tests/golden/upsample.npz), and the C oracle's squared-difference metric returns the reference's 5-nearest
+    indices (torch.topk of sum((p_i - p_j)**2, 2), largest=False)"""
+    import numpy as np
+    import torch
+    from oracle import knn as oknn
+    from oracle.port import fitting as OP
+    g = np.load(os.path.join(golden_dir, "upsample.npz"))
+    for name in ("a", "b"):
+        p = torch.from_numpy(g[name + "_p"])
+        np.testing.assert_array_equal(OP.up_sample_points(p.clone(), 2).numpy(), g[name + "_up2"])
+        np.testing.assert_array_equal(OP.up_sample_points_memory_efficient(p.clone(), 1).numpy(), g[name + "_me1"])
+        d = ((p.unsqueeze(1) - p.unsqueeze(0)) ** 2).sum(2)
+        np.testing.assert_array_equal(oknn.knn(p.numpy()[None], 5, 2)[0], torch.topk(d, 5, 1, largest=False)[1].numpy())
+    np.random.seed(3)
+    mp, mw = OP.up_sample_points_in_range(torch.from_numpy(g["r_p"]), 1400, 1800, weights=torch.from_numpy(g["r_w"]))
+    np.testing.assert_array_equal(mp.numpy(), g["r_out_p"])
+    np.testing.assert_array_equal(mw.numpy(), g["r_out_w"])
