@@ -4,6 +4,12 @@
 #pragma once
 #include "common.cuh"
 
+// the full sort of a row buffer (bitonic network, ~2 k instructions at CAP = 128) is inlined by default; a kernel that calls it
+// from several places defines PN_KNN_SORT_ATTR as __noinline__ before including this header to keep ONE copy
+#ifndef PN_KNN_SORT_ATTR
+#define PN_KNN_SORT_ATTR __forceinline__
+#endif
+
 namespace pn {
 namespace knn {
 
@@ -51,7 +57,7 @@ __device__ __forceinline__ unsigned long long make_key(float d, int j) {
 
 // sort the row buffer, keep the best k, return new count; *tau_out = k-th best value (or -inf)
 template <int CAP, typename BI = int>
-__device__ __forceinline__ int compact_row(float* bv, BI* bi, int n, int k, int lane, float* tau_out) {
+__device__ PN_KNN_SORT_ATTR int compact_row(float* bv, BI* bi, int n, int k, int lane, float* tau_out) {
     constexpr int R = CAP / 32;
     unsigned long long key[R];
 #pragma unroll

@@ -15,6 +15,7 @@
 //     loop has NO CTA-wide barrier; warps only meet through the ring's empty / full mbarriers.
 //   * candidate indices are stored as 16-bit in the row buffers (N < 65536), which keeps two CTAs per SM.
 #include "common.cuh"
+#define PN_KNN_SORT_ATTR __noinline__
 #include "knn_select.cuh"
 #include "tc05.cuh"
 #include <cuda.h>
@@ -68,6 +69,41 @@ __device__ __noinline__ int compact_rare(float* bv, BI* bi, int n, int k, int la
 template <int CAP>
 __device__ __noinline__ int sort_row(float* bv, BI* bi, int n, int k, int lane, float* tau_out) {
     return compact_row<CAP, BI>(bv, bi, n, k, lane, tau_out);
+}
+
+// state of the two query rows a warp-step touches (lower / upper half-warp), passed and returned BY VALUE so that it stays in
+// registers across the out-of-line call
+struct RowState { int n_mine, n_other; float tau; };
+
+// One admission step of a warp: lanes with `pass` append (d, j) to the buffer of their half-warp's row; a row that would
+// overflow is compacted first by the whole warp.  ONE out-of-line copy of this code: inlined into the 32 unrolled steps of a tile
+// it made the kernel ~30 KB of SASS and the instruction fetch its top stall (ncu: no_instruction 3.6 per issue).
+template <int CAP>
+__device__ __noinline__ RowState admit(float* bv_lo, BI* bi_lo, int half, int lane, unsigned lt_mask, unsigned m, bool pass,
+                                       float d, int j, RowState st, int ksel) {
+    const int c_lo = __popc(m & 0xffffu), c_hi = __popc(m >> 16);
+    const int n_lo = half ? st.n_other : st.n_mine, n_hi = half ? st.n_mine : st.n_other;
+    float* bv_hi = bv_lo + 4 * CAP;             // rows 8 warp + a and 8 warp + 4 + a
+    BI* bi_hi = bi_lo + 4 * CAP;
+    if (n_lo + c_lo > CAP) {
+        float t_new;
+        const int n_new = compact_select<CAP, BI>(bv_lo, bi_lo, n_lo, ksel, lane, &t_new);
+        if (!half) { st.n_mine = n_new; st.tau = t_new; } else st.n_other = n_new;
+    }
+    if (n_hi + c_hi > CAP) {
+        float t_new;
+        const int n_new = compact_select<CAP, BI>(bv_hi, bi_hi, n_hi, ksel, lane, &t_new);
+        if (half) { st.n_mine = n_new; st.tau = t_new; } else st.n_other = n_new;
+    }
+    if (pass) {
+        const int pos = st.n_mine + __popc(m & lt_mask);
+        (half ? bv_hi : bv_lo)[pos] = d;
+        (half ? bi_hi : bi_lo)[pos] = (BI)j;
+    }
+    st.n_mine += half ? c_hi : c_lo;
+    st.n_other += half ? c_lo : c_hi;
+    __syncwarp();
+    return st;
 }
 
 template <int CAP, typename IdxT, bool SAMPLED>
@@ -198,9 +234,6 @@ phase_begin:
             // ---- distances + admission straight from registers: half-warp `half` owns rows 8 warp + 4 half + a
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                const int row = 8 * warp + 4 * half + a;            // == 4 tq + a
-                float* bv = bufv + row * CAP;
-                BI* bi = bufi + row * CAP;
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
                     const int j = j0 + tc + 16 * cc;
@@ -210,29 +243,11 @@ phase_begin:
                     const bool pass = d > tau[a];
                     const unsigned m = __ballot_sync(FULL, pass);
                     if (m) {                                          // warp-uniform
-                        const int c_lo = __popc(m & 0xffffu), c_hi = __popc(m >> 16);
-                        // overflow of either row: the whole warp compacts that row (rare); the new state is warp-uniform
-                        const int n_lo = half ? cnt_o[a] : cnt[a], n_hi = half ? cnt[a] : cnt_o[a];
-                        if (n_lo + c_lo > CAP) {
-                            float t_new;
-                            const int n_new = compact_rare<CAP>(bufv + (8 * warp + a) * CAP, bufi + (8 * warp + a) * CAP, n_lo, ksel, lane,
-                                                                &t_new);
-                            if (!half) { cnt[a] = n_new; tau[a] = t_new; } else cnt_o[a] = n_new;
-                        }
-                        if (n_hi + c_hi > CAP) {
-                            float t_new;
-                            const int n_new = compact_rare<CAP>(bufv + (8 * warp + 4 + a) * CAP, bufi + (8 * warp + 4 + a) * CAP, n_hi, ksel,
-                                                                lane, &t_new);
-                            if (half) { cnt[a] = n_new; tau[a] = t_new; } else cnt_o[a] = n_new;
-                        }
-                        if (pass) {
-                            const int pos = cnt[a] + __popc(m & lt_mask);
-                            bv[pos] = d;
-                            bi[pos] = (BI)j;
-                        }
-                        cnt[a] += half ? c_hi : c_lo;
-                        cnt_o[a] += half ? c_lo : c_hi;
-                        __syncwarp();
+                        RowState st;
+                        st.n_mine = cnt[a]; st.n_other = cnt_o[a]; st.tau = tau[a];
+                        st = admit<CAP>(bufv + (8 * warp + a) * CAP, bufi + (8 * warp + a) * CAP, half, lane, lt_mask, m, pass, d, j,
+                                        st, ksel);
+                        cnt[a] = st.n_mine; cnt_o[a] = st.n_other; tau[a] = st.tau;
                     }
                 }
             }
