@@ -75,12 +75,14 @@ __device__ __noinline__ int sort_row(float* bv, BI* bi, int n, int k, int lane, 
 // registers across the out-of-line call
 struct RowState { int n_mine, n_other; float tau; };
 
-// One admission step of a warp: lanes with `pass` append (d, j) to the buffer of their half-warp's row; a row that would
-// overflow is compacted first by the whole warp.  ONE out-of-line copy of this code: inlined into the 32 unrolled steps of a tile
-// it made the kernel ~30 KB of SASS and the instruction fetch its top stall (ncu: no_instruction 3.6 per issue).
+// SLOW path of an admission step (one of the two rows of the step would overflow its buffer): the whole warp compacts that row,
+// then the lanes with `pass` append.  ONE out-of-line copy: inlined into the 32 unrolled steps of a tile the compactions made the
+// kernel ~300 KB of SASS and the instruction fetch its top stall (ncu: no_instruction 3.6 per issue).  The common case (both rows
+// have room) is a dozen inline instructions in the kernel.
 template <int CAP>
 __device__ __noinline__ RowState admit(float* bv_lo, BI* bi_lo, int half, int lane, unsigned lt_mask, unsigned m, bool pass,
                                        float d, int j, RowState st, int ksel) {
+    __syncwarp();                               // the appends of earlier (inline, unsynchronised) steps are visible to the warp
     const int c_lo = __popc(m & 0xffffu), c_hi = __popc(m >> 16);
     const int n_lo = half ? st.n_other : st.n_mine, n_hi = half ? st.n_mine : st.n_other;
     float* bv_hi = bv_lo + 4 * CAP;             // rows 8 warp + a and 8 warp + 4 + a
@@ -243,11 +245,22 @@ phase_begin:
                     const bool pass = d > tau[a];
                     const unsigned m = __ballot_sync(FULL, pass);
                     if (m) {                                          // warp-uniform
-                        RowState st;
-                        st.n_mine = cnt[a]; st.n_other = cnt_o[a]; st.tau = tau[a];
-                        st = admit<CAP>(bufv + (8 * warp + a) * CAP, bufi + (8 * warp + a) * CAP, half, lane, lt_mask, m, pass, d, j,
-                                        st, ksel);
-                        cnt[a] = st.n_mine; cnt_o[a] = st.n_other; tau[a] = st.tau;
+                        const int c_lo = __popc(m & 0xffffu), c_hi = __popc(m >> 16);
+                        const int c_mine = half ? c_hi : c_lo, c_other = half ? c_lo : c_hi;
+                        if (max(cnt[a] + c_mine, cnt_o[a] + c_other) > CAP) {       // same value in every lane
+                            RowState st;
+                            st.n_mine = cnt[a]; st.n_other = cnt_o[a]; st.tau = tau[a];
+                            st = admit<CAP>(bufv + (8 * warp + a) * CAP, bufi + (8 * warp + a) * CAP, half, lane, lt_mask, m, pass,
+                                            d, j, st, ksel);
+                            cnt[a] = st.n_mine; cnt_o[a] = st.n_other; tau[a] = st.tau;
+                        } else {
+                            if (pass) {
+                                const int pos = cnt[a] + __popc(m & lt_mask);
+                                bufv[(4 * tq + a) * CAP + pos] = d;
+                                bufi[(4 * tq + a) * CAP + pos] = (BI)j;
+                            }
+                            cnt[a] += c_mine; cnt_o[a] += c_other;
+                        }
                     }
                 }
             }
