@@ -32,13 +32,14 @@ constexpr int X_BYTES = TC * KC * 4, Q_BYTES = TQ * KC * 4, STAGE_BYTES = X_BYTE
 constexpr int SAMPLE_M = 1024;
 typedef unsigned short BI;
 
-template <int CAP> struct Cfg { static constexpr int NST = (CAP <= 64) ? 3 : 2; };
-
+// shared-memory plan of one CTA (host and device agree through these two functions)
+//   QRES: the CTA's 64 query rows stay resident for the whole kernel ([C/32][64][128 B], loaded once) and a ring stage holds the
+//         candidate tile only (16 KB); otherwise a stage holds candidate + query chunk (24 KB).
 template <int CAP>
-static constexpr size_t smem_bytes() {
-    return (size_t)Cfg<CAP>::NST * STAGE_BYTES + (size_t)TQ * CAP * (sizeof(float) + sizeof(BI)) + 3 * TQ * sizeof(float) +
-           2 * 4 * sizeof(uint64_t) + 1024;
+static inline size_t fixed_bytes() {
+    return (size_t)TQ * CAP * (sizeof(float) + sizeof(BI)) + 3 * TQ * sizeof(float) + 12 * sizeof(uint64_t);
 }
+static inline int stage_bytes(bool qres) { return qres ? X_BYTES : STAGE_BYTES; }
 
 // ld.shared.v4.f32 at a 32-bit shared-window address + compile-time offset (explicit state space: a pointer re-derived
 // through integer arithmetic would compile to generic LD.E loads with 64-bit address math)
@@ -60,12 +61,7 @@ __device__ __forceinline__ void wait_ready(uint64_t* bar, uint32_t parity) {
     if (!done) mbar_wait_guarded(bar, parity);
 }
 
-// out of line on purpose: the compaction's register arrays must not merge into the register allocation of the FMA loop
-// (they would spill the accumulators); the call sits in a rarely taken branch
-template <int CAP>
-__device__ __noinline__ int compact_rare(float* bv, BI* bi, int n, int k, int lane, float* tau_out) {
-    return compact_select<CAP, BI>(bv, bi, n, k, lane, tau_out);
-}
+// out of line on purpose: the sort's register arrays must not merge into the register allocation of the FMA loop
 template <int CAP>
 __device__ __noinline__ int sort_row(float* bv, BI* bi, int n, int k, int lane, float* tau_out) {
     return compact_row<CAP, BI>(bv, bi, n, k, lane, tau_out);
@@ -75,10 +71,10 @@ __device__ __noinline__ int sort_row(float* bv, BI* bi, int n, int k, int lane, 
 // registers across the out-of-line call
 struct RowState { int n_mine, n_other; float tau; };
 
-// SLOW path of an admission step (one of the two rows of the step would overflow its buffer): the whole warp compacts that row,
-// then the lanes with `pass` append.  ONE out-of-line copy: inlined into the 32 unrolled steps of a tile the compactions made the
-// kernel ~300 KB of SASS and the instruction fetch its top stall (ncu: no_instruction 3.6 per issue).  The common case (both rows
-// have room) is a dozen inline instructions in the kernel.
+// SLOW path of the admission (one of the two rows of the step would overflow its buffer), one 16-candidate group at a time: the
+// whole warp compacts the row that is full, then the lanes with `pass` append.  ONE out-of-line copy: inlined into the unrolled
+// steps of a tile the compactions made the kernel ~300 KB of SASS and instruction fetch its top stall (ncu: no_instruction 3.6
+// per issue).  The common case (both rows have room for everything the tile admits) is the inline scan in the kernel.
 template <int CAP>
 __device__ __noinline__ RowState admit(float* bv_lo, BI* bi_lo, int half, int lane, unsigned lt_mask, unsigned m, bool pass,
                                        float d, int j, RowState st, int ksel) {
@@ -108,23 +104,27 @@ __device__ __noinline__ RowState admit(float* bv_lo, BI* bi_lo, int half, int la
     return st;
 }
 
-template <int CAP, typename IdxT, bool SAMPLED>
+template <int CAP, typename IdxT, bool SAMPLED, bool QRES>
 __global__ void __launch_bounds__(NT, 2)
 knn_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mQ, const float* __restrict__ xx,
-               int N, int C, int k, int r_sample, IdxT* __restrict__ idx_out, float* __restrict__ dist_out) {
-    constexpr int NST = Cfg<CAP>::NST;
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t raw_u32 = smem_u32(smem_raw);
-    unsigned char* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);          // (offset from the array: stays a shared pointer)
-    unsigned char* stages = smem;                                                    // NST x (x tile | q tile)
-    const uint32_t stages_u32 = smem_u32(stages);
-    float* bufv = reinterpret_cast<float*>(smem + NST * STAGE_BYTES);                // [TQ][CAP]
+               int N, int C, int k, int r_sample, int nst, IdxT* __restrict__ idx_out, float* __restrict__ dist_out) {
+    // The kernel has no static shared memory, so the dynamic window starts at offset 0 of the CTA's allocation, which is 1024-byte
+    // aligned (what the 128B-swizzled TMA tiles need); the plan has no slack for padding (two CTAs per SM), hence the trap.
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    constexpr int SB = QRES ? X_BYTES : STAGE_BYTES;
+    const int nchunk = C / KC;
+    unsigned char* stages = smem;                                                    // nst x stage
+    unsigned char* qres = smem + nst * SB;                                           // QRES: [nchunk][64][128 B]
+    float* bufv = reinterpret_cast<float*>(qres + (QRES ? nchunk * Q_BYTES : 0));    // [TQ][CAP]
     BI* bufi = reinterpret_cast<BI*>(bufv + TQ * CAP);                               // [TQ][CAP]
     float* tau_s = reinterpret_cast<float*>(bufi + TQ * CAP);                        // [TQ]
     int* cnt_s = reinterpret_cast<int*>(tau_s + TQ);                                 // [TQ]
     float* xxq = reinterpret_cast<float*>(cnt_s + TQ);                               // [TQ]
-    uint64_t* full = reinterpret_cast<uint64_t*>(xxq + TQ);                          // [NST]
-    uint64_t* empty = full + 4;                                                      // [NST]
+    uint64_t* full = reinterpret_cast<uint64_t*>(xxq + TQ);                          // [4]
+    uint64_t* empty = full + 4;                                                      // [4]
+    uint64_t* qbar = full + 8;                                                       // [1]
+    const uint32_t stages_u32 = smem_u32(stages);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y, q0 = blockIdx.x * TQ;
@@ -132,12 +132,14 @@ knn_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ C
     const int tq = tid >> 4;            // queries 4 tq .. 4 tq + 3   (a warp: tq = 2 warp, 2 warp + 1 -> rows 8 warp .. 8 warp + 7)
     const int tc = tid & 15;            // candidates tc + 16 cc, cc = 0..7
     const int half = lane >> 4;         // which of the warp's two query groups this lane belongs to
+    const int hl = lane & 15;           // lane inside the half-warp
     const int kx = tc & 7, kq = 4 * (tq & 1);
     const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
     const unsigned lt_mask = ((1u << lane) - 1u) & hmask;         // lanes of my half below me
 
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NT / 32); }
+        for (int s = 0; s < nst; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NT / 32); }
+        mbar_init(qbar, 1);
         mbar_fence_init();
         tma_prefetch_desc(&mX); tma_prefetch_desc(&mQ);
     }
@@ -146,40 +148,46 @@ knn_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ C
         xxq[tid] = (q < N) ? xxb[q] : 0.f;
     }
     __syncthreads();
+    if constexpr (QRES) {
+        if (tid == 0) {
+            mbar_arrive_expect_tx(qbar, nchunk * Q_BYTES);
+            for (int ci = 0; ci < nchunk; ++ci) tma_load_3d(qres + ci * Q_BYTES, &mQ, qbar, ci * KC, q0, b);
+        }
+    }
 
     // per-thread copies of the state of its 4 query rows (identical in the 16 lanes of a half-warp)
     float tau[4];
-    int cnt[4], cnt_o[4];               // cnt: my half's rows; cnt_o: the other half's rows (every lane tracks both from the ballots)
+    int cnt[4], cnt_o[4];               // cnt: my half's rows; cnt_o: the other half's rows (every lane tracks both)
 #pragma unroll
     for (int a = 0; a < 4; ++a) { tau[a] = -INFINITY; cnt[a] = 0; cnt_o[a] = 0; }
     float xq[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) xq[a] = xxq[4 * tq + a];
 
-    const int nchunk = C / KC;
-    uint32_t issued = 0, consumed = 0;              // chunk counters over the whole kernel (ring position / parity)
+    uint32_t issued = 0, consumed = 0;              // chunk counters over the whole kernel
+    uint32_t is = 0, ip = 0, cs = 0, cp = 0;         // ring slot / phase bit of the next chunk to issue resp. consume
     int jend = N, ksel = k;
     [[maybe_unused]] int phase = 1;
     if constexpr (SAMPLED) { phase = 0; ksel = r_sample; jend = min(N, SAMPLE_M); }
 
     auto issue = [&](int t, int ci) {               // one elected thread: chunk ci of candidate tile t into the next ring slot
-        const int s = issued % NST;
-        mbar_wait_guarded(&empty[s], ((issued / NST) & 1) ^ 1);
-        unsigned char* st = stages + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        tma_load_3d(st, &mX, &full[s], ci * KC, t * TC, b);
-        tma_load_3d(st + X_BYTES, &mQ, &full[s], ci * KC, q0, b);
+        mbar_wait_guarded(&empty[is], ip ^ 1);
+        unsigned char* st = stages + is * SB;
+        mbar_arrive_expect_tx(&full[is], SB);
+        tma_load_3d(st, &mX, &full[is], ci * KC, t * TC, b);
+        if constexpr (!QRES) tma_load_3d(st + X_BYTES, &mQ, &full[is], ci * KC, q0, b);
     };
+    auto issued_step = [&]() { ++issued; if (++is == (uint32_t)nst) { is = 0; ip ^= 1; } };
+    if constexpr (QRES) wait_ready(qbar, 0);
 
 phase_begin:
     {
         const int ntiles = (jend + TC - 1) / TC;
         const int total = ntiles * nchunk;
-        // prologue: fill the ring (issued is only advanced by the producer thread's own bookkeeping, mirrored in all threads)
-        int next = 0;
-        for (; next < min(NST - 1, total); ++next) {
+        int next = 0;                                // chunks of this pass issued so far
+        for (; next < min(nst - 1, total); ++next) {
             if (tid == 0) issue(next / nchunk, next % nchunk);
-            ++issued;
+            issued_step();
         }
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
@@ -199,13 +207,12 @@ phase_begin:
             for (int ci = 0; ci < nchunk; ++ci) {
                 if (next < total) {                                  // keep the ring full: one chunk ahead per chunk consumed
                     if (tid == 0) issue(next / nchunk, next % nchunk);
-                    ++issued; ++next;
+                    issued_step(); ++next;
                 }
-                const int s = consumed % NST;
-                wait_ready(&full[s], (consumed / NST) & 1);
+                wait_ready(&full[cs], cp);
                 // candidate rows tc + 16 cc (swizzle key tc & 7 for all of them), query rows 4 tq + a (key 4 (tq & 1) + a)
-                const uint32_t xrow = stages_u32 + s * STAGE_BYTES + tc * 128;
-                const uint32_t qrow = stages_u32 + s * STAGE_BYTES + X_BYTES + (4 * tq) * 128;
+                const uint32_t xrow = stages_u32 + cs * SB + tc * 128;
+                const uint32_t qrow = (QRES ? stages_u32 + nst * SB + ci * Q_BYTES : stages_u32 + cs * SB + X_BYTES) + (4 * tq) * 128;
 #pragma unroll 2
                 for (int g = 0; g < KC / 4; ++g) {
                     float4 qv[4], xv[8];
@@ -230,36 +237,60 @@ phase_begin:
                         }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                if (lane == 0) mbar_arrive(&empty[cs]);
                 ++consumed;
+                if (++cs == (uint32_t)nst) { cs = 0; cp ^= 1; }
             }
-            // ---- distances + admission straight from registers: half-warp `half` owns rows 8 warp + 4 half + a
+            // ---- distances + admission straight from registers: half-warp `half` owns rows 8 warp + 4 half + a.
+            // Per row: every lane turns its 8 distances into a pass mask, a 16-lane prefix sum gives each lane its slots in the
+            // row buffer, and the (d, j) pairs are stored -- one ballot and one scan per row instead of one ballot per 16
+            // candidates.  A row that would overflow takes the out-of-line group-by-group path (compaction).
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
+                float d8[8];
+                unsigned pm = 0;
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
                     const int j = j0 + tc + 16 * cc;
                     const float inner = __fmul_rn(-2.0f, acc[a][cc]);
                     float d = __fsub_rn(__fsub_rn(-xc8[cc], inner), xq[a]);
                     d = (j < N) ? d : -INFINITY;
-                    const bool pass = d > tau[a];
-                    const unsigned m = __ballot_sync(FULL, pass);
-                    if (m) {                                          // warp-uniform
-                        const int c_lo = __popc(m & 0xffffu), c_hi = __popc(m >> 16);
-                        const int c_mine = half ? c_hi : c_lo, c_other = half ? c_lo : c_hi;
-                        if (max(cnt[a] + c_mine, cnt_o[a] + c_other) > CAP) {       // same value in every lane
+                    d8[cc] = d;
+                    pm |= (d > tau[a]) ? (1u << cc) : 0u;
+                }
+                if (__ballot_sync(FULL, pm != 0) == 0) continue;                    // nothing admitted in either row
+                const int c = __popc(pm);
+                int incl = c;                                                        // inclusive prefix sum inside the half-warp
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (hl >= o) incl += v;
+                }
+                const int tot_mine = __shfl_sync(FULL, incl, 15 + 16 * half);
+                const int tot_other = __shfl_sync(FULL, incl, 15 + 16 * (half ^ 1));
+                if (max(cnt[a] + tot_mine, cnt_o[a] + tot_other) <= CAP) {           // same value in every lane
+                    float* bv = bufv + (4 * tq + a) * CAP + cnt[a] + (incl - c);
+                    BI* bi = bufi + (4 * tq + a) * CAP + cnt[a] + (incl - c);
+                    int w = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) {
+                        if (pm & (1u << cc)) { bv[w] = d8[cc]; bi[w] = (BI)(j0 + tc + 16 * cc); ++w; }
+                    }
+                    cnt[a] += tot_mine; cnt_o[a] += tot_other;
+                } else {
+#pragma unroll 1
+                    for (int cc = 0; cc < 8; ++cc) {
+                        float d = d8[0];                                               // d8[cc] without dynamic register indexing
+#pragma unroll
+                        for (int u = 1; u < 8; ++u) d = (cc == u) ? d8[u] : d;
+                        const bool pass = d > tau[a];                                  // (tau may have risen in this loop)
+                        const unsigned m = __ballot_sync(FULL, pass);
+                        if (m) {
                             RowState st;
                             st.n_mine = cnt[a]; st.n_other = cnt_o[a]; st.tau = tau[a];
                             st = admit<CAP>(bufv + (8 * warp + a) * CAP, bufi + (8 * warp + a) * CAP, half, lane, lt_mask, m, pass,
-                                            d, j, st, ksel);
+                                            d, j0 + tc + 16 * cc, st, ksel);
                             cnt[a] = st.n_mine; cnt_o[a] = st.n_other; tau[a] = st.tau;
-                        } else {
-                            if (pass) {
-                                const int pos = cnt[a] + __popc(m & lt_mask);
-                                bufv[(4 * tq + a) * CAP + pos] = d;
-                                bufi[(4 * tq + a) * CAP + pos] = (BI)j;
-                            }
-                            cnt[a] += c_mine; cnt_o[a] += c_other;
                         }
                     }
                 }
@@ -361,11 +392,21 @@ template <int CAP, typename IdxT>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mq, const float* xx, int B, int N, int C, int k, void* idx,
                   float* dist, cudaStream_t st) {
     const int r = sample_rank(N, k);
-    auto kern = r ? knn_tma_kernel<CAP, IdxT, true> : knn_tma_kernel<CAP, IdxT, false>;
-    const size_t sm = smem_bytes<CAP>();
+    // shared-memory plan for two CTAs per SM (<= 113 KB each): resident queries + 16 KB candidate stages when they fit with
+    // at least 3 stages, else 24 KB (candidate + query) stages; as many stages as fit, at most 4
+    const size_t budget = 113 * 1024, fixed = fixed_bytes<CAP>();          // (228 KB per SM - 1 KB reserved per CTA) / 2
+    const size_t qres_bytes = (size_t)(C / KC) * Q_BYTES;
+    bool qres = fixed + qres_bytes + 3 * (size_t)X_BYTES <= budget;
+    int nst = (int)((budget - fixed - (qres ? qres_bytes : 0)) / stage_bytes(qres));
+    nst = nst > 4 ? 4 : nst;
+    PN_REQUIRE(nst >= 2, "pn_knn_tma: shared-memory plan does not fit (C=%d)", C);
+    const size_t sm = fixed + (qres ? qres_bytes : 0) + (size_t)nst * stage_bytes(qres);
+    void (*kern)(CUtensorMap, CUtensorMap, const float*, int, int, int, int, int, IdxT*, float*) =
+        r ? (qres ? knn_tma_kernel<CAP, IdxT, true, true> : knn_tma_kernel<CAP, IdxT, true, false>)
+          : (qres ? knn_tma_kernel<CAP, IdxT, false, true> : knn_tma_kernel<CAP, IdxT, false, false>);
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(cdiv(N, TQ), B);
-    kern<<<grid, NT, sm, st>>>(mx, mq, xx, N, C, k, r, (IdxT*)idx, dist);
+    kern<<<grid, NT, sm, st>>>(mx, mq, xx, N, C, k, r, nst, (IdxT*)idx, dist);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("knn_tma_kernel");
     return PN_OK;
