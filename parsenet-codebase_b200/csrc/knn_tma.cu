@@ -66,6 +66,13 @@ template <int CAP>
 __device__ __noinline__ int sort_row(float* bv, BI* bi, int n, int k, int lane, float* tau_out) {
     return compact_row<CAP, BI>(bv, bi, n, k, lane, tau_out);
 }
+// k-th best value of a row buffer without ordering it (quickselect; ~4x fewer instructions than the bitonic sort)
+template <int CAP>
+__device__ __noinline__ float kth_best(float* bv, BI* bi, int n, int k, int lane) {
+    float t;
+    compact_select<CAP, BI>(bv, bi, n, k, lane, &t);
+    return t;
+}
 
 // state of the two query rows a warp-step touches (lower / upper half-warp), passed and returned BY VALUE so that it stays in
 // registers across the out-of-line call
@@ -310,8 +317,7 @@ phase_begin:
 #pragma unroll 1
             for (int r = 0; r < 8; ++r) {
                 const int row = warp * 8 + r;
-                float t;
-                sort_row<CAP>(bufv + row * CAP, bufi + row * CAP, cnt_s[row], ksel, lane, &t);
+                const float t = kth_best<CAP>(bufv + row * CAP, bufi + row * CAP, cnt_s[row], ksel, lane);
                 if (lane == 0) { tau_s[row] = t; cnt_s[row] = 0; }
             }
             __syncwarp();
