@@ -256,18 +256,20 @@ def test_evaluation_fitting_loss_vs_reference(golden_dir, variant, stage, monkey
     ref = sorted(zip(g["seg_kind"], g["seg_dist"]))
     assert [k for k, _ in mine] == [k for k, _ in ref]
     for (kind, d_mine), (_, d_ref) in zip(mine, ref):
-        # cylinder: the reference's own radius carries fp32 noise from its rank-deficient solve (see the fit test)
-        tol = 5e-2 if kind == "cylinder" else 1e-3
+        # cylinder: the reference's own radius carries fp32 noise from its rank-deficient solve (measured and explained in
+        # tests/test_cpu_fitsolve.py::test_cylinder_deviation_is_the_references_own_fp32_noise); everything else 1e-4
+        tol = 5e-2 if kind == "cylinder" else 1e-4
         assert abs(d_mine - d_ref) <= tol * d_ref, (kind, d_mine, d_ref)
-    assert abs(res[2] - float(g["spl"])) <= 1e-3 * float(g["spl"])
+    assert abs(res[2] - float(g["spl"])) <= 1e-5 * float(g["spl"])
     assert abs(res[0].item() - float(g["loss"])) <= 3e-2 * abs(float(g["loss"]))
     res[0].backward()
     ge, gr = E.grad.cpu().double().numpy(), g["gradE"].astype(np.float64)
     rel = np.abs(ge - gr).max() / (np.abs(gr).max() + 1e-30)
     print("grad rel err", rel)
     if variant == "e2e_nocyl":
-        assert abs(res[0].item() - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
-        assert rel < 2e-2
+        # measured on B200 (round 2): loss 1.1e-6, gradient 4e-6 relative
+        assert abs(res[0].item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+        assert rel < 1e-4
     # with a cylinder segment the reference gradient carries the 1e4-amplified fp32 noise of its rank-deficient
     # regularised solve (primitive_forward.py:803 -> fitting_utils.py:52-64); only the loss value is compared there
 
