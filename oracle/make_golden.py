@@ -348,7 +348,28 @@ def gen_upsample():
     np.savez_compressed(os.path.join(OUT, "upsample.npz"), **out)
 
 
-GENS = {"upsample": gen_upsample, "guard": gen_guard, "cfg1": gen_cfg1, "knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
+def gen_pipeline():
+    """Dataset.get_train of the unmodified reference (dataset_segments.py:95-157) on synthetic clouds, constructed
+    without its h5 loader: align_canonical with and without normal noise / anisotropic scaling (np.random.seed(11))"""
+    DS = rl.ref("src.dataset_segments")
+    from tools.synth import ALL_KINDS, synth_cloud
+    B, N = 4, 3000
+    pts, nrm, lab, prim = synth_cloud(B, N, seed=77, n_patches=6, kinds=ALL_KINDS)
+    pts = (pts * np.array([1.7, 0.9, 1.2], np.float32)).astype(np.float32)
+    out = {"pts": pts.copy(), "nrm": nrm.copy()}
+    for name, kw in (("plain", dict(if_normal_noise=False, anisotropic=False)),
+                     ("noise_aniso", dict(if_normal_noise=True, anisotropic=True))):
+        d = DS.Dataset.__new__(DS.Dataset)
+        d.batch_size = B; d.normals = True; d.primitives = True
+        d.train_points = pts.copy(); d.train_labels = lab.copy(); d.train_normals = nrm.copy(); d.train_primitives = prim.copy()
+        d.augment_routines = []
+        np.random.seed(11)
+        p, l, n, pr = next(d.get_train(randomize=False, augment=False, align_canonical=True, **kw))
+        out[name + "_p"] = np.asarray(p, np.float32); out[name + "_n"] = np.asarray(n, np.float32)
+    np.savez_compressed(os.path.join(OUT, "pipeline.npz"), **out)
+
+
+GENS = {"pipeline": gen_pipeline, "upsample": gen_upsample, "guard": gen_guard, "cfg1": gen_cfg1, "knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
         "splinenet": gen_splinenet, "e2e": gen_e2e, "e2e_nocyl": lambda: gen_e2e(True, "e2e_nocyl.npz")}
 
 if __name__ == "__main__":

@@ -275,3 +275,21 @@ def test_eval_time_residual_variants_match_the_oracle_port(sqrt, reduce):
         want = OP.DISTANCES[kind](q, ps, sqrt=sqrt, reduce=reduce)
         assert got.shape == want.shape
         assert torch.allclose(got, want, rtol=1e-6, atol=1e-9), kind
+
+
+def test_input_pipeline_vs_reference_dataset(golden_dir):
+    """host rotations (the reference's own 3x3 arithmetic) + the batched rotate / extent / scale expressions of
+    pnb200.input_pipeline (run on CPU tensors here, on the device in tests/test_gpu_fitstage.py) against Dataset.get_train of
+    the unmodified reference (tests/golden/pipeline.npz): aligned points and rotated normals to 2e-6"""
+    import os
+    from pnb200 import input_pipeline as IP
+    g = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    for name, noise, aniso in (("plain", False, False), ("noise_aniso", True, True)):
+        pts, nrm = g["pts"].copy(), g["nrm"].copy()
+        np.random.seed(11)
+        if noise:
+            pts = pts + nrm * IP.normal_noise(pts.shape[1])
+        R = IP.host_rotations(pts)
+        p, n = IP.preprocess_on_device(torch.from_numpy(pts), torch.from_numpy(nrm), torch.from_numpy(R), anisotropic=aniso)
+        assert np.abs(p.numpy() - g[name + "_p"]).max() <= 2e-6, name
+        assert np.abs(n.numpy() - g[name + "_n"]).max() <= 2e-6, name

@@ -347,3 +347,20 @@ def test_weights_normalize_kernel_extreme_bandwidth_vs_float64():
     (want * coef[0, :, :K].double()).sum().backward()
     _close(Wk[0, :, :K], want, 1e-5, "weights, clamp regime")
     _close(a.grad[0, :, :K], r.grad, 1e-3, "d/d similarities, clamp regime")
+
+
+def test_device_input_pipeline_vs_reference_dataset(golden_dir):
+    """SURVEY 8f-4 on the device: DeviceBatchPipeline (host 3x3 rotations, pinned upload, batched rotation / extent / scaling
+    launches) against Dataset.get_train of the unmodified reference (tests/golden/pipeline.npz)"""
+    import os
+    from pnb200.input_pipeline import DeviceBatchPipeline
+    g = np.load(os.path.join(golden_dir, "pipeline.npz"))
+    lab = np.zeros(g["pts"].shape[:2], np.int64)
+    for name, noise, aniso in (("plain", False, False), ("noise_aniso", True, True)):
+        np.random.seed(11)
+        pipe = DeviceBatchPipeline(iter([[g["pts"].copy(), lab, g["nrm"].copy(), lab]]), torch.device("cuda", 0),
+                                   if_normal_noise=noise, anisotropic=aniso)
+        p, _, n, _ = next(pipe)
+        assert p.is_cuda and n.is_cuda
+        assert np.abs(p.cpu().numpy() - g[name + "_p"]).max() <= 3e-6, name
+        assert np.abs(n.cpu().numpy() - g[name + "_n"]).max() <= 3e-6, name

@@ -22,8 +22,10 @@ torch.cuda.set_device(0)
 hp = bench.HotPath(dev, 1)
 B = bench.BATCH_PER_GPU
 host = bench.make_host_batch(B, bench.N_POINTS, seed=0)
-x, lab, prim = (t.to(dev) for t in host)
-lab_np, prim_np = host[1].numpy(), host[2].numpy()
+from pnb200.input_pipeline import host_rotations
+x = bench.device_input(host[0].to(dev), host[1].to(dev), torch.from_numpy(host_rotations(host[0].numpy())).to(dev))
+lab, prim = host[2].to(dev), host[3].to(dev)
+lab_np, prim_np = host[2].numpy(), host[3].numpy()
 
 
 def sync():
