@@ -269,9 +269,11 @@ def run_ours(args):
     t_wall0 = time.time()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     ev0.record()
+    marks_res = []
     for i in range(args.steps):
         flush.zero_()                           # L2 flush between timed iterations (256 MB > 126 MB L2)
         resident_step(i)
+        marks_res.append(torch.cuda.Event(enable_timing=True)); marks_res[-1].record()
     ev1.record()
     barrier()
     ms_res = ev0.elapsed_time(ev1)
@@ -285,9 +287,11 @@ def run_ours(args):
     ev2 = torch.cuda.Event(enable_timing=True); ev3 = torch.cuda.Event(enable_timing=True)
     ev2.record()
     mem0 = torch.cuda.memory_stats(dev)
+    marks_e2e = []
     for i in range(args.steps):
         flush.zero_()
         e2e_step(i, last=(i == args.steps - 1))
+        marks_e2e.append(torch.cuda.Event(enable_timing=True)); marks_e2e[-1].record()
     ev3.record()
     barrier()
     t_wall1 = time.time()
@@ -389,6 +393,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": roof,
     }
+    out["per_step_ms"] = {"resident": [round(a.elapsed_time(b), 2) for a, b in zip([ev0] + marks_res[:-1], marks_res)],
+                          "e2e": [round(a.elapsed_time(b), 2) for a, b in zip([ev2] + marks_e2e[:-1], marks_e2e)]}
     out["config"]["mean_clusters_per_shape_last"] = (float(np.mean(hp.clusters[-4:])) if hp.clusters else None)
     out["config"]["fitted_segments_per_step"] = fits_per_step
     out["config"]["workload_pin"] = ("embedding + %.1f x RMS x code[gt patch]: mean-shift recovers the %d ground-truth patches of "

@@ -143,6 +143,17 @@ int pn_ms_iter_fwd_tc(const float* Y, const float* X, int B, int N, int d, const
 int pn_ms_iter_bwd_tc(const float* gout, const float* Ynew, const float* Yprev, const float* X, const float* den, const float* unorm, int B, int N, int d, const float* cinv, float* ws_Gn, float* ws_gd, float* gYprev, float* gX, int accumulate_gX, void* stream);
 /* replaces: MeanShift.compute_bandwidth: src/mean_shift.py:130-135 — same contract as pn_ms_kth_dist */
 int pn_ms_kth_dist_tc(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K, float* kth, void* stream);
+/* the same selection for the 128-row blocks that contain a row with flags[b][row] != 0 only (other blocks exit at once, their
+   kth entries stay untouched): exact fall-back of pn_ms_kth_dist_tma */
+int pn_ms_kth_dist_tc_flagged(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K, const int* flags, float* kth, void* stream);
+/* replaces: MeanShift.compute_bandwidth: src/mean_shift.py:115-137 with num_samples >= N (all rows against all N points of
+   their shape) — ONE pass over the N x N distance tiles instead of the four radix passes of pn_ms_kth_dist_tc: the b_sample-th
+   smallest distance to the column sample {0, stride, 2 stride, ...} brackets the K-th smallest from above, one TMA-fed tcgen05
+   pass appends every distance below the bracket to per-row lists, a warp per row selects the K-th and recomputes that pair in
+   fp32.  Xs = X - tf32_hi(X) (pn_ms_prepare_operands).  ws_key [B*N][cap] u32, ws_col [B*N][cap] u16, ws_cnt [B*N][2] i32
+   (one list per half of a tile's columns), ws_hi [B*N] f32, cap = 1024.  flags [B*N] is written: 1 = bracket failed for that row, kth not written (run
+   pn_ms_kth_dist_tc_flagged with the same flags next; no host round trip); meanshift_tma.cu */
+int pn_ms_kth_dist_tma(const float* X, const float* Xs, int B, int N, int d, int K, int stride, int b_sample, unsigned* ws_key, unsigned short* ws_col, int* ws_cnt, float* ws_hi, int cap, int* flags, float* kth, void* stream);
 /* replaces: MeanShift.nms arg-selects: src/mean_shift.py:146-149 (mode 0), :163-171 (mode 1) — same contract as pn_ms_argsel for modes 0 and 1; meanshift_tc_argsel.cu */
 int pn_ms_argsel_tc(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream);
 /* the two halves of pn_ms_iter_bwd_tc on their own: prep pass (Gn, gd) and the cols kernel (gX) */

@@ -21,9 +21,11 @@ constexpr int CAND = 8;                                              // distinct
 struct Bars { uint64_t x_full[NSTAGE], x_empty[NSTAGE], s_full[2], s_empty[2], a_ready; };
 
 // grid (ceil(S/128), B).  rows (optional): [B][S] indices into the N points of each shape.
+// flags (optional): [B][S]; a CTA none of whose 128 rows is flagged exits at once (the bracketed path of meanshift_tma.cu
+// uses this kernel as the exact fall-back for the rows whose bracket failed).
 __global__ void __launch_bounds__(NT, 1)
 ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int S, long long shape_stride, int K,
-                 float* __restrict__ kth) {
+                 const int* __restrict__ flags, float* __restrict__ kth) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned* hist = reinterpret_cast<unsigned*>(smem + NSTAGE * STAGE_BYTES);      // [BM][HP]
     __shared__ Bars bars;
@@ -39,6 +41,10 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.y, i0 = blockIdx.x * BM;
+    if (flags) {
+        const int f = (tid < BM && i0 + tid < S) ? flags[(long long)b * S + i0 + tid] : 0;
+        if (!__syncthreads_or(f)) return;
+    }
     const float* Xb = X + (long long)b * shape_stride;
     const int* rb = rows ? rows + (long long)b * S : nullptr;
     const int ntiles = (S + BN - 1) / BN;
@@ -235,16 +241,29 @@ ms_kth_tc_kernel(const float* __restrict__ X, const int* __restrict__ rows, int 
 
 using namespace pn;
 
-extern "C" int pn_ms_kth_dist_tc(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K,
-                                 float* kth, void* stream) {
-    PN_REQUIRE(X && kth, "pn_ms_kth_dist_tc: null pointer");
-    PN_REQUIRE(d == mstck::D, "pn_ms_kth_dist_tc: embedding width must be %d (got %d)", mstck::D, d);
-    PN_REQUIRE(K >= 1 && K <= S && S < (1 << 24), "pn_ms_kth_dist_tc: need 1 <= K <= S < 2^24 (K=%d S=%d)", K, S);
+static int kth_launch(const char* who, const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K,
+                      const int* flags, float* kth, void* stream) {
+    PN_REQUIRE(X && kth, "%s: null pointer", who);
+    PN_REQUIRE(d == mstck::D, "%s: embedding width must be %d (got %d)", who, mstck::D, d);
+    PN_REQUIRE(K >= 1 && K <= S && S < (1 << 24), "%s: need 1 <= K <= S < 2^24 (K=%d S=%d)", who, K, S);
     size_t sm = mstck::NSTAGE * mstck::STAGE_BYTES + (size_t)mstck::BM * mstck::HP * sizeof(unsigned) + 1024;
     PN_CUDA(cudaFuncSetAttribute(mstck::ms_kth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(cdiv(S, mstck::BM), B);
-    mstck::ms_kth_tc_kernel<<<grid, mstck::NT, sm, (cudaStream_t)stream>>>(X, rows, S, shape_stride, K, kth);
+    mstck::ms_kth_tc_kernel<<<grid, mstck::NT, sm, (cudaStream_t)stream>>>(X, rows, S, shape_stride, K, flags, kth);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("ms_kth_tc_kernel");
     return PN_OK;
+}
+
+extern "C" int pn_ms_kth_dist_tc(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K,
+                                 float* kth, void* stream) {
+    return kth_launch("pn_ms_kth_dist_tc", X, rows, B, S, shape_stride, d, K, nullptr, kth, stream);
+}
+
+// the same selection restricted to the 128-row blocks that contain a row with flags[b][row] != 0 (other blocks return at
+// once and their kth entries are left untouched): exact fall-back of pn_ms_kth_dist_tma
+extern "C" int pn_ms_kth_dist_tc_flagged(const float* X, const int* rows, int B, int S, long long shape_stride, int d, int K,
+                                         const int* flags, float* kth, void* stream) {
+    PN_REQUIRE(flags, "pn_ms_kth_dist_tc_flagged: null flags");
+    return kth_launch("pn_ms_kth_dist_tc_flagged", X, rows, B, S, shape_stride, d, K, flags, kth, stream);
 }

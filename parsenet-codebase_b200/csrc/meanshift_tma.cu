@@ -22,6 +22,7 @@
 //   XB_* : 1 slab of [128 d rows][128 B = 32 j], TMA box {32 j, 128 d, 1} of Xt / Xst                      (K = j)
 #include "common.cuh"
 #include "tc05.cuh"
+#include "kth_select.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -722,6 +723,294 @@ ms_bwd_cols_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_cons
     finale<CG>(tb, warp);
 }
 
+// ---------------------------------------------------------------------------------------------- K-th distance, bracketed
+// MeanShift.compute_bandwidth (reference src/mean_shift.py:115-137) needs, per row, the K-th smallest of dist = 2 - 2 X X^T
+// (K = quantile * N, 150 of 10^4).  The radix kernel of meanshift_tc_kth.cu recomputes the N x N distance tiles four times;
+// here they are computed once:
+//   1. collect<ALL>  : distances of every row to a strided SAMPLE of m <= cap columns (a tensor map whose row pitch is
+//                      stride * 128 floats), all m keys stored per row
+//   2. select        : hi_i = b-th smallest of row i's sample (b = K m / N + 7 sigma + 2: an upper bracket of the K-th
+//                      smallest of the full row unless the sample is 7 sigma unlucky)
+//   3. collect       : ONE pass over all N columns, (key, column) of every distance <= hi_i appended to row i's list
+//                      (~ b N / m entries, 4 % of the row)
+//   4. select<EXACT> : K-th smallest key of the list, that pair's distance recomputed with the fp32 FMA chain of the radix
+//                      kernel; rows whose list holds fewer than K entries (bracket too low) or overflowed are FLAGGED
+//   5. the radix kernel re-does the 128-row blocks that contain a flagged row (pn_ms_kth_dist_tc_flagged; exits at once
+//      otherwise), so the result never depends on the sample.
+// The tiles are 64 columns wide (48 MMAs of N = 64 per tile step), operands by TMA as in the forward kernel (row-major
+// forms only), S double-buffered in TMEM, epilogue thread = (row, 32-column half).
+constexpr int KBN = 64;
+constexpr int KSLAB = KBN * 128;                  // one [64 j rows][128 B] slab (d in [32 s, 32 s + 32))
+constexpr int KPART = 4 * KSLAB;                  // 32 KB per operand part
+constexpr int KSTAGE = 2 * KPART;                 // X | Xs
+constexpr int KNST = 3;
+constexpr uint32_t C_KS0 = 256;                   // S(t) at columns 256 + 64 (t & 1)
+
+struct KBars { uint64_t x_full[KNST], x_empty[KNST], s_full[2], s_empty[2], a_ready; };
+
+// grid (ceil(N / 128), B), 320 threads.  mC / mCs: maps of the column set (ncols rows; column r is point r * cstride).
+// ALL: store the key of column r at slot r of the row's list (ncols <= cap); otherwise append (key, point) when dist <= hi.
+template <bool ALL>
+__global__ void __launch_bounds__(NT, 1)
+ms_kth_collect_kernel(const __grid_constant__ CUtensorMap mC, const __grid_constant__ CUtensorMap mCs,
+                      const float* __restrict__ X, int N, int ncols, int cstride, const float* __restrict__ hi, int cap,
+                      unsigned* __restrict__ ckey, unsigned short* __restrict__ ccol, int* __restrict__ cnt_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ KBars bars;
+    __shared__ uint32_t tmem_base_s;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, i0 = blockIdx.x * BM;
+    const float* Xb = X + (long long)b * N * D;
+    const int ntiles = (ncols + KBN - 1) / KBN;
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < KNST; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
+        for (int k = 0; k < 2; ++k) { mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); }
+        mbar_init(&bars.a_ready, EPI_THREADS);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+
+    if (warp < EPI_WARPS) {
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t la = (uint32_t)(q * 32) << 16;
+        const bool ok = (i0 + row) < N;
+        const float* xr = Xb + (long long)(i0 + row) * D + 64 * h;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t vb[16], vs[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+                float4 v = ok ? *reinterpret_cast<const float4*>(xr + c0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float big = tf32_hi(f[u]);
+                    vb[e + u] = __float_as_uint(big);
+                    vs[e + u] = __float_as_uint(f[u] - big);
+                }
+            }
+            tmem_st16(tb + la + C_YB + 64 * h + c0, vb);
+            tmem_st16(tb + la + C_YS + 64 * h + c0, vs);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.a_ready);
+        // admission threshold on S: every s with fl(2 - 2 s) <= hi satisfies s >= 1 - hi / 2 up to two roundings
+        float sthr = INFINITY;                                                                   // rows >= N admit nothing
+        if (!ALL && ok) {
+            sthr = 1.0f - 0.5f * hi[(long long)b * N + i0 + row];
+            sthr -= 4e-7f * fmaxf(1.0f, fabsf(sthr));
+        }
+        const long long lbase = ((long long)b * N + i0 + row) * cap;
+        // appended entries: this thread's half of the tile columns goes to ITS half of the row's list (no atomics)
+        const int half_cap = cap >> 1;
+        unsigned* kdst = ckey + lbase + h * half_cap;
+        unsigned short* cdst = ccol + lbase + h * half_cap;
+        int mine = 0;
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int k = t & 1;
+            const int j0 = t * KBN + 32 * h;
+            mbar_wait_guarded(&bars.s_full[k], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[32];
+            tmem_ld32(tb + la + C_KS0 + 64 * k + 32 * h, sv);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.s_empty[k]);
+            if (ALL) {
+                if (ok) {
+#pragma unroll
+                    for (int u = 0; u < 32; u += 4) {
+                        uint4 kk;                       // raw float bits of the distances (the select kernel orders them)
+                        kk.x = __float_as_uint(2.0f - 2.0f * __uint_as_float(sv[u]));
+                        kk.y = __float_as_uint(2.0f - 2.0f * __uint_as_float(sv[u + 1]));
+                        kk.z = __float_as_uint(2.0f - 2.0f * __uint_as_float(sv[u + 2]));
+                        kk.w = __float_as_uint(2.0f - 2.0f * __uint_as_float(sv[u + 3]));
+                        // columns beyond ncols are zero-filled by TMA (dist = 2): the select kernel only reads ncols slots
+                        if (j0 + u + 3 < cap) *reinterpret_cast<uint4*>(ckey + lbase + j0 + u) = kk;
+                    }
+                }
+            } else {
+                // admitted = { s >= sthr }: fl(2 - 2 s) is monotone in s, so this set is closed towards smaller distances and
+                // contains every distance <= hi -- all the selection needs
+                uint32_t mask = 0u;
+#pragma unroll
+                for (int u = 0; u < 32; ++u) mask |= (__uint_as_float(sv[u]) >= sthr) ? (1u << u) : 0u;
+                if (j0 + 32 > ncols) mask &= (j0 < ncols) ? (0xffffffffu >> (32 - (ncols - j0))) : 0u;
+                if (mask) {
+                    const int add = __popc(mask);
+                    if (mine + add > half_cap) {
+                        mine = half_cap + 1;            // overflow: the row is flagged by the select kernel
+                        sthr = INFINITY;
+                    } else {
+                        // one predicated store pair per column (no divergent branches, no dynamic register indexing)
+                        int slot = mine;
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) {
+                            const uint32_t bit = (mask >> u) & 1u;
+                            const uint32_t key = __float_as_uint(2.0f - 2.0f * __uint_as_float(sv[u]));
+                            asm volatile(
+                                "{\n"
+                                ".reg .pred p;\n"
+                                "setp.ne.u32 p, %0, 0;\n"
+                                "@p st.global.u32 [%1], %2;\n"
+                                "@p st.global.u16 [%3], %4;\n"
+                                "}\n" ::"r"(bit), "l"(kdst + slot), "r"(key), "l"(cdst + slot), "h"((unsigned short)(j0 + u))
+                                : "memory");
+                            slot += (int)bit;
+                        }
+                        mine += add;
+                    }
+                }
+            }
+        }
+        if (!ALL && ok) cnt_out[2 * ((long long)b * N + i0 + row) + h] = mine;
+        tc_fence_before();
+    } else if (warp == TMA_WARP) {
+        if (elect_one()) {
+            tma_prefetch_desc(&mC); tma_prefetch_desc(&mCs);
+#pragma unroll 1
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % KNST;
+                mbar_wait_guarded(&bars.x_empty[s], ((t / KNST) & 1) ^ 1);
+                unsigned char* st = smem + s * KSTAGE;
+                mbar_arrive_expect_tx(&bars.x_full[s], KSTAGE);
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    tma_load_3d(st + sl * KSLAB, &mC, &bars.x_full[s], 32 * sl, t * KBN, b);
+                    tma_load_3d(st + KPART + sl * KSLAB, &mCs, &bars.x_full[s], 32 * sl, t * KBN, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const bool leader = elect_one();
+        const uint32_t idesc_s = make_idesc(2, BM, KBN, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+        mbar_wait_guarded(&bars.a_ready, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % KNST, k = t & 1;
+            mbar_wait_guarded(&bars.x_full[s], (t / KNST) & 1);
+            mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t st = sbase + s * KSTAGE;
+            const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
+            const uint64_t ds0 = make_smem_desc(st + KPART, 16, SBO128, SW128);
+            const uint32_t d_s = tb + C_KS0 + 64 * k;
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < D / 8; ++ks) {
+                    const uint32_t off = (uint32_t)((ks >> 2) * KSLAB + (ks & 3) * 32);
+                    const uint64_t db = db0 + (uint64_t)(off >> 4);
+                    const uint64_t ds = ds0 + (uint64_t)(off >> 4);
+                    mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
+                }
+                mma_commit(&bars.s_full[k]);
+                mma_commit(&bars.x_empty[s]);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+}
+
+// one warp per row: K-th smallest of the row's keys by a bitwise radix select on bit-transposed registers (kth_select.cuh).
+// EXACT = false: the row holds nfix keys in slots [0, nfix) (the sample pass), out = that key as a float.
+// EXACT = true : the row holds cnt[2 row] keys from slot 0 and cnt[2 row + 1] keys from slot CAP / 2 (the two column halves
+// of the collect pass); the selected pair's distance is recomputed with the fp32 FMA chain of ms_kth_tc_kernel; flags[row] = 1
+// when the lists cannot hold the answer (fewer than K entries in total, or a half overflowed).
+template <bool EXACT, int NW>
+__global__ void __launch_bounds__(256)
+ms_kth_select_kernel(const unsigned* __restrict__ ckey, const unsigned short* __restrict__ ccol, const int* __restrict__ cnt,
+                     int nfix, int K, long long rows_total, int N, const float* __restrict__ X, float* __restrict__ out,
+                     int* __restrict__ flags) {
+    constexpr int CAP = 1024 * NW, HALF = CAP / 2;          // NW words of 32 keys per lane
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows_total) return;
+    int n0 = nfix, n1 = 0;
+    if (EXACT) {
+        n0 = cnt[2 * row]; n1 = cnt[2 * row + 1];
+        const bool bad = n0 > HALF || n1 > HALF || n0 + n1 < K;
+        if (lane == 0) flags[row] = bad ? 1 : 0;
+        if (bad) return;
+    }
+    const unsigned* kr = ckey + row * CAP;
+    unsigned Bt[NW][32];
+    unsigned act[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        act[w] = 0u;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int p = w * 1024 + r * 32 + lane;
+            const bool valid = EXACT ? (p < HALF ? p < n0 : p - HALF < n1) : p < n0;
+            Bt[w][r] = valid ? f2ord(__uint_as_float(kr[p])) : 0xffffffffu;
+            act[w] |= valid ? kthsel::reg_bit(r) : 0u;
+        }
+        kthsel::bit_transpose32(Bt[w]);
+    }
+    const int n = n0 + n1;
+    int need = K < n ? K : n;
+    unsigned prefix = 0u;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) c += __popc(kthsel::step_zeros(act[w], Bt[w][i]));
+        c = __reduce_add_sync(FULL, c);
+        const bool zero = c >= need;
+        if (!zero) { need -= c; prefix |= 1u << (31 - i); }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) act[w] = kthsel::step_next(act[w], Bt[w][i], zero);
+    }
+    if (!EXACT) {
+        if (lane == 0) out[row] = ord2f(prefix);
+        return;
+    }
+    // lowest column among the entries that carry the selected key (act marks exactly those)
+    int jbest = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            if (act[w] & kthsel::reg_bit(r)) {
+                const int j = (int)ccol[row * CAP + w * 1024 + r * 32 + lane];
+                jbest = j < jbest ? j : jbest;
+            }
+        }
+    }
+    jbest = __reduce_min_sync(FULL, jbest);
+    if (lane == 0) {
+        const long long b = row / N;
+        const float4* xi = reinterpret_cast<const float4*>(X + row * D);
+        const float4* xj = reinterpret_cast<const float4*>(X + (b * N + jbest) * D);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < D / 4; ++c) {
+            const float4 u4 = xi[c], v4 = xj[c];
+            a0 = fmaf(u4.x, v4.x, a0); a1 = fmaf(u4.y, v4.y, a1);
+            a2 = fmaf(u4.z, v4.z, a2); a3 = fmaf(u4.w, v4.w, a3);
+        }
+        out[row] = 2.0f - 2.0f * ((a0 + a1) + (a2 + a3));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -841,6 +1130,72 @@ extern "C" int pn_ms_iter_fwd_tma(const float* Y, const float* X, const float* X
                    den, unorm));
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("ms_fwd_tma_kernel");
+    return PN_OK;
+}
+
+// K-th smallest of dist = 2 - 2 X X^T per row, every row of every shape against all N points of its shape
+// (MeanShift.compute_bandwidth, reference src/mean_shift.py:115-137, with num_samples >= N), computed with ONE pass over
+// the N x N distance tiles (see the comment above ms_kth_collect_kernel).  Xs = X - tf32_hi(X) (pn_ms_prepare_operands).
+// Workspaces: ws_key [B*N][cap] u32, ws_col [B*N][cap] u16, ws_cnt [B*N][2] i32, ws_hi [B*N] f32; cap = 1024 or 2048.
+// stride / b_sample: the column sample {0, stride, 2 stride, ...} (at most cap columns) and the order statistic of it that
+// brackets the K-th smallest from above.  flags [B*N]: 1 for the rows whose bracket failed -- their kth entry is NOT
+// written; the caller runs pn_ms_kth_dist_tc_flagged with the same flags afterwards (no host round trip).
+extern "C" int pn_ms_kth_dist_tma(const float* X, const float* Xs, int B, int N, int d, int K, int stride, int b_sample,
+                                  unsigned* ws_key, unsigned short* ws_col, int* ws_cnt, float* ws_hi, int cap, int* flags,
+                                  float* kth, void* stream) {
+    PN_REQUIRE(X && Xs && ws_key && ws_col && ws_cnt && ws_hi && flags && kth, "pn_ms_kth_dist_tma: null pointer");
+    PN_REQUIRE(d == mstma::D, "pn_ms_kth_dist_tma: embedding width must be %d (got %d)", mstma::D, d);
+    PN_REQUIRE(cap == 1024 || cap == 2048, "pn_ms_kth_dist_tma: candidate lists are built for cap = 1024 or 2048 (got %d)", cap);
+    PN_REQUIRE(B > 0 && N >= 128 && N < 65536, "pn_ms_kth_dist_tma: need 128 <= N < 65536 (B=%d, N=%d)", B, N);
+    PN_REQUIRE(stride >= 1, "pn_ms_kth_dist_tma: bad sample stride %d", stride);
+    const int m = (N + stride - 1) / stride;
+    PN_REQUIRE(m <= 1024 && (m % 4 == 0 || m + 3 < 1024), "pn_ms_kth_dist_tma: the column sample must hold at most 1024 columns "
+               "(N=%d stride=%d -> %d columns)", N, stride, m);
+    PN_REQUIRE(K >= 1 && K <= N && b_sample >= 1 && b_sample <= m, "pn_ms_kth_dist_tma: need 1 <= K <= N and 1 <= b_sample <= m "
+               "(K=%d b_sample=%d m=%d)", K, b_sample, m);
+    PN_REQUIRE((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xs) | reinterpret_cast<uintptr_t>(ws_key)) % 16 == 0,
+               "pn_ms_kth_dist_tma: X, Xs and ws_key must be 16-byte aligned");
+    const uint64_t dd = (uint64_t)mstma::D;
+    CUtensorMap ms[2], mf[2];
+    if (!(mstma::make_map(&ms[0], X, dd, (uint64_t)m, (uint64_t)B, dd * stride, (uint64_t)N * dd, 32, mstma::KBN) &&
+          mstma::make_map(&ms[1], Xs, dd, (uint64_t)m, (uint64_t)B, dd * stride, (uint64_t)N * dd, 32, mstma::KBN) &&
+          mstma::make_map(&mf[0], X, dd, (uint64_t)N, (uint64_t)B, dd, (uint64_t)N * dd, 32, mstma::KBN) &&
+          mstma::make_map(&mf[1], Xs, dd, (uint64_t)N, (uint64_t)B, dd, (uint64_t)N * dd, 32, mstma::KBN))) {
+        set_error("pn_ms_kth_dist_tma: cuTensorMapEncodeTiled failed or is unavailable");
+        return PN_ERR_CUDA;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t sm = mstma::KNST * mstma::KSTAGE + 1024;
+    auto k_all = mstma::ms_kth_collect_kernel<true>;
+    auto k_thr = mstma::ms_kth_collect_kernel<false>;
+    PN_CUDA(cudaFuncSetAttribute(k_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_CUDA(cudaFuncSetAttribute(k_thr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const dim3 grid(cdiv(N, mstma::BM), B);
+    const long long rows = (long long)B * N;
+    const int* no_cnt = nullptr;
+    const unsigned short* no_col = nullptr;
+    const float* no_hi = nullptr;
+    int* no_flags = nullptr;
+    PN_CUDA(launch(k_all, grid, 1, sm, st, ms[0], ms[1], X, N, m, stride, no_hi, cap, ws_key, ws_col, ws_cnt));
+    PN_COUNT_LAUNCH();
+    // (the sample lists use the first 1024 slots of a row whatever cap is: the row pitch of the select kernel is its CAP)
+    if (cap == 1024)
+        mstma::ms_kth_select_kernel<false, 1><<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(ws_key, no_col, no_cnt, m, b_sample, rows, N,
+                                                                                   X, ws_hi, no_flags);
+    else
+        mstma::ms_kth_select_kernel<false, 2><<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(ws_key, no_col, no_cnt, m, b_sample, rows, N,
+                                                                                   X, ws_hi, no_flags);
+    PN_COUNT_LAUNCH();
+    PN_CUDA(launch(k_thr, grid, 1, sm, st, mf[0], mf[1], X, N, N, 1, (const float*)ws_hi, cap, ws_key, ws_col, ws_cnt));
+    PN_COUNT_LAUNCH();
+    if (cap == 1024)
+        mstma::ms_kth_select_kernel<true, 1><<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(ws_key, ws_col, ws_cnt, 0, K, rows, N, X, kth,
+                                                                                  flags);
+    else
+        mstma::ms_kth_select_kernel<true, 2><<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(ws_key, ws_col, ws_cnt, 0, K, rows, N, X, kth,
+                                                                                  flags);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_kth bracketed kernels");
     return PN_OK;
 }
 

@@ -211,6 +211,71 @@ def mean_shift_iters(X_bnd, bw_b, iterations):
     return MeanShiftItersFn.apply(X_bnd, cinv, int(iterations))
 
 
+KTH_CAPS = (1024, 2048)   # entries per row of the candidate lists of pn_ms_kth_dist_tma (the smallest that fits is used)
+KTH_SAMPLE = 1024         # at most this many sample columns
+# one-pass bracketed K-th distance (csrc/meanshift_tma.cu) when every row is used; PN_MS_KTH_BRACKET=0: four radix passes
+KTH_BRACKET = os.environ.get("PN_MS_KTH_BRACKET", "1") == "1"
+
+
+def kth_bracket_plan(N, K):
+    """(stride, b, cap) of the bracketed selection, or None when lists of 2048 entries cannot be expected to hold the answer:
+    the column sample {0, stride, ...} has m <= 1024 points; the number of them below the K-th smallest of the full row is
+    hypergeometric with mean mu = K m / N, so the b = mu + 7 sigma + 2 -th smallest of the sample lies above it (else the row
+    is flagged and redone exactly); the one full pass then keeps about b N / m entries per row."""
+    if N < 2048 or N >= 65536 or K < 1:
+        return None
+    stride = -(-N // KTH_SAMPLE)
+    m = -(-N // stride)
+    if m % 4 != 0 and m + 3 >= KTH_SAMPLE:
+        return None
+    mu = K * m / N
+    sigma = (mu * (1.0 - K / N) * (N - m) / max(N - 1, 1)) ** 0.5
+    b = int(mu + 7.0 * sigma + 2.0) + 1
+    if b > m:
+        return None
+    # expected list length + 6 sigma of the bracket's rank in the full row; the kernel keeps one list of cap / 2 entries per
+    # half of the tile columns, so leave the binomial split of the entries over the halves its 6 sigma too
+    length = (b + 6.0 * b ** 0.5) * N / m
+    for cap in KTH_CAPS:
+        if length / 2 + 3.0 * length ** 0.5 <= cap / 2:
+            return stride, b, cap
+    return None
+
+
+_KTH_WS = {}
+
+
+def _kth_workspace(dev, rows, cap):
+    """candidate lists of the bracketed selection: 6 bytes x cap per row (1 - 2 GB at 16 x 10^4 rows).  Kept between calls
+    (one per device and stream order: the kernels of a call are enqueued on the caller's stream, a later call on the same
+    stream reuses the lists only after them) so that the caching allocator does not carve the block up in between."""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _KTH_WS.get(key)
+    if ws is None or ws[0].shape[0] < rows or ws[0].shape[1] != cap:
+        ws = (torch.empty((rows, cap), dtype=torch.int32, device=dev), torch.empty((rows, cap), dtype=torch.int16, device=dev),
+              torch.empty((rows, 2), dtype=torch.int32, device=dev), torch.empty((rows,), dtype=torch.float32, device=dev),
+              torch.empty((rows,), dtype=torch.int32, device=dev))
+        _KTH_WS[key] = ws
+    return ws
+
+
+def _kth_all_rows(X, K):
+    """K-th smallest of 2 - 2 X X^T per row, X (B,N,128) contiguous, every row against all N points of its shape"""
+    B, N, d = X.shape
+    kth = torch.empty((B, N), dtype=torch.float32, device=X.device)
+    plan = kth_bracket_plan(N, K) if (KTH_BRACKET and KTH_IMPL == "tc" and USE_TMA and d == 128) else None
+    if plan is None:
+        call(_KTH[KTH_IMPL], _ptr(X), None, B, N, N * d, d, K, _ptr(kth), _stream())
+        return kth
+    stride, b, cap = plan
+    Xs = _operand_forms(X)[0]
+    ws_key, ws_col, ws_cnt, ws_hi, flags = _kth_workspace(X.device, B * N, cap)
+    call("pn_ms_kth_dist_tma", _ptr(X), _ptr(Xs), B, N, d, K, stride, b, _ptr(ws_key), _ptr(ws_col), _ptr(ws_cnt), _ptr(ws_hi),
+         cap, _ptr(flags), _ptr(kth), _stream())
+    call("pn_ms_kth_dist_tc_flagged", _ptr(X), None, B, N, N * d, d, K, _ptr(flags), _ptr(kth), _stream())
+    return kth
+
+
 def compute_bandwidth(X_nd, num_samples, quantile, rng=np.random):
     """mean over sampled rows of sqrt(K-th smallest of 2 - 2 X X^T), K = int(quantile * num_samples)
     [mean_shift.py:115-137].  Consumes np.random.shuffle exactly like the reference."""
@@ -225,8 +290,11 @@ def compute_bandwidth(X_nd, num_samples, quantile, rng=np.random):
     rows = None
     if S < N:                                   # a strict subset: the choice of rows matters
         rows = torch.from_numpy(L[:S].astype(np.int32)).to(X.device)
-    kth = torch.empty((S,), dtype=torch.float32, device=X.device)
-    call(_KTH[KTH_IMPL], _ptr(X), _ptr(rows), 1, S, N * d, d, K, _ptr(kth), _stream())
+    if rows is None:
+        kth = _kth_all_rows(X.unsqueeze(0), K)[0]
+    else:
+        kth = torch.empty((S,), dtype=torch.float32, device=X.device)
+        call(_KTH[KTH_IMPL], _ptr(X), _ptr(rows), 1, S, N * d, d, K, _ptr(kth), _stream())
     return torch.sqrt(torch.clamp(kth, min=SQRT_FLOOR)).mean()
 
 
@@ -242,8 +310,7 @@ def compute_bandwidth_batched(X_bnd, num_samples, quantile, rng=np.random):
         rng.shuffle(np.arange(N))
     K = int(quantile * num_samples)
     X = X_bnd.detach().contiguous()
-    kth = torch.empty((B, N), dtype=torch.float32, device=X.device)
-    call(_KTH[KTH_IMPL], _ptr(X), None, B, N, N * d, d, K, _ptr(kth), _stream())
+    kth = _kth_all_rows(X, K)
     return torch.sqrt(torch.clamp(kth, min=SQRT_FLOOR)).mean(1)
 
 

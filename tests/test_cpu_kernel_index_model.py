@@ -303,3 +303,46 @@ def test_operand_preparation_kernels_index_model():
         assert np.array_equal(C[32 * t:32 * t + n], Y[16 * t:16 * t + n])                 # tile rows 0..15: Y   -> S^T columns
         assert np.array_equal(C[32 * t + 16:32 * t + 16 + n], G[16 * t:16 * t + n])       # tile rows 16..31: Gn -> G^T columns
         assert (C[32 * t + n:32 * t + 16] == 0).all() and (C[32 * t + 16 + n:32 * t + 32] == 0).all()
+
+
+# ------------------------------------------------------------------------------------- bracketed K-th distance (round 2)
+def test_kth_select_host_twin_and_bracket_plan(tmp_path):
+    """csrc/kth_select.cuh: the lane-local code of the warp K-th select (bit-transposed registers, one AND / POPC per key bit)
+    run for 32 emulated lanes on the host (tests/c/kth_select_host.cpp) against a sort, for every list length the kernels
+    use; and pnb200.meanshift.kth_bracket_plan: the sample order statistic sits 7 sigma above the hypergeometric mean and
+    the expected list length fits the chosen capacity"""
+    import ctypes, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "kthsel.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++20", "-fPIC", "-shared", "-I", os.path.join(root, "parsenet-codebase_b200", "csrc"),
+                           os.path.join(root, "tests", "c", "kth_select_host.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.kth_select_host.restype = ctypes.c_uint
+    rng = np.random.default_rng(0)
+    for n, K in [(1, 1), (5, 3), (33, 33), (1000, 43), (1024, 150), (430, 150), (430, 1), (777, 777), (64, 100)]:
+        for _ in range(10):
+            hi = int(rng.choice([8, 1 << 16, 1 << 32]))
+            k = rng.integers(0, hi, size=n, dtype=np.uint64).astype(np.uint32)
+            got = lib.kth_select_host(k.ctypes.data_as(ctypes.c_void_p), n, K)
+            assert got == np.sort(k)[min(K, n) - 1], (n, K)
+    # the plan: read the function out of the module source (importing pnb200 needs the CUDA library)
+    src = open(os.path.join(root, "parsenet-codebase_b200", "pnb200", "meanshift.py")).read()
+    ns = {}
+    exec(src[src.index("KTH_CAPS ="):src.index("# one-pass bracketed K-th distance")] +
+         src[src.index("def kth_bracket_plan"):src.index("def _kth_all_rows")], ns)
+    plan = ns["kth_bracket_plan"]
+    assert plan(10000, 150) == (10, 43, 1024) and plan(10000, 250)[2] == 2048
+    assert plan(1000, 15) is None and plan(70000, 1000) is None and plan(10000, 3000) is None
+    for N, K in [(10000, 150), (10000, 250), (10000, 562), (5000, 75), (2048, 30), (20000, 100)]:
+        p = plan(N, K)
+        assert p is not None, (N, K)
+        stride, b, cap = p
+        m = -(-N // stride)
+        assert m <= 1024 and b <= m
+        # Monte Carlo: how often does a random column sample put fewer than b ... i.e. the b-th sample point below the K-th?
+        fails = 0
+        for _ in range(2000):
+            below = rng.hypergeometric(K, N - K, m)          # sample points among the K smallest
+            fails += below >= b
+        assert fails == 0
+        assert b * N / m < cap / 2 * 1.6

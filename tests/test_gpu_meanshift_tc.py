@@ -87,6 +87,70 @@ def test_tc_kth_distance_matches_fp32_pipe_and_torch(B, S, K):
         assert (o - ref).abs().max().item() < 2e-6
 
 
+def _kth_bracketed(X, K, stride, b, cap=1024):
+    from pnb200.cabi import call
+    B, N, d = X.shape
+    st = torch.cuda.current_stream().cuda_stream
+    Np = (N + 31) // 32 * 32
+    Xs = torch.empty_like(X); Xt = torch.empty(B, d, Np, device="cuda"); Xst = torch.empty(B, d, Np, device="cuda")
+    call("pn_ms_prepare_operands", X.data_ptr(), B, N, d, Np, Xs.data_ptr(), Xt.data_ptr(), Xst.data_ptr(), st)
+    key = torch.empty(B * N, cap, dtype=torch.int32, device="cuda"); col = torch.empty(B * N, cap, dtype=torch.int16, device="cuda")
+    cnt = torch.empty(B * N, 2, dtype=torch.int32, device="cuda"); hi = torch.empty(B * N, device="cuda")
+    flags = torch.empty(B * N, dtype=torch.int32, device="cuda")
+    kth = torch.full((B, N), float("nan"), device="cuda")
+    call("pn_ms_kth_dist_tma", X.data_ptr(), Xs.data_ptr(), B, N, d, K, stride, b, key.data_ptr(), col.data_ptr(), cnt.data_ptr(),
+         hi.data_ptr(), cap, flags.data_ptr(), kth.data_ptr(), st)
+    before = kth.clone()
+    call("pn_ms_kth_dist_tc_flagged", X.data_ptr(), None, B, N, N * d, d, K, flags.data_ptr(), kth.data_ptr(), st)
+    return kth, before, flags.view(B, N), cnt.view(B, N, 2)
+
+
+@pytest.mark.parametrize("B,N,K,clustered", [(2, 2500, 37, False), (3, 4099, 61, True), (16, 10000, 150, True), (2, 10000, 250, False), (1, 10000, 250, True)])
+def test_bracketed_kth_distance_equals_radix_kernel(B, N, K, clustered):
+    """one-pass bracketed K-th distance (pn_ms_kth_dist_tma + flagged fall-back) vs the four-pass radix kernel: both rank the
+    same tensor-core distances and recompute the selected pair in fp32, so they agree to the last bit except where two pairs
+    tie within the tensor-core rounding (then to 2e-6); also vs torch.topk at the small sizes"""
+    from pnb200.cabi import call
+    from pnb200 import meanshift as pms
+    if clustered:
+        g = torch.Generator().manual_seed(N)
+        cen = torch.nn.functional.normalize(torch.randn(8, 128, generator=g), dim=1)
+        lab = torch.randint(0, 8, (B, N), generator=g)
+        X = torch.nn.functional.normalize(cen[lab] + 0.05 * torch.randn(B, N, 128, generator=g), dim=2).cuda().contiguous()
+    else:
+        X, _, _ = _setup(B, N, 5)
+    stride, b, cap = pms.kth_bracket_plan(N, K)
+    kth, before, flags, cnt = _kth_bracketed(X, K, stride, b, cap)
+    ref = torch.empty(B, N, device="cuda")
+    call("pn_ms_kth_dist_tc", X.data_ptr(), None, B, N, N * 128, 128, K, ref.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert not torch.isnan(kth).any()
+    assert (kth - ref).abs().max().item() < 2e-6
+    assert (kth == ref).float().mean().item() > 0.995        # (pairs tied within the tensor-core rounding: either may be picked)
+    # the bracket holds for (nearly) every row, and the lists stay far below their capacity
+    assert flags.float().mean().item() < 1e-3, flags.float().mean().item()
+    assert int(cnt.max()) <= cap // 2
+    if N <= 4099:
+        top = torch.stack([torch.topk(2 - 2 * X[i] @ X[i].t(), K, dim=1, largest=False)[0][:, -1] for i in range(B)])
+        assert (kth - top).abs().max().item() < 2e-6
+    # product entry point
+    got = pms._kth_all_rows(X, K)
+    assert (got - ref).abs().max().item() < 2e-6
+
+
+def test_bracketed_kth_distance_flagged_rows_fall_back_to_the_radix_kernel():
+    """a bracket that is too low (b_sample = 1: the nearest sample column) leaves fewer than K entries in most lists: those
+    rows are flagged, not written by the bracketed entry point, and filled in exactly by the flagged radix launch"""
+    from pnb200.cabi import call
+    B, N, K = 2, 3000, 45
+    X, _, _ = _setup(B, N, 9)
+    kth, before, flags, cnt = _kth_bracketed(X, K, 3, 1)
+    assert flags.float().mean().item() > 0.5
+    assert torch.isnan(before[flags.bool()]).all()               # flagged rows were left to the fall-back
+    ref = torch.empty(B, N, device="cuda")
+    call("pn_ms_kth_dist_tc", X.data_ptr(), None, B, N, N * 128, 128, K, ref.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert not torch.isnan(kth).any() and (kth - ref).abs().max().item() < 2e-6
+
+
 @pytest.mark.parametrize("B,Ma,Nb", [(1, 50, 33), (2, 300, 1000), (3, 2113, 2113)])
 def test_tc_argsel_matches_fp32_pipe(B, Ma, Nb):
     """nms arg-selects (modes 0 and 1) on tcgen05 vs the FP32-pipe kernel: identical picks except on near-ties of the
