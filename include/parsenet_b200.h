@@ -216,6 +216,16 @@ int pn_spline_eval_bwd(const float* Nu, const float* Nv, const float* g, int B, 
 int pn_spline_eval_fwd_f64(const double* Nu, const double* Nv, const double* P, int B, int gu, int gv, int cu, int cv, double* out, void* stream);
 int pn_spline_eval_bwd_f64(const double* Nu, const double* Nv, const double* g, int B, int gu, int gv, int cu, int cv, double* dP, void* stream);
 
+/* ---- kronfit.cu (post-fit control-point optimisation of the inference path) ---- */
+/* replaces: fit_bezier_surface_fit_kronecker: src/approximation.py:338-364 (host Kronecker matrix + numpy lstsq per coordinate).
+   U [S][M][n], V [S][M][m] per-sample basis rows, P [S][M][3] samples (float64) -> ctrl [S][n][m][3] least-squares control
+   points: normal equations assembled and factored (Cholesky) in shared memory, one CTA per surface, n m <= 128.
+   flag [S]: 1 = rank-deficient sampling (pivot below 1e-12 of the largest diagonal entry), ctrl[s] not written */
+int pn_kron_fit(const double* U, const double* V, const double* P, int S, int M, int n, int m, double* ctrl, int* flag, void* stream);
+/* replaces: geomdl surface evaluation at scattered parameters: src/primitive_forward.py:186,258 (evaluate_list) —
+   out [S][M][3] = sum_ab U[s][i][a] V[s][i][b] C[s][a][b][:]; C advances by c_stride doubles per surface (0 = shared) */
+int pn_kron_eval(const double* U, const double* V, const double* C, long long c_stride, int S, int M, int n, int m, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

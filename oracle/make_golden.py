@@ -372,6 +372,43 @@ def gen_pipeline():
 GENS = {"pipeline": gen_pipeline, "upsample": gen_upsample, "guard": gen_guard, "cfg1": gen_cfg1, "knn": gen_knn, "segnet": gen_segnet, "meanshift": gen_meanshift, "fits": gen_fits, "losses": gen_losses,
         "splinenet": gen_splinenet, "e2e": gen_e2e, "e2e_nocyl": lambda: gen_e2e(True, "e2e_nocyl.npz")}
 
+def gen_kronecker():
+    """the pieces of the Kronecker post-fit optimisers that run without geomdl / lapsolver / open3d, from the
+    unmodified reference: DrawSurfs.boundary_parameterization / regular_parameterization, uniform_knot_bspline_ knots,
+    BSpline.basis_functions per sample (the optimisers' NU / NV), and fit_bezier_surface_fit_kronecker on matched points of
+    the optimisers' shape (1600 scattered samples, 10 x 10 control points, degree 2 and 3)."""
+    AP = rl.ref("src.approximation"); CU = rl.ref("src.curve_utils")
+    ds, bs = CU.DrawSurfs(), AP.BSpline()
+    rs = np.random.RandomState(5)
+    out = {"bpar20": ds.boundary_parameterization(20), "bpar30": ds.boundary_parameterization(30),
+           "rpar": ds.regular_parameterization(30, 30)}
+    for deg in (2, 3):
+        bpar = out["bpar20"] if deg == 2 else out["bpar30"]
+        par = np.concatenate([rs.random_sample((1600 - bpar.shape[0], 2)), bpar], 0)
+        _, _, ku, kv = AP.uniform_knot_bspline_(10, 10, deg, deg, 2)
+        NU, NV = [], []
+        for i in range(par.shape[0]):
+            nu, nv = bs.basis_functions(par[i], 10, 10, ku, kv, deg, deg)
+            NU.append(nu); NV.append(nv)
+        NU = np.concatenate(NU, 1).T; NV = np.concatenate(NV, 1).T
+        cp = rs.rand(10, 10, 3)
+        pts = np.einsum("ia,ib,abc->ic", NU, NV, cp) + 0.01 * rs.randn(1600, 3)
+        rec = AP.fit_bezier_surface_fit_kronecker(pts, NU, NV)
+        out.update({f"par{deg}": par, f"NU{deg}": NU, f"NV{deg}": NV, f"pts{deg}": pts, f"rec{deg}": rec,
+                    f"ku{deg}": np.array(ku), f"kv{deg}": np.array(kv)})
+    # basis rows of the predicted 20 x 20 / 21 x 20 cubic surfaces at a few parameters (the optimisers' first evaluation)
+    par = np.concatenate([rs.random_sample((50, 2)), out["bpar20"][:30]], 0)
+    for cu in (20, 21):
+        _, _, ku, kv = AP.uniform_knot_bspline_(cu, 20, 3, 3, 2)
+        rows = [bs.basis_functions(par[i], cu, 20, ku, kv, 3, 3) for i in range(par.shape[0])]
+        out[f"old_NU{cu}"] = np.concatenate([r[0] for r in rows], 1).T
+        out[f"old_NV{cu}"] = np.concatenate([r[1] for r in rows], 1).T
+    out["old_par"] = par
+    np.savez_compressed(os.path.join(OUT, "kronecker.npz"), **out)
+
+
+GENS["kronecker"] = gen_kronecker
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     names = sys.argv[1:] or list(GENS)

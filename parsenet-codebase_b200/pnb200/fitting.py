@@ -302,6 +302,19 @@ def nearest_sqdist(A, Bs):
     return NearestFn.apply(A, Bs)
 
 
+def nearest_index(A, Bs):
+    """A (B,Na,3), Bs (B,Nb,3) -> index of the nearest Bs point of every A point (B,Na) int32 (the argmin the Chamfer kernel
+    keeps for its backward)"""
+    _need_cuda(A, Bs)
+    A = A.detach().contiguous().float()
+    Bs = Bs.detach().contiguous().float()
+    B, Na, _ = A.shape
+    mind = torch.empty((B, Na), dtype=torch.float32, device=A.device)
+    arg = torch.empty((B, Na), dtype=torch.int32, device=A.device)
+    call("pn_chamfer_nn_fwd", _ptr(A), Na, _ptr(Bs), Bs.shape[1], B, _ptr(mind), _ptr(arg), _stream())
+    return arg
+
+
 # ------------------------------------------------------------------------------------------------ spline evaluation
 class SplineEvalFn(torch.autograd.Function):
     """P (B,cu,cv,3) -> (B, gu*gv, 3) = Nu P Nv^T per coordinate.  float32, or float64 when P is float64"""
@@ -365,6 +378,35 @@ def fit_control_points_grid(S_bguv3, nu, nv):
     assert pu.shape[1] == gu and pv.shape[1] == gv, "basis matrices do not match the sample grid"
     out = SplineEvalFn.apply(S_bguv3.double(), pu, pv).view(B, pu.shape[0], pv.shape[0], 3)
     return out.to(S_bguv3.dtype)
+
+
+def kron_fit(P_sm3, U_smn, V_smm):
+    """least-squares control points of scattered surface samples with per-sample basis rows (csrc/kronfit.cu):
+    P (S,M,3), U (S,M,n), V (S,M,m) cuda -> (ctrl (S,n,m,3) float64, flag (S,) int32; flag 1 = rank-deficient, ctrl[s] unset).
+    Replaces fit_bezier_surface_fit_kronecker (reference src/approximation.py:338-364) for a batch of surfaces."""
+    _need_cuda(P_sm3, U_smn, V_smm)
+    P, U, V = (t.detach().to(torch.float64).contiguous() for t in (P_sm3, U_smn, V_smm))
+    S, M, n = U.shape
+    m = V.shape[2]
+    assert P.shape == (S, M, 3) and V.shape[:2] == (S, M)
+    ctrl = torch.zeros((S, n, m, 3), dtype=torch.float64, device=P.device)
+    flag = torch.empty((S,), dtype=torch.int32, device=P.device)
+    call("pn_kron_fit", _ptr(U), _ptr(V), _ptr(P), S, M, n, m, _ptr(ctrl), _ptr(flag), _stream())
+    return ctrl, flag
+
+
+def kron_eval(C_snm3, U_smn, V_smm):
+    """surface points at scattered parameters: out[s,i] = sum_ab U[s,i,a] V[s,i,b] C[s,a,b]  (float64; C (n,m,3) is shared by
+    all surfaces).  Replaces geomdl's evaluate_list in the post-fit optimisers (reference src/primitive_forward.py:186,258)."""
+    _need_cuda(C_snm3, U_smn, V_smm)
+    C, U, V = (t.detach().to(torch.float64).contiguous() for t in (C_snm3, U_smn, V_smm))
+    S, M, n = U.shape
+    m = V.shape[2]
+    shared = C.dim() == 3
+    assert C.shape[-3:] == (n, m, 3) and (shared or C.shape[0] == S)
+    out = torch.empty((S, M, 3), dtype=torch.float64, device=U.device)
+    call("pn_kron_eval", _ptr(U), _ptr(V), _ptr(C), 0 if shared else n * m * 3, S, M, n, m, _ptr(out), _stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ batched fit stage

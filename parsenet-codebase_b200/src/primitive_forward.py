@@ -1,7 +1,9 @@
 """Drop-in for the hot-path part of reference src/primitive_forward.py: Fit (:418, fit_*_torch :708-843),
 fit_one_shape_torch (:925), forward_pass_open_spline (:34), forward_closed_splines (:347) and the SplineNet loaders
-(:88, :400).  The geomdl / ARAP / Hungarian post-fit optimisers (:105-344) and Fit.sample_* are out of scope
-(`if_optimize=True`, `sample_points=True`, `eval=True` raise NotImplementedError)."""
+(:88, :400), and the Kronecker post-fit optimisers optimize_open_spline_kronecker (:229) / optimize_close_spline_kronecker
+(:153) without the ARAP pre-deformation.  ARAP (open3d), the geomdl `approximate_surface` optimisers (:105-150,
+:299-344) and Fit.sample_* are out of scope (`deform=True`, `if_optimize=True`, `sample_points=True`, `eval=True` raise
+NotImplementedError)."""
 import numpy as np
 import torch
 
@@ -22,6 +24,92 @@ def _unstandardize(x, scale, R, mean):
     if Rinv is None:
         Rinv = torch.inverse(R)
     return (Rinv @ t.t()).t() + mean
+
+
+# ------------------------------------------------------------------------------------------------ post-fit optimisation
+def _boundary_parameterization(grid_u):
+    """the 4 (grid_u - 1) boundary nodes of the regular grid_u x grid_u parameter grid, in the reference's order
+    (curve_utils.py:211-221: u = 0 edge, v = 0 edge, v = 1 edge, u = 1 edge without its corners)"""
+    g, last = np.arange(grid_u, dtype=np.float64), float(grid_u - 1)
+    edges = [np.stack([np.zeros(grid_u), g], 1),
+             np.stack([g[1:], np.zeros(grid_u - 1)], 1),
+             np.stack([g[1:], np.full(grid_u - 1, last)], 1),
+             np.stack([np.full(grid_u - 2, last), g[1:-1]], 1)]
+    return np.concatenate(edges, 0) / last
+
+
+def _regular_parameterization(grid_u, grid_v):
+    """(grid_u * grid_v, 2) nodes of linspace(0,1) x linspace(0,1), u-major (curve_utils.py:200-209)"""
+    u, v = np.meshgrid(np.linspace(0, 1, grid_u), np.linspace(0, 1, grid_v), indexing="ij")
+    return np.stack([u.reshape(-1), v.reshape(-1)], 1)
+
+
+def _optimize_spline_kronecker(input_points_, control_points, cp_u, cp_v, boundary, n_input, new_cp_size, new_degree,
+                               subsample, matcher):
+    """shared body of the two Kronecker optimisers (reference src/primitive_forward.py:153-296, deform=False):
+    1600 surface samples of the predicted spline (boundary nodes + random parameters) are matched one-to-one with 1600
+    (up-sampled) input points, a new_cp_size^2 control grid of degree new_degree is fitted to the matched points at the same
+    parameters, and the new surface is sampled on the regular 30 x 30 grid.  Device work: up-sampling (kNN kernel), the two
+    surface evaluations and the 100 x 100 normal-equation solve (csrc/kronfit.cu), the distance matrix.  The assignment is
+    the host's (scipy linear_sum_assignment instead of lapsolver: same optimum) unless matcher == "nearest" (each surface
+    sample takes its nearest input point: the Chamfer argmin kernel, no read-back)."""
+    from scipy.optimize import linear_sum_assignment
+    from src.approximation import basis_rows
+    from src.fitting_utils import up_sample_points_torch_in_range
+    from src.utils import chamfer_argmin
+    dev = input_points_.device
+    bpar = _boundary_parameterization(boundary)
+    parameters = np.concatenate([np.random.random((1600 - bpar.shape[0], 2)), bpar], 0)
+    NU, NV = basis_rows(parameters, cp_u, cp_v, 3, 3)
+    NUd, NVd = torch.from_numpy(NU).to(dev).unsqueeze(0), torch.from_numpy(NV).to(dev).unsqueeze(0)
+    cp = control_points[0].detach().reshape(cp_u, cp_v, 3)
+    points = _f.kron_eval(cp, NUd, NVd)[0]                                    # (1600, 3) float64, on the predicted surface
+    inp = up_sample_points_torch_in_range(input_points_[0].detach(), n_input[0], n_input[1])
+    if subsample:
+        L = np.random.choice(np.arange(inp.shape[0]), 1600, replace=False)
+        inp = inp[torch.from_numpy(L).to(dev)]
+    if matcher == "hungarian":
+        dist = torch.cdist(points, inp.double()).cpu().numpy()
+        _, cids = linear_sum_assignment(dist)
+        matched = inp[torch.from_numpy(cids).to(dev)]
+    elif matcher == "nearest":
+        matched = inp[chamfer_argmin(points.float().unsqueeze(0), inp.float().unsqueeze(0))[0].long()]
+    else:
+        raise ValueError(f"unknown matcher {matcher!r}")
+    NU2, NV2 = basis_rows(parameters, new_cp_size, new_cp_size, new_degree, new_degree)
+    NU2d, NV2d = torch.from_numpy(NU2).to(dev).unsqueeze(0), torch.from_numpy(NV2).to(dev).unsqueeze(0)
+    new_cp, flag = _f.kron_fit(matched.double().unsqueeze(0), NU2d, NV2d)
+    if bool(flag[0]):
+        from src.approximation import fit_bezier_surface_fit_kronecker
+        new_cp = fit_bezier_surface_fit_kronecker(matched.double(), NU2d[0], NV2d[0]).unsqueeze(0)
+    RU, RV = basis_rows(_regular_parameterization(30, 30), new_cp_size, new_cp_size, new_degree, new_degree)
+    out = _f.kron_eval(new_cp[0], torch.from_numpy(RU).to(dev).unsqueeze(0), torch.from_numpy(RV).to(dev).unsqueeze(0))
+    return out[0].float(), new_cp[0]
+
+
+def optimize_open_spline_kronecker(reconstructed_points, input_points_, control_points, new_cp_size=10, new_degree=2,
+                                   deform=False, matcher="hungarian"):
+    """reference src/primitive_forward.py:229-296.  control_points (1, 400, 3) of the predicted 20 x 20 cubic surface, input
+    points (1, n, 3) -> (1, 900, 3) samples of the re-fitted surface.  Consumes np.random like the reference (the random
+    parameters, then the 1600-point subsample)."""
+    if deform:
+        raise NotImplementedError("ARAP pre-deformation (open3d) is outside the hot path: call with deform=False")
+    pts, _ = _optimize_spline_kronecker(input_points_, control_points, 20, 20, 20, (1600, 2000), new_cp_size, new_degree,
+                                        True, matcher)
+    return pts.unsqueeze(0)
+
+
+def optimize_close_spline_kronecker(reconstructed_points, input_points_, control_points, new_cp_size=10, new_degree=3,
+                                    deform=True, matcher="hungarian"):
+    """reference src/primitive_forward.py:153-226.  control_points (1, 21, 20, 3) (the closed grid with its first row
+    repeated), input points (1, n, 3) -> (1, 930, 3): the 30 x 30 samples of the re-fitted surface plus the first row again.
+    The reference's default deform=True needs ARAP (open3d, out of scope): pass deform=False."""
+    if deform:
+        raise NotImplementedError("ARAP pre-deformation (open3d) is outside the hot path: call with deform=False")
+    pts, _ = _optimize_spline_kronecker(input_points_, control_points, 21, 20, 30, (2000, 2100), new_cp_size, new_degree,
+                                        False, matcher)
+    pts = pts.reshape(30, 30, 3)
+    return torch.cat([pts, pts[0:1]], 0).reshape(1, 930, 3)
 
 
 def forward_pass_open_spline(input_points_, control_decoder, nu, nv, viz=False, weights=None, if_optimize=True):

@@ -23,6 +23,13 @@ def chamfer_distance(pred, gt, sqrt=False):
     return torch.mean(d_pred.mean(1) + d_gt.mean(1)) / 2.0
 
 
+def chamfer_argmin(pred, gt):
+    """index of the nearest gt point of every predicted point, (B,Np) int32 (the matcher="nearest" option of the post-fit
+    optimisers)"""
+    from pnb200.fitting import nearest_index
+    return nearest_index(_as_cuda(pred), _as_cuda(gt))
+
+
 def chamfer_distance_one_side(pred, gt, side=1):
     """side 0: every predicted point to its nearest gt; side 1: every gt point to its nearest prediction"""
     pred, gt = _as_cuda(pred), _as_cuda(gt)

@@ -293,3 +293,47 @@ def test_input_pipeline_vs_reference_dataset(golden_dir):
         p, n = IP.preprocess_on_device(torch.from_numpy(pts), torch.from_numpy(nrm), torch.from_numpy(R), anisotropic=aniso)
         assert np.abs(p.numpy() - g[name + "_p"]).max() <= 2e-6, name
         assert np.abs(n.numpy() - g[name + "_n"]).max() <= 2e-6, name
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY 8f-1 (host parts)
+def test_kronecker_optimiser_host_parts_vs_reference(golden_dir):
+    """tests/golden/kronecker.npz (unmodified reference: DrawSurfs parameterisations, BSpline.basis_functions per sample,
+    fit_bezier_surface_fit_kronecker): the oracle port reproduces all of it, and so do the product's vectorised
+    parameterisations / per-sample basis rows (local-support recurrence instead of one Cox-de Boor triangle per entry)"""
+    import os
+    from scipy.interpolate import BSpline
+    from oracle.port import optimize as PO
+    from src import approximation as AP
+    from src import primitive_forward as PF
+    g = np.load(os.path.join(golden_dir, "kronecker.npz"))
+    for grid, key in ((20, "bpar20"), (30, "bpar30")):
+        assert np.array_equal(PO.boundary_parameterization(grid), g[key])
+        assert np.array_equal(PF._boundary_parameterization(grid), g[key])
+    assert np.array_equal(PO.regular_parameterization(30, 30), g["rpar"])
+    assert np.abs(PF._regular_parameterization(30, 30) - g["rpar"]).max() == 0
+    for deg in (2, 3):
+        par = g[f"par{deg}"]
+        nu_o, nv_o = PO.basis_rows(par, 10, 10, deg, deg)
+        nu_p, nv_p = AP.basis_rows(par, 10, 10, deg, deg)
+        for got in (nu_o, nu_p):
+            assert np.abs(got - g[f"NU{deg}"]).max() < 1e-14
+        for got in (nv_o, nv_p):
+            assert np.abs(got - g[f"NV{deg}"]).max() < 1e-14
+        _, _, ku, kv = AP.uniform_knot_bspline_(10, 10, deg, deg, 2)
+        assert np.array_equal(np.array(ku), g[f"ku{deg}"]) and np.array_equal(np.array(kv), g[f"kv{deg}"])
+        # independent check of the rows: scipy's design matrix over the same knots (away from the right end point)
+        inner = par[:, 0] < 1
+        dm = BSpline.design_matrix(par[inner, 0], np.array(ku), deg).toarray()
+        assert np.abs(dm - nu_p[inner]).max() < 1e-14
+        rec = PO.fit_bezier_surface_fit_kronecker(g[f"pts{deg}"], g[f"NU{deg}"], g[f"NV{deg}"])
+        assert np.abs(rec - g[f"rec{deg}"]).max() < 1e-10
+    for cu in (20, 21):
+        nu_p, nv_p = AP.basis_rows(g["old_par"], cu, 20, 3, 3)
+        assert np.abs(nu_p - g[f"old_NU{cu}"]).max() < 1e-14 and np.abs(nv_p - g[f"old_NV{cu}"]).max() < 1e-14
+    # the port's surface evaluation is the tensor-product formula: check it against scipy's BSpline in both directions
+    rs = np.random.RandomState(0)
+    cp = rs.rand(20, 20, 3)
+    par = rs.random_sample((40, 2))
+    ku = np.array(AP.uniform_knot_bspline_(20, 20, 3, 3, 2)[2])
+    want = np.stack([BSpline(ku, BSpline(ku, cp.transpose(1, 0, 2), 3)(v), 3)(u) for u, v in par])
+    assert np.abs(PO.evaluate_list(cp, par, 3, 3) - want).max() < 1e-13
