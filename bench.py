@@ -430,6 +430,7 @@ def inference_path(hp, dev_batch, host_np, dev, reps=3):
     the host.  Device time by CUDA events, host metrics included in the region."""
     from pnb200 import meanshift as _ms
     from pnb200.losses import l2_normalize
+    from pnb200.assign import match_batched
     from src.segment_utils import SIOU_matched_segments, segment_types_batched
     x, lab, prim = dev_batch
     lab_np, prim_np = host_np
@@ -446,18 +447,21 @@ def inference_path(hp, dev_batch, host_np, dev, reps=3):
             Y = _ms.mean_shift_iters(E, bws, 50)
             members = _ms.nearest_center_batched(E, Y)
             ids, labels_dev, K = _ms.nms_batched(Y, E, bws, members)
+            cols = match_batched(labels_dev, lab, 50)[0]          # IoU cost + Hungarian of all shapes on the device
             cluster_np = labels_dev.cpu().numpy()
             onehot = torch.zeros((B, x.shape[2], 64), device=dev).scatter_(2, labels_dev.unsqueeze(2).clamp(max=63), 1.0)
             types = segment_types_batched(torch.max(lp, 1)[1], onehot).cpu().numpy()
-        ious = [SIOU_matched_segments(lab_np[i], cluster_np[i], None, prim_np[i].copy(), None, prim_pred_seg=types[i, :K[i]])[0]
-                for i in range(B)]
+            cols = cols.cpu().numpy()
+        ious = [SIOU_matched_segments(lab_np[i], cluster_np[i], None, prim_np[i].copy(), None, prim_pred_seg=types[i, :K[i]],
+                                      matching=(np.arange(50), cols[i]))[0] for i in range(B)]
         b.record(); torch.cuda.synchronize()
         if rep:
             times.append(a.elapsed_time(b))
     ms = float(np.mean(times))
     return {"value": B / (ms / 1e3), "unit": "shapes/s", "ms_per_batch": ms, "batch": B, "mean_shift_iterations": 50,
             "mean_segment_iou": float(np.mean(ious)),
-            "workload": "generate_predictions.py:131-156: seg-net fwd (no grad) + bandwidth + 50 mean-shift iterations + nms + SIOU, "
+            "workload": "generate_predictions.py:131-156: seg-net fwd (no grad) + bandwidth + 50 mean-shift iterations + nms + SIOU (IoU cost and "
+                        "Hungarian matching of all shapes on the device), "
                         "16 x 10k points"}
 
 

@@ -226,6 +226,15 @@ int pn_kron_fit(const double* U, const double* V, const double* P, int S, int M,
    out [S][M][3] = sum_ab U[s][i][a] V[s][i][b] C[s][a][b][:]; C advances by c_stride doubles per surface (0 = shared) */
 int pn_kron_eval(const double* U, const double* V, const double* C, long long c_stride, int S, int M, int n, int m, double* out, void* stream);
 
+/* ---- assign.cu (segment matching on the device: SURVEY a32 / 8f-2) ---- */
+/* replaces: relaxed_iou_fast(to_one_hot(pred), to_one_hot(gt)) and `1 - cost`: src/segment_utils.py:356-373, src/fitting_utils.py:362-371.
+   pred, gt [B][N] int32 labels in [0, K), K <= 64 -> cost [B][K][K] = 1 - inter / (|p| + |g| - inter + 1e-7) (the reference's fp32
+   expression; counts are exact).  *bad is set to 1 when a label lies outside [0, K) */
+int pn_iou_cost(const int* pred, const int* gt, int B, int N, int K, float* cost, int* bad, void* stream);
+/* replaces: lapsolver.solve_dense(cost): src/fitting_utils.py:372, src/segment_utils.py:173 — optimal assignment of the n x n cost
+   matrices (n <= 64), one warp per matrix (Kuhn-Munkres with potentials in float64); col_of_row [B][n] (rows are 0..n-1 in order) */
+int pn_hungarian(const float* cost, int B, int n, int* col_of_row, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,8 @@ SIGNATURES = {
     "pn_ms_iter_bwd_tma": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     "pn_ms_kth_dist": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
     "pn_ms_kth_dist_tc": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
+    "pn_iou_cost": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
+    "pn_hungarian": [c_p, c_i, c_i, c_p, c_p],
     "pn_kron_fit": [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p],
     "pn_kron_eval": [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_p, c_p],
     "pn_ms_kth_dist_tc_flagged": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p, c_p],

@@ -337,3 +337,31 @@ def test_kronecker_optimiser_host_parts_vs_reference(golden_dir):
     ku = np.array(AP.uniform_knot_bspline_(20, 20, 3, 3, 2)[2])
     want = np.stack([BSpline(ku, BSpline(ku, cp.transpose(1, 0, 2), 3)(v), 3)(u) for u, v in par])
     assert np.abs(PO.evaluate_list(cp, par, 3, 3) - want).max() < 1e-13
+
+
+def test_hungarian_host_twin_matches_scipy(tmp_path):
+    """csrc/assign.cuh (the Kuhn-Munkres template the device kernel instantiates with 32 lanes) run with one lane on the host
+    against scipy.optimize.linear_sum_assignment: same optimal cost on random, heavily tied and IoU-like matrices; the same
+    assignment where the optimum is unique"""
+    so = str(tmp_path / "assign.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(ROOT, "parsenet-codebase_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "c", "assign_host.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 5, 17, 50, 64):
+        for rep in range(12):
+            if rep % 3 == 0:
+                c = rng.random((n, n)).astype(np.float32)
+            elif rep % 3 == 1:
+                c = rng.integers(0, 4, (n, n)).astype(np.float32)
+            else:
+                c = np.ones((n, n), np.float32); k = min(n, 8); c[:k, :k] = 1 - rng.random((k, k)).astype(np.float32)
+            out = np.zeros(n, np.int32)
+            lib.hungarian_host(c.ctypes.data_as(ctypes.c_void_p), n, out.ctypes.data_as(ctypes.c_void_p))
+            assert sorted(out.tolist()) == list(range(n))
+            r, cc = linear_sum_assignment(c)
+            want = c[r, cc].astype(np.float64).sum()
+            assert abs(c[np.arange(n), out].astype(np.float64).sum() - want) < 1e-9 * max(1, abs(want))
+            if rep % 3 == 0:
+                assert np.array_equal(out, cc)
