@@ -93,6 +93,19 @@ int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void*
 /* the same graph build for the 32-channel-multiple feature spaces with TMA-staged point blocks (knn_tma.cu: cp.async.bulk.tensor
    ring, row-major swizzled tiles, admission straight from registers); identical results, identical arguments */
 int pn_knn_tma_supported(const float* x, int N, int C, int ld, int k, int metric);
+/* the same graph for the 64-row tiles that contain a row with flags[b][row] != 0 only (other tiles exit at once and leave their
+   rows of idx_out / dist_out untouched): exact fall-back of pn_knn_tc */
+int pn_knn_tma_flagged(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, float* ws_norms, const int* flags, void* stream);
+/* replaces: knn: src/PointNet.py:9-26, src/model.py:9-22 for C = 64 / 128 — same arguments and the same bit-exact graph as pn_knn /
+   pn_knn_tma, computed with the tensor cores as a FILTER: a split-TF32 tcgen05 pass gives every pair's cost with a proven error
+   interval, a sampled bracket keeps ~6 % of a row in per-row lists, the k-th smallest upper bound bounds the exact k-th cost,
+   and only the survivors (k plus the few inside the interval) get the reference-order fp32 fmaf chain and the final sort.
+   stride / b_sample: column sample {0, stride, ...} (<= 1024 columns) and the order statistic used as bracket.  Workspaces:
+   ws_norms [B*N], ws_xs [B*N*C], ws_colc [B*(Np + mp)] (Np, mp = N and the sample size rounded up to 64), ws_T [B*N], ws_val
+   [B*N][cap] u32, ws_col [B*N][cap] u16, ws_cnt [B*N][2], cap = 1024 or 2048.  flags [B*N] is written: rows with flag 1 could not
+   be decided and are NOT written — run pn_knn_tma_flagged with the same flags next (no host round trip); knn_tc.cu */
+int pn_knn_tc_supported(const float* x, int N, int C, int ld, int k, int metric);
+int pn_knn_tc(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, int stride, int b_sample, float* ws_norms, float* ws_xs, float* ws_colc, float* ws_T, unsigned* ws_val, unsigned short* ws_col, int* ws_cnt, int cap, int* flags, void* stream);
 int pn_knn_tma(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, float* ws_norms, void* stream);
 
 /* ---- linear.cu ---- */

@@ -114,7 +114,14 @@ __device__ __noinline__ RowState admit(float* bv_lo, BI* bi_lo, int half, int la
 template <int CAP, typename IdxT, bool SAMPLED, bool QRES>
 __global__ void __launch_bounds__(NT, 2)
 knn_tma_kernel(const __grid_constant__ CUtensorMap mX, const __grid_constant__ CUtensorMap mQ, const float* __restrict__ xx,
-               int N, int C, int k, int r_sample, int nst, IdxT* __restrict__ idx_out, float* __restrict__ dist_out) {
+               int N, int C, int k, int r_sample, int nst, IdxT* __restrict__ idx_out, float* __restrict__ dist_out,
+               const int* __restrict__ flags) {
+    // flags (optional, [B][N]): a CTA none of whose 64 query rows is flagged exits at once (exact fall-back of knn_tc.cu)
+    if (flags) {
+        const int q = blockIdx.x * TQ + threadIdx.x;
+        const int f = (threadIdx.x < TQ && q < N) ? flags[(size_t)blockIdx.y * N + q] : 0;
+        if (!__syncthreads_or(f)) return;
+    }
     // The kernel has no static shared memory, so the dynamic window starts at offset 0 of the CTA's allocation, which is 1024-byte
     // aligned (what the 128B-swizzled TMA tiles need); the plan has no slack for padding (two CTAs per SM), hence the trap.
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -396,7 +403,7 @@ static int sample_rank(int N, int k) {          // same rule as knn.cu
 
 template <int CAP, typename IdxT>
 static int launch(const CUtensorMap& mx, const CUtensorMap& mq, const float* xx, int B, int N, int C, int k, void* idx,
-                  float* dist, cudaStream_t st) {
+                  float* dist, cudaStream_t st, const int* flags = nullptr) {
     const int r = sample_rank(N, k);
     // shared-memory plan for two CTAs per SM (<= 113 KB each): resident queries + 16 KB candidate stages when they fit with
     // at least 3 stages, else 24 KB (candidate + query) stages; as many stages as fit, at most 4
@@ -407,12 +414,12 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mq, const float* xx,
     nst = nst > 4 ? 4 : nst;
     PN_REQUIRE(nst >= 2, "pn_knn_tma: shared-memory plan does not fit (C=%d)", C);
     const size_t sm = fixed + (qres ? qres_bytes : 0) + (size_t)nst * stage_bytes(qres);
-    void (*kern)(CUtensorMap, CUtensorMap, const float*, int, int, int, int, int, IdxT*, float*) =
+    void (*kern)(CUtensorMap, CUtensorMap, const float*, int, int, int, int, int, IdxT*, float*, const int*) =
         r ? (qres ? knn_tma_kernel<CAP, IdxT, true, true> : knn_tma_kernel<CAP, IdxT, true, false>)
           : (qres ? knn_tma_kernel<CAP, IdxT, false, true> : knn_tma_kernel<CAP, IdxT, false, false>);
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(cdiv(N, TQ), B);
-    kern<<<grid, NT, sm, st>>>(mx, mq, xx, N, C, k, r, nst, (IdxT*)idx, dist);
+    kern<<<grid, NT, sm, st>>>(mx, mq, xx, N, C, k, r, nst, (IdxT*)idx, dist, flags);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("knn_tma_kernel");
     return PN_OK;
@@ -441,10 +448,10 @@ extern "C" int pn_knn_tma_supported(const float* x, int N, int C, int ld, int k,
     return 1;
 }
 
-extern "C" int pn_knn_tma(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64,
-                          float* dist_out, float* ws_norms, void* stream) {
-    PN_REQUIRE(x && idx_out && ws_norms, "pn_knn_tma: null pointer");
-    PN_REQUIRE(B > 0 && pn_knn_tma_supported(x, N, C, ld, k, metric), "pn_knn_tma: unsupported problem (N=%d C=%d ld=%d k=%d)",
+static int knn_tma_run(const char* who, const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out,
+                       int idx_is_i64, float* dist_out, float* ws_norms, const int* flags, void* stream) {
+    PN_REQUIRE(x && idx_out && ws_norms, "%s: null pointer", who);
+    PN_REQUIRE(B > 0 && pn_knn_tma_supported(x, N, C, ld, k, metric), "%s: unsupported problem (N=%d C=%d ld=%d k=%d)", who,
                N, C, ld, k);
     cudaStream_t st = (cudaStream_t)stream;
     const long long rows = (long long)B * N;
@@ -457,9 +464,22 @@ extern "C" int pn_knn_tma(const float* x, int B, int N, int C, int ld, int k, in
         return PN_ERR_CUDA;
     }
     if (k <= 32) {
-        return idx_is_i64 ? knn2::launch<64, long long>(mx, mq, ws_norms, B, N, C, k, idx_out, dist_out, st)
-                          : knn2::launch<64, int>(mx, mq, ws_norms, B, N, C, k, idx_out, dist_out, st);
+        return idx_is_i64 ? knn2::launch<64, long long>(mx, mq, ws_norms, B, N, C, k, idx_out, dist_out, st, flags)
+                          : knn2::launch<64, int>(mx, mq, ws_norms, B, N, C, k, idx_out, dist_out, st, flags);
     }
-    return idx_is_i64 ? knn2::launch<128, long long>(mx, mq, ws_norms, B, N, C, k, idx_out, dist_out, st)
-                      : knn2::launch<128, int>(mx, mq, ws_norms, B, N, C, k, idx_out, dist_out, st);
+    return idx_is_i64 ? knn2::launch<128, long long>(mx, mq, ws_norms, B, N, C, k, idx_out, dist_out, st, flags)
+                      : knn2::launch<128, int>(mx, mq, ws_norms, B, N, C, k, idx_out, dist_out, st, flags);
+}
+
+extern "C" int pn_knn_tma(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64,
+                          float* dist_out, float* ws_norms, void* stream) {
+    return knn_tma_run("pn_knn_tma", x, B, N, C, ld, k, metric, idx_out, idx_is_i64, dist_out, ws_norms, nullptr, stream);
+}
+
+// the same graph for the 64-row tiles that contain a row with flags[b][row] != 0 only (other tiles exit at once, their rows of
+// idx_out / dist_out stay untouched): exact fall-back of pn_knn_tc
+extern "C" int pn_knn_tma_flagged(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64,
+                                  float* dist_out, float* ws_norms, const int* flags, void* stream) {
+    PN_REQUIRE(flags, "pn_knn_tma_flagged: null flags");
+    return knn_tma_run("pn_knn_tma_flagged", x, B, N, C, ld, k, metric, idx_out, idx_is_i64, dist_out, ws_norms, flags, stream);
 }

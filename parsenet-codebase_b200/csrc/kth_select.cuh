@@ -39,3 +39,51 @@ PN_KTH_HD uint32_t step_next(uint32_t act, uint32_t Bi, bool keep_zeros) { retur
 
 }  // namespace kthsel
 }  // namespace pn
+
+#ifdef __CUDACC__
+// one warp per row: out[row] = the K-th smallest of the row's first n float values (stored as raw float bits with row pitch
+// 1024 * NW words), as a float.  The sample stage of the bracketed selections (meanshift_tma.cu keeps its own copy with the
+// exact-recompute tail; knn_tc.cu uses this one).
+namespace pn {
+namespace kthsel {
+template <int NW>
+__global__ void __launch_bounds__(256) kth_smallest_rows_kernel(const unsigned* __restrict__ vals, int n, int K, long long rows_total,
+                                                                float* __restrict__ out) {
+    constexpr int CAP = 1024 * NW;
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows_total) return;
+    const unsigned* kr = vals + row * CAP;
+    unsigned Bt[NW][32];
+    unsigned act[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        act[w] = 0u;
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            const int p = w * 1024 + r * 32 + lane;
+            const bool valid = p < n;
+            const unsigned u = valid ? kr[p] : 0u;
+            Bt[w][r] = valid ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : 0xffffffffu;      // f2ord
+            act[w] |= valid ? reg_bit(r) : 0u;
+        }
+        bit_transpose32(Bt[w]);
+    }
+    int need = K < n ? K : n;
+    unsigned prefix = 0u;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        int c = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) c += __popc(step_zeros(act[w], Bt[w][i]));
+        c = __reduce_add_sync(0xffffffffu, c);
+        const bool zero = c >= need;
+        if (!zero) { need -= c; prefix |= 1u << (31 - i); }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) act[w] = step_next(act[w], Bt[w][i], zero);
+    }
+    if (lane == 0) out[row] = __uint_as_float((prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix);      // ord2f
+}
+}  // namespace kthsel
+}  // namespace pn
+#endif

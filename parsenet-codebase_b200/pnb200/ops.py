@@ -31,7 +31,49 @@ def _need_cuda(*ts):
 
 
 # --------------------------------------------------------------------------------------------- kNN
-KNN_IMPL = os.environ.get("PN_KNN", "tma")          # "tma" | "simt" (A/B tests)
+KNN_IMPL = os.environ.get("PN_KNN", "tc")           # "tc" | "tma" | "simt" (A/B tests; all three give the same graph)
+_KNN_WS = {}
+
+
+def knn_tc_plan(N, k):
+    """(stride, b, cap) of the tensor-core-filtered kNN (csrc/knn_tc.cu), or None when its lists cannot be expected to hold the
+    answer: the sample {0, stride, ...} has m <= 1024 columns, of which a hypergeometric number with mean mu = k m / N belongs
+    to the k nearest; the b = mu + 7 sigma + 2 -th smallest upper bound of the sample is the admission bracket, which keeps
+    about b N / m entries per row (one list of cap / 2 per half of the tile columns)."""
+    if N < 2048 or N >= 65536:
+        return None
+    stride = -(-N // 1024)
+    m = -(-N // stride)
+    mu = k * m / N
+    sigma = (mu * (1.0 - k / N) * (N - m) / max(N - 1, 1)) ** 0.5
+    b = int(mu + 7.0 * sigma + 2.0) + 1
+    if b > m:
+        return None
+    length = (b + 6.0 * b ** 0.5) * N / m
+    for cap in (1024, 2048):
+        if length / 2 + 3.0 * length ** 0.5 <= cap / 2:
+            return stride, b, cap
+    return None
+
+
+def _knn_tc_workspace(dev, B, N, C, cap, stride):
+    """workspaces of pn_knn_tc, kept per (device, stream) and grown on demand (6 bytes x cap per row)"""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    rows = B * N
+    Np, mp = (N + 63) // 64 * 64, (-(-N // stride) + 63) // 64 * 64
+    need = (rows, cap, rows * C, B * (Np + mp))
+    ws = _KNN_WS.get(key)
+    if ws is None or ws["rows"] < rows or ws["cap"] != cap or ws["xs"].numel() < need[2] or ws["colc"].numel() < need[3]:
+        ws = {"rows": rows, "cap": cap,
+              "val": torch.empty((rows, cap), dtype=torch.int32, device=dev),
+              "col": torch.empty((rows, cap), dtype=torch.int16, device=dev),
+              "cnt": torch.empty((rows, 2), dtype=torch.int32, device=dev),
+              "T": torch.empty((rows,), dtype=torch.float32, device=dev),
+              "flags": torch.empty((rows,), dtype=torch.int32, device=dev),
+              "xs": torch.empty((need[2],), dtype=torch.float32, device=dev),
+              "colc": torch.empty((need[3],), dtype=torch.float32, device=dev)}
+        _KNN_WS[key] = ws
+    return ws
 
 
 def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
@@ -49,8 +91,22 @@ def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
     # feature spaces with whole 32-channel chunks go through the TMA-staged kernel (csrc/knn_tma.cu); positions (+ normals),
     # very large k or N >= 65536 through the loader-thread kernel (csrc/knn.cu).  Same results (both bit-exact vs the oracle).
     entry = "pn_knn"
-    if KNN_IMPL == "tma" and lib.pn_knn_tma_supported(x_bnc.data_ptr(), N, C, ld, k, metric):
+    if KNN_IMPL in ("tma", "tc") and lib.pn_knn_tma_supported(x_bnc.data_ptr(), N, C, ld, k, metric):
         entry = "pn_knn_tma"
+    plan = knn_tc_plan(N, k) if (KNN_IMPL == "tc" and entry == "pn_knn_tma"
+                                 and lib.pn_knn_tc_supported(x_bnc.data_ptr(), N, C, ld, k, metric)) else None
+    if plan is not None:
+        # tensor-core filter + exact refinement of the survivors (csrc/knn_tc.cu); rows it could not decide are flagged and
+        # redone by the TMA kernel (tiles without a flagged row exit at once): same graph, no host round trip
+        stride, b, cap = plan
+        w = _knn_tc_workspace(x_bnc.device, B, N, C, cap, stride)
+        i64 = 1 if out_dtype == torch.int64 else 0
+        with torch.cuda.device(x_bnc.device):
+            call("pn_knn_tc", _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), i64, _ptr(dist), stride, b, _ptr(ws), _ptr(w["xs"]),
+                 _ptr(w["colc"]), _ptr(w["T"]), _ptr(w["val"]), _ptr(w["col"]), _ptr(w["cnt"]), cap, _ptr(w["flags"]), _stream())
+            call("pn_knn_tma_flagged", _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), i64, _ptr(dist), _ptr(ws), _ptr(w["flags"]),
+                 _stream())
+        return (idx, dist) if return_dist else idx
     with torch.cuda.device(x_bnc.device):
         call(entry, _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), 1 if out_dtype == torch.int64 else 0,
                          _ptr(dist), _ptr(ws), _stream())

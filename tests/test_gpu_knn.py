@@ -179,3 +179,61 @@ def test_up_sampling_helpers_vs_reference(golden_dir):
     np.random.seed(4)
     assert up_sample_points_torch_in_range(torch.from_numpy(g["r_p"]).cuda(), 1000, 1500).shape == (1500, 3)
     assert up_sample_points_torch_in_range(torch.from_numpy(g["b_p"]).cuda(), 100, 600).shape == (600, 3)
+
+
+# ---------------------------------------------------------------------------------------------- tensor-core filter (knn_tc.cu)
+def _tc_inputs(kind, B, N, C, seed):
+    g = torch.Generator().manual_seed(seed)
+    if kind == "randn":
+        return (torch.randn(B, N, C, generator=g) * 0.3).cuda()
+    if kind == "offset":                 # large common offset: norms >> distances, the error interval is wide relative to the gaps
+        return (torch.randn(B, N, C, generator=g) * 0.05 + 3.0).cuda()
+    if kind == "dups":                   # many exactly repeated points: ties resolved by index, windows full of equal costs
+        base = torch.randn(B, N // 8, C, generator=g)
+        return base.repeat(1, 8, 1)[:, torch.randperm(N // 8 * 8, generator=g)].contiguous().cuda()
+    u = torch.rand(B, N, 3, generator=g)
+    W1 = torch.randn(3, 32, generator=g); W2 = torch.randn(32, C, generator=g) * 0.3
+    h = torch.nn.functional.leaky_relu(torch.sin(3 * u @ W1), 0.2)
+    return torch.nn.functional.leaky_relu(h @ W2 + 0.5, 0.2).cuda().contiguous()
+
+
+@pytest.mark.parametrize("kind,B,N,C,k", [("randn", 2, 10000, 64, 80), ("feat", 2, 10000, 64, 80), ("feat", 3, 5000, 128, 10),
+                                          ("offset", 2, 4099, 64, 20), ("dups", 2, 4096, 128, 10), ("feat", 1, 2048, 64, 96)])
+def test_tensor_core_filtered_knn_equals_the_exact_kernel(kind, B, N, C, k):
+    """csrc/knn_tc.cu (tcgen05 filter with a proven error interval + exact fp32 refinement of the survivors + flagged fall-back)
+    must give the bit-identical graph AND ranked values of the exact kernels, on ordinary features, on features with a large
+    common offset (wide intervals), and on clouds full of exact duplicates (index tie-breaks, overflowing windows)"""
+    from pnb200 import ops
+    x = _tc_inputs(kind, B, N, C, 11)
+    old = ops.KNN_IMPL
+    try:
+        ops.KNN_IMPL = "tma"
+        i0, d0 = ops.knn_graph(x, k, 0, return_dist=True)
+        ops.KNN_IMPL = "tc"
+        assert ops.knn_tc_plan(N, k) is not None
+        i1, d1 = ops.knn_graph(x, k, 0, return_dist=True)
+    finally:
+        ops.KNN_IMPL = old
+    assert torch.equal(i0, i1)
+    assert torch.equal(d0, d1)
+    flags = next(iter(ops._KNN_WS.values()))["flags"][: B * N]
+    if kind in ("randn", "feat"):
+        assert flags.float().mean().item() < 0.01, flags.float().mean().item()
+
+
+def test_tensor_core_filtered_knn_on_a_channel_slice_vs_oracle():
+    """a 64-channel slice of a 256-wide buffer (the encoder's concat buffer: row pitch 256), int64 output, against the C oracle"""
+    from pnb200 import ops
+    B, N, k = 1, 3000, 80
+    g = torch.Generator().manual_seed(5)
+    wide = torch.randn(B, N, 256, generator=g).cuda()
+    x = wide[:, :, 64:128]
+    old = ops.KNN_IMPL
+    try:
+        ops.KNN_IMPL = "tc"
+        idx = ops.knn_graph(x, k, 0, out_dtype=torch.int64)
+    finally:
+        ops.KNN_IMPL = old
+    from oracle import knn as oknn
+    want = oknn.knn(x.contiguous().cpu().numpy(), k, 0)
+    assert np.array_equal(idx.cpu().numpy(), want)
