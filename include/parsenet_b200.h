@@ -92,6 +92,18 @@ int pn_grid_laplacian_bwd(const float* l_ws, int B, int g, int l1, const float* 
 int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, float* ws_norms, void* stream);
 /* the same graph build for the 32-channel-multiple feature spaces with TMA-staged point blocks (knn_tma.cu: cp.async.bulk.tensor
    ring, row-major swizzled tiles, admission straight from registers); identical results, identical arguments */
+/* the same graph for the tiles of query rows that contain a row with flags[b][row] != 0 only (other tiles exit at once and leave
+   their rows of idx_out / dist_out untouched): exact fall-back of pn_knn_lowdim */
+int pn_knn_flagged(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, float* ws_norms, const int* flags, void* stream);
+/* replaces: knn_points_normals src/PointNet.py:29-69 (metric 1, C = 6), knn on raw positions src/PointNet.py:9-26 / src/model.py:9-22
+   (metric 0, C = 3), the 5-nearest search of up_sample_points_torch src/fitting_utils.py:150-163 (metric 2) — same arguments and
+   the same bit-exact graph as pn_knn with a one-pass bracketed selection instead of the streaming top-k: exact costs of every
+   row to a strided column sample give a per-row bracket, one pass appends the costs below it to per-row lists, a warp per row
+   selects the k-th smallest, sorts the entries up to it by (cost, index) and writes the first k.  Workspaces: ws_norms [B*N],
+   ws_T [B*N], ws_val [B*N][cap] u32, ws_col [B*N][cap] u16, ws_cnt [B*N][2], cap = 1024 or 2048 (a list may use cap / 2 entries).
+   flags [B*N] is written: rows with flag 1 are NOT written — run pn_knn_flagged with the same flags next; knn_lowdim.cu */
+int pn_knn_lowdim_supported(int N, int C, int k, int metric);
+int pn_knn_lowdim(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out, int idx_is_i64, float* dist_out, int stride, int b_sample, float* ws_norms, float* ws_T, unsigned* ws_val, unsigned short* ws_col, int* ws_cnt, int cap, int* flags, void* stream);
 int pn_knn_tma_supported(const float* x, int N, int C, int ld, int k, int metric);
 /* the same graph for the 64-row tiles that contain a row with flags[b][row] != 0 only (other tiles exit at once and leave their
    rows of idx_out / dist_out untouched): exact fall-back of pn_knn_tc */

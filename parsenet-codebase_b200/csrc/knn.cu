@@ -55,7 +55,13 @@ constexpr int SAMPLE_M = 1024;
 template <int METRIC, int CAP, typename IdxT, bool SAMPLED = false>
 __global__ void __launch_bounds__(NT, 2)
 knn_kernel(const float* __restrict__ x, const float* __restrict__ xx, int N, int C, int ld, int k, int vec,
-           IdxT* __restrict__ idx_out, float* __restrict__ dist_out) {
+           IdxT* __restrict__ idx_out, float* __restrict__ dist_out, const int* __restrict__ flags) {
+    // flags (optional, [B][N]): a CTA none of whose TQ query rows is flagged exits at once (exact fall-back of knn_lowdim.cu)
+    if (flags) {
+        const int q = blockIdx.x * TQ + threadIdx.x;
+        const int f = (threadIdx.x < TQ && q < N) ? flags[(size_t)blockIdx.y * N + q] : 0;
+        if (!__syncthreads_or(f)) return;
+    }
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout
     float* xs = reinterpret_cast<float*>(smem_raw);           // [KC][TC]   (aliased by Dt [TQ][TC])
@@ -334,14 +340,14 @@ static int sample_rank(int N, int k) {
 
 template <int METRIC, int CAP, typename IdxT>
 static int launch(const float* x, const float* xx, int B, int N, int C, int ld, int k, void* idx, float* dist,
-                  cudaStream_t st) {
+                  cudaStream_t st, const int* flags) {
     const int r = sample_rank(N, k);
     auto kern = r ? knn_kernel<METRIC, CAP, IdxT, true> : knn_kernel<METRIC, CAP, IdxT, false>;
     size_t sm = smem_bytes(CAP);
     PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid(cdiv(N, TQ), B);
     const int vec = ((C % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0)) | (r << 8);
-    kern<<<grid, NT, sm, st>>>(x, xx, N, C, ld, k, vec, (IdxT*)idx, dist);
+    kern<<<grid, NT, sm, st>>>(x, xx, N, C, ld, k, vec, (IdxT*)idx, dist, flags);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("knn_kernel");
     return PN_OK;
@@ -349,7 +355,7 @@ static int launch(const float* x, const float* xx, int B, int N, int C, int ld, 
 
 template <int METRIC, typename IdxT>
 static int dispatch_cap(const float* x, const float* xx, int B, int N, int C, int ld, int k, void* idx, float* dist,
-                        cudaStream_t st) {
+                        cudaStream_t st, const int* flags) {
     // experiment knob (read per call): PN_KNN_CAP=256 gives a k = 80 row 176 instead of 48 entries of headroom between
     // compactions (3.7x fewer, 2x larger quickselects) at 1 instead of 2 resident CTAs per SM; results are identical
     // for every capacity >= k (the buffer content after a compaction does not depend on when it happens)
@@ -358,9 +364,9 @@ static int dispatch_cap(const float* x, const float* xx, int B, int N, int C, in
         const int want = atoi(e);
         if ((want == 128 || want == 256) && want >= cap) cap = want;
     }
-    if (cap == 64) return launch<METRIC, 64, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st);
-    if (cap == 128) return launch<METRIC, 128, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st);
-    return launch<METRIC, 256, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st);
+    if (cap == 64) return launch<METRIC, 64, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st, flags);
+    if (cap == 128) return launch<METRIC, 128, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st, flags);
+    return launch<METRIC, 256, IdxT>(x, xx, B, N, C, ld, k, idx, dist, st, flags);
 }
 
 }  // namespace knn
@@ -368,26 +374,39 @@ static int dispatch_cap(const float* x, const float* xx, int B, int N, int C, in
 
 using namespace pn;
 
-extern "C" int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out,
-                      int idx_is_i64, float* dist_out, float* ws_norms, void* stream) {
-    PN_REQUIRE(x && idx_out && ws_norms, "pn_knn: null pointer");
-    PN_REQUIRE(B > 0 && N > 0 && C > 0 && ld >= C, "pn_knn: bad shape B=%d N=%d C=%d ld=%d", B, N, C, ld);
-    PN_REQUIRE(k > 0 && k <= N && k <= 224, "pn_knn: need 0 < k <= min(N,224), got k=%d N=%d", k, N);
+static int knn_run(const char* who, const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out,
+                   int idx_is_i64, float* dist_out, float* ws_norms, const int* flags, void* stream) {
+    PN_REQUIRE(x && idx_out && ws_norms, "%s: null pointer", who);
+    PN_REQUIRE(B > 0 && N > 0 && C > 0 && ld >= C, "%s: bad shape B=%d N=%d C=%d ld=%d", who, B, N, C, ld);
+    PN_REQUIRE(k > 0 && k <= N && k <= 224, "%s: need 0 < k <= min(N,224), got k=%d N=%d", who, k, N);
     PN_REQUIRE(metric == 0 || (metric == 1 && C == 6) || (metric == 2 && C == 3),
-               "pn_knn: metric 1 needs C == 6, metric 2 needs C == 3");
+               "%s: metric 1 needs C == 6, metric 2 needs C == 3", who);
     cudaStream_t st = (cudaStream_t)stream;
     long long rows = (long long)B * N;
     knn::norms_kernel<<<cdiv(rows, 256), 256, 0, st>>>(x, rows, ld, 0, metric == 1 ? 3 : C, ws_norms);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("knn norms_kernel");
     if (metric == 0) {
-        return idx_is_i64 ? knn::dispatch_cap<0, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st)
-                          : knn::dispatch_cap<0, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st);
+        return idx_is_i64 ? knn::dispatch_cap<0, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st, flags)
+                          : knn::dispatch_cap<0, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st, flags);
     }
     if (metric == 2) {
-        return idx_is_i64 ? knn::dispatch_cap<2, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st)
-                          : knn::dispatch_cap<2, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st);
+        return idx_is_i64 ? knn::dispatch_cap<2, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st, flags)
+                          : knn::dispatch_cap<2, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st, flags);
     }
-    return idx_is_i64 ? knn::dispatch_cap<1, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st)
-                      : knn::dispatch_cap<1, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st);
+    return idx_is_i64 ? knn::dispatch_cap<1, long long>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st, flags)
+                      : knn::dispatch_cap<1, int>(x, ws_norms, B, N, C, ld, k, idx_out, dist_out, st, flags);
+}
+
+extern "C" int pn_knn(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out,
+                      int idx_is_i64, float* dist_out, float* ws_norms, void* stream) {
+    return knn_run("pn_knn", x, B, N, C, ld, k, metric, idx_out, idx_is_i64, dist_out, ws_norms, nullptr, stream);
+}
+
+// the same graph for the tiles of query rows that contain a row with flags[b][row] != 0 only (other tiles exit at once and leave
+// their rows of idx_out / dist_out untouched): exact fall-back of pn_knn_lowdim
+extern "C" int pn_knn_flagged(const float* x, int B, int N, int C, int ld, int k, int metric, void* idx_out,
+                              int idx_is_i64, float* dist_out, float* ws_norms, const int* flags, void* stream) {
+    PN_REQUIRE(flags, "pn_knn_flagged: null flags");
+    return knn_run("pn_knn_flagged", x, B, N, C, ld, k, metric, idx_out, idx_is_i64, dist_out, ws_norms, flags, stream);
 }

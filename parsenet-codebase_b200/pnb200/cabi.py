@@ -62,6 +62,8 @@ SIGNATURES = {
     "pn_ms_iter_bwd_tma": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p],
     "pn_ms_kth_dist": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
     "pn_ms_kth_dist_tc": [c_p, c_p, c_i, c_i, c_ll, c_i, c_i, c_p, c_p],
+    "pn_knn_lowdim": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
+    "pn_knn_flagged": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p],
     "pn_knn_tc": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p],
     "pn_knn_tma_flagged": [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_i, c_p, c_p, c_p, c_p],
     "pn_iou_cost": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
@@ -103,6 +105,7 @@ _SPECIAL = {
     "pn_abi_version": (c_i, []),
     "pn_knn_tma_supported": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i]),
     "pn_knn_tc_supported": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i]),
+    "pn_knn_lowdim_supported": (c_i, [c_i, c_i, c_i, c_i]),
     "pn_linear_fwd_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i]),
     "pn_linear_bwd_weight_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_i, c_i, c_i]),
     "pn_linear_bwd_data_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i]),

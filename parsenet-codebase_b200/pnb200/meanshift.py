@@ -351,13 +351,20 @@ def nms(centers_nd, X_nd, b, member=None):
     return kept, ids, labels
 
 
-def nms_batched(Y_bnd, X_bnd, bw_b, member=None):
+NMS_WIDTH = 64        # kept centres per shape handled without a second read-back (the fit stage allows at most 49)
+
+
+def nms_batched(Y_bnd, X_bnd, bw_b, member=None, also=None):
     """nms (mean_shift.py:139-179) for a batch of shapes with ONE blocking read-back instead of ~5 per shape.
     Returns (ids, labels, K): ids = list of (K_b,) int64 device tensors (kept centre rows of Y, ascending),
     labels (B,N) int64 device tensor (position of the nearest kept centre), K = list of K_b (host ints).
     Same arithmetic as nms(): the occupied-centre rows of the neighbour arg-select are a subset of the all-rows
     launch used here, and padding the kept list with a repeat of its first entry cannot win an arg-max tie
-    (first occurrence wins)."""
+    (first occurrence wins).
+    The kept rows are selected on the device into a fixed NMS_WIDTH-wide table (ascending ids, padded), so the label
+    arg-select is enqueued without waiting for the host; the single read-back at the end brings K, the labels and the
+    float tensors listed in `also` to the host together: with `also` given the return value is
+    (ids, labels, K, labels_host (B,N) int32 numpy, [numpy copies of also])."""
     _check_width(Y_bnd.shape[-1])
     Y = Y_bnd.detach().contiguous()
     X = X_bnd.detach().contiguous()
@@ -375,21 +382,41 @@ def nms_batched(Y_bnd, X_bnd, bw_b, member=None):
     tgt = torch.where(counts > 0, nbr.long(), torch.full_like(nbr, N, dtype=torch.int64))
     mark = torch.zeros((B, N + 1), dtype=torch.bool, device=dev)
     mark.scatter_(1, tgt, torch.ones((B, N), dtype=torch.bool, device=dev))
-    kept = mark[:, :N].nonzero().cpu().numpy()                       # (T,2) rows sorted by (shape, id): THE sync
-    K = np.bincount(kept[:, 0], minlength=B).astype(np.int64)
-    Kmax = int(K.max())
-    starts = np.concatenate([[0], np.cumsum(K)])
-    pad = np.empty((B, Kmax), dtype=np.int64)
-    for b in range(B):
-        ids_b = kept[starts[b]:starts[b + 1], 1]
-        pad[b, :K[b]] = ids_b
-        pad[b, K[b]:] = ids_b[0]
-    from .staging import arena
-    stage = arena("nms", dev)
-    stage.reset()
-    pad_d = stage.upload(pad, dev)
-    centres = torch.gather(Y, 1, pad_d.unsqueeze(2).expand(B, Kmax, d)).contiguous()
+    W = min(NMS_WIDTH, N)
+    ar = torch.arange(N, device=dev, dtype=torch.int32)
+    cand = torch.where(mark[:, :N], ar, torch.full((), N, dtype=torch.int32, device=dev))           # (B,N): id or N
+    table = torch.topk(cand, W, dim=1, largest=False, sorted=True)[0]                                # ascending ids, N = empty
+    Kd = mark[:, :N].sum(1, dtype=torch.int32)                                                       # (B,) kept rows per shape
+    pad_d = torch.where(table < N, table, table[:, :1]).long()                                       # padded with the first id
+    centres = torch.gather(Y, 1, pad_d.unsqueeze(2).expand(B, W, d)).contiguous()
     lab = torch.empty((B, N), dtype=torch.int32, device=dev)
-    call("pn_ms_argsel", 2, _ptr(X), N * d, N, _ptr(centres), Kmax * d, Kmax, B, d, None, None, _ptr(lab), _stream())
+    call("pn_ms_argsel", 2, _ptr(X), N * d, N, _ptr(centres), W * d, W, B, d, None, None, _ptr(lab), _stream())
+    extra = [t.detach().to(torch.float32).reshape(-1) for t in (also or [])]
+    pack = torch.cat([Kd, lab.reshape(-1)] + [t.view(torch.int32) for t in extra]).cpu().numpy()     # THE read-back
+    K = pack[:B].astype(np.int64)
+    if int(K.max()) > W:                                # more kept centres than the table holds: redo the tail on the host
+        kept = mark[:, :N].nonzero().cpu().numpy()
+        Kmax = int(K.max())
+        starts = np.concatenate([[0], np.cumsum(K)])
+        pad = np.empty((B, Kmax), dtype=np.int64)
+        for b in range(B):
+            ids_b = kept[starts[b]:starts[b + 1], 1]
+            pad[b, :K[b]] = ids_b
+            pad[b, K[b]:] = ids_b[0]
+        from .staging import arena
+        stage = arena("nms", dev)
+        stage.reset()
+        pad_d = stage.upload(pad, dev)
+        centres = torch.gather(Y, 1, pad_d.unsqueeze(2).expand(B, Kmax, d)).contiguous()
+        call("pn_ms_argsel", 2, _ptr(X), N * d, N, _ptr(centres), Kmax * d, Kmax, B, d, None, None, _ptr(lab), _stream())
+        lab_host = lab.cpu().numpy()
+    else:
+        lab_host = pack[B:B + B * N].reshape(B, N)
     ids = [pad_d[b, :int(K[b])] for b in range(B)]
-    return ids, lab.long(), [int(k) for k in K]
+    if also is None:
+        return ids, lab.long(), [int(k) for k in K]
+    outs, o = [], B + B * N
+    for t, src in zip(extra, also):
+        outs.append(pack[o:o + t.numel()].view(np.float32).reshape(tuple(src.shape)))
+        o += t.numel()
+    return ids, lab.long(), [int(k) for k in K], lab_host, outs

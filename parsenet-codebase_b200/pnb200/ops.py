@@ -35,7 +35,7 @@ KNN_IMPL = os.environ.get("PN_KNN", "tc")           # "tc" | "tma" | "simt" (A/B
 _KNN_WS = {}
 
 
-def knn_tc_plan(N, k):
+def knn_tc_plan(N, k, single_list=False):
     """(stride, b, cap) of the tensor-core-filtered kNN (csrc/knn_tc.cu), or None when its lists cannot be expected to hold the
     answer: the sample {0, stride, ...} has m <= 1024 columns, of which a hypergeometric number with mean mu = k m / N belongs
     to the k nearest; the b = mu + 7 sigma + 2 -th smallest upper bound of the sample is the admission bracket, which keeps
@@ -51,28 +51,36 @@ def knn_tc_plan(N, k):
         return None
     length = (b + 6.0 * b ** 0.5) * N / m
     for cap in (1024, 2048):
-        if length / 2 + 3.0 * length ** 0.5 <= cap / 2:
+        # knn_tc.cu keeps one list of cap / 2 per half of the tile columns; knn_lowdim.cu one list of cap / 2 per row
+        if (length if single_list else length / 2 + 3.0 * length ** 0.5) <= cap / 2:
             return stride, b, cap
     return None
 
 
 def _knn_tc_workspace(dev, B, N, C, cap, stride):
-    """workspaces of pn_knn_tc, kept per (device, stream) and grown on demand (6 bytes x cap per row)"""
-    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
+    """workspaces of pn_knn_tc / pn_knn_lowdim, kept per (device, stream, list capacity) and grown on demand (6 bytes x cap
+    per row): the layers of one step alternate between the two capacities, and a block of 1 - 2 GB that is freed and carved up
+    between calls would make the caching allocator churn"""
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream, cap)
     rows = B * N
     Np, mp = (N + 63) // 64 * 64, (-(-N // stride) + 63) // 64 * 64
-    need = (rows, cap, rows * C, B * (Np + mp))
+    n_xs, n_colc = rows * C, B * (Np + mp)
     ws = _KNN_WS.get(key)
-    if ws is None or ws["rows"] < rows or ws["cap"] != cap or ws["xs"].numel() < need[2] or ws["colc"].numel() < need[3]:
-        ws = {"rows": rows, "cap": cap,
+    if ws is None or ws["rows"] < rows:
+        ws = {"rows": rows,
               "val": torch.empty((rows, cap), dtype=torch.int32, device=dev),
               "col": torch.empty((rows, cap), dtype=torch.int16, device=dev),
               "cnt": torch.empty((rows, 2), dtype=torch.int32, device=dev),
               "T": torch.empty((rows,), dtype=torch.float32, device=dev),
               "flags": torch.empty((rows,), dtype=torch.int32, device=dev),
-              "xs": torch.empty((need[2],), dtype=torch.float32, device=dev),
-              "colc": torch.empty((need[3],), dtype=torch.float32, device=dev)}
+              "xs": torch.empty((n_xs,), dtype=torch.float32, device=dev),
+              "colc": torch.empty((n_colc,), dtype=torch.float32, device=dev)}
         _KNN_WS[key] = ws
+    if ws["xs"].numel() < n_xs:
+        ws["xs"] = torch.empty((n_xs,), dtype=torch.float32, device=dev)
+    if ws["colc"].numel() < n_colc:
+        ws["colc"] = torch.empty((n_colc,), dtype=torch.float32, device=dev)
+    ws["last"] = True
     return ws
 
 
@@ -105,6 +113,20 @@ def knn_graph(x_bnc, k, metric=0, out_dtype=torch.int32, return_dist=False):
             call("pn_knn_tc", _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), i64, _ptr(dist), stride, b, _ptr(ws), _ptr(w["xs"]),
                  _ptr(w["colc"]), _ptr(w["T"]), _ptr(w["val"]), _ptr(w["col"]), _ptr(w["cnt"]), cap, _ptr(w["flags"]), _stream())
             call("pn_knn_tma_flagged", _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), i64, _ptr(dist), _ptr(ws), _ptr(w["flags"]),
+                 _stream())
+        return (idx, dist) if return_dist else idx
+    plan = knn_tc_plan(N, k, single_list=True) if (KNN_IMPL == "tc" and entry == "pn_knn"
+                                                   and lib.pn_knn_lowdim_supported(N, C, k, metric)) else None
+    if plan is not None:
+        # positions (+ normals): exact costs for every pair, one-pass bracketed selection (csrc/knn_lowdim.cu), flagged rows
+        # redone by the loader-thread kernel
+        stride, b, cap = plan
+        w = _knn_tc_workspace(x_bnc.device, B, N, 1, cap, stride)
+        i64 = 1 if out_dtype == torch.int64 else 0
+        with torch.cuda.device(x_bnc.device):
+            call("pn_knn_lowdim", _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), i64, _ptr(dist), stride, b, _ptr(ws), _ptr(w["T"]),
+                 _ptr(w["val"]), _ptr(w["col"]), _ptr(w["cnt"]), cap, _ptr(w["flags"]), _stream())
+            call("pn_knn_flagged", _ptr(x_bnc), B, N, C, ld, k, metric, _ptr(idx), i64, _ptr(dist), _ptr(ws), _ptr(w["flags"]),
                  _stream())
         return (idx, dist) if return_dist else idx
     with torch.cuda.device(x_bnc.device):

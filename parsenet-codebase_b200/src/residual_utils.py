@@ -81,9 +81,8 @@ class Evaluation:
             shifted = _ms.mean_shift_iters(embedding, bws, iterations)
         with torch.no_grad():
             members = _ms.nearest_center_batched(embedding, shifted)
-            ids, labels_dev, _ = _ms.nms_batched(shifted, embedding, bws, members)   # one blocking read-back
-        cluster_np = labels_dev.cpu().numpy()
-        bw_host = bws.detach().cpu().numpy()
+            # one blocking read-back: kept-centre counts, the cluster id of every point and the bandwidths together
+            ids, labels_dev, _, cluster_np, (bw_host,) = _ms.nms_batched(shifted, embedding, bws, members, also=[bws])
         n_clusters = [np.unique(cluster_np[b]).shape[0] for b in range(B)]
         if FIT_STAGE == "batched" and embedding.shape[2] == 128 and max(n_clusters) <= 49:
             return self._fitting_loss_batched(embedding, ms_state if sparse else None, shifted, ids, bws, points, normals,

@@ -216,7 +216,7 @@ def test_tensor_core_filtered_knn_equals_the_exact_kernel(kind, B, N, C, k):
         ops.KNN_IMPL = old
     assert torch.equal(i0, i1)
     assert torch.equal(d0, d1)
-    flags = next(iter(ops._KNN_WS.values()))["flags"][: B * N]
+    flags = [v for kk, v in ops._KNN_WS.items() if kk[2] == ops.knn_tc_plan(N, k)[2]][0]["flags"][: B * N]
     if kind in ("randn", "feat"):
         assert flags.float().mean().item() < 0.01, flags.float().mean().item()
 
@@ -237,3 +237,60 @@ def test_tensor_core_filtered_knn_on_a_channel_slice_vs_oracle():
     from oracle import knn as oknn
     want = oknn.knn(x.contiguous().cpu().numpy(), k, 0)
     assert np.array_equal(idx.cpu().numpy(), want)
+
+
+# ---------------------------------------------------------------------------------------------- low-dimensional metrics (knn_lowdim.cu)
+def _lowdim_inputs(kind, B, N, metric, seed):
+    g = torch.Generator().manual_seed(seed)
+    C = 6 if metric == 1 else 3
+    if kind == "dups":
+        base = torch.randn(B, N // 4, C, generator=g) * 0.3
+        x = base.repeat(1, 4, 1)[:, torch.randperm(N // 4 * 4, generator=g)].contiguous()
+    elif kind == "grid":                 # points on a regular lattice: masses of exactly tied distances
+        side = int(round(N ** (1 / 3))) + 1
+        ax = torch.arange(side, dtype=torch.float32) / side
+        pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), -1).reshape(-1, 3)[:N]
+        x = pts.unsqueeze(0).repeat(B, 1, 1)
+        if C == 6:
+            x = torch.cat([x, torch.randn(B, N, 3, generator=g)], 2)
+    else:
+        x = torch.randn(B, N, C, generator=g) * 0.3
+    if metric == 1:
+        x[..., 3:] = torch.nn.functional.normalize(x[..., 3:], dim=-1)
+    return x.cuda().contiguous()
+
+
+@pytest.mark.parametrize("kind,B,N,k,metric", [("randn", 2, 10000, 80, 1), ("randn", 3, 5000, 10, 0), ("randn", 2, 4099, 5, 2),
+                                               ("dups", 2, 4096, 80, 1), ("grid", 1, 4000, 10, 0), ("randn", 1, 2048, 96, 1)])
+def test_lowdim_bracketed_knn_equals_the_loader_thread_kernel(kind, B, N, k, metric):
+    """csrc/knn_lowdim.cu (exact costs, one-pass bracketed selection, flagged fall-back) against the loader-thread kernel of
+    knn.cu (itself bit-exact vs the C oracle): identical indices and ranked values for positions + normals, raw positions and
+    the squared-difference metric; duplicates and lattice points exercise the index tie-breaks and the overflow flags"""
+    from pnb200 import ops
+    x = _lowdim_inputs(kind, B, N, metric, 21)
+    old = ops.KNN_IMPL
+    try:
+        ops.KNN_IMPL = "tma"
+        i0, d0 = ops.knn_graph(x, k, metric, return_dist=True)
+        ops.KNN_IMPL = "tc"
+        assert ops.knn_tc_plan(N, k, single_list=True) is not None
+        i1, d1 = ops.knn_graph(x, k, metric, return_dist=True)
+    finally:
+        ops.KNN_IMPL = old
+    assert torch.equal(i0, i1)
+    assert torch.equal(d0, d1)
+
+
+def test_lowdim_bracketed_knn_vs_oracle_int64():
+    from oracle import knn as oknn
+    from pnb200 import ops
+    x = _lowdim_inputs("randn", 1, 3000, 1, 8)
+    old = ops.KNN_IMPL
+    try:
+        ops.KNN_IMPL = "tc"
+        idx, dist = ops.knn_graph(x, 80, 1, out_dtype=torch.int64, return_dist=True)
+    finally:
+        ops.KNN_IMPL = old
+    want, wdist = oknn.knn(x.cpu().numpy(), 80, 1, return_dist=True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), want)
+    np.testing.assert_array_equal(dist.cpu().numpy(), wdist)

@@ -126,3 +126,37 @@ def test_nms_batched_equals_per_shape_nms():
         assert K[b] == ids_b.shape[0]
         np.testing.assert_array_equal(ids[b].cpu().numpy(), ids_b.cpu().numpy())
         np.testing.assert_array_equal(lab[b].cpu().numpy(), lab_b.cpu().numpy())
+
+
+def test_nms_batched_wide_tables_and_packed_read_back():
+    """more kept centres than the fixed-width device table holds (tiny bandwidth after one iteration: hundreds of clusters):
+    the tail path reproduces the per-shape nms too; and the packed read-back returns the labels / extra tensors unchanged"""
+    from oracle.make_golden_helpers import clustered_embedding
+    from oracle.port import meanshift as port
+    from pnb200 import meanshift as pms
+    Xs, Ys = [], []
+    for seed, ncl in ((27, 5), (28, 9)):
+        X, _ = clustered_embedding(900, 128, ncl, seed)
+        Xs.append(X)
+        Ys.append(port.mean_shift_iters(X, torch.tensor(0.02), 1))
+    X, Y = torch.stack(Xs).cuda(), torch.stack(Ys).cuda()
+    bw = torch.tensor([0.02, 0.02]).cuda()
+    ids, lab, K, lab_host, (bw_host,) = pms.nms_batched(Y, X, bw, also=[bw])
+    assert max(K) > pms.NMS_WIDTH
+    np.testing.assert_array_equal(lab_host, lab.cpu().numpy())
+    np.testing.assert_array_equal(bw_host, bw.cpu().numpy())
+    for b in range(2):
+        _, ids_b, lab_b = pms.nms(Y[b], X[b], bw[b])
+        assert K[b] == ids_b.shape[0]
+        np.testing.assert_array_equal(ids[b].cpu().numpy(), ids_b.cpu().numpy())
+        np.testing.assert_array_equal(lab[b].cpu().numpy(), lab_b.cpu().numpy())
+    # the narrow case through the same interface
+    Y2 = torch.stack([port.mean_shift_iters(x, torch.tensor(0.3), 6) for x in Xs]).cuda()
+    bw2 = torch.tensor([0.3, 0.3]).cuda()
+    ids, lab, K, lab_host, _ = pms.nms_batched(Y2, X, bw2, also=[bw2])
+    assert max(K) <= pms.NMS_WIDTH
+    np.testing.assert_array_equal(lab_host, lab.cpu().numpy())
+    for b in range(2):
+        _, ids_b, lab_b = pms.nms(Y2[b], X[b], bw2[b])
+        np.testing.assert_array_equal(ids[b].cpu().numpy(), ids_b.cpu().numpy())
+        np.testing.assert_array_equal(lab[b].cpu().numpy(), lab_b.cpu().numpy())

@@ -33,16 +33,22 @@ def timed(fn, reps=4):
 
 
 print(f"data = {data}, B = {B}")
-print("| N | C | k | TMA exact ms | TC filter ms | speed-up | identical idx | identical dist | flagged rows | plan | mean / max list | ")
+print("| N | C | k | exact kernel ms | bracketed ms | speed-up | identical idx | identical dist | flagged rows | plan | mean / max list | ")
 print("|---|---|---|---:|---:|---:|---|---|---:|---|---|")
-for N, C, k in ((10000, 64, 80), (5000, 64, 10), (5000, 128, 10)):
-    x = features(N, C)
+for N, C, k, metric in ((10000, 64, 80, 0), (5000, 64, 10, 0), (5000, 128, 10, 0), (10000, 6, 80, 1), (5000, 3, 10, 0)):
+    if C <= 6:
+        x = torch.randn(B, N, C, device="cuda") * 0.3
+        if metric == 1:
+            x[..., 3:] = torch.nn.functional.normalize(x[..., 3:], dim=-1)
+    else:
+        x = features(N, C)
     ops.KNN_IMPL = "tma"
-    (i0, d0), t0 = timed(lambda: ops.knn_graph(x, k, 0, return_dist=True))
+    (i0, d0), t0 = timed(lambda: ops.knn_graph(x, k, metric, return_dist=True))
     ops.KNN_IMPL = "tc"
-    (i1, d1), t1 = timed(lambda: ops.knn_graph(x, k, 0, return_dist=True))
-    w = next(iter(ops._KNN_WS.values()))
+    (i1, d1), t1 = timed(lambda: ops.knn_graph(x, k, metric, return_dist=True))
+    plan = ops.knn_tc_plan(N, k, single_list=C <= 6)
+    w = [v for kk, v in ops._KNN_WS.items() if kk[2] == plan[2]][0]
     flagged = w["flags"][: B * N].float().mean().item()
     cnt = w["cnt"][: B * N].sum(1).float()
     print(f"| {N} | {C} | {k} | {t0:.2f} | {t1:.2f} | {t0 / t1:.2f}x | {torch.equal(i0, i1)} | {torch.equal(d0, d1)} | {flagged:.5f} | "
-          f"{ops.knn_tc_plan(N, k)} | {cnt.mean().item():.0f} / {cnt.max().item():.0f} |", flush=True)
+          f"{plan} | {cnt.mean().item():.0f} / {cnt.max().item():.0f} |", flush=True)
