@@ -244,17 +244,29 @@ def run_ours(args):
             loss_ready[i % 2].synchronize()
             losses.append(float(loss_host[i % 2]))
 
+    # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up: its start-up (NVML initialisation, enumeration of
+    # every GPU of the box) takes about a second on multi-GPU boxes and stalls kernel launches of all ranks while it lasts --
+    # started right before the timed loop it inflated the first timed steps 1.3 - 2.5x (profiles/r02_scaling.md); its rows
+    # are filtered to the timed region afterwards
+    sampler = ClockSampler(local)
+    if rank == 0 and not os.environ.get("PN_BENCH_NO_SAMPLER"):      # (diagnostic switch; the driver's runs keep the sampler)
+        sampler.start()
     for i in range(args.warmup):
+        flush.zero_()
         resident_step(i)
+        flush.zero_()
         e2e_step(i, last=True)
+    if world > 1:
+        # first use of the barrier (and whatever NCCL sets up lazily behind it) belongs to the warm-up, not to the first timed
+        # step; one more untimed step lets the ranks settle after it
+        barrier()
+        flush.zero_()
+        resident_step(args.warmup)
     # both timed loops start from the SAME model / optimizer state (the clustering, hence the number and kind of fitted
     # segments, drifts with every Adam step: without this the two loops would time different workloads)
     import copy
     snap = (copy.deepcopy(hp.model.state_dict()), copy.deepcopy(hp.opt.state_dict()))
     # ---- timed: resident inputs
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start(); time.sleep(0.3)
     dominant = "pn_ms_iter_fwd_tc" if FIT_STAGE else "pn_knn"
     cabi.TIMED[dominant] = []
     if FIT_STAGE:
