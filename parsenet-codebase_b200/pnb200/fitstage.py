@@ -48,7 +48,9 @@ class Plan:
 
 
 def make_plan(labels, cluster_np, primitives, N, match_fn):
-    """fit_one_shape_torch's segment rules (training mode) for every shape; host only"""
+    """fit_one_shape_torch's segment rules (training mode) for every shape; host only.  Per shape the point counts of every gt
+    segment / cluster and the majority primitive of every gt segment come from three bincounts (not from one boolean pass over
+    the points per matched pair), the per-point slot table from one look-up."""
     B = labels.shape[0]
     plan = Plan(B, N)
     n_half = (N + 1) // 2
@@ -56,29 +58,40 @@ def make_plan(labels, cluster_np, primitives, N, match_fn):
     for b in range(B):
         rows, cols, _, unique_pred = match_fn(labels[b], cluster_np[b])
         plan.matching.append((rows, cols))
+        lab = np.asarray(labels[b]).astype(np.int64)
+        cl = np.asarray(cluster_np[b]).astype(np.int64)
+        pr = np.asarray(primitives[b]).astype(np.int64)
+        L = int(max(lab.max(), cl.max(), np.max(cols), np.max(unique_pred))) + 1
+        n_lab = np.bincount(lab, minlength=L)
+        n_cl = np.bincount(cl, minlength=L)
+        P = int(pr.max()) + 1
+        # majority primitive id of every gt segment; argmax = smallest of the most frequent, like scipy.stats.mode
+        prim_of = np.bincount(lab * P + pr, minlength=L * P).reshape(L, P).argmax(1)
+        slot_of_label = np.full(L, -1, np.int32)
         spline_count = 0
         for index, i in enumerate(unique_pred):
-            gt_i = labels[b] == cols[i]
-            if gt_i.sum() == 0 or (cluster_np[b] == i).sum() == 0:
+            c = int(cols[i])
+            if n_lab[c] == 0 or n_cl[int(i)] == 0:
                 continue
-            prim = int(np.bincount(primitives[b][gt_i]).argmax())   # == scipy.stats.mode (smallest of the most frequent)
+            prim = int(prim_of[c])
             key = int(i)
             if prim in CLOSED_IDS + OPEN_IDS:
                 spline_count += 1
                 if spline_count > 4 or n_half < 20 or n_half < 100:
                     plan.keys[b][key] = (None, index)
                     continue
-                plan.splines.append((b, index, key, prim in CLOSED_IDS, np.nonzero(gt_i)[0]))
+                plan.splines.append((b, index, key, prim in CLOSED_IDS, np.nonzero(lab == c)[0]))
                 plan.keys[b][key] = ("closed" if prim in CLOSED_IDS else "open", index)
             elif prim in ANALYTIC_KIND:
                 if n_quarter < 20:
                     plan.keys[b][key] = (None, index)
                     continue
                 plan.kind[b, index] = ANALYTIC_KIND[prim]
-                plan.seg[b, gt_i] = index
+                slot_of_label[c] = index
                 plan.keys[b][key] = (KIND_NAME[ANALYTIC_KIND[prim]], index)
             else:
                 raise ValueError(f"unknown primitive id {prim} (the reference handles 0-9 except torus-like ids)")
+        plan.seg[b] = slot_of_label[lab]
     return plan
 
 

@@ -97,7 +97,15 @@ def weights_normalize(weights, bw):
 def match(target, pred_labels):
     """Hungarian matching of predicted clusters to gt segments on 1 - relaxed IoU (50x50)"""
     rids, cids = solve_dense(iou_cost_host(pred_labels, target))
-    return rids, cids, np.unique(target), np.unique(pred_labels)
+    return rids, cids, _unique_labels(target), _unique_labels(pred_labels)
+
+
+def _unique_labels(a):
+    """np.unique for a vector of small non-negative integer labels (sorted distinct values, same dtype) without the sort"""
+    a = np.asarray(a)
+    if a.dtype.kind not in "iu" or a.size == 0 or a.min() < 0:
+        return np.unique(a)
+    return np.nonzero(np.bincount(a.reshape(-1)))[0].astype(a.dtype)
 
 
 def rotation_matrix_a_to_b(A, B):

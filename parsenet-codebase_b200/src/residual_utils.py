@@ -83,7 +83,7 @@ class Evaluation:
             members = _ms.nearest_center_batched(embedding, shifted)
             # one blocking read-back: kept-centre counts, the cluster id of every point and the bandwidths together
             ids, labels_dev, _, cluster_np, (bw_host,) = _ms.nms_batched(shifted, embedding, bws, members, also=[bws])
-        n_clusters = [np.unique(cluster_np[b]).shape[0] for b in range(B)]
+        n_clusters = [int(np.count_nonzero(np.bincount(cluster_np[b]))) for b in range(B)]      # distinct cluster ids per shape
         if FIT_STAGE == "batched" and embedding.shape[2] == 128 and max(n_clusters) <= 49:
             return self._fitting_loss_batched(embedding, ms_state if sparse else None, shifted, ids, bws, points, normals,
                                               labels, primitives, prim_pred_dev, cluster_np, lamb)
@@ -144,15 +144,16 @@ class Evaluation:
         self.last_fit = out                                            # (fitstage.segment_distances(out, b) for debugging)
         with torch.no_grad():
             seg_types = segment_types_batched(prim_pred_dev, out["raw"])                 # (B, SLOTS) int64
+        # segment-IoU bookkeeping of every shape while the fit kernels still run (needs nothing from the device)
+        from src.segment_utils import siou_finish, siou_prepare
+        prepared = [siou_prepare(labels[b], cluster_np[b], primitives[b], out["plan"].matching[b]) for b in range(B)]
         # ---- ONE read-back for every statistic of the step
         host = torch.cat([out["stats"].reshape(-1), seg_types.reshape(-1).double()]).cpu().numpy()
         stats = host[:2 * B].reshape(B, 2)
         types = host[2 * B:].reshape(B, -1).astype(np.int64)
         res = []
         for b in range(B):
-            rows, cols = out["plan"].matching[b]
-            s_iou, p_iou, _, _ = SIOU_matched_segments(labels[b], cluster_np[b], None, primitives[b], None,
-                                                       prim_pred_seg=types[b, :K[b]], matching=(rows, cols))
+            s_iou, p_iou = siou_finish(prepared[b], types[b, :K[b]])
             loss_b = out["loss"][b] if out["has_terms"][b] else torch.zeros(1, device=embedding.device)
             res = res + [loss_b] + [None if np.isnan(v) else float(v) for v in stats[b]] + [s_iou, p_iou]
         parameters = fitstage.parameters_of_shape(out, B - 1)

@@ -64,6 +64,36 @@ def mean_IOU_primitive_segment(matching, predicted_labels, labels, pred_prim, gt
     return np.mean(ious), np.mean(prim_ious), pairs
 
 
+def siou_prepare(target, pred_labels, primitives, matching):
+    """the part of SIOU_matched_segments that needs no predicted segment types: the segment IoU of one shape and, per counted
+    pair, (gt type, predicted cluster id).  The training step computes this while the fit kernels still run and finishes with
+    siou_finish once the predicted types have been read back.  `primitives` is merged in place like SIOU_matched_segments does."""
+    lut = np.arange(max(int(primitives.max()) + 1, 10))
+    for src, dst in _MERGE:
+        lut[src] = dst
+    primitives[...] = lut[primitives]
+    pl, gl = np.asarray(pred_labels).astype(np.int64), np.asarray(target).astype(np.int64)
+    K = int(max(pl.max(), gl.max(), max(matching[0]), max(matching[1]))) + 1
+    conf = np.bincount(pl * K + gl, minlength=K * K).reshape(K, K)
+    n_p, n_g = conf.sum(1), conf.sum(0)
+    first = np.full(K, -1, dtype=np.int64)
+    first[gl[::-1]] = np.arange(gl.shape[0] - 1, -1, -1)
+    iou_b, todo = [], []
+    for r, c in zip(*matching):
+        if n_g[c] == 0 or n_p[r] == 0 or n_g[c] < 100:
+            continue
+        inter = conf[r, c]
+        iou_b.append(inter / (n_p[r] + n_g[c] - inter + 1e-8))
+        todo.append((primitives[first[c]], r))
+    return np.mean(iou_b), todo
+
+
+def siou_finish(prepared, prim_pred_seg):
+    """(segment IoU, primitive-type IoU) of one shape from siou_prepare's result and the (K,) predicted segment types"""
+    s_iou, todo = prepared
+    return np.mean([s_iou]), np.mean(np.mean([g_t == prim_pred_seg[r] for g_t, r in todo]))
+
+
 _MERGE = ((0, 9), (6, 9), (7, 9), (8, 2))          # closed splines -> 9, open splines -> 2 (reference :151-159)
 _MERGE_LUT = {}
 
