@@ -243,11 +243,12 @@ def run(evaluation, embedding, centers, K, bws, points, normals, labels, primiti
     dev = embedding.device
     stage = arena("fitstage", dev)
     stage.reset()
+    # (the similarities and membership weights need nothing from the plan: enqueued first, they run while the host plans)
+    raw = torch.bmm(embedding, centers.transpose(1, 2))                                   # (B,N,SLOTS)
+    Wn = normalized_weights(raw, bws, K, stage)
     plan = make_plan(labels, cluster_np, primitives, N, match_fn)
     n_half = (N + 1) // 2
     n_quarter = (n_half + 1) // 2
-    raw = torch.bmm(embedding, centers.transpose(1, 2))                                   # (B,N,SLOTS)
-    Wn = normalized_weights(raw, bws, K, stage)
     kind = stage.upload(plan.kind, dev)
     terms = []                       # (shape, value index, weight, is_spline)
     values = []
