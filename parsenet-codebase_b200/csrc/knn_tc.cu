@@ -256,6 +256,210 @@ collect_kernel(const __grid_constant__ CUtensorMap mC, const __grid_constant__ C
     if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------- tensor-core pass, C = 256
+// Both split parts of 128 query rows x 256 channels would fill all 512 TMEM columns and leave no room for the accumulator.
+// Here a CTA owns 64 query rows and stacks the two parts along the LANES ("virtual rows"): lanes 0-63 hold tf32_hi(x_i), lanes
+// 64-127 hold x_i - tf32_hi(x_i), 256 columns.  One MMA chain against the raw column tile (the tensor core truncates it to its
+// big part) and one against its small part accumulate into the same D: lanes 0-63 end up with hi.hi + hi.lo, lanes 64-127 with
+// lo.hi + lo.lo, and the product of row i is D[i] + D[64 + i] (all four terms, two MMAs per K step instead of three).  The two
+// halves live in different warps: warps 2, 3 (+4) hand theirs over through shared memory, warps 0, 1 (+4) add and run the
+// admission.  A stage holds 128 of the 256 channels of a 64-column tile (64 KB, as for C = 128): every tile consumes two.
+// grid (ceil(N / 64), B), 320 threads.
+constexpr int QR = 64;                                 // query rows per CTA of the C = 256 kernel
+
+template <bool ALL>
+__global__ void __launch_bounds__(NT, 1)
+collect256_kernel(const __grid_constant__ CUtensorMap mC, const __grid_constant__ CUtensorMap mCs, const float* __restrict__ X,
+                  int ld, int N, int ncols, const float* __restrict__ xx, const float* __restrict__ colc, int colp,
+                  const float* __restrict__ T, float c0, float c0a, int cap, unsigned* __restrict__ cval,
+                  unsigned short* __restrict__ ccol, int* __restrict__ cnt_out) {
+    constexpr int C = 256, NSL = 4, KPART = NSL * KSLAB, KSTAGE = 2 * KPART;          // one stage = 128 channels, X | Xs
+    constexpr uint32_t C_A = 0, C_S0 = 256, TMEM_COLS = 512;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ Bars bars;
+    __shared__ uint32_t tmem_base_s;
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* xchg = reinterpret_cast<float*>(smem + KNST * KSTAGE);                      // [64 rows][64 columns + 1]
+    constexpr int XP = KBN + 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, i0 = blockIdx.x * QR;
+    const int ntiles = (ncols + KBN - 1) / KBN;
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < KNST; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
+        for (int k = 0; k < 2; ++k) { mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); }
+        mbar_init(&bars.a_ready, EPI_THREADS);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+
+    if (warp < EPI_WARPS) {
+        const int q = warp & 3, h = warp >> 2;
+        const int L = q * 32 + lane;                   // TMEM lane
+        const int row = L & 63;                        // query row of the CTA
+        const bool lo_part = L >= 64;
+        const uint32_t la = (uint32_t)(q * 32) << 16;
+        const bool ok = (i0 + row) < N;
+        const float* xr = X + ((long long)b * N + i0 + row) * ld + 128 * h;
+#pragma unroll 1
+        for (int c0_ = 0; c0_ < 128; c0_ += 16) {
+            uint32_t va[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+                float4 v = ok ? *reinterpret_cast<const float4*>(xr + c0_ + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float big = tf32_hi(f[u]);
+                    va[e + u] = __float_as_uint(lo_part ? f[u] - big : big);
+                }
+            }
+            tmem_st16(tb + la + C_A + 128 * h + c0_, va);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.a_ready);
+        const long long grow = (long long)b * N + i0 + row;
+        const float xxi = ok ? xx[grow] : 0.f;
+        const float rowc = ALL ? xxi * (1.0f + c0) : ((ok ? T[grow] : -INFINITY) - xxi * (1.0f - c0a));
+        const float* cc = colc + (long long)b * colp;
+        const long long lbase = grow * cap;
+        const int half_cap = cap >> 1;
+        unsigned* kdst = cval + lbase + h * half_cap;
+        unsigned short* cdst = ccol + lbase + h * half_cap;
+        int mine = 0;
+        bool dead = !ok;
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int k = t & 1;
+            const int j0 = t * KBN + 32 * h;
+            mbar_wait_guarded(&bars.s_full[k], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[32];
+            tmem_ld32(tb + la + C_S0 + KBN * k + 32 * h, sv);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.s_empty[k]);
+            if (lo_part) {
+#pragma unroll
+                for (int u = 0; u < 32; ++u) xchg[row * XP + 32 * h + u] = __uint_as_float(sv[u]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (!lo_part) {
+#pragma unroll
+                for (int u = 0; u < 32; ++u) sv[u] = __float_as_uint(__uint_as_float(sv[u]) + xchg[row * XP + 32 * h + u]);
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (lo_part) continue;
+            float cj[32];
+#pragma unroll
+            for (int u = 0; u < 32; u += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(cc + j0 + u);
+                cj[u] = v.x; cj[u + 1] = v.y; cj[u + 2] = v.z; cj[u + 3] = v.w;
+            }
+            if (ALL) {
+                if (ok) {
+#pragma unroll
+                    for (int u = 0; u < 32; u += 4) {
+                        uint4 kk;
+                        kk.x = __float_as_uint(fmaf(-2.0f, __uint_as_float(sv[u]), cj[u]) + rowc);
+                        kk.y = __float_as_uint(fmaf(-2.0f, __uint_as_float(sv[u + 1]), cj[u + 1]) + rowc);
+                        kk.z = __float_as_uint(fmaf(-2.0f, __uint_as_float(sv[u + 2]), cj[u + 2]) + rowc);
+                        kk.w = __float_as_uint(fmaf(-2.0f, __uint_as_float(sv[u + 3]), cj[u + 3]) + rowc);
+                        if (j0 + u + 3 < 1024) *reinterpret_cast<uint4*>(cval + lbase + j0 + u) = kk;
+                    }
+                }
+            } else if (!dead) {
+                uint32_t mask = 0u;
+#pragma unroll
+                for (int u = 0; u < 32; ++u) mask |= (fmaf(-2.0f, __uint_as_float(sv[u]), cj[u]) <= rowc) ? (1u << u) : 0u;
+                if (mask) {
+                    const int add = __popc(mask);
+                    if (mine + add > half_cap) {
+                        mine = half_cap + 1;
+                        dead = true;
+                    } else {
+                        int slot = mine;
+#pragma unroll
+                        for (int u = 0; u < 32; ++u) {
+                            const uint32_t bit = (mask >> u) & 1u;
+                            asm volatile(
+                                "{\n"
+                                ".reg .pred p;\n"
+                                "setp.ne.u32 p, %0, 0;\n"
+                                "@p st.global.u32 [%1], %2;\n"
+                                "@p st.global.u16 [%3], %4;\n"
+                                "}\n" ::"r"(bit), "l"(kdst + slot), "r"(sv[u]), "l"(cdst + slot), "h"((unsigned short)(j0 + u))
+                                : "memory");
+                            slot += (int)bit;
+                        }
+                        mine += add;
+                    }
+                }
+            }
+        }
+        if (!ALL && ok && !lo_part) cnt_out[2 * grow + h] = mine;
+        tc_fence_before();
+    } else if (warp == TMA_WARP) {
+        if (elect_one()) {
+            tma_prefetch_desc(&mC); tma_prefetch_desc(&mCs);
+#pragma unroll 1
+            for (int u = 0; u < 2 * ntiles; ++u) {       // stage use u = (tile, channel half)
+                const int s = u % KNST, t = u >> 1, kh = u & 1;
+                mbar_wait_guarded(&bars.x_empty[s], ((u / KNST) & 1) ^ 1);
+                unsigned char* st = smem + s * KSTAGE;
+                mbar_arrive_expect_tx(&bars.x_full[s], KSTAGE);
+#pragma unroll
+                for (int sl = 0; sl < NSL; ++sl) {
+                    tma_load_3d(st + sl * KSLAB, &mC, &bars.x_full[s], 128 * kh + 32 * sl, t * KBN, b);
+                    tma_load_3d(st + KPART + sl * KSLAB, &mCs, &bars.x_full[s], 128 * kh + 32 * sl, t * KBN, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const bool leader = elect_one();
+        const uint32_t idesc_s = make_idesc(2, BM, KBN, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+        mbar_wait_guarded(&bars.a_ready, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int u = 0; u < 2 * ntiles; ++u) {
+            const int s = u % KNST, t = u >> 1, kh = u & 1, k = t & 1;
+            mbar_wait_guarded(&bars.x_full[s], (u / KNST) & 1);
+            if (kh == 0) mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t st = sbase + s * KSTAGE;
+            const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
+            const uint64_t ds0 = make_smem_desc(st + KPART, 16, SBO128, SW128);
+            const uint32_t d_s = tb + C_S0 + KBN * k;
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) {
+                    const uint32_t off = (uint32_t)((ks >> 2) * KSLAB + (ks & 3) * 32);
+                    const uint64_t db = db0 + (uint64_t)(off >> 4);
+                    const uint64_t ds = ds0 + (uint64_t)(off >> 4);
+                    const uint32_t acol = tb + C_A + 128 * kh + ks * 8;
+                    mma_tf32_ts(d_s, acol, ds, idesc_s, (kh == 0 && ks == 0) ? 0u : 1u);
+                    mma_tf32_ts(d_s, acol, db, idesc_s, 1);
+                }
+                if (kh == 1) mma_commit(&bars.s_full[k]);
+                mma_commit(&bars.x_empty[s]);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+    (void)C;
+}
+
 // ---------------------------------------------------------------------------------------------- final: select, refine, sort
 // one warp per row.  Lists as written by collect_kernel<C, false>: cnt[2 row + h] entries from slot h * CAP / 2.
 template <int NW, typename IdxT>
@@ -431,6 +635,28 @@ static int run_collect(const CUtensorMap* ms, const CUtensorMap* mf, const float
     return PN_OK;
 }
 
+static int run_collect256(const CUtensorMap* ms, const CUtensorMap* mf, const float* x, int ld, int B, int N, int m, const float* xx,
+                          const float* an, int Np, const float* ap, int mp, float* T, int b_sample, float c0, float c0a, int cap,
+                          unsigned* ws_val, unsigned short* ws_col, int* ws_cnt, cudaStream_t st) {
+    const size_t sm = (size_t)KNST * 2 * 4 * KSLAB + (size_t)QR * (KBN + 1) * sizeof(float) + 1024;
+    auto k_all = collect256_kernel<true>;
+    auto k_thr = collect256_kernel<false>;
+    PN_CUDA(cudaFuncSetAttribute(k_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    PN_CUDA(cudaFuncSetAttribute(k_thr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const dim3 grid(cdiv(N, QR), B);
+    const long long rows = (long long)B * N;
+    const float* noT = nullptr;
+    k_all<<<grid, NT, sm, st>>>(ms[0], ms[1], x, ld, N, m, xx, ap, mp, noT, c0, c0a, cap, ws_val, ws_col, ws_cnt);
+    PN_COUNT_LAUNCH();
+    if (cap == 1024) kthsel::kth_smallest_rows_kernel<1><<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(ws_val, m, b_sample, rows, T);
+    else kthsel::kth_smallest_rows_kernel<2><<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(ws_val, m, b_sample, rows, T);
+    PN_COUNT_LAUNCH();
+    k_thr<<<grid, NT, sm, st>>>(mf[0], mf[1], x, ld, N, N, xx, an, Np, (const float*)T, c0, c0a, cap, ws_val, ws_col, ws_cnt);
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("knn_tc collect256 kernels");
+    return PN_OK;
+}
+
 template <typename IdxT>
 static int run_final(int cap, const unsigned* ws_val, const unsigned short* ws_col, const int* ws_cnt, const float* T,
                      const float* xx, const float* x, int ld, int C, int N, int k, float c0, long long rows, void* idx, float* dist,
@@ -452,9 +678,9 @@ static int run_final(int cap, const unsigned* ws_val, const unsigned short* ws_c
 
 using namespace pn;
 
-// 1 if pn_knn_tc takes this problem: feature-space metric, C = 64 or 128, TMA-compatible addressing, 16-bit column indices
+// 1 if pn_knn_tc takes this problem: feature-space metric, C = 64, 128 or 256, TMA-compatible addressing, 16-bit column indices
 extern "C" int pn_knn_tc_supported(const float* x, int N, int C, int ld, int k, int metric) {
-    if (metric != 0 || (C != 64 && C != 128) || ld % 4 || (reinterpret_cast<uintptr_t>(x) & 15u)) return 0;
+    if (metric != 0 || (C != 64 && C != 128 && C != 256) || ld % 4 || (reinterpret_cast<uintptr_t>(x) & 15u)) return 0;
     if (N >= 65536 || N < 2048 || k < 1 || k > 96) return 0;
     return 1;
 }
@@ -496,8 +722,10 @@ extern "C" int pn_knn_tc(const float* x, int B, int N, int C, int ld, int k, int
     }
     int rc = (C == 64) ? knntc::run_collect<64>(ms, mf, x, ld, B, N, m, ws_norms, an, Np, ap, mp, ws_T, b_sample, c0, c0a, cap,
                                                 ws_val, ws_col, ws_cnt, st)
-                       : knntc::run_collect<128>(ms, mf, x, ld, B, N, m, ws_norms, an, Np, ap, mp, ws_T, b_sample, c0, c0a, cap,
-                                                 ws_val, ws_col, ws_cnt, st);
+           : (C == 128) ? knntc::run_collect<128>(ms, mf, x, ld, B, N, m, ws_norms, an, Np, ap, mp, ws_T, b_sample, c0, c0a, cap,
+                                                  ws_val, ws_col, ws_cnt, st)
+                        : knntc::run_collect256(ms, mf, x, ld, B, N, m, ws_norms, an, Np, ap, mp, ws_T, b_sample, c0, c0a, cap,
+                                                ws_val, ws_col, ws_cnt, st);
     if (rc != PN_OK) return rc;
     const long long rows = (long long)B * N;
     return idx_is_i64 ? knntc::run_final<long long>(cap, ws_val, ws_col, ws_cnt, ws_T, ws_norms, x, ld, C, N, k, c0, rows, idx_out,

@@ -198,7 +198,9 @@ def _tc_inputs(kind, B, N, C, seed):
 
 
 @pytest.mark.parametrize("kind,B,N,C,k", [("randn", 2, 10000, 64, 80), ("feat", 2, 10000, 64, 80), ("feat", 3, 5000, 128, 10),
-                                          ("offset", 2, 4099, 64, 20), ("dups", 2, 4096, 128, 10), ("feat", 1, 2048, 64, 96)])
+                                          ("offset", 2, 4099, 64, 20), ("dups", 2, 4096, 128, 10), ("feat", 1, 2048, 64, 96),
+                                          ("feat", 3, 5000, 256, 10), ("randn", 2, 4099, 256, 80), ("dups", 1, 4096, 256, 10),
+                                          ("offset", 1, 3000, 256, 20)])
 def test_tensor_core_filtered_knn_equals_the_exact_kernel(kind, B, N, C, k):
     """csrc/knn_tc.cu (tcgen05 filter with a proven error interval + exact fp32 refinement of the survivors + flagged fall-back)
     must give the bit-identical graph AND ranked values of the exact kernels, on ordinary features, on features with a large

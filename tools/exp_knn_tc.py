@@ -35,7 +35,7 @@ def timed(fn, reps=4):
 print(f"data = {data}, B = {B}")
 print("| N | C | k | exact kernel ms | bracketed ms | speed-up | identical idx | identical dist | flagged rows | plan | mean / max list | ")
 print("|---|---|---|---:|---:|---:|---|---|---:|---|---|")
-for N, C, k, metric in ((10000, 64, 80, 0), (5000, 64, 10, 0), (5000, 128, 10, 0), (10000, 6, 80, 1), (5000, 3, 10, 0)):
+for N, C, k, metric in ((10000, 64, 80, 0), (5000, 64, 10, 0), (5000, 128, 10, 0), (5000, 256, 10, 0), (10000, 6, 80, 1), (5000, 3, 10, 0)):
     if C <= 6:
         x = torch.randn(B, N, C, device="cuda") * 0.3
         if metric == 1:
