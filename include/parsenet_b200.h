@@ -154,7 +154,7 @@ int pn_ms_kth_dist(const float* X, const int* rows, int B, int S, long long shap
 /* replaces: MeanShift.nms: src/mean_shift.py:146-149 (mode 0), :163-171 (mode 1), :177-178 (mode 2) */
 int pn_ms_argsel(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream);
 
-/* EXPERIMENTAL (opt-in PN_MS_SPARSE_BWD=1, not yet run on a GPU): backward of one mean-shift iteration restricted to a compact
+/* Default in Evaluation.fitting_loss since round 2 (PN_MS_SPARSE_BWD=0: dense backward): backward of one mean-shift iteration restricted to a compact
    set of R = 64 rows per shape.  In Evaluation.fitting_loss the loss sees the shifted points only through the <= 49 cluster
    centres (src/mean_shift.py:41 `center = new_X[indices]`, src/residual_utils.py:118), row i of Y_t depends on row i of
    Y_{t-1} alone, so every other row of the autograd pass of src/mean_shift.py:58-77 contributes exactly zero.
@@ -185,7 +185,7 @@ int pn_ms_argsel_tc(int mode, const float* A, long long a_stride, int Ma, const 
 int pn_ms_bwd_prep_tc(const float* gout, const float* Ynew, const float* den, const float* unorm, int B, int N, int d, float* ws_Gn, float* ws_gd, void* stream);
 int pn_ms_bwd_cols_tc(const float* Yprev, const float* X, int B, int N, int d, const float* cinv, const float* ws_Gn, const float* ws_gd, float* gX, int accumulate_gX, void* stream);
 
-/* ---- meanshift_tma.cu (EXPERIMENTAL, opt-in PN_MS_TMA=1: streamed operand tiles fetched by TMA; not yet run on a GPU) ---- */
+/* ---- meanshift_tma.cu (default since round 2; PN_MS_TMA=0 selects the loader-warp kernels: streamed operand tiles fetched by TMA) ---- */
 /* once per MeanShift.mean_shift_ call (X is constant over the iterations, src/mean_shift.py:58-77):
    Xs = X - tf32_hi(X) [B][N][128], Xt / Xst = transposes [B][128][Np], Np = N rounded up to a multiple of 32 */
 int pn_ms_prepare_operands(const float* X, int B, int N, int d, int Np, float* Xs, float* Xt, float* Xst, void* stream);

@@ -56,7 +56,7 @@ SIGNATURES = {
     "pn_ms_rows_bwd": [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "pn_ms_bwd_prep_tc": [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p],
     "pn_ms_bwd_cols_tc": [c_p, c_p, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p],
-    # meanshift_tma.cu (experimental, PN_MS_TMA=1)
+    # meanshift_tma.cu (default path; PN_MS_TMA=0: loader-warp kernels)
     "pn_ms_prepare_operands": [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
     "pn_ms_iter_fwd_tma": [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "pn_ms_iter_bwd_tma": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_p],

@@ -74,7 +74,7 @@ class Evaluation:
         prim_pred_dev = torch.max(primitives_log_prob, 1)[1]                          # (B,N), stays on the device
         with torch.no_grad():
             bws = torch.clamp(_ms.compute_bandwidth_batched(embedding, 10000, quantile), min=_ms.BW_FLOOR)
-        sparse = _ms.SPARSE_BWD and embedding.shape[2] == 128      # experimental: backward over the centre rows only
+        sparse = _ms.SPARSE_BWD and embedding.shape[2] == 128      # backward over the centre rows only (exact; PN_MS_SPARSE_BWD=0: dense)
         if sparse:
             shifted, ms_state = _ms.mean_shift_iters_keep(embedding, bws, iterations)
         else:
