@@ -181,6 +181,10 @@ int pn_ms_kth_dist_tc_flagged(const float* X, const int* rows, int B, int S, lon
 int pn_ms_kth_dist_tma(const float* X, const float* Xs, int B, int N, int d, int K, int stride, int b_sample, unsigned* ws_key, unsigned short* ws_col, int* ws_cnt, float* ws_hi, int cap, int* flags, float* kth, void* stream);
 /* replaces: MeanShift.nms arg-selects: src/mean_shift.py:146-149 (mode 0), :163-171 (mode 1) — same contract as pn_ms_argsel for modes 0 and 1; meanshift_tc_argsel.cu */
 int pn_ms_argsel_tc(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, int* out, void* stream);
+/* the same arg-selects with the column tiles fetched by TMA (64-column tiles, N = 64 MMAs); Bm contiguous [B][Nb][128], 16-byte
+   aligned; ws_Bms [B][Nb][128] receives its small split part.  Identical picks; meanshift_tma.cu */
+int pn_ms_argsel_tma_supported(const float* Bm, long long b_stride, int Nb, int d);
+int pn_ms_argsel_tma(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb, int B, int d, const float* cnt, const float* thr, float* ws_Bms, int* out, void* stream);
 /* the two halves of pn_ms_iter_bwd_tc on their own: prep pass (Gn, gd) and the cols kernel (gX) */
 int pn_ms_bwd_prep_tc(const float* gout, const float* Ynew, const float* den, const float* unorm, int B, int N, int d, float* ws_Gn, float* ws_gd, void* stream);
 int pn_ms_bwd_cols_tc(const float* Yprev, const float* X, int B, int N, int d, const float* cinv, const float* ws_Gn, const float* ws_gd, float* gX, int accumulate_gX, void* stream);

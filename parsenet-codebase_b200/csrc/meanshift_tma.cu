@@ -929,6 +929,186 @@ ms_kth_collect_kernel(const __grid_constant__ CUtensorMap mC, const __grid_const
     if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------- nms arg-selects, TMA-fed
+// MeanShift.nms (reference src/mean_shift.py:146-149, :163-171): per row of A the column of Bm with the smallest distance
+// (mode 0), or with the largest occupancy count among the columns closer than the bandwidth (mode 1); first occurrence on ties.
+// Same tensor-core products and the same epilogue rule as ms_argsel_tc_kernel (meanshift_tc_argsel.cu), with the tile pipeline
+// of ms_kth_collect_kernel: 64-column tiles fetched by TMA from Bm and its small split part (written by split_small_kernel),
+// N = 64 MMAs -- an N = 32 MMA occupies the tensor pipe as long as an N = 64 one.
+__global__ void split_small_kernel(const float* __restrict__ x, long long n, float* __restrict__ xs) {
+    const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(x + e);
+        *reinterpret_cast<float4*>(xs + e) = make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+    } else {
+        for (long long i = e; i < n; ++i) xs[i] = x[i] - tf32_hi(x[i]);
+    }
+}
+
+// grid (ceil(Ma / 128), B), 320 threads
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1)
+ms_argsel_tma_kernel(const __grid_constant__ CUtensorMap mC, const __grid_constant__ CUtensorMap mCs, const float* __restrict__ A,
+                     long long a_stride, int Ma, int Nb, const float* __restrict__ cnt, const float* __restrict__ thr,
+                     int* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ KBars bars;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float part_v[BM];
+    __shared__ int part_j[BM];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.y, i0 = blockIdx.x * BM;
+    const float* Ab = A + (long long)b * a_stride;
+    const int ntiles = (Nb + KBN - 1) / KBN;
+
+    if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, TMEM_COLS);
+    if (tid == 0) {
+        for (int s = 0; s < KNST; ++s) { mbar_init(&bars.x_full[s], 1); mbar_init(&bars.x_empty[s], 1); }
+        for (int k = 0; k < 2; ++k) { mbar_init(&bars.s_full[k], 1); mbar_init(&bars.s_empty[k], EPI_THREADS); }
+        mbar_init(&bars.a_ready, EPI_THREADS);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+
+    if (warp < EPI_WARPS) {
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t la = (uint32_t)(q * 32) << 16;
+        const bool ok = (i0 + row) < Ma;
+        const float* xr = Ab + (long long)(ok ? i0 + row : 0) * D + 64 * h;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t vb[16], vs[16];
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+                float4 v = ok ? *reinterpret_cast<const float4*>(xr + c0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float big = tf32_hi(f[u]);
+                    vb[e + u] = __float_as_uint(big);
+                    vs[e + u] = __float_as_uint(f[u] - big);
+                }
+            }
+            tmem_st16(tb + la + C_YB + 64 * h + c0, vb);
+            tmem_st16(tb + la + C_YS + 64 * h + c0, vs);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.a_ready);
+        const float* cb = (MODE == 1) ? cnt + (long long)b * Nb : nullptr;
+        const float th = (MODE == 1) ? thr[b] : 0.f;
+        const bool vec_cnt = (MODE == 1) && ((reinterpret_cast<uintptr_t>(cb) & 15u) == 0);
+        float best = (MODE == 0) ? INFINITY : -INFINITY;
+        int bj = 0x7fffffff;
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int k = t & 1;
+            const int j0 = t * KBN + 32 * h;
+            float cv[32];
+            if (MODE == 1) {                       // occupancy counts of this thread's 32 columns (the same for every row)
+                if (vec_cnt && j0 + 32 <= Nb) {
+#pragma unroll
+                    for (int u = 0; u < 32; u += 4) {
+                        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cb + j0 + u));
+                        cv[u] = c4.x; cv[u + 1] = c4.y; cv[u + 2] = c4.z; cv[u + 3] = c4.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) cv[u] = (j0 + u < Nb) ? __ldg(cb + j0 + u) : 0.f;
+                }
+            }
+            mbar_wait_guarded(&bars.s_full[k], (t >> 1) & 1);
+            tc_fence_after();
+            uint32_t sv[32];
+            tmem_ld32(tb + la + C_KS0 + 64 * k + 32 * h, sv);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.s_empty[k]);
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                const int jj = j0 + u;
+                if (jj < Nb) {
+                    const float dist = 2.0f - 2.0f * __uint_as_float(sv[u]);
+                    float v;
+                    bool better;
+                    if (MODE == 0) { v = dist; better = v < best; }
+                    else { v = (dist < th) ? cv[u] : 0.f; better = v > best; }
+                    best = better ? v : best;      // jj increases: the first occurrence of the extreme is kept
+                    bj = better ? jj : bj;
+                }
+            }
+        }
+        // merge the two column halves of every row: within a tile the half h = 0 holds the lower columns, but over the tiles
+        // the halves interleave -- ties go to the lower index
+        if (h == 1) { part_v[row] = best; part_j[row] = bj; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (h == 0 && ok) {
+            const float ov = part_v[row];
+            const int oj = part_j[row];
+            const bool take = (MODE == 0) ? (ov < best || (ov == best && oj < bj)) : (ov > best || (ov == best && oj < bj));
+            out[(long long)b * Ma + i0 + row] = take ? oj : bj;
+        }
+        tc_fence_before();
+    } else if (warp == TMA_WARP) {
+        if (elect_one()) {
+            tma_prefetch_desc(&mC); tma_prefetch_desc(&mCs);
+#pragma unroll 1
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % KNST;
+                mbar_wait_guarded(&bars.x_empty[s], ((t / KNST) & 1) ^ 1);
+                unsigned char* st = smem + s * KSTAGE;
+                mbar_arrive_expect_tx(&bars.x_full[s], KSTAGE);
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    tma_load_3d(st + sl * KSLAB, &mC, &bars.x_full[s], 32 * sl, t * KBN, b);
+                    tma_load_3d(st + KPART + sl * KSLAB, &mCs, &bars.x_full[s], 32 * sl, t * KBN, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const bool leader = elect_one();
+        const uint32_t idesc_s = make_idesc(2, BM, KBN, 0, 0);
+        const uint32_t sbase = smem_u32(smem);
+        mbar_wait_guarded(&bars.a_ready, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % KNST, k = t & 1;
+            mbar_wait_guarded(&bars.x_full[s], (t / KNST) & 1);
+            mbar_wait_guarded(&bars.s_empty[k], ((t >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t st = sbase + s * KSTAGE;
+            const uint64_t db0 = make_smem_desc(st, 16, SBO128, SW128);
+            const uint64_t ds0 = make_smem_desc(st + KPART, 16, SBO128, SW128);
+            const uint32_t d_s = tb + C_KS0 + 64 * k;
+            if (leader) {
+#pragma unroll
+                for (int ks = 0; ks < D / 8; ++ks) {
+                    const uint32_t off = (uint32_t)((ks >> 2) * KSLAB + (ks & 3) * 32);
+                    const uint64_t db = db0 + (uint64_t)(off >> 4);
+                    const uint64_t ds = ds0 + (uint64_t)(off >> 4);
+                    mma_tf32_ts(d_s, tb + C_YS + ks * 8, db, idesc_s, ks > 0 ? 1u : 0u);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, ds, idesc_s, 1);
+                    mma_tf32_ts(d_s, tb + C_YB + ks * 8, db, idesc_s, 1);
+                }
+                mma_commit(&bars.s_full[k]);
+                mma_commit(&bars.x_empty[s]);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tb, TMEM_COLS);
+}
+
 // one warp per row: K-th smallest of the row's keys by a bitwise radix select on bit-transposed registers (kth_select.cuh).
 // EXACT = false: the row holds nfix keys in slots [0, nfix) (the sample pass), out = that key as a float.
 // EXACT = true : the row holds cnt[2 row] keys from slot 0 and cnt[2 row + 1] keys from slot CAP / 2 (the two column halves
@@ -1196,6 +1376,47 @@ extern "C" int pn_ms_kth_dist_tma(const float* X, const float* Xs, int B, int N,
                                                                                   flags);
     PN_COUNT_LAUNCH();
     PN_LAUNCH_CHECK("ms_kth bracketed kernels");
+    return PN_OK;
+}
+
+// same contract as pn_ms_argsel_tc (modes 0 and 1 of MeanShift.nms, reference src/mean_shift.py:146-149, :163-171) with the
+// column tiles fetched by TMA; Bm must be contiguous [B][Nb][128] and 16-byte aligned, ws_Bms [B][Nb][128] receives its small
+// split part (one extra launch).  Identical picks (same tensor-core products, same first-occurrence rule).
+extern "C" int pn_ms_argsel_tma_supported(const float* Bm, long long b_stride, int Nb, int d) {
+    return (d == mstma::D && Nb >= mstma::KBN && b_stride == (long long)Nb * d && (reinterpret_cast<uintptr_t>(Bm) & 15u) == 0) ? 1 : 0;
+}
+
+extern "C" int pn_ms_argsel_tma(int mode, const float* A, long long a_stride, int Ma, const float* Bm, long long b_stride, int Nb,
+                                int B, int d, const float* cnt, const float* thr, float* ws_Bms, int* out, void* stream) {
+    PN_REQUIRE(A && Bm && ws_Bms && out, "pn_ms_argsel_tma: null pointer");
+    PN_REQUIRE((mode == 0) || (mode == 1 && cnt && thr), "pn_ms_argsel_tma: modes 0 and 1 only (mode 1 needs cnt, thr)");
+    PN_REQUIRE(Ma > 0 && B > 0 && pn_ms_argsel_tma_supported(Bm, b_stride, Nb, d), "pn_ms_argsel_tma: unsupported problem (Nb=%d d=%d)",
+               Nb, d);
+    PN_REQUIRE((reinterpret_cast<uintptr_t>(ws_Bms) & 15u) == 0, "pn_ms_argsel_tma: ws_Bms must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)B * Nb * d;
+    mstma::split_small_kernel<<<(unsigned)cdiv(cdiv(n, 4), 256), 256, 0, st>>>(Bm, n, ws_Bms);
+    PN_COUNT_LAUNCH();
+    const uint64_t dd = (uint64_t)mstma::D;
+    CUtensorMap m[2];
+    if (!(mstma::make_map(&m[0], Bm, dd, (uint64_t)Nb, (uint64_t)B, dd, (uint64_t)Nb * dd, 32, mstma::KBN) &&
+          mstma::make_map(&m[1], ws_Bms, dd, (uint64_t)Nb, (uint64_t)B, dd, (uint64_t)Nb * dd, 32, mstma::KBN))) {
+        set_error("pn_ms_argsel_tma: cuTensorMapEncodeTiled failed or is unavailable");
+        return PN_ERR_CUDA;
+    }
+    const size_t sm = mstma::KNST * mstma::KSTAGE + 1024;
+    const dim3 grid(cdiv(Ma, mstma::BM), B);
+    if (mode == 0) {
+        auto kern = mstma::ms_argsel_tma_kernel<0>;
+        PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        PN_CUDA(launch(kern, grid, 1, sm, st, m[0], m[1], A, a_stride, Ma, Nb, cnt, thr, out));
+    } else {
+        auto kern = mstma::ms_argsel_tma_kernel<1>;
+        PN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        PN_CUDA(launch(kern, grid, 1, sm, st, m[0], m[1], A, a_stride, Ma, Nb, cnt, thr, out));
+    }
+    PN_COUNT_LAUNCH();
+    PN_LAUNCH_CHECK("ms_argsel_tma_kernel");
     return PN_OK;
 }
 

@@ -74,6 +74,7 @@ SIGNATURES = {
     "pn_ms_kth_dist_tma": [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p],
     "pn_ms_argsel": [c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
     "pn_ms_argsel_tc": [c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p],
+    "pn_ms_argsel_tma": [c_i, c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     # chamfer.cu / spline.cu / fit.cu / primitives.cu
     "pn_chamfer_nn_fwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p],
     "pn_chamfer_nn_bwd": [c_p, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
@@ -105,6 +106,7 @@ _SPECIAL = {
     "pn_abi_version": (c_i, []),
     "pn_knn_tma_supported": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i]),
     "pn_knn_tc_supported": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i]),
+    "pn_ms_argsel_tma_supported": (c_i, [c_p, c_ll, c_i, c_i]),
     "pn_knn_lowdim_supported": (c_i, [c_i, c_i, c_i, c_i]),
     "pn_linear_fwd_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_p, c_ll, c_i, c_i, c_i, c_i, c_i]),
     "pn_linear_bwd_weight_tc_supported": (c_i, [c_p, c_ll, c_p, c_ll, c_i, c_i, c_i]),

@@ -37,6 +37,21 @@ def _check_width(d):
 
 def _argsel_entry(mode, d):
     return "pn_ms_argsel_tc" if (ARGSEL_IMPL == "tc" and mode in (0, 1) and d == 128) else "pn_ms_argsel"
+
+
+def _launch_argsel(mode, A, a_stride, Ma, Bm, b_stride, Nb, B, d, cnt, thr, out):
+    """nms arg-select (modes 0 / 1 / 2): the TMA-fed tcgen05 kernel when it applies (csrc/meanshift_tma.cu: 64-column tiles;
+    needs the small split part of Bm, one extra launch), else the loader-warp tcgen05 kernel, else the FP32-pipe kernel.
+    Same picks from all three up to tensor-core near-ties."""
+    from .cabi import lib
+    if (USE_TMA and ARGSEL_IMPL == "tc" and mode in (0, 1)
+            and lib.pn_ms_argsel_tma_supported(Bm.data_ptr(), b_stride, Nb, d)):
+        ws = torch.empty((B * Nb * d,), dtype=torch.float32, device=Bm.device)
+        call("pn_ms_argsel_tma", mode, _ptr(A), a_stride, Ma, _ptr(Bm), b_stride, Nb, B, d, _ptr(cnt), _ptr(thr), _ptr(ws),
+             _ptr(out), _stream())
+        return
+    call(_argsel_entry(mode, d), mode, _ptr(A), a_stride, Ma, _ptr(Bm), b_stride, Nb, B, d, _ptr(cnt), _ptr(thr), _ptr(out),
+         _stream())
 SQRT_FLOOR = 1e-6     # guard_sqrt(top_k, 1e-6), mean_shift.py:135
 
 
@@ -319,7 +334,7 @@ def nearest_center_batched(X_bnd, Y_bnd):
     B, N, d = X_bnd.shape
     X, Y = X_bnd.detach().contiguous(), Y_bnd.detach().contiguous()
     out = torch.empty((B, N), dtype=torch.int32, device=X.device)
-    call(_argsel_entry(0, d), 0, _ptr(X), N * d, N, _ptr(Y), N * d, N, B, d, None, None, _ptr(out), _stream())
+    _launch_argsel(0, X, N * d, N, Y, N * d, N, B, d, None, None, out)
     return out
 
 
@@ -376,8 +391,7 @@ def nms_batched(Y_bnd, X_bnd, bw_b, member=None, also=None):
     counts.scatter_add_(1, member.long(), torch.ones((B, N), dtype=torch.float32, device=dev))
     thr = bw_b.detach().to(torch.float32).reshape(B).contiguous()
     nbr = torch.empty((B, N), dtype=torch.int32, device=dev)
-    call(_argsel_entry(1, d), 1, _ptr(Y), N * d, N, _ptr(Y), N * d, N, B, d, _ptr(counts), _ptr(thr), _ptr(nbr),
-         _stream())
+    _launch_argsel(1, Y, N * d, N, Y, N * d, N, B, d, counts, thr, nbr)
     # neighbours chosen by OCCUPIED centres are kept; unoccupied rows scatter into a dump column
     tgt = torch.where(counts > 0, nbr.long(), torch.full_like(nbr, N, dtype=torch.int64))
     mark = torch.zeros((B, N + 1), dtype=torch.bool, device=dev)

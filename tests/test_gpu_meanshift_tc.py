@@ -268,3 +268,26 @@ def test_tma_fed_kernels_match_default_tc_kernels(B, N, cg, monkeypatch):
         res.append((gY, gX))
     for a, b in zip(*res):
         assert ((a - b).abs().max() / a.abs().max()).item() < 1e-6
+
+
+@pytest.mark.parametrize("B,Ma,Nb", [(1, 50, 64), (2, 300, 1000), (3, 2113, 2113), (16, 10000, 10000)])
+def test_tma_fed_argsel_equals_the_loader_warp_kernel(B, Ma, Nb):
+    """nms arg-selects with TMA-fed 64-column tiles (pn_ms_argsel_tma) vs the loader-warp tcgen05 kernel: the same split-TF32
+    products and the same first-occurrence rule, so the picks are identical for both modes"""
+    from pnb200.cabi import call
+    g = torch.Generator().manual_seed(Ma + Nb)
+    Bm = torch.nn.functional.normalize(torch.randn(B, Nb, 128, generator=g), dim=2).cuda().contiguous()
+    A = torch.nn.functional.normalize(Bm[:, torch.randint(0, Nb, (Ma,), generator=g)] +
+                                      0.3 * torch.randn(B, Ma, 128, generator=g).cuda(), dim=2).contiguous()
+    cnt = torch.randint(0, 5, (B, Nb), generator=g).float().cuda()
+    thr = torch.tensor([0.9, 1.2, 0.6][:B] + [0.8] * max(0, B - 3)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    ws = torch.empty(B * Nb * 128, device="cuda")
+    for mode in (0, 1):
+        o0 = torch.full((B, Ma), -1, dtype=torch.int32, device="cuda")
+        o1 = torch.full((B, Ma), -1, dtype=torch.int32, device="cuda")
+        call("pn_ms_argsel_tc", mode, A.data_ptr(), Ma * 128, Ma, Bm.data_ptr(), Nb * 128, Nb, B, 128, cnt.data_ptr(), thr.data_ptr(),
+             o0.data_ptr(), st)
+        call("pn_ms_argsel_tma", mode, A.data_ptr(), Ma * 128, Ma, Bm.data_ptr(), Nb * 128, Nb, B, 128, cnt.data_ptr(),
+             thr.data_ptr(), ws.data_ptr(), o1.data_ptr(), st)
+        assert torch.equal(o0, o1), (mode, (o0 != o1).sum().item())
