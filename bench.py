@@ -44,16 +44,42 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled every 100 ms while the timed loops run.  In-process NVML (pynvml:
+    initialised once, before the warm-up; a query is two cheap driver calls) -- the `nvidia-smi -lms 100` child process used
+    before stalled kernel launches for 0.5 - 1 s some seconds after its start (NVML initialisation and enumeration of every GPU
+    of the box in a second process), which inflated the first timed steps on some boxes (profiles/r02_scaling.md).  Falls back
+    to nvidia-smi when pynvml is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows = []
+        self.rows = []          # (time, sm_mhz, sm_max_mhz, set of reasons)
         self.proc = None
         self.idx = gpu_index
+        self.nvml = None
+        self.stop_flag = False
+        self.t = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES re-numbers the devices torch sees: resolve the physical device through its UUID-free PCI id
+            try:
+                bus = torch.cuda.get_device_properties(self.idx).pci_bus_id
+                dom = torch.cuda.get_device_properties(self.idx).pci_domain_id
+                dev = torch.cuda.get_device_properties(self.idx).pci_device_id
+                h = pynvml.nvmlDeviceGetHandleByPciBusId("%08x:%02x:%02x.0" % (dom, bus, dev))
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nvml = (pynvml, h)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -63,28 +89,50 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                 ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                 ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
+        bits = [(n, getattr(pynvml, a, None) or getattr(pynvml, b_, 0)) for n, a, b_ in names]
+        while not self.stop_flag:
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((time.time(), sm, self.smax, {n for n, bit in bits if bit and (mask & bit)}))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ts, line in self.rows:
-            if ts < t0 or ts > t1:
-                continue
-            f = [x.strip() for x in line.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             try:
-                sm.append(float(f[1])); smax = float(f[2])
+                sm, smax = float(f[1]), float(f[2])
             except Exception:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            reasons = {n for n, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9])
+                       if v.lower().startswith("active")}
+            self.rows.append((time.time(), sm, smax, reasons))
+
+    def stop(self, t0, t1):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, v, vmax, rs in self.rows:
+            if ts < t0 or ts > t1:
+                continue
+            sm.append(v); smax = vmax
+            reasons |= rs
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml (in-process)" if self.nvml is not None else "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -244,10 +292,8 @@ def run_ours(args):
             loss_ready[i % 2].synchronize()
             losses.append(float(loss_host[i % 2]))
 
-    # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up: its start-up (NVML initialisation, enumeration of
-    # every GPU of the box) takes about a second on multi-GPU boxes and stalls kernel launches of all ranks while it lasts --
-    # started right before the timed loop it inflated the first timed steps 1.3 - 2.5x (profiles/r02_scaling.md); its rows
-    # are filtered to the timed region afterwards
+    # the clock sampler is initialised BEFORE the warm-up (NVML initialisation is the expensive part); its rows are filtered to
+    # the timed region afterwards
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get("PN_BENCH_NO_SAMPLER"):      # (diagnostic switch; the driver's runs keep the sampler)
         sampler.start()
@@ -256,12 +302,26 @@ def run_ours(args):
         resident_step(i)
         flush.zero_()
         e2e_step(i, last=True)
-    if world > 1:
-        # first use of the barrier (and whatever NCCL sets up lazily behind it) belongs to the warm-up, not to the first timed
-        # step; one more untimed step lets the ranks settle after it
-        barrier()
+    # Settling: on fresh boxes the first steps after the warm-up were repeatedly 1.2 - 2.5x slower than the steady state, for
+    # 0.1 - 1 s, in the first process of a box only and for 1 as well as for N GPUs (profiles/r02_scaling.md: not the clock
+    # sampler, not the first barrier -- something outside the process).  The W warm-up steps are therefore followed by untimed
+    # steps until three consecutive step times agree within 5 % (at most 12; the decision is the max over ranks, so every rank
+    # runs the same number of steps).  The count is reported as config.settle_steps.
+    barrier()
+    settle_ms = []
+    while len(settle_ms) < 12:
+        a = torch.cuda.Event(enable_timing=True); b_ = torch.cuda.Event(enable_timing=True)
         flush.zero_()
-        resident_step(args.warmup)
+        a.record()
+        resident_step(args.warmup + len(settle_ms))
+        b_.record(); torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b_)], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        settle_ms.append(float(t.item()))
+        if len(settle_ms) >= 3 and max(settle_ms[-3:]) <= 1.05 * min(settle_ms[-3:]):
+            break
     # both timed loops start from the SAME model / optimizer state (the clustering, hence the number and kind of fitted
     # segments, drifts with every Adam step: without this the two loops would time different workloads)
     import copy
@@ -407,6 +467,8 @@ def run_ours(args):
     }
     out["per_step_ms"] = {"resident": [round(a.elapsed_time(b), 2) for a, b in zip([ev0] + marks_res[:-1], marks_res)],
                           "e2e": [round(a.elapsed_time(b), 2) for a, b in zip([ev2] + marks_e2e[:-1], marks_e2e)]}
+    out["config"]["settle_steps"] = len(settle_ms)
+    out["config"]["settle_ms"] = [round(v, 1) for v in settle_ms]
     out["config"]["mean_clusters_per_shape_last"] = (float(np.mean(hp.clusters[-4:])) if hp.clusters else None)
     out["config"]["fitted_segments_per_step"] = fits_per_step
     out["config"]["workload_pin"] = ("embedding + %.1f x RMS x code[gt patch]: mean-shift recovers the %d ground-truth patches of "
