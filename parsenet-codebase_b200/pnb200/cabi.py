@@ -193,6 +193,8 @@ def _take_launch_device():
 
 # ---- optional per-entry-point device timing (bench.py uses it for the roofline of the dominant kernel)
 TIMED = {}          # name -> list of (start_event, end_event); register a name to start collecting
+EVENT_POOL = []     # optional pre-created timing events (bench.py fills it before its timed loop: creating an event is a driver
+                    # call that can block behind other driver activity; recording one is not)
 
 
 def call(name, *args):
@@ -211,7 +213,8 @@ def _call_on_current(name, fn, args, dev):
     if ev is not None:
         import torch
         st = torch.cuda.current_stream(dev)
-        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a = EVENT_POOL.pop() if EVENT_POOL else torch.cuda.Event(enable_timing=True)
+        b = EVENT_POOL.pop() if EVENT_POOL else torch.cuda.Event(enable_timing=True)
         a.record(st)
         rc = fn(*args)
         b.record(st)
