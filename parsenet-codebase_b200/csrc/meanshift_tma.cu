@@ -934,7 +934,7 @@ ms_kth_collect_kernel(const __grid_constant__ CUtensorMap mC, const __grid_const
 // (mode 0), or with the largest occupancy count among the columns closer than the bandwidth (mode 1); first occurrence on ties.
 // Same tensor-core products and the same epilogue rule as ms_argsel_tc_kernel (meanshift_tc_argsel.cu), with the tile pipeline
 // of ms_kth_collect_kernel: 64-column tiles fetched by TMA from Bm and its small split part (written by split_small_kernel),
-// N = 64 MMAs -- an N = 32 MMA occupies the tensor pipe as long as an N = 64 one.
+// N = 64 MMAs: half as many tile hand-overs (barrier round trips, TMEM loads) per column as the 32-column loader-warp kernel.
 __global__ void split_small_kernel(const float* __restrict__ x, long long n, float* __restrict__ xs) {
     const long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (e + 3 < n) {

@@ -4,11 +4,7 @@
 #include "tc05.cuh"
 using namespace tc05;
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-    return pred != 0;
-}
+// (elect_one comes from the shipped tc05.cuh)
 __device__ __forceinline__ void mma_ts_nopred(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n"
                  ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
@@ -62,8 +58,8 @@ __global__ void __launch_bounds__(128) rate_kernel(int reps, long long* out) {
 
 template <int N, int MODE> void run(long long* d) {
     int reps = 50;
-    cudaFuncSetAttribute(rate_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    rate_kernel<N, MODE><<<1, 128, 64 * 1024>>>(reps, d);
+    cudaFuncSetAttribute(rate_kernel<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    rate_kernel<N, MODE><<<1, 128, 200 * 1024>>>(reps, d);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return; }
     long long h[2]; cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
@@ -72,6 +68,6 @@ template <int N, int MODE> void run(long long* d) {
 }
 int main() {
     long long* d; cudaMalloc(&d, 16);
-    run<32, 0>(d); run<32, 1>(d); run<64, 0>(d); run<64, 1>(d); run<128, 1>(d);
+    run<16, 1>(d); run<32, 0>(d); run<32, 1>(d); run<64, 0>(d); run<64, 1>(d); run<128, 1>(d); run<256, 1>(d);
     return 0;
 }
