@@ -3,6 +3,8 @@ sparse-row mean-shift backward, written without GPU access): the 256 threads of 
 SAME index expressions as the CUDA source (tile loaders, register-tile orientation, the three P tiles, gemm_pr, the
 partial-sum layout), and the result is compared with the closed form of oracle/port/meanshift.py.  A transposed tile or a
 swapped (i, j) in the kernel's indexing shows up here as a wrong gradient."""
+import os
+import pytest
 import numpy as np
 import torch
 
@@ -346,3 +348,52 @@ def test_kth_select_host_twin_and_bracket_plan(tmp_path):
             fails += below >= b
         assert fails == 0
         assert b * N / m < cap / 2 * 1.6
+
+
+# ------------------------------------------------------------------------------------- error model of the kNN filter (round 2)
+def _tf32_trunc(x):
+    return (x.view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+
+
+def _f32_toward_zero(v64):
+    f = v64.astype(np.float32)
+    over = np.abs(f.astype(np.float64)) > np.abs(v64)
+    f[over] = np.nextafter(f[over], np.float32(0))
+    return f
+
+
+@pytest.mark.parametrize("C,kind", [(64, "randn"), (128, "offset"), (256, "randn"), (256, "offset")])
+def test_knn_filter_error_interval_covers_a_pessimistic_tensor_core_model(C, kind):
+    """csrc/knn_tc.cu ranks pairs by a split-TF32 tensor-core cost and relies on |cost~ - cost| <= c0 (xx_i + xx_j) with
+    c0 = knn_tc_c0(C).  Numpy model of the worst the hardware may do -- operands truncated to tf32 (big part) and the small
+    part truncated again, the small x small product dropped (C = 64 / 128) , every K = 8 group summed exactly but the fp32
+    accumulator rounded TOWARD ZERO after each of the 3 C / 8 MMAs -- against the reference-order fp32 fmaf chain the exact
+    kernels use: the observed error must stay below HALF of the interval the kernel uses."""
+    rs = np.random.RandomState(C)
+    n = 300
+    x = (rs.randn(n, C) * (0.05 if kind == "offset" else 0.3) + (3.0 if kind == "offset" else 0.0)).astype(np.float32)
+    hi = _tf32_trunc(x)
+    lo = _tf32_trunc((x - hi).astype(np.float32))
+    # exact kernels: fmaf chain in channel order (float64 product is exact for fp32 operands; one rounding per step)
+    chain = np.zeros((n, n), np.float32)
+    for c in range(C):
+        chain = (chain.astype(np.float64) + x[:, c:c + 1].astype(np.float64) * x[None, :, c].astype(np.float64)).astype(np.float32)
+    xx = np.zeros(n, np.float32)
+    for c in range(C):
+        xx = (xx.astype(np.float64) + x[:, c].astype(np.float64) ** 2).astype(np.float32)
+    inner = (np.float32(-2.0) * chain).astype(np.float32)
+    cost = -(((-xx[None, :]) - inner).astype(np.float32) - xx[:, None]).astype(np.float32)
+    # tensor-core model
+    acc = np.zeros((n, n), np.float32)
+    H, L = hi.astype(np.float64), lo.astype(np.float64)
+    for k0 in range(0, C, 8):
+        for A, B in ((L, H), (H, L), (H, H)):
+            acc = _f32_toward_zero(acc.astype(np.float64) + A[:, k0:k0 + 8] @ B[:, k0:k0 + 8].T)
+    cost_tc = ((np.float32(-2.0) * acc + xx[None, :]).astype(np.float32) + xx[:, None]).astype(np.float32)
+    e = 3.0 / 1048576.0 + (3.0 * C / 8.0 + 8.0) / 4194304.0 + C / 16777216.0 + 8.0 / 16777216.0
+    c0 = np.float32(1.25 * e)                                    # knn_tc_c0 (csrc/knn_tc.cu)
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "parsenet-codebase_b200", "csrc",
+                            "knn_tc.cu")).read()
+    assert "3.0 / 1048576.0 + (3.0 * C / 8.0 + 8.0) / 4194304.0 + C / 16777216.0 + 8.0 / 16777216.0" in src and "1.25 * e" in src
+    ratio = np.abs(cost_tc.astype(np.float64) - cost.astype(np.float64)) / (c0 * (xx[:, None] + xx[None, :]).astype(np.float64))
+    assert ratio.max() < 0.5, ratio.max()
