@@ -384,11 +384,22 @@ def test_knn_filter_error_interval_covers_a_pessimistic_tensor_core_model(C, kin
     inner = (np.float32(-2.0) * chain).astype(np.float32)
     cost = -(((-xx[None, :]) - inner).astype(np.float32) - xx[:, None]).astype(np.float32)
     # tensor-core model
-    acc = np.zeros((n, n), np.float32)
     H, L = hi.astype(np.float64), lo.astype(np.float64)
-    for k0 in range(0, C, 8):
-        for A, B in ((L, H), (H, L), (H, H)):
-            acc = _f32_toward_zero(acc.astype(np.float64) + A[:, k0:k0 + 8] @ B[:, k0:k0 + 8].T)
+    if C == 256:
+        # collect256_kernel: the two split parts of the query rows are stacked along the TMEM lanes, two MMA chains (against the
+        # small and the big part of the column tile) accumulate hi.(lo + hi) in one half of the lanes and lo.(lo + hi) in the
+        # other; the halves are added in fp32 afterwards
+        acc_h = np.zeros((n, n), np.float32); acc_l = np.zeros((n, n), np.float32)
+        for k0 in range(0, C, 8):
+            for B in (L, H):
+                acc_h = _f32_toward_zero(acc_h.astype(np.float64) + H[:, k0:k0 + 8] @ B[:, k0:k0 + 8].T)
+                acc_l = _f32_toward_zero(acc_l.astype(np.float64) + L[:, k0:k0 + 8] @ B[:, k0:k0 + 8].T)
+        acc = (acc_h + acc_l).astype(np.float32)
+    else:
+        acc = np.zeros((n, n), np.float32)
+        for k0 in range(0, C, 8):
+            for A, B in ((L, H), (H, L), (H, H)):
+                acc = _f32_toward_zero(acc.astype(np.float64) + A[:, k0:k0 + 8] @ B[:, k0:k0 + 8].T)
     cost_tc = ((np.float32(-2.0) * acc + xx[None, :]).astype(np.float32) + xx[:, None]).astype(np.float32)
     e = 3.0 / 1048576.0 + (3.0 * C / 8.0 + 8.0) / 4194304.0 + C / 16777216.0 + 8.0 / 16777216.0
     c0 = np.float32(1.25 * e)                                    # knn_tc_c0 (csrc/knn_tc.cu)
