@@ -174,7 +174,6 @@ final_kernel(const unsigned* __restrict__ cval, const unsigned short* __restrict
         if (lane == 0) flags[row] = 1;
         return;
     }
-    constexpr int NR = NW * 16;                          // registers per lane covering the HALF slots the list can use
     unsigned Bt[NW][32];
     unsigned act[NW], valid[NW];
 #pragma unroll
@@ -189,7 +188,6 @@ final_kernel(const unsigned* __restrict__ cval, const unsigned short* __restrict
         }
         valid[w] = act[w];
     }
-    (void)NR;
     unsigned keep[NW][32];
 #pragma unroll
     for (int w = 0; w < NW; ++w) {

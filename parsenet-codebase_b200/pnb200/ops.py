@@ -80,7 +80,6 @@ def _knn_tc_workspace(dev, B, N, C, cap, stride):
         ws["xs"] = torch.empty((n_xs,), dtype=torch.float32, device=dev)
     if ws["colc"].numel() < n_colc:
         ws["colc"] = torch.empty((n_colc,), dtype=torch.float32, device=dev)
-    ws["last"] = True
     return ws
 
 
